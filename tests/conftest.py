@@ -1,0 +1,27 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def goldens():
+    with open(os.path.join(GOLDEN_DIR, "witness_goldens.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def ref_graphs():
+    with open(os.path.join(GOLDEN_DIR, "graphs.json")) as f:
+        return json.load(f)
