@@ -1,0 +1,167 @@
+/* qcdsim.h -- C ABI of the B200-native noisy-circuit sampling engine (libqcdsim.so).
+ *
+ * The reference (nlaanait/qcdenoise) has NO plugin / FFI interface on this path: its only seam is the Python
+ * call into qiskit-aer,
+ *     qk.execute(circuit, backend=AerSimulator, noise_model=..., shots=n_shots).result().get_counts()
+ *                                                                   qcdenoise/samplers.py:308-326
+ * followed by pure-Python reductions (samplers.py:195-202, witnesses.py:40-67).  Each entry point below cites the
+ * reference interface it replaces; INTEGRATION.md shows the ctypes stub a qcdenoise maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no C++/torch types; every function returns 0 on success, a QCD_E_* code
+ *     otherwise; qcd_last_error() gives the message of the last failure on that context.  Nothing throws.
+ *   - pointers marked [dev] are CUDA device pointers owned by the caller (e.g. torch tensors' data_ptr());
+ *     pointers marked [host] are ordinary host memory.  Work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  Functions that must size device work from device results
+ *     synchronise the stream internally (documented per function); outputs are complete on return only when
+ *     stated, otherwise after the caller synchronises `stream`.
+ *   - one qcd_ctx per (process, device); not thread-safe (one host thread per context, one process per GPU).
+ *   - bit order: state index bit q <-> qubit q; histogram bin x <-> qiskit Counts key format(x, '0{n}b').
+ *   - RNG: Philox4x32-10, key = (seed lo, seed hi), counter = (shot lo, shot hi, stream, circuit); `shot` is the
+ *     shot index inside its circuit, `stream` = ordinal of the stochastic op in the circuit's op list,
+ *     QCD_STREAM_MEASURE for the measurement draw, QCD_STREAM_READOUT + q/4 (32-bit word q%4) for the readout
+ *     flip of qubit q.  Results are therefore a pure function of (seed, circuit, shot): identical for any
+ *     partition of the shot range over GPUs and with trajectory de-duplication on or off.
+ */
+#ifndef QCDSIM_H
+#define QCDSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCD_ABI_VERSION 1
+
+/* error codes */
+#define QCD_OK 0
+#define QCD_E_INVALID 1     /* bad argument / malformed program */
+#define QCD_E_CUDA 2        /* CUDA runtime error (message has the cudaError string) */
+#define QCD_E_NOMEM 3       /* device memory budget too small for the request */
+#define QCD_E_UNSUPPORTED 4 /* valid request the engine does not implement (message says what) */
+#define QCD_E_STATE 5       /* call order (e.g. run before upload) */
+
+/* Gate-list IR: one qcd_op per instruction of the circuit, in program order.  This is the content of the qiskit
+ * QuantumCircuit the reference builds in graph_circuit.py:81-99,114-130,151-173 and stabilizers.py:136-156, plus the
+ * quantum errors its NoiseModel attaches (samplers.py:404-412, :588-608), made explicit.
+ * param_off indexes the shared `params` array (doubles).  Matrices are row-major, complex entries as (re, im)
+ * pairs, little-endian basis: index s = bit(q0) + 2*bit(q1). */
+typedef struct qcd_op {
+    uint16_t opcode;    /* QCD_OP_* */
+    uint8_t q0;         /* first qubit (control for CX) */
+    uint8_t q1;         /* second qubit or 0xFF */
+    uint32_t param_off; /* offset of this op's parameters in params[] (ignored when it has none) */
+} qcd_op;
+
+enum {
+    QCD_OP_ID = 0, QCD_OP_H, QCD_OP_X, QCD_OP_Y, QCD_OP_Z, QCD_OP_S, QCD_OP_SDG, QCD_OP_T, QCD_OP_TDG,
+    QCD_OP_RX, QCD_OP_RY, QCD_OP_RZ, /* params: theta */
+    QCD_OP_U1Q,                      /* params: 8 doubles (2x2 complex) */
+    QCD_OP_CX, QCD_OP_CZ, QCD_OP_SWAP,
+    QCD_OP_U2Q,                      /* params: 32 doubles (4x4 complex) */
+    /* stochastic ops ("sites"); each consumes one Philox stream, numbered in program order */
+    QCD_OP_KRAUS1Q,  /* params: m, then m * 8 doubles  (m Kraus matrices 2x2) */
+    QCD_OP_KRAUS2Q,  /* params: m, then m * 32 doubles (m Kraus matrices 4x4) -- density-matrix mode only */
+    QCD_OP_PAULI1Q,  /* params: 4 probabilities  (I, X, Y, Z) */
+    QCD_OP_PAULI2Q,  /* params: 16 probabilities, index = P(q0) + 4 P(q1) */
+    QCD_OP_RESET,    /* reset q0 to |0> */
+    QCD_OP_COUNT
+};
+
+#define QCD_STREAM_MEASURE 0xFFFFFFFFu
+#define QCD_STREAM_READOUT 0xFFFF0000u
+
+/* run flags */
+#define QCD_RUN_NO_DEDUP 1u /* one state per trajectory (literal Aer behaviour); default shares states between
+                               trajectories with identical branch histories -- same results, fewer sweeps */
+
+typedef struct qcd_ctx qcd_ctx;
+
+/* run statistics, filled by the last qcd_run_* call */
+typedef struct qcd_stats {
+    uint64_t sweep_launches;   /* state-sweep kernel launches */
+    uint64_t aux_launches;     /* all other kernels of ours (decide, scan, sample, parity, ...) */
+    uint64_t node_sweeps;      /* (state, sweep) pairs executed = full read+write passes over one state */
+    uint64_t sweep_bytes;      /* algorithmic bytes moved by sweeps: reads + writes of amplitudes */
+    uint64_t leaves;           /* distinct final states sampled */
+    uint64_t trajectories;     /* trajectories (shots) simulated */
+    uint64_t max_live_states;  /* high-water mark of resident states */
+    double sweep_ms;           /* CUDA-event time spent inside sweep kernels (only when timing is enabled) */
+} qcd_stats;
+
+int qcd_abi_version(void);
+
+/* Context.  mem_budget_bytes = device memory the engine may allocate for states (0 = 80% of free memory). */
+int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out);
+void qcd_destroy(qcd_ctx* ctx);
+const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of the last failed qcd_create */
+int qcd_set_option(qcd_ctx* ctx, const char* key, double value); /* "time_sweeps" 0/1, "tile_bits", "max_chunk" */
+int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
+
+/* Replaces: building `circuit` + `noise_model` and handing them to qk.execute (samplers.py:322-324).
+ * Uploads B circuits of n_qubits each: circuit c owns ops[op_offsets[c] .. op_offsets[c+1]).  [host] pointers;
+ * data is copied.  Lowering (gate fusion, CX -> H.CZ.H, sweep scheduling) happens here, on the host. */
+int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
+                        size_t n_params, int n_circuits, int n_qubits);
+
+/* Replaces: AerSimulator `statevector` method under a noise model, i.e. execute(...).result().get_counts() for
+ * shots <= 2^n or n > ~14 (samplers.py:308-326; stabilizers.py:214).  Global shot index g in
+ * [shot_begin, shot_end) of the flattened [n_circuits][shots_per_circuit] space: circuit = g / shots_per_circuit,
+ * shot = g % shots_per_circuit  (the multi-GPU partition: rank r takes a contiguous slice).
+ *   precision: 32 (complex64) or 64 (complex128).
+ *   readout [host, may be NULL]: [n_circuits][n_qubits][2][2] doubles, row = true bit, col = measured bit.
+ *   hist [dev, may be NULL]: [n_circuits][2^n] uint32, ADDED to (caller zeroes).
+ *   outcomes [dev, may be NULL]: [shot_end - shot_begin] uint32 basis indices (requires n_qubits <= 32).
+ * Synchronises `stream` internally (tree scheduling needs device counts); results are complete on return. */
+int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
+                            uint64_t shot_begin, uint64_t shot_end, const double* readout, uint32_t* hist,
+                            uint32_t* outcomes, uint32_t flags, void* stream);
+
+/* Replaces: AerSimulator `density_matrix` method (what Aer selects for noisy circuits with shots > 2^n), up to
+ * the exact outcome distribution.  probs_out [dev]: [n_circuits][2^n] float (precision 32) or double (64): the
+ * diagonal of rho after the last op (before classical readout error).  circuit_begin/end select a slice.
+ * Asynchronous on `stream`. */
+int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,
+                           void* stream);
+
+/* Classical readout error applied to probability vectors, in place: probs [dev] [n_vectors][2^n] (float/double by
+ * precision), readout [host] [n_vectors][n][2][2].  Replaces Aer's ReadoutError on `measure` in distribution. */
+int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,
+                            const double* readout, void* stream);
+
+/* Replaces: Aer `sample_measure` on an exact distribution.  Draws shots_per_vector outcomes from each of the
+ * n_vectors distributions probs [dev] by inverse CDF with the QCD_STREAM_MEASURE draw of (seed, first_circuit + v,
+ * shot) for shot in [shot_begin, shot_end); optional readout flips as above ([host], may be NULL).
+ * hist [dev] [n_vectors][2^n] uint32 is ADDED to.  Asynchronous on `stream`. */
+int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+                          uint64_t shot_begin, uint64_t shot_end, uint64_t seed, uint32_t first_circuit,
+                          const double* readout, uint32_t* hist, void* stream);
+
+/* Replaces: Witness._construct_diagonals + igmit.expectation_value (witnesses.py:40-67) without ever building the
+ * 2^n diagonals:  D[x] = (-1)^popcount(x & mask).
+ *   hist [dev] [n_vectors][2^n] uint32 counts ->
+ *   signed_sums [dev] [n_vectors][n_masks] int64 = sum_x hist[x] * D_mask[x]     (bit-exact integer arithmetic)
+ *   totals      [dev] [n_vectors] int64          = sum_x hist[x]
+ * masks [host] [n_vectors][n_masks] uint32 when per_vector_masks != 0, else [n_masks] shared.
+ * mean = signed/total, std = sqrt((1 - mean^2)/total) are formed by the caller in double.  Asynchronous. */
+int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_qubits, const uint32_t* masks,
+                      int n_masks, int per_vector_masks, int64_t* signed_sums, int64_t* totals, void* stream);
+
+/* Same reduction on exact probabilities (float/double by precision): expvals [dev] [n_vectors][n_masks] double =
+ * sum_x p[x] D_mask[x], accumulated in double with a fixed reduction order (deterministic). Asynchronous. */
+int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+                     const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream);
+
+/* Host-only introspection (no GPU needed): lower + schedule ONE circuit and write a JSON description of the sweep
+ * program (tile bits, passes, fused matrices, sign terms, site groups) into buf.  mode: 0 = statevector
+ * trajectories, 1 = density matrix.  Returns QCD_E_NOMEM if cap is too small (required size in *needed).
+ * Used by the CPU tests to check the host logic against the oracle. */
+int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
+                            int mode, int precision, int tile_bits, char* buf, size_t cap, size_t* needed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCDSIM_H */

@@ -1,0 +1,610 @@
+// kernels.cu -- decide (trajectory tree), prefix-sum sampling, density-matrix helpers and parity reductions.
+#include "kernels.cuh"
+
+#include "../../include/qcdsim.h"
+
+namespace qcd {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 draw(uint64_t seed, uint32_t circuit, uint64_t shot, uint32_t stream) {
+    return philox4x32_10(make_uint4((uint32_t)shot, (uint32_t)(shot >> 32), stream, circuit),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ double u53(uint4 w) {
+    uint64_t x = ((uint64_t)w.y << 32) | (uint64_t)w.x;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------ decide
+__global__ void node_probs_kernel(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles,
+                                  double* P) {
+    // one CTA (128 threads) per node: P[b] = sum over tiles of partials[slot][tile][b], fixed order
+    __shared__ double red[128][4];
+    const uint32_t nd = blockIdx.x;
+    const double* p = partials + (uint64_t)nodes[nd].dst_slot * tiles * 4u;
+    double acc[4] = {0, 0, 0, 0};
+    for (uint32_t t = threadIdx.x; t < tiles; t += 128) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[b] += p[(uint64_t)t * 4u + b];
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) red[threadIdx.x][b] = acc[b];
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) red[threadIdx.x][b] += red[threadIdx.x + o][b];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) P[(uint64_t)nd * 4u + threadIdx.x] = red[0][threadIdx.x];
+}
+
+// Resolve the decisions of one site group for one trajectory (force < 0) or replay a given branch word (force >= 0)
+// to obtain the rescale factor.  Returns the branch word; *scale_out (if given) = 1/sqrt(prod p_j) over the
+// non-unit decisions.
+__device__ __forceinline__ uint32_t resolve_group(const Group& G, const SubSite* subs, const double* gdata,
+                                                  const double* Pin, uint64_t seed, uint32_t circuit, uint64_t shot,
+                                                  long long force, double* scale_out) {
+    double P[4] = {1.0, 0.0, 0.0, 0.0};
+    if (G.q[0] >= 0) {
+        P[0] = Pin[0];
+        P[1] = Pin[1];
+        P[2] = Pin[2];
+        P[3] = Pin[3];
+    }
+    uint32_t word = 0;
+    double norm2 = 1.0;
+    for (uint32_t u = G.sub_begin; u < G.sub_end; u++) {
+        const SubSite ss = subs[u];
+        const double* d = gdata + ss.data_off;
+        double tot = 0.0;
+        for (int j = 0; j < ss.nbranch; j++) {
+            const double* w = d + j * 20;
+            tot += w[0] * P[0] + w[1] * P[1] + w[2] * P[2] + w[3] * P[3];
+        }
+        int sel;
+        if (force >= 0) {
+            sel = (int)((force >> ss.shift) & ((1u << ss.nbits) - 1u));
+        } else {
+            const double target = u53(draw(seed, circuit, shot, ss.stream)) * tot;
+            double cum = 0.0;
+            sel = ss.nbranch - 1;
+            for (int j = 0; j < ss.nbranch; j++) {
+                const double* w = d + j * 20;
+                cum += w[0] * P[0] + w[1] * P[1] + w[2] * P[2] + w[3] * P[3];
+                if (cum > target) {
+                    sel = j;
+                    break;
+                }
+            }
+        }
+        const double* w = d + sel * 20;
+        const double pj = w[0] * P[0] + w[1] * P[1] + w[2] * P[2] + w[3] * P[3];
+        const double psum = P[0] + P[1] + P[2] + P[3];
+        if (!ss.unit) norm2 *= pj / psum;
+        const double* Tm = w + 4;
+        double Q[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) Q[x] = Tm[x * 4] * P[0] + Tm[x * 4 + 1] * P[1] + Tm[x * 4 + 2] * P[2] + Tm[x * 4 + 3] * P[3];
+        const double inv = pj > 0.0 ? 1.0 / pj : 0.0;
+        // keep sum(P) (the squared norm of the stored state) unchanged: P' = T P * (psum / p_j)
+#pragma unroll
+        for (int x = 0; x < 4; x++) P[x] = Q[x] * inv * psum;
+        word |= (uint32_t)sel << ss.shift;
+    }
+    if (scale_out) {
+        // the stored state has squared norm sum(Pin) (~1); renormalise to exactly 1 as well
+        double n0 = G.q[0] >= 0 ? (Pin[0] + Pin[1] + Pin[2] + Pin[3]) : 1.0;
+        *scale_out = 1.0 / sqrt(norm2 * n0);
+    }
+    return word;
+}
+
+template <typename T>
+__global__ void traj_branch_kernel(DevProgram<T> prog, const NodeRec* parents, const double* P, const uint32_t* owner,
+                                   const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    const uint32_t o = owner[i];
+    const NodeRec nd = parents[o];
+    const Sweep& S = prog.sweeps[nd.sweep + 1];
+    uint32_t word = 0;
+    if (S.group >= 0)
+        word = resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)o * 4u, seed, nd.circuit,
+                             shots[i], -1, nullptr);
+    keys[i] = ((uint64_t)o << 32) | word;
+}
+
+template <typename T>
+__global__ void child_scale_kernel(DevProgram<T> prog, NodeRec* children, uint32_t n_children, const double* P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_children) return;
+    NodeRec& c = children[i];
+    const Sweep& S = prog.sweeps[c.sweep];
+    double sc = 1.0;
+    if (S.group >= 0)
+        resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)c.parent * 4u, 0, 0, 0,
+                      (long long)c.branch, &sc);
+    c.scale = sc;
+}
+
+__global__ void fill_owner_kernel(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    // nodes are sorted by traj_off (relative to nodes[0].traj_off): last node with traj_off <= i + base
+    const uint32_t base = nodes[0].traj_off;
+    uint32_t lo = 0, hi = n_nodes - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (nodes[mid].traj_off - base <= i) lo = mid;
+        else hi = mid - 1;
+    }
+    owner[i] = lo;
+}
+
+__global__ void iota_kernel(uint32_t* p, uint32_t n, uint32_t start) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = start + i;
+}
+
+// ------------------------------------------------------------------------------------------------ scans
+// inclusive scan of up to 1024 doubles by 256 threads (4 consecutive each), fixed association order
+__device__ __forceinline__ void block_scan_1024(double (&v)[4], double* warp_tot /*[8]*/, double carry_in) {
+    v[1] += v[0];
+    v[2] += v[1];
+    v[3] += v[2];
+    double t = v[3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double n = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += n;
+    }
+    if (lane == 31) warp_tot[wid] = t;
+    __syncthreads();
+    double off = carry_in;
+    for (int w = 0; w < wid; w++) off += warp_tot[w];
+    off += t - v[3];
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] += off;
+    __syncthreads();
+}
+
+// level 1: each CTA scans one block of 1024 chunk sums in place, writes the block total
+__global__ void scan_l1_kernel(const NodeRec* leaves, const uint32_t* slots, double* chunk_sums, uint64_t chunk_stride,
+                               double* block_sums, uint64_t block_stride, uint32_t n_chunks) {
+    __shared__ double warp_tot[8];
+    const uint32_t item = blockIdx.y;
+    uint32_t slot;
+    if (leaves) {
+        if (!(leaves[item].flags & NODE_LEAF)) return;
+        slot = leaves[item].dst_slot;
+    } else {
+        slot = slots ? slots[item] : item;
+    }
+    double* cs = chunk_sums + (uint64_t)slot * chunk_stride;
+    const uint32_t b = blockIdx.x;
+    const uint32_t base = (b << SCAN_BLOCK_LOG) + threadIdx.x * 4u;
+    double v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] = (base + e < n_chunks) ? cs[base + e] : 0.0;
+    block_scan_1024(v, warp_tot, 0.0);
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+        if (base + e < n_chunks) cs[base + e] = v[e];
+    if (threadIdx.x == 255) block_sums[(uint64_t)slot * block_stride + b] = v[3];
+}
+
+// level 2: one CTA per state scans its block totals in place
+__global__ void scan_l2_kernel(const NodeRec* leaves, const uint32_t* slots, double* block_sums, uint64_t block_stride,
+                               uint32_t n_blocks) {
+    __shared__ double warp_tot[8];
+    __shared__ double s_carry;
+    const uint32_t item = blockIdx.x;
+    uint32_t slot;
+    if (leaves) {
+        if (!(leaves[item].flags & NODE_LEAF)) return;
+        slot = leaves[item].dst_slot;
+    } else {
+        slot = slots ? slots[item] : item;
+    }
+    double* bs = block_sums + (uint64_t)slot * block_stride;
+    double carry = 0.0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const uint32_t base = b0 + threadIdx.x * 4u;
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (base + e < n_blocks) ? bs[base + e] : 0.0;
+        block_scan_1024(v, warp_tot, carry);
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (base + e < n_blocks) bs[base + e] = v[e];
+        if (threadIdx.x == 255) s_carry = v[3];
+        __syncthreads();
+        carry = s_carry;
+        __syncthreads();
+    }
+}
+
+// first index in [lo, hi) with arr[i] > target, or hi - 1
+__device__ __forceinline__ uint32_t upper_search(const double* arr, uint32_t lo, uint32_t hi, double target) {
+    uint32_t a = lo, b = hi;  // invariant: answer in [a, b]
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if (arr[mid] > target) b = mid;
+        else a = mid + 1;
+    }
+    return a < hi ? a : hi - 1;
+}
+
+__device__ __forceinline__ uint32_t readout_flips(uint32_t x, int n, const double* flip, uint64_t seed,
+                                                  uint32_t circuit, uint64_t shot) {
+    for (int blk = 0; blk * 4 < n; blk++) {
+        const uint4 w = draw(seed, circuit, shot, QCD_STREAM_READOUT + blk);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = blk * 4 + j;
+            if (q < n) {
+                const uint32_t bit = (x >> q) & 1u;
+                const double pf = flip[((uint64_t)circuit * n + q) * 2u + bit];
+                if ((double)ww[j] * (1.0 / 4294967296.0) < pf) x ^= 1u << q;
+            }
+        }
+    }
+    return x;
+}
+
+template <typename T>
+__global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_t slot_stride, const double* chunk_sums,
+                              uint64_t chunk_stride, const double* block_sums, uint64_t block_stride, uint32_t n_chunks,
+                              int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj, uint64_t seed,
+                              const double* flip, uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit,
+                              uint64_t shot_begin) {
+    typedef typename Cplx<T>::type C;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    const NodeRec nd = leaves[owner[i]];
+    if (!(nd.flags & NODE_LEAF)) return;
+    const uint64_t shot = shots[i];
+    const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
+    const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
+    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+    const double tot = bs[n_blocks - 1];
+    double target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * tot;
+    const uint32_t b = upper_search(bs, 0, n_blocks, target);
+    if (b > 0) target -= bs[b - 1];
+    const uint32_t cbeg = b << SCAN_BLOCK_LOG;
+    const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
+    const uint32_t c = upper_search(cs, cbeg, cend, target);
+    if (c > cbeg) target -= cs[c - 1];
+    const int chunk_log = n_bits < CHUNK_LOG ? n_bits : CHUNK_LOG;
+    const C* amp = reinterpret_cast<const C*>(states) + (uint64_t)nd.dst_slot * slot_stride + ((uint64_t)c << chunk_log);
+    const uint32_t len = 1u << chunk_log;
+    uint32_t e_sel = len - 1;
+    double acc = 0.0;
+    for (uint32_t e = 0; e < len; e++) {
+        const C a = amp[e];
+        const T w = a.x * a.x + a.y * a.y;
+        acc += (double)w;
+        if (acc > target) {
+            e_sel = e;
+            break;
+        }
+    }
+    uint32_t x = (c << chunk_log) + e_sel;
+    if (flip) x = readout_flips(x, n_bits, flip, seed, nd.circuit, shot);
+    if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
+    if (outcomes) outcomes[(uint64_t)nd.circuit * shots_per_circuit + shot - shot_begin] = x;
+}
+
+// ------------------------------------------------------------------------------------------------ DM helpers
+template <typename T>
+__global__ void extract_diag_kernel(const void* states, uint64_t slot_stride, const uint32_t* slots, int n, T* probs) {
+    typedef typename Cplx<T>::type C;
+    const uint32_t v = blockIdx.y;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (1u << n)) return;
+    const C* st = reinterpret_cast<const C*>(states) + (uint64_t)slots[v] * slot_stride;
+    probs[((uint64_t)v << n) + x] = st[(uint64_t)x * ((1ull << n) + 1ull)].x;
+}
+
+template <typename T>
+__global__ void readout_probs_kernel(T* probs, int n, int q, const double* conf) {
+    // pairs (x with bit q = 0, x | 1<<q): p0' = c00 p0 + c10 p1 ; p1' = c01 p0 + c11 p1   (row = true, col = measured)
+    const uint32_t v = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << (n - 1))) return;
+    const uint32_t x0 = ((i >> q) << (q + 1)) | (i & ((1u << q) - 1u));
+    T* p = probs + ((uint64_t)v << n);
+    const double* c = conf + ((uint64_t)v * n + q) * 4u;
+    const double p0 = (double)p[x0], p1 = (double)p[x0 | (1u << q)];
+    p[x0] = (T)(c[0] * p0 + c[2] * p1);
+    p[x0 | (1u << q)] = (T)(c[1] * p0 + c[3] * p1);
+}
+
+template <typename T>
+__global__ void prob_chunks_kernel(const T* probs, int n, double* chunk_sums, uint64_t chunk_stride) {
+    const uint32_t v = blockIdx.y;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk_log = n < CHUNK_LOG ? n : CHUNK_LOG;
+    const uint32_t n_chunks = 1u << (n - chunk_log);
+    if (c >= n_chunks) return;
+    const T* p = probs + ((uint64_t)v << n) + ((uint64_t)c << chunk_log);
+    double acc = 0.0;
+    for (uint32_t e = 0; e < (1u << chunk_log); e++) acc += (double)p[e];
+    chunk_sums[(uint64_t)v * chunk_stride + c] = acc;
+}
+
+template <typename T>
+__global__ void sample_probs_kernel(const T* probs, int n, const double* chunk_sums, uint64_t chunk_stride,
+                                    const double* block_sums, uint64_t block_stride, uint32_t n_chunks,
+                                    uint64_t shot_begin, uint64_t n_shots, uint64_t seed, uint32_t first_circuit,
+                                    const double* flip, uint32_t* hist) {
+    const uint32_t v = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_shots) return;
+    const uint64_t shot = shot_begin + i;
+    const uint32_t circuit = first_circuit + v;
+    const double* cs = chunk_sums + (uint64_t)v * chunk_stride;
+    const double* bs = block_sums + (uint64_t)v * block_stride;
+    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+    double target = u53(draw(seed, circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+    const uint32_t b = upper_search(bs, 0, n_blocks, target);
+    if (b > 0) target -= bs[b - 1];
+    const uint32_t cbeg = b << SCAN_BLOCK_LOG;
+    const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
+    const uint32_t c = upper_search(cs, cbeg, cend, target);
+    if (c > cbeg) target -= cs[c - 1];
+    const int chunk_log = n < CHUNK_LOG ? n : CHUNK_LOG;
+    const T* p = probs + ((uint64_t)v << n) + ((uint64_t)c << chunk_log);
+    const uint32_t len = 1u << chunk_log;
+    uint32_t e_sel = len - 1;
+    double acc = 0.0;
+    for (uint32_t e = 0; e < len; e++) {
+        acc += (double)p[e];
+        if (acc > target) {
+            e_sel = e;
+            break;
+        }
+    }
+    uint32_t x = (c << chunk_log) + e_sel;
+    if (flip) x = readout_flips(x, n, flip, seed, v /* flip table is indexed by vector */, shot);
+    atomicAdd(hist + ((uint64_t)v << n) + x, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ parity
+// signed_sums[v][m] = sum_x hist[v][x] * (-1)^popc(x & mask[m]) ; integer arithmetic -> order independent
+constexpr int PAR_GROUP = 8;
+__global__ void parity_counts_kernel(const uint32_t* hist, int n, const uint32_t* masks, int n_masks, int per_vec,
+                                     long long* signed_sums, long long* totals) {
+    const uint32_t v = blockIdx.y;
+    const uint32_t* h = hist + ((uint64_t)v << n);
+    const uint32_t* mk = masks + (per_vec ? (uint64_t)v * n_masks : 0);
+    const uint64_t N = 1ull << n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int m0 = 0; m0 < n_masks; m0 += PAR_GROUP) {
+        uint32_t mm[PAR_GROUP];
+        long long acc[PAR_GROUP];
+#pragma unroll
+        for (int j = 0; j < PAR_GROUP; j++) {
+            mm[j] = (m0 + j < n_masks) ? mk[m0 + j] : 0u;
+            acc[j] = 0;
+        }
+        long long tot = 0;
+        for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < N; x += stride) {
+            const long long c = (long long)h[x];
+            if (c == 0) continue;
+            tot += c;
+#pragma unroll
+            for (int j = 0; j < PAR_GROUP; j++) acc[j] += (__popc((uint32_t)x & mm[j]) & 1) ? -c : c;
+        }
+#pragma unroll
+        for (int j = 0; j < PAR_GROUP; j++) {
+            long long a = acc[j];
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+            if ((threadIdx.x & 31) == 0 && m0 + j < n_masks && a != 0)
+                atomicAdd((unsigned long long*)(signed_sums + (uint64_t)v * n_masks + m0 + j), (unsigned long long)a);
+        }
+        if (m0 == 0) {
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+            if ((threadIdx.x & 31) == 0 && tot != 0)
+                atomicAdd((unsigned long long*)(totals + v), (unsigned long long)tot);
+        }
+    }
+}
+
+// expvals from exact probabilities: per-CTA partial sums (fixed order), then a second kernel adds the partials in order
+template <typename T>
+__global__ void parity_probs_kernel(const T* probs, int n, const uint32_t* masks, int n_masks, int per_vec,
+                                    double* partial /*[v][m][gridDim.x]*/) {
+    __shared__ double red[8];
+    const uint32_t v = blockIdx.y;
+    const T* p = probs + ((uint64_t)v << n);
+    const uint32_t* mk = masks + (per_vec ? (uint64_t)v * n_masks : 0);
+    const uint64_t N = 1ull << n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int m = 0; m < n_masks; m++) {
+        const uint32_t mm = mk[m];
+        double acc = 0.0;
+        for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < N; x += stride) {
+            const double c = (double)p[x];
+            acc += (__popc((uint32_t)x & mm) & 1) ? -c : c;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+            partial[((uint64_t)v * n_masks + m) * gridDim.x + blockIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+__global__ void parity_final_kernel(const double* partial, uint32_t n_part, uint32_t n_out, double* expvals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    double t = 0.0;
+    for (uint32_t j = 0; j < n_part; j++) t += partial[(uint64_t)i * n_part + j];
+    expvals[i] = t;
+}
+
+inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}  // namespace
+
+// ==================================================================================================== launchers
+void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles, double* P,
+                       cudaStream_t st) {
+    if (n_nodes) node_probs_kernel<<<n_nodes, 128, 0, st>>>(nodes, n_nodes, partials, tiles, P);
+}
+template <typename T>
+void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
+                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st) {
+    if (n_traj) traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, shots, n_traj, seed, keys);
+}
+template <typename T>
+void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t n_children, const double* P,
+                        cudaStream_t st) {
+    if (n_children) child_scale_kernel<T><<<cdiv(n_children, 128), 128, 0, st>>>(prog, children, n_children, P);
+}
+void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj, cudaStream_t st) {
+    if (n_traj) fill_owner_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(nodes, n_nodes, owner, n_traj);
+}
+void launch_iota(uint32_t* p, uint32_t n, uint32_t start, cudaStream_t st) {
+    if (n) iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n, start);
+}
+void launch_scan_chunks(const NodeRec* leaves, uint32_t n_leaves, double* chunk_sums, uint64_t chunk_stride,
+                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st) {
+    if (!n_leaves) return;
+    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+    for (uint32_t y0 = 0; y0 < n_leaves; y0 += 32768) {
+        uint32_t ny = n_leaves - y0 < 32768 ? n_leaves - y0 : 32768;
+        scan_l1_kernel<<<dim3(n_blocks, ny), 256, 0, st>>>(leaves + y0, nullptr, chunk_sums, chunk_stride, block_sums,
+                                                           block_stride, n_chunks);
+    }
+    scan_l2_kernel<<<n_leaves, 256, 0, st>>>(leaves, nullptr, block_sums, block_stride, n_blocks);
+}
+void launch_scan_vectors(uint32_t n_vec, double* chunk_sums, uint64_t chunk_stride, double* block_sums,
+                         uint64_t block_stride, uint32_t n_chunks, cudaStream_t st) {
+    if (!n_vec) return;
+    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        scan_l1_kernel<<<dim3(n_blocks, ny), 256, 0, st>>>(nullptr, nullptr, chunk_sums + (uint64_t)y0 * chunk_stride,
+                                                           chunk_stride, block_sums + (uint64_t)y0 * block_stride,
+                                                           block_stride, n_chunks);
+    }
+    scan_l2_kernel<<<n_vec, 256, 0, st>>>(nullptr, nullptr, block_sums, block_stride, n_blocks);
+}
+template <typename T>
+void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states, uint64_t slot_stride,
+                   const double* chunk_sums, uint64_t chunk_stride, const double* block_sums, uint64_t block_stride,
+                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj,
+                   uint64_t seed, const double* flip, uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit,
+                   uint64_t shot_begin, cudaStream_t st) {
+    (void)n_leaves;
+    if (n_traj)
+        sample_kernel<T><<<cdiv(n_traj, 128), 128, 0, st>>>(leaves, states, slot_stride, chunk_sums, chunk_stride,
+                                                            block_sums, block_stride, n_chunks, n_bits, owner, shots,
+                                                            n_traj, seed, flip, hist, outcomes, shots_per_circuit,
+                                                            shot_begin);
+}
+template <typename T>
+void launch_extract_diag(const void* states, uint64_t slot_stride, const uint32_t* slots, uint32_t n_vec, int n,
+                         T* probs, cudaStream_t st) {
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        extract_diag_kernel<T><<<dim3(cdiv(1ull << n, 256), ny), 256, 0, st>>>(states, slot_stride, slots + y0, n,
+                                                                                probs + ((uint64_t)y0 << n));
+    }
+}
+template <typename T>
+void launch_readout_probs(T* probs, uint32_t n_vec, int n, const double* conf, cudaStream_t st) {
+    for (int q = 0; q < n; q++)
+        for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+            uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+            readout_probs_kernel<T><<<dim3(cdiv(1ull << (n - 1), 256), ny), 256, 0, st>>>(
+                probs + ((uint64_t)y0 << n), n, q, conf + (uint64_t)y0 * n * 4u);
+        }
+}
+template <typename T>
+void launch_prob_chunks(const T* probs, uint32_t n_vec, int n, double* chunk_sums, uint64_t chunk_stride,
+                        cudaStream_t st) {
+    const int chunk_log = n < CHUNK_LOG ? n : CHUNK_LOG;
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        prob_chunks_kernel<T><<<dim3(cdiv(1ull << (n - chunk_log), 128), ny), 128, 0, st>>>(
+            probs + ((uint64_t)y0 << n), n, chunk_sums + (uint64_t)y0 * chunk_stride, chunk_stride);
+    }
+}
+template <typename T>
+void launch_sample_probs(const T* probs, uint32_t n_vec, int n, const double* chunk_sums, uint64_t chunk_stride,
+                         const double* block_sums, uint64_t block_stride, uint32_t n_chunks, uint64_t shot_begin,
+                         uint64_t n_shots, uint64_t seed, uint32_t first_circuit, const double* flip, uint32_t* hist,
+                         cudaStream_t st) {
+    if (!n_shots) return;
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        sample_probs_kernel<T><<<dim3(cdiv(n_shots, 128), ny), 128, 0, st>>>(
+            probs + ((uint64_t)y0 << n), n, chunk_sums + (uint64_t)y0 * chunk_stride, chunk_stride,
+            block_sums + (uint64_t)y0 * block_stride, block_stride, n_chunks, shot_begin, n_shots, seed,
+            first_circuit + y0, flip ? flip + (uint64_t)y0 * n * 2u : nullptr, hist + ((uint64_t)y0 << n));
+    }
+}
+void launch_parity_counts(const uint32_t* hist, uint32_t n_vec, int n, const uint32_t* masks, int n_masks,
+                          int per_vec, long long* signed_sums, long long* totals, cudaStream_t st) {
+    uint32_t gx = cdiv(1ull << n, 256 * 8);
+    if (gx > 1184) gx = 1184;
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        parity_counts_kernel<<<dim3(gx, ny), 256, 0, st>>>(hist + ((uint64_t)y0 << n), n,
+                                                          masks + (per_vec ? (uint64_t)y0 * n_masks : 0), n_masks,
+                                                          per_vec, signed_sums + (uint64_t)y0 * n_masks, totals + y0);
+    }
+}
+template <typename T>
+void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* masks, int n_masks, int per_vec,
+                         double* partial, uint32_t n_part, double* expvals, cudaStream_t st) {
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        parity_probs_kernel<T><<<dim3(n_part, ny), 256, 0, st>>>(probs + ((uint64_t)y0 << n), n,
+                                                                 masks + (per_vec ? (uint64_t)y0 * n_masks : 0), n_masks,
+                                                                 per_vec, partial + (uint64_t)y0 * n_masks * n_part);
+    }
+    parity_final_kernel<<<cdiv((uint64_t)n_vec * n_masks, 128), 128, 0, st>>>(partial, n_part, n_vec * n_masks, expvals);
+}
+
+#define INST(T)                                                                                                        \
+    template void launch_traj_branch<T>(const DevProgram<T>&, const NodeRec*, const double*, const uint32_t*,         \
+                                        const uint32_t*, uint32_t, uint64_t, uint64_t*, cudaStream_t);                \
+    template void launch_child_scale<T>(const DevProgram<T>&, NodeRec*, uint32_t, const double*, cudaStream_t);       \
+    template void launch_sample<T>(const NodeRec*, uint32_t, const void*, uint64_t, const double*, uint64_t,          \
+                                   const double*, uint64_t, uint32_t, int, const uint32_t*, const uint32_t*, uint32_t, \
+                                   uint64_t, const double*, uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);  \
+    template void launch_extract_diag<T>(const void*, uint64_t, const uint32_t*, uint32_t, int, T*, cudaStream_t);    \
+    template void launch_readout_probs<T>(T*, uint32_t, int, const double*, cudaStream_t);                            \
+    template void launch_prob_chunks<T>(const T*, uint32_t, int, double*, uint64_t, cudaStream_t);                    \
+    template void launch_sample_probs<T>(const T*, uint32_t, int, const double*, uint64_t, const double*, uint64_t,   \
+                                         uint32_t, uint64_t, uint64_t, uint64_t, uint32_t, const double*, uint32_t*,  \
+                                         cudaStream_t);                                                               \
+    template void launch_parity_probs<T>(const T*, uint32_t, int, const uint32_t*, int, int, double*, uint32_t,       \
+                                         double*, cudaStream_t);
+INST(float)
+INST(double)
+
+}  // namespace qcd

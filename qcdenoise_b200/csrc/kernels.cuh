@@ -1,0 +1,118 @@
+// kernels.cuh -- hand-written sm_100a kernels of the sampling engine.
+//
+//  sweep_kernel      one full read+write pass over a batch of states: a CTA owns a 2^k-amplitude tile (contiguous
+//                    2^L runs + scattered high bits) staged in XOR-swizzled shared memory; passes keep 2^4
+//                    amplitudes per thread in registers and apply every fused op of the pass there; the store phase
+//                    also reduces the joint populations the next stochastic site needs and, on the final sweep, the
+//                    32-amplitude probability chunk sums used for measurement sampling.           (HBM bound)
+//  node_probs / traj_branch / child_scale / fill_owner   the per-level "decide" step of the trajectory tree,
+//                    Philox4x32-10 keyed (seed; shot, stream, circuit)
+//  scan_* / sample_* hierarchical prefix sums + inverse-CDF measurement sampling into histograms
+//  parity_*          bitmask-parity stabilizer reductions
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace qcd {
+
+struct NodeRec {
+    uint32_t src_slot;   // parent state (ignored for SW_PREP sweeps)
+    uint32_t dst_slot;
+    uint32_t sweep;      // absolute index into sweeps[] of the sweep that PRODUCES this node
+    uint32_t branch;     // branch word resolved for that sweep's group
+    double scale;        // 1/sqrt(prod p_j) applied while loading
+    uint32_t circuit;
+    uint32_t traj_off;   // trajectories of this node: [traj_off, traj_off + traj_cnt) of the level's array
+    uint32_t traj_cnt;
+    uint32_t parent;     // index of the parent in the previous level's node array
+    uint32_t flags;      // NODE_LEAF: `sweep` is the circuit's last sweep
+    uint32_t pad;
+};
+constexpr uint32_t NODE_LEAF = 1;
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { typedef float2 type; };
+template <> struct Cplx<double> { typedef double2 type; };
+
+template <typename T>
+struct DevProgram {
+    const Sweep* sweeps;
+    const Pass* passes;
+    const KOp* kops;
+    const typename Cplx<T>::type* pool;
+    const uint32_t* masks;
+    const Group* groups;
+    const SubSite* subs;
+    const double* gdata;
+};
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int CHUNK_LOG = 5;        // probability chunk = 32 amplitudes
+constexpr int SCAN_BLOCK_LOG = 10;  // 1024 chunks per scan block
+
+struct SweepArgs {
+    const NodeRec* nodes;
+    void* states;            // base of the slot arena
+    uint64_t slot_stride;    // amplitudes per slot
+    double* partials;        // [slot][tiles][4]
+    double* chunk_sums;      // [slot][2^(n_bits - chunk_log)]
+    uint64_t chunk_stride;   // doubles per slot in chunk_sums
+    uint32_t tiles_log2;     // log2(tiles per state)
+    uint32_t n_items;        // nodes * tiles
+};
+
+template <typename T>
+void launch_sweep(const DevProgram<T>& prog, const SweepArgs& a, int k, cudaStream_t st);
+template <typename T>
+cudaError_t configure_sweep(int k);
+
+// ---- decide
+void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles, double* P,
+                       cudaStream_t st);
+template <typename T>
+void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
+                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st);
+template <typename T>
+void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t n_children, const double* P,
+                        cudaStream_t st);
+void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj, cudaStream_t st);
+void launch_iota(uint32_t* p, uint32_t n, uint32_t start, cudaStream_t st);
+
+// ---- sampling
+void launch_scan_chunks(const NodeRec* leaves, uint32_t n_leaves, double* chunk_sums, uint64_t chunk_stride,
+                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st);
+template <typename T>
+void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states, uint64_t slot_stride,
+                   const double* chunk_sums, uint64_t chunk_stride, const double* block_sums, uint64_t block_stride,
+                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj,
+                   uint64_t seed, const double* flip /*dev [circuit][n][2] = P(1|0), P(0|1); or null*/,
+                   uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin,
+                   cudaStream_t st);
+
+// ---- density-matrix helpers / probability vectors
+template <typename T>
+void launch_extract_diag(const void* states, uint64_t slot_stride, const uint32_t* slots, uint32_t n_vec, int n,
+                         T* probs, cudaStream_t st);
+template <typename T>
+void launch_readout_probs(T* probs, uint32_t n_vec, int n, const double* conf /*dev [vec][n][4]*/, cudaStream_t st);
+template <typename T>
+void launch_prob_chunks(const T* probs, uint32_t n_vec, int n, double* chunk_sums, uint64_t chunk_stride,
+                        cudaStream_t st);
+template <typename T>
+void launch_sample_probs(const T* probs, uint32_t n_vec, int n, const double* chunk_sums, uint64_t chunk_stride,
+                         const double* block_sums, uint64_t block_stride, uint32_t n_chunks, uint64_t shot_begin,
+                         uint64_t n_shots, uint64_t seed, uint32_t first_circuit, const double* flip, uint32_t* hist,
+                         cudaStream_t st);
+void launch_scan_vectors(uint32_t n_vec, double* chunk_sums, uint64_t chunk_stride, double* block_sums,
+                         uint64_t block_stride, uint32_t n_chunks, cudaStream_t st);
+
+// ---- parity
+void launch_parity_counts(const uint32_t* hist, uint32_t n_vec, int n, const uint32_t* masks, int n_masks,
+                          int per_vec, long long* signed_sums, long long* totals, cudaStream_t st);
+template <typename T>
+void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* masks, int n_masks, int per_vec,
+                         double* partial, uint32_t n_part, double* expvals, cudaStream_t st);
+
+}  // namespace qcd

@@ -1,0 +1,41 @@
+// lower.h -- host-side compiler: gate-list IR (include/qcdsim.h) -> fused, tiled sweep program (program.h).
+#pragma once
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/qcdsim.h"
+#include "program.h"
+
+namespace qcd {
+
+typedef std::complex<double> cd;
+
+enum Mode { MODE_SV = 0, MODE_DM = 1 };
+
+struct Program {
+    int n_qubits = 0;
+    int n_bits = 0;   // n_qubits (MODE_SV) or 2 n_qubits (MODE_DM)
+    int mode = MODE_SV;
+    int k_max = 13;   // tile bits for this precision
+    int max_group_bits = 0;
+    int max_sweeps = 0;
+    std::vector<Sweep> sweeps;
+    std::vector<Pass> passes;
+    std::vector<KOp> kops;
+    std::vector<cd> pool;
+    std::vector<uint64_t> masks;
+    std::vector<Group> groups;
+    std::vector<SubSite> subs;
+    std::vector<double> gdata;
+    std::vector<CircuitInfo> circuits;
+};
+
+// Appends one circuit to P. Returns QCD_OK or an error code with a message in err.
+int compile_circuit(Program& P, const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params,
+                    std::string& err);
+
+// JSON description of circuit `c` of P (for the CPU-side schedule interpreter in tests/).
+std::string program_to_json(const Program& P, int c);
+
+}  // namespace qcd
