@@ -35,6 +35,12 @@ extern "C" {
 
 #define QCD_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define QCD_API __attribute__((visibility("default")))
+#else
+#define QCD_API
+#endif
+
 /* error codes */
 #define QCD_OK 0
 #define QCD_E_INVALID 1     /* bad argument / malformed program */
@@ -91,19 +97,19 @@ typedef struct qcd_stats {
     double sweep_ms;           /* CUDA-event time spent inside sweep kernels (only when timing is enabled) */
 } qcd_stats;
 
-int qcd_abi_version(void);
+QCD_API int qcd_abi_version(void);
 
 /* Context.  mem_budget_bytes = device memory the engine may allocate for states (0 = 80% of free memory). */
-int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out);
-void qcd_destroy(qcd_ctx* ctx);
-const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of the last failed qcd_create */
-int qcd_set_option(qcd_ctx* ctx, const char* key, double value); /* "time_sweeps" 0/1, "tile_bits", "max_chunk" */
-int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
+QCD_API int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out);
+QCD_API void qcd_destroy(qcd_ctx* ctx);
+QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of the last failed qcd_create */
+QCD_API int qcd_set_option(qcd_ctx* ctx, const char* key, double value); /* "time_sweeps" 0/1, "tile_bits", "max_chunk" */
+QCD_API int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
 
 /* Replaces: building `circuit` + `noise_model` and handing them to qk.execute (samplers.py:322-324).
  * Uploads B circuits of n_qubits each: circuit c owns ops[op_offsets[c] .. op_offsets[c+1]).  [host] pointers;
  * data is copied.  Lowering (gate fusion, CX -> H.CZ.H, sweep scheduling) happens here, on the host. */
-int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
+QCD_API int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
                         size_t n_params, int n_circuits, int n_qubits);
 
 /* Replaces: AerSimulator `statevector` method under a noise model, i.e. execute(...).result().get_counts() for
@@ -115,7 +121,7 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
  *   hist [dev, may be NULL]: [n_circuits][2^n] uint32, ADDED to (caller zeroes).
  *   outcomes [dev, may be NULL]: [shot_end - shot_begin] uint32 basis indices (requires n_qubits <= 32).
  * Synchronises `stream` internally (tree scheduling needs device counts); results are complete on return. */
-int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
+QCD_API int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
                             uint64_t shot_begin, uint64_t shot_end, const double* readout, uint32_t* hist,
                             uint32_t* outcomes, uint32_t flags, void* stream);
 
@@ -123,19 +129,19 @@ int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circ
  * the exact outcome distribution.  probs_out [dev]: [n_circuits][2^n] float (precision 32) or double (64): the
  * diagonal of rho after the last op (before classical readout error).  circuit_begin/end select a slice.
  * Asynchronous on `stream`. */
-int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,
+QCD_API int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,
                            void* stream);
 
 /* Classical readout error applied to probability vectors, in place: probs [dev] [n_vectors][2^n] (float/double by
  * precision), readout [host] [n_vectors][n][2][2].  Replaces Aer's ReadoutError on `measure` in distribution. */
-int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,
+QCD_API int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,
                             const double* readout, void* stream);
 
 /* Replaces: Aer `sample_measure` on an exact distribution.  Draws shots_per_vector outcomes from each of the
  * n_vectors distributions probs [dev] by inverse CDF with the QCD_STREAM_MEASURE draw of (seed, first_circuit + v,
  * shot) for shot in [shot_begin, shot_end); optional readout flips as above ([host], may be NULL).
  * hist [dev] [n_vectors][2^n] uint32 is ADDED to.  Asynchronous on `stream`. */
-int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+QCD_API int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
                           uint64_t shot_begin, uint64_t shot_end, uint64_t seed, uint32_t first_circuit,
                           const double* readout, uint32_t* hist, void* stream);
 
@@ -146,19 +152,19 @@ int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_
  *   totals      [dev] [n_vectors] int64          = sum_x hist[x]
  * masks [host] [n_vectors][n_masks] uint32 when per_vector_masks != 0, else [n_masks] shared.
  * mean = signed/total, std = sqrt((1 - mean^2)/total) are formed by the caller in double.  Asynchronous. */
-int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_qubits, const uint32_t* masks,
+QCD_API int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_qubits, const uint32_t* masks,
                       int n_masks, int per_vector_masks, int64_t* signed_sums, int64_t* totals, void* stream);
 
 /* Same reduction on exact probabilities (float/double by precision): expvals [dev] [n_vectors][n_masks] double =
  * sum_x p[x] D_mask[x], accumulated in double with a fixed reduction order (deterministic). Asynchronous. */
-int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+QCD_API int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
                      const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream);
 
 /* Host-only introspection (no GPU needed): lower + schedule ONE circuit and write a JSON description of the sweep
  * program (tile bits, passes, fused matrices, sign terms, site groups) into buf.  mode: 0 = statevector
  * trajectories, 1 = density matrix.  Returns QCD_E_NOMEM if cap is too small (required size in *needed).
  * Used by the CPU tests to check the host logic against the oracle. */
-int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
+QCD_API int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
                             int mode, int precision, int tile_bits, char* buf, size_t cap, size_t* needed);
 
 #ifdef __cplusplus

@@ -1,0 +1,851 @@
+// engine.cu -- the C ABI of libqcdsim.so (include/qcdsim.h): contexts, program upload, and the host-side drivers
+// that turn a compiled sweep program (lower.cpp) into kernel launches (sweep.cu, kernels.cu).
+//
+// Statevector trajectories are executed as a TREE: level d holds the distinct states reached after d sweeps; the
+// trajectories of a node that draw the same branch word at the next site group share one child state.  Results are
+// identical to one-state-per-shot execution (every draw is a pure function of (seed, circuit, shot, stream)), the
+// number of state sweeps is not.  The tree is walked breadth-first while state slots last and depth-first beyond
+// that (children are swept in chunks, each chunk is finished before the next), so any circuit depth runs in
+// max_sweeps + 1 slots.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qcdsim.h"
+#include "kernels.cuh"
+#include "lower.h"
+
+using namespace qcd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool zero = false) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        if (zero) e = cudaMemset(p, 0, want);
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct DevProg {
+    bool valid = false;
+    Program P;
+    DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits;
+    void release() {
+        sweeps.release(); passes.release(); kops.release(); pool.release(); masks.release();
+        groups.release(); subs.release(); gdata.release(); circuits.release();
+        valid = false;
+        P = Program();
+    }
+};
+
+}  // namespace
+
+struct qcd_ctx {
+    int device = 0;
+    size_t budget = 0;
+    std::string err;
+    // options
+    bool time_sweeps = false;
+    int tile_bits = 0;           // 0 = default for the precision
+    uint64_t max_chunk = 1u << 20;
+    int table_cap_log2 = 22;
+    uint64_t max_slots = 0;      // 0 = as many as the budget allows
+    // programs (host copy of the IR; compiled lazily per (mode, precision))
+    int n_qubits = 0, n_circuits = 0;
+    std::vector<qcd_op> ops;
+    std::vector<uint32_t> offsets;
+    std::vector<double> params;
+    DevProg prog[2][2];  // [mode][precision == 64]
+    int prog_tile_bits[2][2] = {{0, 0}, {0, 0}};
+    // arenas / scratch
+    DevBuf states, partials, chunk_sums, block_sums;
+    DevBuf owner, keys, probs4, table, offs, children, counter, bsum, flip, masks, scratch, slots;
+    std::vector<DevBuf> level_nodes, level_shots;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    qcd_stats stats;
+};
+
+namespace {
+
+int fail(qcd_ctx* c, int code, const std::string& m) {
+    c->err = m;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, QCD_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+template <typename U>
+int upload_vec(qcd_ctx* ctx, DevBuf& b, const std::vector<U>& v) {
+    CU(b.ensure(std::max<size_t>(v.size(), 1) * sizeof(U)));
+    if (!v.empty()) CU(cudaMemcpy(b.p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice));
+    return QCD_OK;
+}
+
+int default_tile_bits(int precision) { return precision == 64 ? 12 : 13; }
+
+// compile + upload the program for (mode, precision) if not done yet
+int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
+    if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
+    int pi = precision == 64 ? 1 : 0;
+    int kb = ctx->tile_bits > 0 ? ctx->tile_bits : default_tile_bits(precision);
+    DevProg& dp = ctx->prog[mode][pi];
+    if (dp.valid && ctx->prog_tile_bits[mode][pi] == kb) {
+        *out = &dp;
+        return QCD_OK;
+    }
+    dp.release();
+    Program& P = dp.P;
+    P.n_qubits = ctx->n_qubits;
+    P.mode = mode;
+    P.n_bits = mode == MODE_DM ? 2 * ctx->n_qubits : ctx->n_qubits;
+    P.k_max = kb;
+    if (P.n_bits > 30) return fail(ctx, QCD_E_UNSUPPORTED, "state of more than 30 index bits");
+    for (int c = 0; c < ctx->n_circuits; c++) {
+        std::string err;
+        uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
+        int rc = compile_circuit(P, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
+        if (rc != QCD_OK) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+    }
+    int rc;
+    if ((rc = upload_vec(ctx, dp.sweeps, P.sweeps))) return rc;
+    if ((rc = upload_vec(ctx, dp.passes, P.passes))) return rc;
+    if ((rc = upload_vec(ctx, dp.kops, P.kops))) return rc;
+    if (precision == 64) {
+        std::vector<double2> pool(P.pool.size());
+        for (size_t i = 0; i < pool.size(); i++) pool[i] = make_double2(P.pool[i].real(), P.pool[i].imag());
+        if ((rc = upload_vec(ctx, dp.pool, pool))) return rc;
+    } else {
+        std::vector<float2> pool(P.pool.size());
+        for (size_t i = 0; i < pool.size(); i++) pool[i] = make_float2((float)P.pool[i].real(), (float)P.pool[i].imag());
+        if ((rc = upload_vec(ctx, dp.pool, pool))) return rc;
+    }
+    std::vector<uint32_t> masks(P.masks.size());
+    for (size_t i = 0; i < masks.size(); i++) masks[i] = (uint32_t)P.masks[i];
+    if ((rc = upload_vec(ctx, dp.masks, masks))) return rc;
+    if ((rc = upload_vec(ctx, dp.groups, P.groups))) return rc;
+    if ((rc = upload_vec(ctx, dp.subs, P.subs))) return rc;
+    if ((rc = upload_vec(ctx, dp.gdata, P.gdata))) return rc;
+    if ((rc = upload_vec(ctx, dp.circuits, P.circuits))) return rc;
+    int k = std::min(P.k_max, P.n_bits);
+    if (precision == 64) CU(configure_sweep<double>(k));
+    else CU(configure_sweep<float>(k));
+    dp.valid = true;
+    ctx->prog_tile_bits[mode][pi] = kb;
+    *out = &dp;
+    return QCD_OK;
+}
+
+template <typename T>
+DevProgram<T> dev_view(const DevProg& dp) {
+    DevProgram<T> v;
+    v.sweeps = dp.sweeps.as<Sweep>();
+    v.passes = dp.passes.as<Pass>();
+    v.kops = dp.kops.as<KOp>();
+    v.pool = dp.pool.as<typename Cplx<T>::type>();
+    v.masks = dp.masks.as<uint32_t>();
+    v.groups = dp.groups.as<Group>();
+    v.subs = dp.subs.as<SubSite>();
+    v.gdata = dp.gdata.as<double>();
+    return v;
+}
+
+size_t usable_budget(qcd_ctx* ctx) {
+    if (ctx->budget) return ctx->budget;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
+    // memory we already hold for states is reusable
+    fr += ctx->states.cap + ctx->partials.cap + ctx->chunk_sums.cap + ctx->block_sums.cap;
+    return (size_t)(0.8 * (double)fr);
+}
+
+cudaEvent_t next_event(qcd_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+int finish_timing(qcd_ctx* ctx) {
+    if (!ctx->time_sweeps) return QCD_OK;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        CU(cudaEventSynchronize(ctx->ev_pool[i + 1]));
+        CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        ctx->stats.sweep_ms += ms;
+    }
+    ctx->ev_used = 0;
+    return QCD_OK;
+}
+
+// ============================================================================================ statevector trajectories
+template <typename T>
+struct SvRunner {
+    typedef typename Cplx<T>::type C;
+    qcd_ctx* ctx;
+    DevProg* dp;
+    DevProgram<T> prog;
+    cudaStream_t st;
+    int n = 0, k = 0, gbits = 0, max_sweeps = 0;
+    uint32_t tiles_log2 = 0, tiles = 1, n_chunks = 1, n_blocks = 1;
+    uint64_t slot_stride = 0;
+    uint64_t seed = 0, spc = 0, shot_begin = 0;
+    const double* flip_dev = nullptr;
+    uint32_t* hist = nullptr;
+    uint32_t* outcomes = nullptr;
+    std::vector<uint32_t> free_slots;
+    uint64_t table_cap = 0;
+    uint64_t live = 0;
+
+    uint32_t alloc_slot() {
+        uint32_t s = free_slots.back();
+        free_slots.pop_back();
+        live++;
+        if (live > ctx->stats.max_live_states) ctx->stats.max_live_states = live;
+        return s;
+    }
+    void free_slot(uint32_t s) {
+        free_slots.push_back(s);
+        live--;
+    }
+
+    SweepArgs sweep_args(const NodeRec* nodes_dev, uint32_t n_nodes) {
+        SweepArgs a;
+        a.nodes = nodes_dev;
+        a.states = ctx->states.p;
+        a.slot_stride = slot_stride;
+        a.partials = ctx->partials.as<double>();
+        a.chunk_sums = ctx->chunk_sums.as<double>();
+        a.chunk_stride = n_chunks;
+        a.tiles_log2 = tiles_log2;
+        a.n_items = n_nodes * tiles;
+        return a;
+    }
+
+    // nodes[begin, end) at depth d have executed their sweep (d == 0: virtual roots); their device copy is
+    // level_nodes[d] + begin and their trajectories are level_shots[d][traj_off ...).
+    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root) {
+        const size_t n_nodes = end - begin;
+        if (n_nodes == 0) return QCD_OK;
+        if (((uint64_t)n_nodes << gbits) > table_cap && n_nodes > 1) {
+            const size_t piece = std::max<uint64_t>(1, table_cap >> gbits);
+            for (size_t b = begin; b < end; b += piece) {
+                int rc = process(d, nodes, b, std::min(end, b + piece), is_root);
+                if (rc) return rc;
+            }
+            return QCD_OK;
+        }
+        const uint32_t t0 = nodes[begin].traj_off;
+        const uint32_t tc = nodes[end - 1].traj_off + nodes[end - 1].traj_cnt - t0;
+        const NodeRec* ndev = ctx->level_nodes[d].as<NodeRec>() + begin;
+        uint32_t* shots_d = ctx->level_shots[d].as<uint32_t>() + t0;
+        uint32_t* owner = ctx->owner.as<uint32_t>();
+        double* P = ctx->probs4.as<double>();
+        CU(ctx->probs4.ensure(n_nodes * 4 * sizeof(double)));
+        P = ctx->probs4.as<double>();
+
+        launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
+        ctx->stats.aux_launches++;
+        bool any_leaf = false, any_inner = false;
+        if (is_root) {
+            launch_root_shots(ndev, owner, shots_d, tc, st);
+            launch_fill_root_probs(P, (uint32_t)n_nodes, st);
+            ctx->stats.aux_launches += 2;
+            any_inner = true;
+        } else {
+            for (size_t i = begin; i < end; i++) {
+                if (nodes[i].flags & NODE_LEAF) any_leaf = true;
+                else any_inner = true;
+            }
+            if (any_leaf) {
+                launch_scan_chunks(ndev, (uint32_t)n_nodes, ctx->chunk_sums.as<double>(), n_chunks,
+                                   ctx->block_sums.as<double>(), n_blocks, n_chunks, st);
+                launch_sample<T>(ndev, (uint32_t)n_nodes, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(),
+                                 n_chunks, ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed,
+                                 flip_dev, hist, outcomes, spc, shot_begin, st);
+                ctx->stats.aux_launches += 3;
+                for (size_t i = begin; i < end; i++)
+                    if (nodes[i].flags & NODE_LEAF) {
+                        free_slot(nodes[i].dst_slot);
+                        ctx->stats.leaves++;
+                    }
+            }
+            if (!any_inner) return QCD_OK;
+            launch_node_probs(ndev, (uint32_t)n_nodes, ctx->partials.as<double>(), tiles, P, st);
+            ctx->stats.aux_launches++;
+        }
+        // ---- decide: branch word per trajectory, then group trajectories into children
+        uint64_t* keys = ctx->keys.as<uint64_t>();
+        launch_traj_branch<T>(prog, ndev, P, owner, shots_d, tc, seed, keys, st);
+        const uint32_t M = (uint32_t)(n_nodes << gbits);
+        const uint32_t max_children = (uint32_t)std::min<uint64_t>(tc, M);
+        CU(ctx->table.ensure((size_t)M * 4, true));
+        CU(ctx->offs.ensure((size_t)M * 4));
+        CU(ctx->bsum.ensure(((size_t)M / 1024 + 2) * sizeof(uint2)));
+        CU(ctx->children.ensure((size_t)max_children * sizeof(NodeRec)));
+        CU(ctx->counter.ensure(2 * sizeof(uint32_t)));
+        uint32_t* shots_next = ctx->level_shots[d + 1].as<uint32_t>() + t0;
+        launch_group_children(keys, shots_d, tc, gbits, ctx->table.as<uint32_t>(), M, ctx->bsum.as<uint2>(),
+                              ctx->counter.as<uint32_t>(), ndev, dp->circuits.as<CircuitInfo>(), t0,
+                              ctx->offs.as<uint32_t>(), ctx->children.as<NodeRec>(), shots_next, st);
+        launch_child_scale<T>(prog, ctx->children.as<NodeRec>(), max_children, ctx->counter.as<uint32_t>() + 1, P, st);
+        ctx->stats.aux_launches += 7;
+        uint32_t totals[2] = {0, 0};
+        CU(cudaMemcpyAsync(totals, ctx->counter.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t n_children = totals[1];
+        if (n_children == 0) return fail(ctx, QCD_E_CUDA, "internal: inner nodes produced no children");
+        std::vector<NodeRec> ch(n_children);
+        CU(cudaMemcpyAsync(ch.data(), ctx->children.p, (size_t)n_children * sizeof(NodeRec), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+
+        // ---- sweep the children in chunks; finish each chunk's subtree before the next
+        size_t pos = 0;
+        size_t next_parent_to_free = 0;  // relative to `begin`
+        const int reserve = std::max(0, max_sweeps - (d + 1));
+        while (pos < n_children) {
+            const long long avail = (long long)free_slots.size() - reserve;
+            if (avail < 1)
+                return fail(ctx, QCD_E_NOMEM, "not enough state slots for this circuit depth (raise the memory budget)");
+            const size_t c = (size_t)std::min<long long>((long long)(n_children - pos), avail);
+            std::vector<NodeRec> chunk(ch.begin() + pos, ch.begin() + pos + c);
+            for (NodeRec& r : chunk) r.dst_slot = alloc_slot();
+            CU(ctx->level_nodes[d + 1].ensure(c * sizeof(NodeRec)));
+            NodeRec* cdev = ctx->level_nodes[d + 1].as<NodeRec>();
+            CU(cudaMemcpyAsync(cdev, chunk.data(), c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            launch_sweep<T>(prog, sweep_args(cdev, (uint32_t)c), k, st);
+            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            CU(cudaGetLastError());
+            ctx->stats.sweep_launches++;
+            ctx->stats.node_sweeps += c;
+            ctx->stats.sweep_bytes += (uint64_t)c * slot_stride * sizeof(C) * (is_root ? 1 : 2);
+            pos += c;
+            if (!is_root) {
+                const size_t done_to = pos == n_children ? n_nodes : ch[pos].parent;
+                for (size_t p = next_parent_to_free; p < done_to; p++)
+                    if (!(nodes[begin + p].flags & NODE_LEAF)) free_slot(nodes[begin + p].dst_slot);
+                next_parent_to_free = done_to;
+            }
+            int rc = process(d + 1, chunk, 0, c, false);
+            if (rc) return rc;
+        }
+        return QCD_OK;
+    }
+};
+
+template <typename T>
+int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot_begin, uint64_t shot_end,
+           const double* readout, uint32_t* hist, uint32_t* outcomes, uint32_t flags, cudaStream_t st) {
+    typedef typename Cplx<T>::type C;
+    SvRunner<T> R;
+    R.ctx = ctx;
+    R.dp = dp;
+    R.prog = dev_view<T>(*dp);
+    R.st = st;
+    const Program& P = dp->P;
+    const int n = P.n_bits;
+    R.n = n;
+    R.k = std::min(P.k_max, n);
+    R.gbits = P.max_group_bits;
+    R.max_sweeps = P.max_sweeps;
+    R.tiles_log2 = (uint32_t)(n - R.k);
+    R.tiles = 1u << R.tiles_log2;
+    const int chunk_log = std::min(n, CHUNK_LOG);
+    R.n_chunks = 1u << (n - chunk_log);
+    R.n_blocks = (R.n_chunks + (1u << SCAN_BLOCK_LOG) - 1) >> SCAN_BLOCK_LOG;
+    R.slot_stride = (uint64_t)1 << n;
+    R.seed = seed;
+    R.spc = spc;
+    R.shot_begin = shot_begin;
+    R.hist = hist;
+    R.outcomes = outcomes;
+    R.table_cap = (uint64_t)1 << ctx->table_cap_log2;
+    if (((uint64_t)1 << R.gbits) > R.table_cap) R.table_cap = (uint64_t)1 << R.gbits;
+
+    const uint64_t total = shot_end - shot_begin;
+    const uint64_t T_chunk = std::min<uint64_t>(total, ctx->max_chunk);
+    const bool no_dedup = (flags & QCD_RUN_NO_DEDUP) != 0;
+
+    // ---- state slots
+    const size_t slot_bytes = R.slot_stride * sizeof(C);
+    const size_t per_slot = slot_bytes + (size_t)R.tiles * 32 + (size_t)R.n_chunks * 8 + (size_t)R.n_blocks * 8;
+    const size_t budget = usable_budget(ctx);
+    uint64_t n_slots = budget / per_slot;
+    const uint64_t wanted = 2 * T_chunk + 8 + (uint64_t)R.max_sweeps;
+    n_slots = std::min<uint64_t>(n_slots, wanted);
+    if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
+    if (n_slots < (uint64_t)R.max_sweeps + 1)
+        return fail(ctx, QCD_E_NOMEM,
+                    "memory budget holds " + std::to_string(n_slots) + " states; this program needs at least " +
+                        std::to_string(R.max_sweeps + 1));
+    CU(ctx->states.ensure(n_slots * slot_bytes));
+    CU(ctx->partials.ensure(n_slots * (size_t)R.tiles * 32));
+    CU(ctx->chunk_sums.ensure(n_slots * (size_t)R.n_chunks * 8));
+    CU(ctx->block_sums.ensure(n_slots * (size_t)R.n_blocks * 8));
+    R.free_slots.resize(n_slots);
+    for (uint64_t i = 0; i < n_slots; i++) R.free_slots[i] = (uint32_t)(n_slots - 1 - i);
+
+    // ---- per-level trajectory arrays
+    const int n_levels = R.max_sweeps + 2;
+    if ((int)ctx->level_nodes.size() < n_levels) ctx->level_nodes.resize(n_levels);
+    if ((int)ctx->level_shots.size() < n_levels) ctx->level_shots.resize(n_levels);
+    for (int l = 0; l < n_levels; l++) CU(ctx->level_shots[l].ensure(T_chunk * 4));
+    CU(ctx->owner.ensure(T_chunk * 4));
+    CU(ctx->keys.ensure(T_chunk * 8));
+    if (ctx->table.p) CU(cudaMemsetAsync(ctx->table.p, 0, ctx->table.cap, st));  // a failed run may have left counts
+
+    // ---- readout flip table [circuit][n][2] = P(1|0), P(0|1)
+    if (readout) {
+        std::vector<double> flip((size_t)ctx->n_circuits * n * 2);
+        for (size_t cq = 0; cq < (size_t)ctx->n_circuits * n; cq++) {
+            flip[cq * 2] = readout[cq * 4 + 1];
+            flip[cq * 2 + 1] = readout[cq * 4 + 2];
+        }
+        int rc = upload_vec(ctx, ctx->flip, flip);
+        if (rc) return rc;
+        R.flip_dev = ctx->flip.as<double>();
+    }
+
+    // ---- outer loop over trajectory chunks of the flattened [circuit][shot] space
+    for (uint64_t g0 = shot_begin; g0 < shot_end; g0 += T_chunk) {
+        const uint64_t g1 = std::min(shot_end, g0 + T_chunk);
+        std::vector<NodeRec> roots;
+        uint32_t off = 0;
+        for (uint64_t c = g0 / spc; c <= (g1 - 1) / spc; c++) {
+            const uint64_t s0 = std::max(g0, c * spc) - c * spc, s1 = std::min(g1, (c + 1) * spc) - c * spc;
+            NodeRec r;
+            memset(&r, 0, sizeof(r));
+            r.sweep = P.circuits[c].sweep_begin - 1u;
+            r.circuit = (uint32_t)c;
+            r.scale = 1.0;
+            if (no_dedup) {
+                for (uint64_t s = s0; s < s1; s++) {
+                    r.traj_off = off++;
+                    r.traj_cnt = 1;
+                    r.pad = (uint32_t)s;
+                    roots.push_back(r);
+                }
+            } else {
+                r.traj_off = off;
+                r.traj_cnt = (uint32_t)(s1 - s0);
+                r.pad = (uint32_t)s0;
+                off += r.traj_cnt;
+                roots.push_back(r);
+            }
+        }
+        CU(ctx->level_nodes[0].ensure(roots.size() * sizeof(NodeRec)));
+        CU(cudaMemcpyAsync(ctx->level_nodes[0].p, roots.data(), roots.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+        int rc = R.process(0, roots, 0, roots.size(), true);
+        if (rc) return rc;
+        ctx->stats.trajectories += g1 - g0;
+    }
+    CU(cudaStreamSynchronize(st));
+    return finish_timing(ctx);
+}
+
+// ============================================================================================ density matrix
+template <typename T>
+int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStream_t st) {
+    typedef typename Cplx<T>::type C;
+    const Program& P = dp->P;
+    const int nb = P.n_bits, n = P.n_qubits;
+    const int k = std::min(P.k_max, nb);
+    const uint32_t tiles_log2 = (uint32_t)(nb - k);
+    const uint32_t tiles = 1u << tiles_log2;
+    const uint64_t slot_stride = (uint64_t)1 << nb;
+    const size_t slot_bytes = slot_stride * sizeof(C);
+    uint64_t n_slots = usable_budget(ctx) / slot_bytes;
+    n_slots = std::min<uint64_t>(n_slots, (uint64_t)(ce - cb));
+    if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
+    if (n_slots < 1) return fail(ctx, QCD_E_NOMEM, "memory budget too small for one density matrix");
+    if (n_slots * tiles > 0x7fffffffull) n_slots = 0x7fffffffull / tiles;
+    CU(ctx->states.ensure(n_slots * slot_bytes));
+    DevProgram<T> prog = dev_view<T>(*dp);
+    T* out = reinterpret_cast<T*>(probs_out);
+    for (int c0 = cb; c0 < ce; c0 += (int)n_slots) {
+        const int c1 = (int)std::min<uint64_t>((uint64_t)ce, (uint64_t)c0 + n_slots);
+        // one NodeRec per (circuit, sweep), grouped by sweep ordinal; the sweep works in place (src == dst)
+        std::vector<NodeRec> recs;
+        std::vector<size_t> lvl_off;
+        for (int l = 0;; l++) {
+            size_t before = recs.size();
+            for (int c = c0; c < c1; c++) {
+                const CircuitInfo& ci = P.circuits[c];
+                if (ci.sweep_begin + l >= ci.sweep_end) continue;
+                NodeRec r;
+                memset(&r, 0, sizeof(r));
+                r.src_slot = r.dst_slot = (uint32_t)(c - c0);
+                r.sweep = ci.sweep_begin + l;
+                r.scale = 1.0;
+                r.circuit = (uint32_t)c;
+                recs.push_back(r);
+            }
+            if (recs.size() == before) break;
+            lvl_off.push_back(before);
+        }
+        lvl_off.push_back(recs.size());
+        CU(ctx->children.ensure(recs.size() * sizeof(NodeRec)));
+        CU(cudaMemcpyAsync(ctx->children.p, recs.data(), recs.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+        for (size_t l = 0; l + 1 < lvl_off.size(); l++) {
+            const uint32_t cnt = (uint32_t)(lvl_off[l + 1] - lvl_off[l]);
+            SweepArgs a;
+            a.nodes = ctx->children.as<NodeRec>() + lvl_off[l];
+            a.states = ctx->states.p;
+            a.slot_stride = slot_stride;
+            a.partials = nullptr;
+            a.chunk_sums = nullptr;
+            a.chunk_stride = 0;
+            a.tiles_log2 = tiles_log2;
+            a.n_items = cnt * tiles;
+            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            launch_sweep<T>(prog, a, k, st);
+            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            CU(cudaGetLastError());
+            ctx->stats.sweep_launches++;
+            ctx->stats.node_sweeps += cnt;
+            ctx->stats.sweep_bytes += (uint64_t)cnt * slot_bytes * (l == 0 ? 1 : 2);
+        }
+        std::vector<uint32_t> slots(c1 - c0);
+        for (int i = 0; i < c1 - c0; i++) slots[i] = (uint32_t)i;
+        CU(ctx->slots.ensure(slots.size() * 4));
+        CU(cudaMemcpyAsync(ctx->slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
+        launch_extract_diag<T>(ctx->states.p, slot_stride, ctx->slots.as<uint32_t>(), (uint32_t)(c1 - c0), n,
+                               out + ((size_t)(c0 - cb) << n), st);
+        CU(cudaGetLastError());
+        ctx->stats.aux_launches++;
+        ctx->stats.leaves += c1 - c0;
+    }
+    if (ctx->time_sweeps) {
+        CU(cudaStreamSynchronize(st));
+        return finish_timing(ctx);
+    }
+    return QCD_OK;
+}
+
+int upload_flip(qcd_ctx* ctx, const double* readout, int n_vec, int n, const double** out) {
+    *out = nullptr;
+    if (!readout) return QCD_OK;
+    std::vector<double> flip((size_t)n_vec * n * 2);
+    for (size_t cq = 0; cq < (size_t)n_vec * n; cq++) {
+        flip[cq * 2] = readout[cq * 4 + 1];
+        flip[cq * 2 + 1] = readout[cq * 4 + 2];
+    }
+    int rc = upload_vec(ctx, ctx->flip, flip);
+    if (rc) return rc;
+    *out = ctx->flip.as<double>();
+    return QCD_OK;
+}
+
+}  // namespace
+
+// ==================================================================================================== C ABI
+extern "C" {
+
+int qcd_abi_version(void) { return QCD_ABI_VERSION; }
+
+int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out) {
+    if (!out) {
+        g_create_error = "qcd_create: out is NULL";
+        return QCD_E_INVALID;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("qcd_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); this engine has no CPU fallback";
+        return QCD_E_CUDA;
+    }
+    if (cuda_device < 0 || cuda_device >= count) {
+        g_create_error = "qcd_create: device index out of range";
+        return QCD_E_INVALID;
+    }
+    e = cudaSetDevice(cuda_device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return QCD_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cuda_device);
+    if (prop.major < 10) {
+        g_create_error = "qcd_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; libqcdsim is built for sm_100a (B200) only";
+        return QCD_E_UNSUPPORTED;
+    }
+    qcd_ctx* c = new qcd_ctx();
+    c->device = cuda_device;
+    c->budget = mem_budget_bytes;
+    memset(&c->stats, 0, sizeof(c->stats));
+    *out = c;
+    return QCD_OK;
+}
+
+void qcd_destroy(qcd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int m = 0; m < 2; m++)
+        for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
+    DevBuf* bufs[] = {&ctx->states, &ctx->partials, &ctx->chunk_sums, &ctx->block_sums, &ctx->owner, &ctx->keys,
+                      &ctx->probs4, &ctx->table, &ctx->offs, &ctx->children, &ctx->counter, &ctx->bsum, &ctx->flip,
+                      &ctx->masks, &ctx->scratch, &ctx->slots};
+    for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : ctx->level_nodes) b.release();
+    for (DevBuf& b : ctx->level_shots) b.release();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char* qcd_last_error(qcd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
+    if (!ctx || !key) return QCD_E_INVALID;
+    std::string k(key);
+    if (k == "time_sweeps") ctx->time_sweeps = value != 0;
+    else if (k == "tile_bits") {
+        if (value != 0 && (value < 5 || value > 13)) return fail(ctx, QCD_E_INVALID, "tile_bits must be 0 or in [5, 13]");
+        ctx->tile_bits = (int)value;
+    } else if (k == "max_chunk") {
+        if (value < 1) return fail(ctx, QCD_E_INVALID, "max_chunk must be >= 1");
+        ctx->max_chunk = (uint64_t)value;
+    } else if (k == "table_cap_log2") {
+        if (value < 4 || value > 28) return fail(ctx, QCD_E_INVALID, "table_cap_log2 must be in [4, 28]");
+        ctx->table_cap_log2 = (int)value;
+    } else if (k == "max_slots") ctx->max_slots = (uint64_t)value;
+    else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
+    return QCD_OK;
+}
+
+int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out) {
+    if (!ctx || !out) return QCD_E_INVALID;
+    *out = ctx->stats;
+    return QCD_OK;
+}
+
+int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
+                        size_t n_params, int n_circuits, int n_qubits) {
+    if (!ctx) return QCD_E_INVALID;
+    if (!op_offsets || n_circuits < 1) return fail(ctx, QCD_E_INVALID, "need at least one circuit");
+    if (n_qubits < 1 || n_qubits > 30) return fail(ctx, QCD_E_INVALID, "n_qubits must be in [1, 30]");
+    const uint32_t n_ops = op_offsets[n_circuits];
+    if (n_ops && !ops) return fail(ctx, QCD_E_INVALID, "ops is NULL");
+    if (n_params && !params) return fail(ctx, QCD_E_INVALID, "params is NULL");
+    for (int c = 0; c < n_circuits; c++)
+        if (op_offsets[c] > op_offsets[c + 1]) return fail(ctx, QCD_E_INVALID, "op_offsets must be non-decreasing");
+    // validate by lowering one mode now, so that malformed programs fail at upload time
+    {
+        Program P;
+        P.n_qubits = n_qubits;
+        P.mode = MODE_DM;
+        P.n_bits = 2 * n_qubits;
+        P.k_max = 13;
+        for (int c = 0; c < n_circuits; c++) {
+            std::string err;
+            int rc = compile_circuit(P, ops + op_offsets[c], op_offsets[c + 1] - op_offsets[c], params, n_params, err);
+            if (rc == QCD_E_INVALID) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+        }
+    }
+    cudaSetDevice(ctx->device);
+    ctx->ops.assign(ops, ops + n_ops);
+    ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
+    ctx->params.assign(params, params + n_params);
+    ctx->n_circuits = n_circuits;
+    ctx->n_qubits = n_qubits;
+    for (int m = 0; m < 2; m++)
+        for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
+    return QCD_OK;
+}
+
+int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
+                            uint64_t shot_begin, uint64_t shot_end, const double* readout, uint32_t* hist,
+                            uint32_t* outcomes, uint32_t flags, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
+    if (shots_per_circuit < 1 || shots_per_circuit > 0xffffffffull)
+        return fail(ctx, QCD_E_INVALID, "shots_per_circuit must be in [1, 2^32)");
+    if (shot_begin > shot_end || shot_end > shots_per_circuit * (uint64_t)ctx->n_circuits)
+        return fail(ctx, QCD_E_INVALID, "shot range outside [0, n_circuits * shots_per_circuit]");
+    if (!hist && !outcomes) return fail(ctx, QCD_E_INVALID, "hist and outcomes are both NULL");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->ev_used = 0;
+    if (shot_begin == shot_end) return QCD_OK;
+    DevProg* dp = nullptr;
+    int rc = get_program(ctx, MODE_SV, precision, &dp);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 64)
+        return run_sv<double>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, readout, hist, outcomes, flags, st);
+    return run_sv<float>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, readout, hist, outcomes, flags, st);
+}
+
+int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,
+                           void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
+    if (circuit_begin < 0 || circuit_begin > circuit_end || circuit_end > ctx->n_circuits)
+        return fail(ctx, QCD_E_INVALID, "circuit range outside [0, n_circuits]");
+    if (!probs_out) return fail(ctx, QCD_E_INVALID, "probs_out is NULL");
+    if (ctx->n_qubits > 15) return fail(ctx, QCD_E_UNSUPPORTED, "density-matrix mode supports at most 15 qubits");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->ev_used = 0;
+    if (circuit_begin == circuit_end) return QCD_OK;
+    DevProg* dp = nullptr;
+    int rc = get_program(ctx, MODE_DM, precision, &dp);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 64) return run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
+    return run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
+}
+
+int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,
+                            const double* readout, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (!probs || !readout || n_vectors < 0 || n_qubits < 1 || n_qubits > 30)
+        return fail(ctx, QCD_E_INVALID, "bad arguments to qcd_apply_readout_probs");
+    if (n_vectors == 0) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    std::vector<double> conf(readout, readout + (size_t)n_vectors * n_qubits * 4);
+    int rc = upload_vec(ctx, ctx->flip, conf);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 64) launch_readout_probs<double>((double*)probs, n_vectors, n_qubits, ctx->flip.as<double>(), st);
+    else launch_readout_probs<float>((float*)probs, n_vectors, n_qubits, ctx->flip.as<double>(), st);
+    CU(cudaGetLastError());
+    return QCD_OK;
+}
+
+int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+                          uint64_t shot_begin, uint64_t shot_end, uint64_t seed, uint32_t first_circuit,
+                          const double* readout, uint32_t* hist, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (!probs || !hist || n_vectors < 0 || n_qubits < 1 || n_qubits > 30 || shot_begin > shot_end)
+        return fail(ctx, QCD_E_INVALID, "bad arguments to qcd_sample_from_probs");
+    if (n_vectors == 0 || shot_begin == shot_end) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    const int n = n_qubits;
+    const int chunk_log = std::min(n, CHUNK_LOG);
+    const uint32_t n_chunks = 1u << (n - chunk_log);
+    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1) >> SCAN_BLOCK_LOG;
+    CU(ctx->chunk_sums.ensure((size_t)n_vectors * n_chunks * 8));
+    CU(ctx->block_sums.ensure((size_t)n_vectors * n_blocks * 8));
+    const double* flip = nullptr;
+    int rc = upload_flip(ctx, readout, n_vectors, n, &flip);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* cs = ctx->chunk_sums.as<double>();
+    double* bs = ctx->block_sums.as<double>();
+    if (precision == 64) {
+        launch_prob_chunks<double>((const double*)probs, n_vectors, n, cs, n_chunks, st);
+        launch_scan_vectors(n_vectors, cs, n_chunks, bs, n_blocks, n_chunks, st);
+        launch_sample_probs<double>((const double*)probs, n_vectors, n, cs, n_chunks, bs, n_blocks, n_chunks, shot_begin,
+                                    shot_end - shot_begin, seed, first_circuit, flip, hist, st);
+    } else {
+        launch_prob_chunks<float>((const float*)probs, n_vectors, n, cs, n_chunks, st);
+        launch_scan_vectors(n_vectors, cs, n_chunks, bs, n_blocks, n_chunks, st);
+        launch_sample_probs<float>((const float*)probs, n_vectors, n, cs, n_chunks, bs, n_blocks, n_chunks, shot_begin,
+                                   shot_end - shot_begin, seed, first_circuit, flip, hist, st);
+    }
+    CU(cudaGetLastError());
+    return QCD_OK;
+}
+
+int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_qubits, const uint32_t* masks,
+                      int n_masks, int per_vector_masks, int64_t* signed_sums, int64_t* totals, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (!hist || !masks || !signed_sums || !totals || n_vectors < 0 || n_masks < 1 || n_qubits < 1 || n_qubits > 30)
+        return fail(ctx, QCD_E_INVALID, "bad arguments to qcd_parity_counts");
+    if (n_vectors == 0) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nm = (size_t)n_masks * (per_vector_masks ? n_vectors : 1);
+    std::vector<uint32_t> mk(masks, masks + nm);
+    int rc = upload_vec(ctx, ctx->masks, mk);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(signed_sums, 0, (size_t)n_vectors * n_masks * 8, st));
+    CU(cudaMemsetAsync(totals, 0, (size_t)n_vectors * 8, st));
+    launch_parity_counts(hist, n_vectors, n_qubits, ctx->masks.as<uint32_t>(), n_masks, per_vector_masks,
+                         (long long*)signed_sums, (long long*)totals, st);
+    CU(cudaGetLastError());
+    return QCD_OK;
+}
+
+int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
+                     const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (!probs || !masks || !expvals || n_vectors < 0 || n_masks < 1 || n_qubits < 1 || n_qubits > 30)
+        return fail(ctx, QCD_E_INVALID, "bad arguments to qcd_parity_probs");
+    if (n_vectors == 0) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nm = (size_t)n_masks * (per_vector_masks ? n_vectors : 1);
+    std::vector<uint32_t> mk(masks, masks + nm);
+    int rc = upload_vec(ctx, ctx->masks, mk);
+    if (rc) return rc;
+    uint32_t n_part = (uint32_t)std::min<uint64_t>(((uint64_t)1 << n_qubits) / 256 + 1, 64);
+    CU(ctx->scratch.ensure((size_t)n_vectors * n_masks * n_part * 8));
+    if (precision == 64)
+        launch_parity_probs<double>((const double*)probs, n_vectors, n_qubits, ctx->masks.as<uint32_t>(), n_masks,
+                                    per_vector_masks, ctx->scratch.as<double>(), n_part, expvals, st);
+    else
+        launch_parity_probs<float>((const float*)probs, n_vectors, n_qubits, ctx->masks.as<uint32_t>(), n_masks,
+                                   per_vector_masks, ctx->scratch.as<double>(), n_part, expvals, st);
+    CU(cudaGetLastError());
+    return QCD_OK;
+}
+
+int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
+                            int mode, int precision, int tile_bits, char* buf, size_t cap, size_t* needed) {
+    if (n_qubits < 1 || n_qubits > 30 || (mode != 0 && mode != 1)) return QCD_E_INVALID;
+    Program P;
+    P.n_qubits = n_qubits;
+    P.mode = mode;
+    P.n_bits = mode == MODE_DM ? 2 * n_qubits : n_qubits;
+    P.k_max = tile_bits > 0 ? tile_bits : default_tile_bits(precision);
+    std::string err;
+    int rc = compile_circuit(P, ops, n_ops, params, n_params, err);
+    std::string js = rc == QCD_OK ? program_to_json(P, 0) : ("{\"error\":\"" + err + "\"}");
+    if (needed) *needed = js.size() + 1;
+    if (!buf || cap < js.size() + 1) return QCD_E_NOMEM;
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return rc;
+}
+
+}  // extern "C"

@@ -120,6 +120,10 @@ __global__ void traj_branch_kernel(DevProgram<T> prog, const NodeRec* parents, c
     if (i >= n_traj) return;
     const uint32_t o = owner[i];
     const NodeRec nd = parents[o];
+    if (nd.flags & NODE_LEAF) {  // finished circuit: no next sweep, no children
+        keys[i] = ~0ull;
+        return;
+    }
     const Sweep& S = prog.sweeps[nd.sweep + 1];
     uint32_t word = 0;
     if (S.group >= 0)
@@ -129,9 +133,9 @@ __global__ void traj_branch_kernel(DevProgram<T> prog, const NodeRec* parents, c
 }
 
 template <typename T>
-__global__ void child_scale_kernel(DevProgram<T> prog, NodeRec* children, uint32_t n_children, const double* P) {
+__global__ void child_scale_kernel(DevProgram<T> prog, NodeRec* children, const uint32_t* n_children, const double* P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_children) return;
+    if (i >= *n_children) return;
     NodeRec& c = children[i];
     const Sweep& S = prog.sweeps[c.sweep];
     double sc = 1.0;
@@ -158,6 +162,153 @@ __global__ void fill_owner_kernel(const NodeRec* nodes, uint32_t n_nodes, uint32
 __global__ void iota_kernel(uint32_t* p, uint32_t n, uint32_t start) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = start + i;
+}
+
+
+// ------------------------------------------------------------------------------------------------ grouping
+// Trajectories -> child nodes without a sort: a counting table indexed (owner << gbits | branch word).
+//   count_keys  : table[idx]++                                   (atomics; integer -> order independent)
+//   group_l1/l2/l3 : exclusive scan of (count, count != 0) over the table; every non-empty entry becomes one child
+//                 NodeRec (children are therefore ordered by parent, then branch word -- deterministic)
+//   scatter     : shots_out[offs[idx] + (--table[idx])] = shot   (leaves the table all-zero for the next use)
+__global__ void count_keys_kernel(const uint64_t* keys, uint32_t n_traj, int gbits, uint32_t* table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    const uint64_t key = keys[i];
+    if (key == ~0ull) return;
+    atomicAdd(table + (((uint64_t)(key >> 32) << gbits) | (uint32_t)key), 1u);
+}
+
+// exclusive scan of up to 1024 (count, flag) pairs by 256 threads (4 consecutive each); returns block totals
+__device__ __forceinline__ uint2 block_excl_scan_pairs(uint2 (&v)[4], uint2* warp_tot /*[8]*/) {
+    uint2 t = make_uint2(v[0].x + v[1].x + v[2].x + v[3].x, v[0].y + v[1].y + v[2].y + v[3].y);
+    const uint2 mine = t;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t nx = __shfl_up_sync(0xffffffffu, t.x, o), ny = __shfl_up_sync(0xffffffffu, t.y, o);
+        if (lane >= o) {
+            t.x += nx;
+            t.y += ny;
+        }
+    }
+    if (lane == 31) warp_tot[wid] = t;
+    __syncthreads();
+    uint2 off = make_uint2(t.x - mine.x, t.y - mine.y), tot = make_uint2(0, 0);
+    for (int w = 0; w < 8; w++) {
+        if (w < wid) {
+            off.x += warp_tot[w].x;
+            off.y += warp_tot[w].y;
+        }
+        tot.x += warp_tot[w].x;
+        tot.y += warp_tot[w].y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint2 x = v[e];
+        v[e] = off;
+        off.x += x.x;
+        off.y += x.y;
+    }
+    return tot;
+}
+
+__global__ void group_l1_kernel(const uint32_t* table, uint32_t M, uint2* bsum) {
+    __shared__ uint2 warp_tot[8];
+    const uint32_t base = blockIdx.x * 1024u + threadIdx.x * 4u;
+    uint2 v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t c = (base + e < M) ? table[base + e] : 0u;
+        v[e] = make_uint2(c, c ? 1u : 0u);
+    }
+    const uint2 tot = block_excl_scan_pairs(v, warp_tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void group_l2_kernel(uint2* bsum, uint32_t n_blocks, uint32_t* totals /*[2]: trajectories, children*/) {
+    __shared__ uint2 warp_tot[8];
+    uint2 carry = make_uint2(0, 0);
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024u) {
+        const uint32_t base = b0 + threadIdx.x * 4u;
+        uint2 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (base + e < n_blocks) ? bsum[base + e] : make_uint2(0, 0);
+        const uint2 tot = block_excl_scan_pairs(v, warp_tot);
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (base + e < n_blocks) bsum[base + e] = make_uint2(v[e].x + carry.x, v[e].y + carry.y);
+        carry.x += tot.x;
+        carry.y += tot.y;
+    }
+    if (threadIdx.x == 0) {
+        totals[0] = carry.x;
+        totals[1] = carry.y;
+    }
+}
+
+__global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, const uint2* bsum, const NodeRec* parents,
+                                const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children) {
+    __shared__ uint2 warp_tot[8];
+    const uint32_t base = blockIdx.x * 1024u + threadIdx.x * 4u;
+    uint2 v[4];
+    uint32_t cnt[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        cnt[e] = (base + e < M) ? table[base + e] : 0u;
+        v[e] = make_uint2(cnt[e], cnt[e] ? 1u : 0u);
+    }
+    block_excl_scan_pairs(v, warp_tot);
+    const uint2 boff = bsum[blockIdx.x];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        if (base + e >= M) continue;
+        const uint32_t excl = v[e].x + boff.x;
+        offs[base + e] = excl;
+        if (cnt[e]) {
+            const uint32_t idx = base + e;
+            const uint32_t par = idx >> gbits;
+            const NodeRec pn = parents[par];
+            NodeRec c;
+            c.src_slot = pn.dst_slot;
+            c.dst_slot = 0xFFFFFFFFu;
+            c.sweep = pn.sweep + 1u;
+            c.branch = idx & ((1u << gbits) - 1u);
+            c.scale = 1.0;
+            c.circuit = pn.circuit;
+            c.traj_off = traj_base + excl;
+            c.traj_cnt = cnt[e];
+            c.parent = par;
+            c.flags = (c.sweep + 1u == circuits[pn.circuit].sweep_end) ? NODE_LEAF : 0u;
+            c.pad = 0;
+            children[v[e].y + boff.y] = c;
+        }
+    }
+}
+
+__global__ void scatter_kernel(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits,
+                               const uint32_t* offs, uint32_t* table, uint32_t* shots_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    const uint64_t key = keys[i];
+    if (key == ~0ull) return;
+    const uint64_t idx = ((uint64_t)(key >> 32) << gbits) | (uint32_t)key;
+    const uint32_t pos = offs[idx] + atomicSub(table + idx, 1u) - 1u;
+    shots_out[pos] = shots_in[i];
+}
+
+// virtual root parents: node.pad = first shot of the node's range
+__global__ void root_shots_kernel(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj) return;
+    const NodeRec nd = nodes[owner[i]];
+    shots[i] = nd.pad + (i - (nd.traj_off - nodes[0].traj_off));
+}
+
+__global__ void fill_root_probs_kernel(double* P, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P[i] = (i & 3u) ? 0.0 : 1.0;
 }
 
 // ------------------------------------------------------------------------------------------------ scans
@@ -250,7 +401,8 @@ __device__ __forceinline__ uint32_t upper_search(const double* arr, uint32_t lo,
     return a < hi ? a : hi - 1;
 }
 
-__device__ __forceinline__ uint32_t readout_flips(uint32_t x, int n, const double* flip, uint64_t seed,
+// flip_c = this circuit's row of the flip table: [n][2] = P(1|0), P(0|1)
+__device__ __forceinline__ uint32_t readout_flips(uint32_t x, int n, const double* flip_c, uint64_t seed,
                                                   uint32_t circuit, uint64_t shot) {
     for (int blk = 0; blk * 4 < n; blk++) {
         const uint4 w = draw(seed, circuit, shot, QCD_STREAM_READOUT + blk);
@@ -260,7 +412,7 @@ __device__ __forceinline__ uint32_t readout_flips(uint32_t x, int n, const doubl
             const int q = blk * 4 + j;
             if (q < n) {
                 const uint32_t bit = (x >> q) & 1u;
-                const double pf = flip[((uint64_t)circuit * n + q) * 2u + bit];
+                const double pf = flip_c[q * 2 + bit];
                 if ((double)ww[j] * (1.0 / 4294967296.0) < pf) x ^= 1u << q;
             }
         }
@@ -306,7 +458,7 @@ __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_
         }
     }
     uint32_t x = (c << chunk_log) + e_sel;
-    if (flip) x = readout_flips(x, n_bits, flip, seed, nd.circuit, shot);
+    if (flip) x = readout_flips(x, n_bits, flip + (uint64_t)nd.circuit * n_bits * 2u, seed, nd.circuit, shot);
     if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
     if (outcomes) outcomes[(uint64_t)nd.circuit * shots_per_circuit + shot - shot_begin] = x;
 }
@@ -382,7 +534,7 @@ __global__ void sample_probs_kernel(const T* probs, int n, const double* chunk_s
         }
     }
     uint32_t x = (c << chunk_log) + e_sel;
-    if (flip) x = readout_flips(x, n, flip, seed, v /* flip table is indexed by vector */, shot);
+    if (flip) x = readout_flips(x, n, flip + (uint64_t)v * n * 2u, seed, circuit, shot);
     atomicAdd(hist + ((uint64_t)v << n) + x, 1u);
 }
 
@@ -478,9 +630,27 @@ void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const
     if (n_traj) traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, shots, n_traj, seed, keys);
 }
 template <typename T>
-void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t n_children, const double* P,
-                        cudaStream_t st) {
-    if (n_children) child_scale_kernel<T><<<cdiv(n_children, 128), 128, 0, st>>>(prog, children, n_children, P);
+void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
+                        const double* P, cudaStream_t st) {
+    if (max_children) child_scale_kernel<T><<<cdiv(max_children, 128), 128, 0, st>>>(prog, children, n_children, P);
+}
+void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
+                           uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
+                           const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
+                           uint32_t* shots_out, cudaStream_t st) {
+    if (!n_traj || !M) return;
+    const uint32_t nb = cdiv(M, 1024);
+    count_keys_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, n_traj, gbits, table);
+    group_l1_kernel<<<nb, 256, 0, st>>>(table, M, bsum);
+    group_l2_kernel<<<1, 256, 0, st>>>(bsum, nb, totals);
+    group_l3_kernel<<<nb, 256, 0, st>>>(table, M, gbits, bsum, parents, circuits, traj_base, offs, children);
+    scatter_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, shots_in, n_traj, gbits, offs, table, shots_out);
+}
+void launch_root_shots(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj, cudaStream_t st) {
+    if (n_traj) root_shots_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(nodes, owner, shots, n_traj);
+}
+void launch_fill_root_probs(double* P, uint32_t n_nodes, cudaStream_t st) {
+    if (n_nodes) fill_root_probs_kernel<<<cdiv((uint64_t)n_nodes * 4u, 256), 256, 0, st>>>(P, n_nodes * 4u);
 }
 void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj, cudaStream_t st) {
     if (n_traj) fill_owner_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(nodes, n_nodes, owner, n_traj);
@@ -592,7 +762,8 @@ void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* 
 #define INST(T)                                                                                                        \
     template void launch_traj_branch<T>(const DevProgram<T>&, const NodeRec*, const double*, const uint32_t*,         \
                                         const uint32_t*, uint32_t, uint64_t, uint64_t*, cudaStream_t);                \
-    template void launch_child_scale<T>(const DevProgram<T>&, NodeRec*, uint32_t, const double*, cudaStream_t);       \
+    template void launch_child_scale<T>(const DevProgram<T>&, NodeRec*, uint32_t, const uint32_t*, const double*,    \
+                                        cudaStream_t);                                                                \
     template void launch_sample<T>(const NodeRec*, uint32_t, const void*, uint64_t, const double*, uint64_t,          \
                                    const double*, uint64_t, uint32_t, int, const uint32_t*, const uint32_t*, uint32_t, \
                                    uint64_t, const double*, uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);  \

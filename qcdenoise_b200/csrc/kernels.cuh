@@ -75,8 +75,17 @@ template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
                         const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st);
 template <typename T>
-void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t n_children, const double* P,
-                        cudaStream_t st);
+void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
+                        const double* P, cudaStream_t st);
+// trajectories (keys = owner << 32 | branch word, ~0 = finished) -> child NodeRecs (dst_slot unassigned) ordered by
+// (parent, word), totals[0] = trajectories placed, totals[1] = children; shots permuted so that each child's
+// trajectories are contiguous.  table [M = n_parents << gbits] must be all-zero on entry and is all-zero on exit.
+void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
+                           uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
+                           const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
+                           uint32_t* shots_out, cudaStream_t st);
+void launch_root_shots(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj, cudaStream_t st);
+void launch_fill_root_probs(double* P, uint32_t n_nodes, cudaStream_t st);
 void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj, cudaStream_t st);
 void launch_iota(uint32_t* p, uint32_t n, uint32_t start, cudaStream_t st);
 

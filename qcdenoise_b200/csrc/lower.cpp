@@ -400,7 +400,16 @@ struct Lowerer {
             if (x.kind == LOp::M1) {
                 // diagonal single-variant matrices become D1 / SIGN early (they commute with other diagonals)
                 int j = last_toucher(out, x.q[0]);
-                if (j >= 0 && out[j].kind == LOp::M1 && (x.nvar == 1 || out[j].nvar == 1)) {
+                // A per-branch (variant) op may only absorb DIAGONAL neighbours: the decide step tracks the joint
+                // populations through the site's own Kraus operators, so nothing that moves population (H, X, ...)
+                // may hide inside a variant matrix.
+                const bool x_diag = x.nvar == 1 && is_diag(x.mats.data(), 2);
+                const bool p_diag = j >= 0 && out[j].kind == LOp::M1 && out[j].nvar == 1 && is_diag(out[j].mats.data(), 2);
+                const bool both_plain = j >= 0 && out[j].kind == LOp::M1 && x.nvar == 1 && out[j].nvar == 1;
+                const bool can_fuse = j >= 0 && out[j].kind == LOp::M1 &&
+                                      (both_plain || (x.nvar > 1 && out[j].nvar == 1 && p_diag) ||
+                                       (x.nvar == 1 && out[j].nvar > 1 && x_diag));
+                if (can_fuse) {
                     LOp& p = out[j];  // x after p : new = x * p
                     int nv = std::max(x.nvar, p.nvar);
                     std::vector<cd> m;
@@ -437,6 +446,7 @@ struct Lowerer {
             }
             if ((x.kind == LOp::M2 || x.kind == LOp::M4) && x.nvar == 1) {
                 int d = 1 << x.nq;
+                if (is_identity(x.mats, d)) continue;  // e.g. the reference's labelled identity `unitary` markers
                 // same-support predecessor: multiply
                 bool merged = false;
                 {
@@ -684,7 +694,7 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
         SweepB& s = sw[si];
         Tile t;
         if (!choose_tile(s.active, nb, P.k_max, t)) {
-            err = "internal: sweep does not fit a tile";
+            err = "an operator does not fit a " + std::to_string(P.k_max) + "-bit tile (tile_bits too small)";
             return QCD_E_UNSUPPORTED;
         }
         Sweep S;

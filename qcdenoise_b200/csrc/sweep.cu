@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, Tr<T>::MINB) sweep_kernel(DevPr
     // ------------------------------------------------------------------ phase 3: store + reductions
     const int rq0 = S.red_q[0], rq1 = S.red_q[1];
     const bool do_red = rq0 >= 0;
-    const bool do_chunks = (S.flags & SW_FINAL) != 0;
+    const bool do_chunks = (S.flags & SW_FINAL) != 0 && args.chunk_sums != nullptr;
     const int chunk_log = n_bits < CHUNK_LOG ? n_bits : CHUNK_LOG;
     double* csum = args.chunk_sums + (uint64_t)N.dst_slot * args.chunk_stride;
     T p0 = 0, p1 = 0, p2 = 0, p3 = 0;

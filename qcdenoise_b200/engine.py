@@ -1,0 +1,193 @@
+"""Thin Python handle on a libqcdsim context: torch owns device memory and the stream, the library owns the
+kernels.  Everything that computes goes through the C ABI (include/qcdsim.h)."""
+import ctypes
+import json
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ir import encode_programs
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return ctypes.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One context per (process, device).  Not thread-safe."""
+
+    def __init__(self, device=0, mem_budget_bytes=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("qcdenoise_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)   # make sure the primary context exists before the library uses it
+        h = ctypes.c_void_p()
+        rc = self.lib.qcd_create(self.device.index, mem_budget_bytes, ctypes.byref(h))
+        if rc:
+            raise _lib.QcdError(rc, self.lib.qcd_last_error(None).decode())
+        self._h = h
+        self.n_qubits = 0
+        self.n_circuits = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.qcd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise _lib.QcdError(rc, self.lib.qcd_last_error(self._h).decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_option(self, key, value):
+        self._check(self.lib.qcd_set_option(self._h, key.encode(), float(value)))
+
+    def stats(self):
+        s = _lib.Stats()
+        self._check(self.lib.qcd_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    # ---------------------------------------------------------------- programs
+    def upload(self, circuits):
+        """circuits: list of ir.Circuit (same qubit count), or the tuple returned by ir.encode_programs."""
+        enc = circuits if isinstance(circuits, tuple) else encode_programs(circuits)
+        ops, offsets, params, n = enc
+        self._check(self.lib.qcd_upload_programs(self._h, _ptr(ops) if len(ops) else None, _ptr(offsets),
+                                                 _ptr(params) if len(params) else None, len(params),
+                                                 len(offsets) - 1, n))
+        self.n_qubits = n
+        self.n_circuits = len(offsets) - 1
+        return self
+
+    @staticmethod
+    def _readout_array(readout, n_vec, n):
+        if readout is None:
+            return None
+        r = np.ascontiguousarray(np.asarray(readout, dtype=np.float64))
+        if r.shape == (n, 2, 2):
+            r = np.ascontiguousarray(np.broadcast_to(r, (n_vec, n, 2, 2)))
+        if r.shape != (n_vec, n, 2, 2):
+            raise ValueError(f"readout must have shape ({n_vec}, {n}, 2, 2)")
+        return r
+
+    # ---------------------------------------------------------------- simulation
+    def run_trajectories(self, shots, seed=1234, precision=32, shot_range=None, readout=None, hist=None,
+                         want_outcomes=False, dedup=True):
+        """Statevector trajectories.  Returns (hist [B, 2^n] int32 or None, outcomes [range] int32 or None).
+        shot_range = (begin, end) in the flattened [circuit][shot] space (default: everything)."""
+        n, B = self.n_qubits, self.n_circuits
+        begin, end = shot_range if shot_range is not None else (0, B * shots)
+        with torch.cuda.device(self.device):
+            if hist is None and n <= 26:
+                hist = torch.zeros((B, 2 ** n), dtype=torch.int32, device=self.device)
+            outcomes = torch.empty((max(end - begin, 1),), dtype=torch.int32, device=self.device) \
+                if (want_outcomes or hist is None) else None
+            r = self._readout_array(readout, B, n)
+            self._check(self.lib.qcd_run_sv_trajectories(
+                self._h, precision, shots, seed, begin, end, _ptr(r), _ptr(hist), _ptr(outcomes),
+                0 if dedup else _lib.QCD_RUN_NO_DEDUP, self._stream()))
+        if outcomes is not None:
+            outcomes = outcomes[: end - begin]
+        return hist, outcomes
+
+    def run_density_matrix(self, precision=32, circuit_range=None, out=None):
+        """Exact outcome distributions (diagonal of rho): tensor [count, 2^n] float32/float64."""
+        n, B = self.n_qubits, self.n_circuits
+        cb, ce = circuit_range if circuit_range is not None else (0, B)
+        dt = torch.float64 if precision == 64 else torch.float32
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((ce - cb, 2 ** n), dtype=dt, device=self.device)
+            self._check(self.lib.qcd_run_density_matrix(self._h, precision, cb, ce, _ptr(out), self._stream()))
+        return out
+
+    def apply_readout(self, probs, readout):
+        n_vec, N = probs.shape
+        n = N.bit_length() - 1
+        r = self._readout_array(readout, n_vec, n)
+        prec = 64 if probs.dtype == torch.float64 else 32
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qcd_apply_readout_probs(self._h, prec, _ptr(probs), n_vec, n, _ptr(r), self._stream()))
+        return probs
+
+    def sample_from_probs(self, probs, shots, seed=1234, first_circuit=0, shot_range=None, readout=None, hist=None):
+        n_vec, N = probs.shape
+        n = N.bit_length() - 1
+        begin, end = shot_range if shot_range is not None else (0, shots)
+        prec = 64 if probs.dtype == torch.float64 else 32
+        with torch.cuda.device(self.device):
+            if hist is None:
+                hist = torch.zeros((n_vec, N), dtype=torch.int32, device=self.device)
+            r = self._readout_array(readout, n_vec, n)
+            self._check(self.lib.qcd_sample_from_probs(self._h, prec, _ptr(probs), n_vec, n, begin, end, seed,
+                                                       first_circuit, _ptr(r), _ptr(hist), self._stream()))
+        return hist
+
+    # ---------------------------------------------------------------- stabilizer reductions
+    @staticmethod
+    def _masks(masks, n_vec):
+        m = np.ascontiguousarray(np.asarray(masks, dtype=np.uint32))
+        if m.ndim == 1:
+            return m, m.shape[0], 0
+        if m.shape[0] != n_vec:
+            raise ValueError("per-vector masks must have one row per vector")
+        return m, m.shape[1], 1
+
+    def parity_counts(self, hist, masks):
+        """-> (signed_sums int64 [B, M], totals int64 [B]); bit-exact integer arithmetic."""
+        n_vec, N = hist.shape
+        n = N.bit_length() - 1
+        m, n_masks, per = self._masks(masks, n_vec)
+        with torch.cuda.device(self.device):
+            ss = torch.empty((n_vec, n_masks), dtype=torch.int64, device=self.device)
+            tot = torch.empty((n_vec,), dtype=torch.int64, device=self.device)
+            self._check(self.lib.qcd_parity_counts(self._h, _ptr(hist), n_vec, n, _ptr(m), n_masks, per, _ptr(ss),
+                                                   _ptr(tot), self._stream()))
+        return ss, tot
+
+    def parity_probs(self, probs, masks):
+        n_vec, N = probs.shape
+        n = N.bit_length() - 1
+        m, n_masks, per = self._masks(masks, n_vec)
+        prec = 64 if probs.dtype == torch.float64 else 32
+        with torch.cuda.device(self.device):
+            ev = torch.empty((n_vec, n_masks), dtype=torch.float64, device=self.device)
+            self._check(self.lib.qcd_parity_probs(self._h, prec, _ptr(probs), n_vec, n, _ptr(m), n_masks, per,
+                                                  _ptr(ev), self._stream()))
+        return ev
+
+
+def debug_schedule(circuit, mode=0, precision=32, tile_bits=0):
+    """Host-only: the sweep program the scheduler emits for one circuit, as a dict (no GPU needed)."""
+    lib = _lib.load()
+    ops, offsets, params, n = encode_programs([circuit])
+    cap = 1 << 20
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        need = ctypes.c_size_t()
+        rc = lib.qcd_debug_schedule_json(_ptr(ops) if len(ops) else None, len(ops),
+                                         _ptr(params) if len(params) else None, len(params), n, mode, precision,
+                                         tile_bits, buf, cap, ctypes.byref(need))
+        if rc == _lib.QCD_E_NOMEM and need.value > cap:
+            cap = need.value + 16
+            continue
+        d = json.loads(buf.value.decode())
+        if rc:
+            raise _lib.QcdError(rc, d.get("error", "schedule failed"))
+        return d

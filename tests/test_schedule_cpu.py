@@ -1,0 +1,121 @@
+"""CPU checks of the host scheduler (csrc/lower.cpp, through the C ABI's qcd_debug_schedule_json): the emitted
+sweep program, interpreted with numpy exactly the way the kernels execute it, must reproduce the oracle --
+density-matrix probabilities to 1e-12 and trajectory outcomes shot for shot."""
+import numpy as np
+import pytest
+
+import qcdenoise_b200 as qb
+from oracle import sim
+from tests import circuits, schedule_interp as si
+
+
+def _sched(n, ops, mode, tile_bits=0, precision=64):
+    return qb.debug_schedule(qb.Circuit(n, ops), mode=mode, precision=precision, tile_bits=tile_bits)
+
+
+@pytest.mark.parametrize("n,tile_bits", [(4, 0), (5, 9), (6, 9), (7, 0), (7, 10)])
+def test_dm_graph_amp_damp(n, tile_bits):
+    rng = np.random.default_rng(100 + n)
+    for i in range(3):
+        ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n if n in (4, 5, 7) else 5, i)[: n - 1] if n == 6
+                                              else circuits.ref_graph(n, i), rng, max_prob=0.3)
+        prog = _sched(n, ops, 1, tile_bits)
+        np.testing.assert_allclose(si.run_dm(prog), sim.density_matrix_probs(ops, n), atol=1e-12)
+
+
+@pytest.mark.parametrize("builder", ["cx", "cz", "cphase"])
+def test_dm_builders(builder):
+    rng = np.random.default_rng(7)
+    n = 5
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, 2), rng, builder=builder, all_sites=True)
+    np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dm_random_circuits(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 6))
+    ops = circuits.random_circuit(n, 40, rng)
+    tb = [0, 9, 9][seed % 3]
+    np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1, tb)), sim.density_matrix_probs(ops, n), atol=1e-12)
+
+
+def test_dm_device_noise():
+    rng = np.random.default_rng(3)
+    n = 5
+    ops, _ = circuits.device_noise_circuit(n, circuits.ref_graph(n, 1), rng)
+    np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ideal_statevector(seed):
+    rng = np.random.default_rng(50 + seed)
+    n = int(rng.integers(3, 10))
+    ops = circuits.random_circuit(n, 60, rng, noise_sites=False)
+    prog = _sched(n, ops, 0, [0, 7, 7, 8][seed])
+    state, _ = si.run_trajectory(prog, 1, 0, 0)
+    np.testing.assert_allclose(state, sim.ideal_statevector(ops, n), atol=1e-12)
+
+
+def _check_trajectories(n, ops, shots, seed, tile_bits=0, circuit=0):
+    prog = _sched(n, ops, 0, tile_bits)
+    got = si.run_shots(prog, seed, circuit, shots)
+    want = sim.run_trajectories(ops, n, shots, seed, circuit=circuit)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} of {shots} outcomes differ"
+    return prog
+
+
+@pytest.mark.parametrize("n,tile_bits", [(4, 0), (6, 0), (8, 0), (8, 7)])
+def test_trajectories_graph_amp_damp(n, tile_bits):
+    rng = np.random.default_rng(200 + n)
+    g = circuits.ref_graph(8 if n == 8 else 4 if n == 4 else 5, 1)
+    if n == 6:
+        g = g + [(4, 5)]
+    ops = circuits.graph_circuit_amp_damp(n, g, rng, max_prob=0.35, all_sites=True)
+    prog = _check_trajectories(n, ops, 300, seed=99, tile_bits=tile_bits, circuit=3)
+    # one sweep per state-dependent site group + the prep sweep, not one per gate
+    n_sites = sum(1 for op in ops if op[0] == "unitary")
+    assert len(prog["sweeps"]) <= n_sites + 1 + (2 if tile_bits else 0) * n_sites
+
+
+def test_trajectories_depolarizing_C1():
+    ops = circuits.depolarizing_circuit(4, circuits.ref_graph(4, 2), p1=0.05, p2=0.2)
+    _check_trajectories(4, ops, 400, seed=5)
+
+
+def test_trajectories_device_noise():
+    rng = np.random.default_rng(11)
+    n = 5
+    ops, _ = circuits.device_noise_circuit(n, circuits.ref_graph(n, 0), rng, gate_error=0.2, gate_len_ns=(500, 5000))
+    _check_trajectories(n, ops, 300, seed=2)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_trajectories_random_circuits(seed):
+    rng = np.random.default_rng(300 + seed)
+    n = int(rng.integers(2, 7))
+    ops = circuits.random_circuit(n, 30, rng)
+    _check_trajectories(n, ops, 200, seed=seed, tile_bits=[0, 7][seed % 2])
+
+
+def test_schedule_fuses_reference_circuit():
+    """n=20 reference circuit: sweeps = state-dependent site groups + 1 (+ tile-fit splits), every non-diagonal
+    target inside the tile (asserted by the interpreter), <= 4 register bits per pass."""
+    rng = np.random.default_rng(1)
+    n = 20
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, 0), rng)
+    K = sum(1 for op in ops if op[0] == "unitary")
+    prog = _sched(n, ops, 0, precision=32)
+    assert K + 1 <= len(prog["sweeps"]) <= 2 * K + 2
+    for sw in prog["sweeps"]:
+        assert sw["k"] == 13 and sw["L"] >= 5 and len(sw["high"]) == sw["k"] - sw["L"]
+        for ps in sw["passes"]:
+            assert len(ps["rbits"]) == 4
+
+
+def test_invalid_programs_rejected():
+    from qcdenoise_b200 import _lib
+    with pytest.raises(_lib.QcdError):
+        qb.debug_schedule(qb.Circuit(3, [("pauli", (0,), np.array([0.5, 0.2, 0.2, 0.2]))]))
+    with pytest.raises(_lib.QcdError):
+        qb.debug_schedule(qb.Circuit(3, [("cx", (0, 5))]))
