@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes), against the CPU oracle on the same seeded
+inputs.  Tolerances (BASELINE.json north_star): exact probabilities 1e-5 in complex64 / 1e-10 in complex128;
+integer work (outcomes with identical Philox draws, histograms, parity sums) bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import ref_glue, sim
+from tests import circuits
+
+pytestmark = pytest.mark.gpu
+
+TOL = {32: 1e-5, 64: 1e-10}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import qcdenoise_b200 as qb
+    e = qb.Engine(0)
+    yield e
+    e.close()
+
+
+def _circ(n, ops):
+    import qcdenoise_b200 as qb
+    return qb.Circuit(n, ops)
+
+
+def _reset_opts(eng):
+    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 20)):
+        eng.set_option(k, v)
+
+
+# ------------------------------------------------------------------------------------------- density matrix
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("n,tile_bits", [(4, 0), (5, 9), (6, 0), (7, 10), (8, 0)])
+def test_dm_probs_graph_amp_damp(eng, precision, n, tile_bits):
+    _reset_opts(eng)
+    eng.set_option("tile_bits", tile_bits)
+    rng = np.random.default_rng(n)
+    src = {6: 5}.get(n, n)
+    batch = []
+    for i in range(4):
+        g = circuits.ref_graph(src, i)
+        if n == 6:
+            g = g + [(4, 5)]
+        batch.append(circuits.graph_circuit_amp_damp(n, g, rng, max_prob=0.3))
+    eng.upload([_circ(n, ops) for ops in batch])
+    probs = eng.run_density_matrix(precision).cpu().numpy()
+    for i, ops in enumerate(batch):
+        np.testing.assert_allclose(probs[i], sim.density_matrix_probs(ops, n), atol=TOL[precision], rtol=0)
+    _reset_opts(eng)
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_dm_probs_random_and_device(eng, precision):
+    _reset_opts(eng)
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        n = 5
+        ops = circuits.random_circuit(n, 40, rng)
+        dev, conf = circuits.device_noise_circuit(n, circuits.ref_graph(n, seed), rng)
+        eng.upload([_circ(n, ops), _circ(n, dev)])
+        probs = eng.run_density_matrix(precision)
+        want = [sim.density_matrix_probs(ops, n), sim.density_matrix_probs(dev, n)]
+        got = probs.cpu().numpy()
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, atol=TOL[precision], rtol=0)
+        # classical readout error on the exact distribution
+        eng.apply_readout(probs, np.stack([conf, conf]))
+        got = probs.cpu().numpy()
+        np.testing.assert_allclose(got[1], sim.apply_readout_to_probs(want[1], n, conf), atol=TOL[precision], rtol=0)
+
+
+def test_dm_C1_depolarizing_witness(eng):
+    """BASELINE config C1: 4-qubit linear graph, depolarizing noise; exact probs + Toth stabilizer expectations."""
+    _reset_opts(eng)
+    n, edges = 4, [(0, 1), (1, 2), (2, 3)]
+    base = circuits.depolarizing_circuit(n, edges)
+    nbrs = {v: [b if a == v else a for a, b in edges if v in (a, b)] for v in range(n)}
+    gens = ref_glue.get_generators(n, range(n), nbrs)
+    settings = gens + ["I" * n]
+    circs = [base + ref_glue.stabilizer_basis_change(name) for name in settings]
+    eng.upload([_circ(n, ops) for ops in circs])
+    masks = np.array([[sum(1 << i for i, ch in enumerate(name[::-1]) if ch != "I")] for name in settings], dtype=np.uint32)
+    for precision in (32, 64):
+        probs = eng.run_density_matrix(precision)
+        ev = eng.parity_probs(probs, masks).cpu().numpy()[:, 0]
+        for i, name in enumerate(settings):
+            p = sim.density_matrix_probs(circs[i], n)
+            want = float(np.dot(p, ref_glue.construct_diagonal(name)))
+            assert abs(ev[i] - want) < TOL[precision]
+
+
+# ------------------------------------------------------------------------------------------- trajectories
+def _oracle_outcomes(ops, n, shots, seed, circuit, readout=None):
+    return sim.run_trajectories(ops, n, shots, seed, circuit=circuit, readout=readout).astype(np.int64)
+
+
+@pytest.mark.parametrize("n,tile_bits", [(4, 0), (6, 0), (8, 0), (8, 7), (10, 8)])
+def test_trajectories_match_oracle_fp64(eng, n, tile_bits):
+    """complex128 + identical Philox draws: outcomes agree shot for shot; histograms bit-exact."""
+    _reset_opts(eng)
+    eng.set_option("tile_bits", tile_bits)
+    rng = np.random.default_rng(40 + n)
+    src = {6: 5}.get(n, n)
+    batch = []
+    for i in range(3):
+        g = circuits.ref_graph(src, i)
+        if n == 6:
+            g = g + [(4, 5)]
+        batch.append(circuits.graph_circuit_amp_damp(n, g, rng, max_prob=0.35, all_sites=(i == 0)))
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 500, 77
+    hist, out = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
+    out = out.cpu().numpy().reshape(3, shots)
+    hist = hist.cpu().numpy()
+    for c, ops in enumerate(batch):
+        want = _oracle_outcomes(ops, n, shots, seed, c)
+        assert np.array_equal(out[c], want), f"circuit {c}: {np.count_nonzero(out[c] != want)} outcomes differ"
+        assert np.array_equal(hist[c], sim.histogram(want, n))
+    st = eng.stats()
+    assert st["trajectories"] == 3 * shots and st["leaves"] <= 3 * shots
+    _reset_opts(eng)
+
+
+def test_trajectories_all_noise_kinds_fp64(eng):
+    _reset_opts(eng)
+    n = 5
+    rng = np.random.default_rng(8)
+    dev, conf = circuits.device_noise_circuit(n, circuits.ref_graph(n, 0), rng, gate_error=0.2, gate_len_ns=(500, 5000))
+    dep = circuits.depolarizing_circuit(n, circuits.ref_graph(n, 1), p1=0.05, p2=0.2)
+    rnd = circuits.random_circuit(n, 30, rng)
+    batch = [dev, dep, rnd]
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 400, 3
+    readout = np.stack([conf] * 3)
+    _, out = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True, readout=readout)
+    out = out.cpu().numpy().reshape(3, shots)
+    for c, ops in enumerate(batch):
+        want = _oracle_outcomes(ops, n, shots, seed, c, readout=conf)
+        assert np.array_equal(out[c], want), f"circuit {c}: {np.count_nonzero(out[c] != want)} outcomes differ"
+
+
+def test_dedup_equals_literal_per_shot(eng):
+    _reset_opts(eng)
+    n = 8
+    rng = np.random.default_rng(5)
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, 3), rng, max_prob=0.3, all_sites=True)
+    eng.upload([_circ(n, ops)] * 2)
+    for precision in (32, 64):
+        h1, o1 = eng.run_trajectories(300, seed=9, precision=precision, want_outcomes=True)
+        s1 = eng.stats()
+        h2, o2 = eng.run_trajectories(300, seed=9, precision=precision, want_outcomes=True, dedup=False)
+        s2 = eng.stats()
+        assert bool((o1 == o2).all()) and bool((h1 == h2).all())
+        assert s2["leaves"] == 600 and s1["node_sweeps"] < s2["node_sweeps"]
+
+
+def test_memory_limited_recursion_and_table_split(eng):
+    """Few state slots (depth-first chunks) and a tiny grouping table give the same outcomes."""
+    _reset_opts(eng)
+    n = 8
+    rng = np.random.default_rng(6)
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, 4), rng, max_prob=0.35, all_sites=True)
+    eng.upload([_circ(n, ops)])
+    _, ref = eng.run_trajectories(400, seed=1, precision=64, want_outcomes=True)
+    n_sweeps = 1 + sum(1 for op in ops if op[0] == "unitary")
+    eng.set_option("max_slots", n_sweeps + 3)
+    eng.set_option("table_cap_log2", 4)
+    eng.set_option("max_chunk", 150)
+    _, got = eng.run_trajectories(400, seed=1, precision=64, want_outcomes=True)
+    assert bool((ref == got).all())
+    assert eng.stats()["max_live_states"] <= n_sweeps + 3
+    eng.set_option("max_slots", 2)
+    from qcdenoise_b200._lib import QcdError
+    with pytest.raises(QcdError):
+        eng.run_trajectories(10, seed=1, precision=64)
+    _reset_opts(eng)
+
+
+def test_shot_range_partition_is_rank_invariant(eng):
+    """The multi-GPU partition: any split of the flattened shot range gives the same union."""
+    _reset_opts(eng)
+    n = 6
+    rng = np.random.default_rng(12)
+    batch = [circuits.graph_circuit_amp_damp(n, circuits.ref_graph(5, i) + [(4, 5)], rng, max_prob=0.3) for i in range(3)]
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots = 200
+    whole, _ = eng.run_trajectories(shots, seed=4, precision=32)
+    acc = None
+    for lo, hi in ((0, 130), (130, 470), (470, 600)):
+        acc, _ = eng.run_trajectories(shots, seed=4, precision=32, shot_range=(lo, hi), hist=acc)
+    assert bool((whole == acc).all())
+
+
+def test_trajectories_fp32_statistics(eng):
+    """complex64 trajectories: histogram vs exact density-matrix probabilities (chi-square, TVD)."""
+    _reset_opts(eng)
+    n = 6
+    rng = np.random.default_rng(21)
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(5, 2) + [(2, 5)], rng, max_prob=0.3, all_sites=True)
+    eng.upload([_circ(n, ops)])
+    shots = 200000
+    hist, _ = eng.run_trajectories(shots, seed=31, precision=32)
+    h = hist.cpu().numpy()[0].astype(np.float64)
+    p = sim.density_matrix_probs(ops, n)
+    assert h.sum() == shots
+    tvd = 0.5 * np.abs(h / shots - p).sum()
+    assert tvd < 0.02
+    sel = p * shots > 5
+    chi2 = (((h - p * shots) ** 2) / (p * shots))[sel].sum()
+    dof = sel.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof)
+
+
+def test_empty_and_edge_inputs(eng):
+    _reset_opts(eng)
+    from qcdenoise_b200._lib import QcdError
+    # empty circuit: |0...0> with certainty
+    eng.upload([_circ(3, [])])
+    hist, _ = eng.run_trajectories(50, seed=1, precision=32)
+    assert hist.cpu().numpy()[0].tolist() == [50] + [0] * 7
+    assert eng.run_density_matrix(64).cpu().numpy()[0].tolist() == [1.0] + [0.0] * 7
+    # empty shot range is a no-op
+    h, _ = eng.run_trajectories(50, seed=1, precision=32, shot_range=(10, 10))
+    assert int(h.sum()) == 0
+    with pytest.raises(QcdError):
+        eng.run_trajectories(50, seed=1, precision=16)
+    with pytest.raises(QcdError):
+        eng.run_trajectories(50, seed=1, shot_range=(0, 51))
+    # 1-qubit: amplitude damping on |1> gives P(0) = gamma
+    from oracle import noise
+    g = 0.3
+    eng.upload([_circ(1, [("x", (0,)), ("kraus", (0,), noise.amplitude_damping_kraus(g))])])
+    p = eng.run_density_matrix(64).cpu().numpy()[0]
+    np.testing.assert_allclose(p, [g, 1 - g], atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------- sampling / parity
+@pytest.mark.parametrize("n", [3, 8, 13])
+def test_sample_from_probs_matches_oracle(eng, n):
+    import torch
+    rng = np.random.default_rng(n)
+    p = rng.random((3, 2 ** n)) ** 4
+    p /= p.sum(axis=1, keepdims=True)
+    conf = np.array([[[0.97, 0.03], [0.08, 0.92]]] * n)
+    probs = torch.tensor(p, dtype=torch.float64, device="cuda")
+    shots, seed = 2000, 17
+    hist = eng.sample_from_probs(probs, shots, seed=seed, first_circuit=5, readout=np.stack([conf] * 3)).cpu().numpy()
+    for v in range(3):
+        want = sim.sample_from_probs(p[v], shots, seed, circuit=5 + v, readout=conf)
+        assert np.array_equal(hist[v], sim.histogram(want, n))
+
+
+@pytest.mark.parametrize("n", [4, 10, 16])
+def test_parity_counts_bit_exact(eng, n, goldens):
+    import torch
+    rng = np.random.default_rng(n)
+    h = rng.integers(0, 1000, size=(3, 2 ** n)).astype(np.int32)
+    h[rng.random(h.shape) < 0.5] = 0
+    masks = rng.integers(0, 2 ** n, size=(3, n + 1)).astype(np.uint32)
+    masks[:, -1] = 0
+    ss, tot = eng.parity_counts(torch.tensor(h, device="cuda"), masks)
+    ss, tot = ss.cpu().numpy(), tot.cpu().numpy()
+    x = np.arange(2 ** n, dtype=np.uint64)
+    for v in range(3):
+        assert tot[v] == h[v].sum()
+        for m in range(n + 1):
+            par = np.array([bin(int(t)).count("1") & 1 for t in (x & np.uint64(masks[v, m]))]) if n <= 10 else \
+                (np.unpackbits((x & np.uint64(masks[v, m])).view(np.uint8)).reshape(-1, 64).sum(axis=1) & 1)
+            assert ss[v, m] == int((h[v].astype(np.int64) * (1 - 2 * par.astype(np.int64))).sum())
+
+
+def test_parity_counts_golden_G1(eng, goldens):
+    """Reference notebook counts -> <S> exactly as recorded (graph_witness_refractored.ipynb#c45-47)."""
+    import torch
+    g = goldens["G1"]
+    names = g["stabilizer_order"]
+    n = 4
+    h = np.zeros((len(names), 16), dtype=np.int32)
+    for i, counts in enumerate(g["counts"]):
+        for key, c in counts.items():
+            h[i, int(key, 2)] = c
+    masks = np.array([[sum(1 << i for i, ch in enumerate(name[::-1]) if ch != "I")] for name in names], dtype=np.uint32)
+    ss, tot = eng.parity_counts(torch.tensor(h, device="cuda"), masks)
+    ss, tot = ss.cpu().numpy()[:, 0], tot.cpu().numpy()
+    got = dict(zip(names, ss / tot))
+    for name, (mean, std) in g["stabilizer_measurements"]:
+        assert got[name] == mean
+        shots = int(tot[names.index(name)])
+        assert np.sqrt(max(1 - mean * mean, 0) / shots) == pytest.approx(std, rel=1e-12, abs=1e-18)
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+def test_n20_ideal_graph_state_stabilizers(eng):
+    """BASELINE-size state (n = 20): every Toth generator of the ideal graph state has <S> = +1 on sampled counts
+    (size-independent property: all sampled outcomes must have even parity under the generator mask)."""
+    _reset_opts(eng)
+    n = 20
+    edges = circuits.ref_graph(n, 0)
+    base, _ = ref_glue.cx_gate_circuit(n, edges)
+    nbrs = {v: [b if a == v else a for a, b in edges if v in (a, b)] for v in range(n)}
+    settings = []
+    for v in range(0, n, 5):
+        name = ["I"] * n
+        name[v] = "X"
+        for w in nbrs[v]:
+            name[w] = "Z"
+        settings.append("".join(name)[::-1])
+    circs = [base + [("h", (i,)) for i, ch in enumerate(s[::-1]) if ch == "X"] for s in settings]
+    eng.upload([_circ(n, ops) for ops in circs])
+    masks = np.array([[sum(1 << i for i, ch in enumerate(s[::-1]) if ch != "I")] for s in settings], dtype=np.uint32)
+    hist, _ = eng.run_trajectories(4096, seed=2, precision=32)
+    ss, tot = eng.parity_counts(hist, masks)
+    assert tot.cpu().tolist() == [4096] * len(settings)
+    assert ss.cpu().numpy()[:, 0].tolist() == [4096] * len(settings)
