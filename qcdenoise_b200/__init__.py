@@ -7,3 +7,9 @@ _lib.load()
 
 from .ir import Circuit, encode_programs  # noqa: E402
 from .engine import Engine, debug_schedule  # noqa: E402
+from .graph_circuit import *  # noqa: E402,F401,F403
+from .graph_state import *  # noqa: E402,F401,F403
+from .samplers import *  # noqa: E402,F401,F403
+from .stabilizers import *  # noqa: E402,F401,F403
+from .witnesses import *  # noqa: E402,F401,F403
+from .simulate import *  # noqa: E402,F401,F403

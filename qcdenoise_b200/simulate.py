@@ -1,0 +1,181 @@
+"""Orchestration with the reference's spec dataclasses and `simulate()` signature (qcdenoise/simulate.py:43-326).
+The reference loops over circuits, one qiskit call each; here all circuits of a run are built first and simulated
+in ONE batched engine call per stage (sampling, stabilizer settings)."""
+from copy import deepcopy
+from dataclasses import dataclass
+from typing import Any, Dict
+
+import numpy as np
+
+from .graph_state import GraphData, GraphDB, GraphState
+from .samplers import CircuitSampler, DeviceNoiseSampler, NoiseSpec, UnitaryNoiseSampler, get_engine
+from .stabilizers import StabilizerSampler, TothStabilizer, pauli_mask
+from .witnesses import GenuineWitness
+
+__all__ = ["GraphSpecs", "SamplingSpecs", "CircuitSpecs", "AdjTensorSpecs", "EntanglementSpecs", "SimulationSpecs",
+           "simulate", "circuit_sampling_op", "estimate_entanglement_op"]
+
+
+@dataclass(init=True)
+class GraphSpecs:
+    min_num_edges: int = 2
+    max_num_edges: int = 3
+    directed: bool = False
+    min_vertex_cover: int = 1
+    max_itr: int = 1
+
+
+@dataclass(init=True)
+class SamplingSpecs:
+    sampler: Any
+    noise_specs: NoiseSpec
+    sample_options: dict = None
+    transpile_options: dict = None
+    n_shots: int = 1024
+
+
+@dataclass(init=True)
+class CircuitSpecs:
+    builder: Any
+    stochastic: bool
+    build_options: dict = None
+    gate_type: str = "none"
+
+
+@dataclass(init=True)
+class AdjTensorSpecs:
+    tensor_shape: tuple
+    fixed_size: bool = True
+    directed: bool = False
+
+
+@dataclass(init=True)
+class EntanglementSpecs:
+    witness: Any
+    stabilizer: Any
+    stabilizer_sampler: Any = StabilizerSampler
+    n_shots: int = 1024
+    noisy: bool = False     # reference behaviour (quirk Q7): stabilizer settings are simulated WITHOUT noise
+
+
+@dataclass(init=True)
+class SimulationSpecs:
+    n_qubits: int
+    n_circuits: int
+    data: Any
+    circuit: CircuitSpecs
+    backend: Any = None
+
+
+def circuit_sampling_op(graph, circ_builder, circ_specs, sampler, sampler_specs) -> Dict:
+    circ_dict = circ_builder.build(graph, **circ_specs.build_options) if circ_specs.build_options \
+        else circ_builder.build(graph)
+    if isinstance(sampler, UnitaryNoiseSampler):
+        prob_vec = sampler.sample(circ_dict["circuit"], circ_dict["ops"])
+    else:
+        prob_vec = sampler.sample(circ_dict["circuit"], **(sampler_specs.sample_options or {}))
+    return {"prob_vec": prob_vec, "graph": graph, "circuit": circ_dict["circuit"],
+            "noise_model": deepcopy(sampler.noise_model)}
+
+
+def estimate_entanglement_op(graph, graph_circuit, entangle_specs, n_qubits, backend=None, noise_model=None):
+    stabilizer = entangle_specs.stabilizer(graph, n_qubits)
+    stab_circs = stabilizer.build()
+    sampler = entangle_specs.stabilizer_sampler(n_shots=entangle_specs.n_shots, backend=backend)
+    counts = sampler.sample(stabilizer_circuits=stab_circs, graph_circuit=graph_circuit,
+                            noise_model=noise_model if entangle_specs.noisy else None)
+    witness = entangle_specs.witness(n_qubits=n_qubits, stabilizer_circuits=stab_circs, stabilizer_counts=counts)
+    return witness.estimate(graph=graph)
+
+
+def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None) -> Dict:
+    """-> {i: {"graph_data": edges, "prob_vec": np.ndarray (2^n,), ["entanglement": {"value", "variance"}]}}."""
+    if not isinstance(sim_specs, SimulationSpecs):
+        raise AssertionError("sim_specs must be an instance of SimulationSpecs")
+    if not isinstance(sampler_specs, SamplingSpecs):
+        raise AssertionError("sampler_specs must be an instance of SamplingSpecs")
+    if not isinstance(graph_specs, GraphSpecs):
+        raise AssertionError("graph_specs must be an instance of GraphSpecs")
+    if adj_tensor_specs is not None:
+        raise NotImplementedError("adjacency tensors need the qiskit transpiler DAG (reference simulate.py:105-134); "
+                                  "out of this engine's scope")
+    if entangle_specs is not None and not isinstance(entangle_specs, EntanglementSpecs):
+        raise AssertionError("entangle_specs must be an instance of EntanglementSpecs")
+    n = sim_specs.n_qubits
+    graph_db = GraphDB(graph_data=sim_specs.data, directed=graph_specs.directed)
+    graph_state = GraphState(graph_db, n_qubits=n, min_num_edges=graph_specs.min_num_edges,
+                             max_num_edges=graph_specs.max_num_edges, directed=graph_specs.directed)
+    builder = sim_specs.circuit.builder(n_qubits=n, stochastic=sim_specs.circuit.stochastic)
+    sampler = sampler_specs.sampler(n_shots=sampler_specs.n_shots, backend=sim_specs.backend,
+                                    noise_specs=sampler_specs.noise_specs)
+    if sim_specs.circuit.stochastic and not isinstance(sampler, UnitaryNoiseSampler):
+        raise AssertionError("stochastic gates need sampler=UnitaryNoiseSampler")
+
+    results = {i: {} for i in range(sim_specs.n_circuits)}
+    graphs, circuits, models = [], [], []
+    for num in range(sim_specs.n_circuits):
+        graph = graph_state.sample(min_vertex_cover=graph_specs.min_vertex_cover, max_itr=graph_specs.max_itr)
+        results[num]["graph_data"] = list(graph.edges())
+        cd = builder.build(graph, **sim_specs.circuit.build_options) if sim_specs.circuit.build_options \
+            else builder.build(graph)
+        if isinstance(sampler, UnitaryNoiseSampler):
+            sampler.build_noise_model(cd["ops"])
+        else:
+            sampler.transpile_circuit(cd["circuit"], {})
+            sampler.build_noise_model(n, **(sampler_specs.sample_options or {}))
+        graphs.append(graph)
+        circuits.append(cd["circuit"])
+        models.append(deepcopy(sampler.noise_model))
+
+    # ---- stage 1: all noisy circuits in one engine call
+    prob_vecs = _batched_counts(sampler, circuits, models)
+    for num in range(sim_specs.n_circuits):
+        results[num]["prob_vec"] = prob_vecs[num].hist.astype(np.float64) / sampler_specs.n_shots
+
+    # ---- stage 2: all stabilizer settings of all circuits in one engine call
+    if entangle_specs is not None:
+        stab_sampler = entangle_specs.stabilizer_sampler(n_shots=entangle_specs.n_shots, backend=sim_specs.backend)
+        all_circs, all_models, spans, stab_dicts = [], [], [], []
+        for num in range(sim_specs.n_circuits):
+            stab_circs = entangle_specs.stabilizer(graphs[num], n).build()
+            stab_dicts.append(stab_circs)
+            spans.append((len(all_circs), len(all_circs) + len(stab_circs)))
+            for name, sc in stab_circs.items():
+                all_circs.append(circuits[num].copy(name=name).compose(sc))
+                all_models.append(models[num] if entangle_specs.noisy else None)
+        stab_sampler.noisy = entangle_specs.noisy
+        counts = _batched_counts(stab_sampler, all_circs, all_models)
+        for num in range(sim_specs.n_circuits):
+            lo, hi = spans[num]
+            wit = entangle_specs.witness(n_qubits=n, stabilizer_circuits=stab_dicts[num],
+                                         stabilizer_counts=counts[lo:hi])
+            w = wit.estimate(graph=graphs[num])
+            if isinstance(w, dict):
+                results[num]["entanglement"] = {"value": [x.value for x in w.values()],
+                                                "variance": [x.variance for x in w.values()]}
+            else:
+                results[num]["entanglement"] = {"value": w.value, "variance": w.variance}
+    return results
+
+
+def _batched_counts(sampler: CircuitSampler, circuits, models):
+    """Instantiate each circuit with ITS noise model and simulate the whole batch at once."""
+    from .samplers import Counts, NoiseModel
+    inst = [(m if m is not None else NoiseModel()).instantiate(c) for c, m in zip(circuits, models)]
+    progs = [c for c, _ in inst]
+    n = progs[0].n_qubits
+    readout = None
+    if any(r is not None for _, r in inst):
+        readout = np.stack([r if r is not None else np.tile(np.eye(2), (n, 1, 1)) for _, r in inst])
+    noisy = any(op[0] in ("kraus", "pauli", "reset") for c in progs for op in c.ops)
+    eng = get_engine(sampler.device)
+    eng.upload(progs)
+    seed = sampler._next_seed()
+    if sampler._pick_method(n, noisy) == "density_matrix":
+        probs = eng.run_density_matrix(sampler.precision)
+        sampler.last_probs = probs
+        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
+    else:
+        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
+    h = hist.cpu().numpy()
+    return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(progs))]

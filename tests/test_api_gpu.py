@@ -1,0 +1,123 @@
+"""GPU tests of the reference-facing Python API: the reference's own tests (shape / length / "runs" assertions,
+tests/test_samplers.py, test_stabilizers.py, test_simulate.py) plus the value-level goldens G1-G4."""
+import random
+
+import networkx as nx
+import numpy as np
+import pytest
+
+from oracle import sim
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qcd():
+    import qcdenoise_b200 as q
+    return q
+
+
+def _graph(n, seed, qcd):
+    random.seed(seed)
+    np.random.seed(seed)
+    return qcd.GraphState(qcd.GraphDB(), n_qubits=n, min_num_edges=2, max_num_edges=7).sample()
+
+
+def test_unitary_noise_sampler_shape_and_distribution(qcd):
+    n = 5
+    g = _graph(n, 1, qcd)
+    cd = qcd.CXGateCircuit(n_qubits=n, stochastic=True).build(g)
+    sampler = qcd.UnitaryNoiseSampler(None, n_shots=4096, noise_specs=qcd.NoiseSpec(
+        specs={"type": "phase_amplitude_damping_error", "max_prob": 0.3}), seed=5)
+    n_ops = len(cd["circuit"])
+    p = sampler.sample(cd["circuit"], cd["ops"])
+    assert p.shape == (2 ** n,) and p.dtype == np.float64 and abs(p.sum() - 1) < 1e-12     # reference test: shape
+    assert len(cd["circuit"]) == n_ops                                                     # caller's circuit untouched
+    # 4096 > 2^5 and noisy -> density-matrix method: exact probs equal the oracle on the instantiated circuit
+    inst, _ = sampler.noise_model.instantiate(cd["circuit"])
+    exact = sampler.last_probs.cpu().numpy()[0]
+    np.testing.assert_allclose(exact, sim.density_matrix_probs(inst.ops, n), atol=1e-5)
+    assert 0.5 * np.abs(p - exact).sum() < 0.08
+    # forced trajectories give a statistically equal histogram
+    s2 = qcd.UnitaryNoiseSampler(None, n_shots=4096, method="statevector", seed=6)
+    s2.noise_model, s2.noisy = sampler.noise_model, True
+    c2 = s2.simulate_circuit(cd["circuit"])
+    assert c2.shots() == 4096
+    assert 0.5 * np.abs(c2.hist / 4096 - exact).sum() < 0.08
+
+
+def test_device_noise_sampler_shape(qcd):
+    n = 5
+    g = _graph(n, 2, qcd)
+    cd = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 100.0, "readout_error": 0.05, "prob_meas0_prep1": 0.05,
+                                          "prob_meas1_prep0": 0.05},
+                                "cx": {"gate_error": 0.1, "gate_length": 400.0},
+                                "h": {"gate_error": 0.01, "gate_length": 50.0}})
+    sampler = qcd.DeviceNoiseSampler(None, n_shots=2048, noise_specs=spec, precision=64, seed=1)
+    p = sampler.sample(cd["circuit"], user_backend=False)
+    assert p.shape == (2 ** n,) and abs(p.sum() - 1) < 1e-12
+    inst, ro = sampler.noise_model.instantiate(cd["circuit"])
+    want = sim.apply_readout_to_probs(sim.density_matrix_probs(inst.ops, n), n, ro)
+    assert 0.5 * np.abs(p - want).sum() < 0.12
+    np.testing.assert_allclose(sampler.last_probs.cpu().numpy()[0], sim.density_matrix_probs(inst.ops, n), atol=1e-10)
+
+
+def test_stabilizer_sampler_ideal_G4(qcd, goldens):
+    """Ideal P4 graph state: n+1 Counts, the recorded 8-outcome supports, <S> = 1, genuine witness -1."""
+    g = nx.path_graph(4)
+    cd = qcd.CXGateCircuit(n_qubits=4, stochastic=False).build(g)
+    stab = qcd.TothStabilizer(g, n_qubits=4).build()
+    counts = qcd.StabilizerSampler(None, n_shots=1024, seed=3).sample(stab, cd["circuit"])
+    assert len(counts) == 5                                            # reference tests/test_stabilizers.py:46-53
+    g4 = goldens["G4"]
+    order = g4["stabilizer_order_c18"]
+    for name, c in zip(stab, counts):
+        assert c.shots() == 1024
+        assert set(c.keys()) <= set(g4["ideal_counts"][order.index(name)].keys())
+    w = qcd.GenuineWitness(4, stab, counts)
+    assert all(m == (1.0, 0.0) for m in w.stabilizer_measurements.values())
+    res = w.estimate(g)
+    assert res.value == -1.0 and res.variance == 0.0
+    for r in qcd.BiSeparableWitness(4, stab, counts).estimate(g).values():
+        assert r.value == -1.0
+
+
+def test_witnesses_from_recorded_counts_G1_G2_G3(qcd, goldens):
+    from collections import OrderedDict
+    g1 = goldens["G1"]
+    names = g1["stabilizer_order"]
+    circs = OrderedDict((nm, None) for nm in names)
+    wit = qcd.GenuineWitness(4, circs, g1["counts"])
+    for name, (mean, std) in g1["stabilizer_measurements"]:
+        assert wit.stabilizer_measurements[name][0] == mean
+        assert wit.stabilizer_measurements[name][1] == pytest.approx(std, rel=1e-13, abs=1e-18)
+    for name, diag in g1["diagonals"]:
+        np.testing.assert_array_equal(wit.diagonals[name], np.array(diag))
+    g = nx.Graph()
+    g.add_edges_from([tuple(e) for e in g1["edges"]])
+    res = wit.estimate(g)
+    assert res.value == goldens["G2"]["genuine"]["value"]
+    assert res.variance == pytest.approx(goldens["G2"]["genuine"]["variance"], abs=5e-9)
+    bis = qcd.BiSeparableWitness(4, OrderedDict((nm, None) for nm in names), g1["counts"]).estimate(g)
+    for idx, exp in enumerate(goldens["G3"]["bisep"]):
+        assert list(bis[idx].W_ij) == exp["W_ij"] and bis[idx].value == exp["value"]
+        assert bis[idx].variance == pytest.approx(exp["variance"], abs=5e-9)
+
+
+@pytest.mark.parametrize("with_witness", [False, True])
+def test_simulate(qcd, with_witness):
+    """Reference tests/test_simulate.py: 4 qubits, 10 circuits, runs and returns the documented dict."""
+    random.seed(0)
+    np.random.seed(0)
+    sim_specs = qcd.SimulationSpecs(n_qubits=4, n_circuits=10, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=True))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.UnitaryNoiseSampler, noise_specs=qcd.unitary_noise_spec, n_shots=1024)
+    ent = qcd.EntanglementSpecs(witness=qcd.GenuineWitness, stabilizer=qcd.TothStabilizer, n_shots=1024) \
+        if with_witness else None
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), entangle_specs=ent)
+    assert sorted(res) == list(range(10))
+    for r in res.values():
+        assert r["prob_vec"].shape == (16,) and abs(r["prob_vec"].sum() - 1) < 1e-12 and r["graph_data"]
+        if with_witness:
+            assert r["entanglement"]["value"] == -1.0        # stabilizer settings are ideal (reference quirk Q7)
