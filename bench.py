@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native noisy-circuit sampling engine.
+
+Workload (BASELINE.json configs[3], "C4" in SURVEY.md 8d -- the largest single-GPU configuration the metric's
+20-28 qubit range is quoted on): one 20-qubit reference-sampled graph state, CXGateCircuit gate list with
+stochastic labelled sites, two amplitude-damping Kraus channels per site (max_prob 0.1), 1,000,000 noisy
+statevector-trajectory shots of the graph circuit AND of each of its n+1 = 21 Toth stabilizer settings
+(22 circuits x 1M shots per step), dense 2^20 histograms, bitmask-parity <S> for the 21 settings -> genuine witness.
+complex64 amplitudes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--shots S] [--literal]
+
+One step = one pass of that path.  `value` = noisy shots/s with the lowered programs resident on the GPU (timed with
+CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API (UnitaryNoiseSampler.sample
++ StabilizerSampler.sample + GenuineWitness.estimate) from host gate lists to host numpy results, every step
+including encode, upload + lowering, and the device->host copies of all 22 histograms.  `roofline` = algorithmic
+bytes moved by the state-sweep kernel / its CUDA-event time, against the measured HBM copy bandwidth.
+`cpu_baseline` / `--impl reference` = the compiled CPU port of the qiskit-Aer statevector-trajectory algorithm
+(oracle/cpu_sim.c, OpenMP over shots) on a bounded number of shots of the same noisy circuit.
+
+N > 1 (torchrun): every rank simulates its own graph (same per-GPU work: weak scaling, circuits partitioned by
+rank index, no data-path collective); one NCCL all_gather assembles the dataset histograms and parity sums.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_QUBITS = 20
+SEED = 1234
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(graph_index, shots):
+    """Gate lists of the step for graph `graph_index` of tests/golden/graphs.json (reference-sampled, n = 20)."""
+    import networkx as nx
+
+    import qcdenoise_b200 as qcd
+    with open(os.path.join(ROOT, "tests", "golden", "graphs.json")) as f:
+        graphs = json.load(f)["graphs"][str(N_QUBITS)]
+    edges = [tuple(e) for e in graphs[graph_index % len(graphs)]]
+    g = nx.Graph()
+    g.add_nodes_from(range(N_QUBITS))
+    g.add_edges_from(edges)
+    np.random.seed(SEED + graph_index)                       # coins and channel draws of the reference API use np.random
+    cd = qcd.CXGateCircuit(n_qubits=N_QUBITS, stochastic=True).build(g)
+    sampler = qcd.UnitaryNoiseSampler(None, n_shots=shots, noise_specs=qcd.unitary_noise_spec, method="statevector",
+                                      precision=32, seed=SEED)
+    sampler.build_noise_model(cd["ops"])
+    stab = qcd.TothStabilizer(g, n_qubits=N_QUBITS).build()
+    circuits = [cd["circuit"]] + [cd["circuit"].copy(name=nm).compose(sc) for nm, sc in stab.items()]
+    programs = [sampler.noise_model.instantiate(c)[0] for c in circuits]
+    masks = np.array([[0]] + [[qcd.pauli_mask(nm)] for nm in stab], dtype=np.uint32)
+    return {"graph": g, "edges": edges, "circuit_dict": cd, "stab": stab, "programs": programs, "masks": masks,
+            "noise_model": sampler.noise_model, "n_sites": len(cd["ops"])}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(work, n_shots, threads=0):
+    """Literal one-trajectory-per-shot CPU port on the noisy graph circuit.  Returns (shots/s, seconds, threads)."""
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    enc = encode_programs([work["programs"][0]])
+    cores = threads or cpu_build.max_threads()
+    t0 = time.perf_counter()
+    cpu_build.run_trajectories(enc, n_shots, SEED, circuit=0, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return n_shots / dt, dt, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cpu_build
+    work = build_workload(0, args.shots)
+    cores = cpu_build.max_threads()
+    per_step = max(4 * cores, 8)
+    for _ in range(args.warmup):
+        cpu_arm(work, max(cores // 4, 2))
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt, _ = cpu_arm(work, per_step)
+        t += dt
+    v = per_step * args.steps / t
+    sample = f"{per_step} shots per step of the {N_QUBITS}-qubit noisy graph circuit (circuit 0 of the step), one " \
+             f"trajectory per shot, complex128"
+    line = {"impl": "reference", "metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
+            "value": v, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic", "config": workload_config(work, args.shots),
+            "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(work, shots):
+    return {"workload": "C4: 20-qubit graph-state stochastic-trajectory sampling, 1M shots, stabilizer witnesses "
+                        "(BASELINE.json configs[3])",
+            "n_qubits": N_QUBITS, "graph_edges": len(work["edges"]), "noise_sites": work["n_sites"],
+            "kraus_channels": 2 * work["n_sites"], "max_prob": 0.1, "circuits_per_step": len(work["programs"]),
+            "shots_per_circuit": shots, "precision": "complex64",
+            "cache": "working set per tree level (up to thousands of 8 MiB states) >> 126 MB L2; "
+                     "histograms re-zeroed every step"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shots", type=int, default=1_000_000, help="shots per circuit (1M = the BASELINE config)")
+    ap.add_argument("--literal", action="store_true", help="one state per shot (no trajectory-tree sharing)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import qcdenoise_b200 as qcd
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    work = build_workload(rank, args.shots)
+    B = len(work["programs"])
+    N = 2 ** N_QUBITS
+    eng = qcd.get_engine(local)
+    eng.upload(work["programs"])
+    eng.set_option("time_sweeps", 1)
+    hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
+    if world > 1:
+        gathered_rows = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(world)]
+        gathered_sums = [torch.empty((B,), dtype=torch.int64, device=dev) for _ in range(world)]
+
+    def step():
+        hist.zero_()
+        eng.run_trajectories(args.shots, seed=SEED, precision=32, hist=hist, dedup=not args.literal)
+        st = eng.stats()
+        ss, tot = eng.parity_counts(hist, work["masks"])
+        if world > 1:   # assemble the dataset rows (noisy histogram of each rank's graph circuit) and the <S> sums
+            dist.all_gather(gathered_rows, hist[0])
+            dist.all_gather(gathered_sums, ss[:, 0].contiguous())
+        return st, ss, tot
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"sweep_launches": 0, "aux_launches": 0, "sweep_bytes": 0, "sweep_ms": 0.0, "node_sweeps": 0, "leaves": 0}
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            st, ss, tot = step()
+            for k in agg:
+                agg[k] += st[k]
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert tot.cpu().tolist() == [args.shots] * B, "histograms do not hold every shot"
+    shots_per_step = B * args.shots * world
+    value = shots_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the reference-facing API (host gate lists in, host numpy out), rank-local
+    e2e = None
+    if not args.no_e2e:
+        g, cd, stab = work["graph"], work["circuit_dict"], work["stab"]
+        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=32, seed=SEED)
+        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=32, seed=SEED + 1)
+
+        def e2e_step():
+            np.random.seed(SEED + rank)
+            p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
+            counts = ssam.sample(stab, cd["circuit"], noise_model=sampler.noise_model)   # 21 Counts (host histograms)
+            w = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
+            return p, w
+
+        eng.set_option("time_sweeps", 0)
+        e2e_step()
+        barrier()
+        k_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            p, w = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        from qcdenoise_b200.ir import encode_programs
+        enc = encode_programs(work["programs"])
+        h2d = int(enc[0].nbytes + enc[1].nbytes + enc[2].nbytes)
+        d2h = int(B * N * 4 + (B - 1) * 16)
+        e2e = {"value": shots_per_step * k_e2e / dt, "unit": "shots/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e, "witness_value": float(w.value),
+               "api": "UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    achieved = agg["sweep_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9 if agg["sweep_ms"] > 0 else None
+    roofline = {"bound": "hbm", "kernel": "qcd::sweep_kernel<float>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": agg["sweep_bytes"] / max(agg["sweep_launches"], 1),
+                "avg_launch_ms": agg["sweep_ms"] / max(agg["sweep_launches"], 1),
+                "sweep_share_of_step": agg["sweep_ms"] / ms,
+                "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep]; "
+                                     "one sweep per state-dependent noise-site group"}
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cpu_build
+        cores = cpu_build.max_threads()
+        n_cpu = max(16 * cores, 16)
+        v, dt_cpu, cores = cpu_arm(work, n_cpu)
+        cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} shots of the noisy 20-qubit graph circuit (circuit 0 of the step), one trajectory "
+                         f"per shot, complex128, {dt_cpu:.1f} s"}
+    line = {"metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
+            "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c64", "data": "synthetic", "config": workload_config(work, args.shots),
+            "circuits_per_s": B * world * args.steps / (ms * 1e-3),
+            "trajectory_sharing": not args.literal,
+            "states_swept_per_step": agg["node_sweeps"] / args.steps, "leaf_states_per_step": agg["leaves"] / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(agg["sweep_launches"] + agg["aux_launches"] + args.steps),
+            "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

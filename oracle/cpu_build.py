@@ -1,0 +1,57 @@
+"""Build oracle/cpu_sim.c -> oracle/_build/libcpusim.so (gcc, OpenMP) and bind it with ctypes.
+TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cpu_sim.c")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libcpusim.so")
+_lib = None
+
+
+def build(force=False):
+    hdr = os.path.join(HERE, "..", "include", "qcdsim.h")
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["gcc", "-O3", "-march=x86-64-v3", "-ffast-math", "-fno-finite-math-only", "-fopenmp", "-shared", "-fPIC",
+           "-std=c11", SRC, "-o", LIB, "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + r.stdout)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(build())
+        lib.cpu_run_trajectories.restype = ctypes.c_int
+        lib.cpu_run_trajectories.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                             ctypes.c_void_p, ctypes.c_int]
+        lib.cpu_max_threads.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def run_trajectories(encoded, shots, seed, circuit=0, shot_begin=0, n_threads=0):
+    """encoded = (ops, offsets, params, n) of ONE circuit in the C-ABI encoding (qcdenoise_b200.ir.encode_programs
+    output format; the encoder itself is pure numpy host code).  Returns outcomes uint64[shots]."""
+    ops, offsets, params, n = encoded
+    lib = load()
+    out = np.empty(shots, dtype=np.uint64)
+    params = np.ascontiguousarray(params if len(params) else np.zeros(1))
+    rc = lib.cpu_run_trajectories(ops.ctypes.data, len(ops), params.ctypes.data, n, shot_begin, shot_begin + shots, seed,
+                                  circuit, out.ctypes.data, n_threads)
+    if rc:
+        raise RuntimeError("cpu_run_trajectories failed")
+    return out
+
+
+def max_threads():
+    return load().cpu_max_threads()
