@@ -54,8 +54,11 @@ struct DevBuf {
 struct DevProg {
     bool valid = false;
     Program P;
-    DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits;
+    DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits, direct;
+    std::vector<DirectSweep> direct_host;
     void release() {
+        direct.release();
+        direct_host.clear();
         sweeps.release(); passes.release(); kops.release(); pool.release(); masks.release();
         groups.release(); subs.release(); gdata.release(); circuits.release();
         valid = false;
@@ -75,6 +78,7 @@ struct qcd_ctx {
     uint64_t max_chunk = 1u << 20;
     int table_cap_log2 = 22;
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
+    bool use_direct = true;      // register-only kernel for single-pass sweeps
     // programs (host copy of the IR; compiled lazily per (mode, precision))
     int n_qubits = 0, n_circuits = 0;
     std::vector<qcd_op> ops;
@@ -156,6 +160,42 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     if ((rc = upload_vec(ctx, dp.subs, P.subs))) return rc;
     if ((rc = upload_vec(ctx, dp.gdata, P.gdata))) return rc;
     if ((rc = upload_vec(ctx, dp.circuits, P.circuits))) return rc;
+    // direct (register-only) descriptors for single-pass sweeps
+    dp.direct_host.assign(P.sweeps.size(), DirectSweep());
+    for (size_t si = 0; si < P.sweeps.size(); si++) {
+        const Sweep& S = P.sweeps[si];
+        DirectSweep& D = dp.direct_host[si];
+        memset(&D, 0, sizeof(D));
+        if ((S.flags & SW_PREP) || S.pass_end - S.pass_begin != 1 || S.n_bits < 13) continue;
+        const Pass& ps = P.passes[S.pass_begin];
+        const uint32_t nops = ps.op_end - ps.op_begin;
+        if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) continue;
+        uint32_t n_signs = 0;
+        bool ok = true;
+        for (uint32_t o = 0; o < nops; o++) {
+            KOp op = P.kops[ps.op_begin + o];
+            if (op.kind == K_SIGNS) {
+                if (n_signs + op.count > 48 || n_signs > 255) ok = false;
+                op.t1 = (uint8_t)n_signs;
+                n_signs += op.count;
+            }
+            if (op.kind == K_M4) ok = false;  // 16x16 superoperators stay on the tiled kernel
+            D.ops[o] = op;
+        }
+        if (!ok) continue;
+        D.ok = 1;
+        D.n_bits = S.n_bits;
+        D.nreg = ps.nreg;
+        D.nops = (uint8_t)nops;
+        for (int i = 0; i < REG_BITS; i++) {
+            const int b = ps.rbits[i];
+            D.rbit[i] = (uint8_t)(b < S.L ? b : S.high[b - S.L]);
+        }
+        D.red_q[0] = S.red_q[0];
+        D.red_q[1] = S.red_q[1];
+        D.flags = S.flags;
+    }
+    if ((rc = upload_vec(ctx, dp.direct, dp.direct_host))) return rc;
     int k = std::min(P.k_max, P.n_bits);
     if (precision == 64) CU(configure_sweep<double>(k));
     else CU(configure_sweep<float>(k));
@@ -176,6 +216,7 @@ DevProgram<T> dev_view(const DevProg& dp) {
     v.groups = dp.groups.as<Group>();
     v.subs = dp.subs.as<SubSite>();
     v.gdata = dp.gdata.as<double>();
+    v.direct = dp.direct.as<DirectSweep>();
     return v;
 }
 
@@ -218,7 +259,7 @@ struct SvRunner {
     DevProgram<T> prog;
     cudaStream_t st;
     int n = 0, k = 0, gbits = 0, max_sweeps = 0;
-    uint32_t tiles_log2 = 0, tiles = 1, n_chunks = 1, n_blocks = 1;
+    uint32_t tiles_log2 = 0, tiles = 1, n_chunks = 1, n_blocks = 1, part_stride = 1;
     uint64_t slot_stride = 0;
     uint64_t seed = 0, spc = 0, shot_begin = 0;
     const double* flip_dev = nullptr;
@@ -250,18 +291,20 @@ struct SvRunner {
         a.chunk_stride = n_chunks;
         a.tiles_log2 = tiles_log2;
         a.n_items = n_nodes * tiles;
+        a.part_stride = part_stride;
+        a.direct_vec = 0;
         return a;
     }
 
     // nodes[begin, end) at depth d have executed their sweep (d == 0: virtual roots); their device copy is
     // level_nodes[d] + begin and their trajectories are level_shots[d][traj_off ...).
-    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root) {
+    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root, uint32_t n_parts) {
         const size_t n_nodes = end - begin;
         if (n_nodes == 0) return QCD_OK;
         if (((uint64_t)n_nodes << gbits) > table_cap && n_nodes > 1) {
             const size_t piece = std::max<uint64_t>(1, table_cap >> gbits);
             for (size_t b = begin; b < end; b += piece) {
-                int rc = process(d, nodes, b, std::min(end, b + piece), is_root);
+                int rc = process(d, nodes, b, std::min(end, b + piece), is_root, n_parts);
                 if (rc) return rc;
             }
             return QCD_OK;
@@ -302,7 +345,7 @@ struct SvRunner {
                     }
             }
             if (!any_inner) return QCD_OK;
-            launch_node_probs(ndev, (uint32_t)n_nodes, ctx->partials.as<double>(), tiles, P, st);
+            launch_node_probs(ndev, (uint32_t)n_nodes, ctx->partials.as<double>(), part_stride, n_parts, P, st);
             ctx->stats.aux_launches++;
         }
         // ---- decide: branch word per trajectory, then group trajectories into children
@@ -344,8 +387,28 @@ struct SvRunner {
             CU(ctx->level_nodes[d + 1].ensure(c * sizeof(NodeRec)));
             NodeRec* cdev = ctx->level_nodes[d + 1].as<NodeRec>();
             CU(cudaMemcpyAsync(cdev, chunk.data(), c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+            // single-pass sweeps run on the register-only kernel; anything else on the shared-memory tile kernel
+            bool direct = ctx->use_direct, vec = true;
+            for (const NodeRec& r : chunk) {
+                const DirectSweep& D = dp->direct_host[r.sweep];
+                direct = direct && D.ok;
+                vec = vec && D.rbit[0] == 0;
+            }
+            SweepArgs sa = sweep_args(cdev, (uint32_t)c);
+            uint32_t parts_used = tiles;
+            if (direct) {
+                // CTAs per state: 8 register groups per thread when there are plenty of states, fewer otherwise
+                int pl = std::max(0, n - 4 - 8 - 3);
+                while (pl < n - 4 - 8 && ((uint64_t)c << pl) < 1184) pl++;
+                while (((uint64_t)c << pl) > 0x7fffffffull) pl--;
+                sa.tiles_log2 = (uint32_t)pl;
+                sa.n_items = (uint32_t)(c << pl);
+                sa.direct_vec = vec ? 1 : 0;
+                parts_used = 1u << pl;
+            }
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
-            launch_sweep<T>(prog, sweep_args(cdev, (uint32_t)c), k, st);
+            if (direct) launch_sweep_direct<T>(prog, sa, st);
+            else launch_sweep<T>(prog, sa, k, st);
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
             CU(cudaGetLastError());
             ctx->stats.sweep_launches++;
@@ -358,7 +421,7 @@ struct SvRunner {
                     if (!(nodes[begin + p].flags & NODE_LEAF)) free_slot(nodes[begin + p].dst_slot);
                 next_parent_to_free = done_to;
             }
-            int rc = process(d + 1, chunk, 0, c, false);
+            int rc = process(d + 1, chunk, 0, c, false, parts_used);
             if (rc) return rc;
         }
         return QCD_OK;
@@ -400,7 +463,8 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
 
     // ---- state slots
     const size_t slot_bytes = R.slot_stride * sizeof(C);
-    const size_t per_slot = slot_bytes + (size_t)R.tiles * 32 + (size_t)R.n_chunks * 8 + (size_t)R.n_blocks * 8;
+    R.part_stride = std::max<uint32_t>(R.tiles, n >= 12 ? 1u << (n - 12) : 1u);
+    const size_t per_slot = slot_bytes + (size_t)R.part_stride * 32 + (size_t)R.n_chunks * 8 + (size_t)R.n_blocks * 8;
     const size_t budget = usable_budget(ctx);
     uint64_t n_slots = budget / per_slot;
     const uint64_t wanted = 2 * T_chunk + 8 + (uint64_t)R.max_sweeps;
@@ -411,7 +475,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
                     "memory budget holds " + std::to_string(n_slots) + " states; this program needs at least " +
                         std::to_string(R.max_sweeps + 1));
     CU(ctx->states.ensure(n_slots * slot_bytes));
-    CU(ctx->partials.ensure(n_slots * (size_t)R.tiles * 32));
+    CU(ctx->partials.ensure(n_slots * (size_t)R.part_stride * 32));
     CU(ctx->chunk_sums.ensure(n_slots * (size_t)R.n_chunks * 8));
     CU(ctx->block_sums.ensure(n_slots * (size_t)R.n_blocks * 8));
     R.free_slots.resize(n_slots);
@@ -467,7 +531,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
         }
         CU(ctx->level_nodes[0].ensure(roots.size() * sizeof(NodeRec)));
         CU(cudaMemcpyAsync(ctx->level_nodes[0].p, roots.data(), roots.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
-        int rc = R.process(0, roots, 0, roots.size(), true);
+        int rc = R.process(0, roots, 0, roots.size(), true, 1);
         if (rc) return rc;
         ctx->stats.trajectories += g1 - g0;
     }
@@ -529,6 +593,8 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             a.chunk_stride = 0;
             a.tiles_log2 = tiles_log2;
             a.n_items = cnt * tiles;
+            a.part_stride = tiles;
+            a.direct_vec = 0;
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
             launch_sweep<T>(prog, a, k, st);
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -643,6 +709,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
         if (value < 4 || value > 28) return fail(ctx, QCD_E_INVALID, "table_cap_log2 must be in [4, 28]");
         ctx->table_cap_log2 = (int)value;
     } else if (k == "max_slots") ctx->max_slots = (uint64_t)value;
+    else if (k == "use_direct") ctx->use_direct = value != 0;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }

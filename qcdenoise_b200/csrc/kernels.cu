@@ -28,12 +28,12 @@ __device__ __forceinline__ double u53(uint4 w) {
 }
 
 // ------------------------------------------------------------------------------------------------ decide
-__global__ void node_probs_kernel(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles,
-                                  double* P) {
+__global__ void node_probs_kernel(const NodeRec* nodes, uint32_t n_nodes, const double* partials,
+                                  uint32_t part_stride, uint32_t tiles, double* P) {
     // one CTA (128 threads) per node: P[b] = sum over tiles of partials[slot][tile][b], fixed order
     __shared__ double red[128][4];
     const uint32_t nd = blockIdx.x;
-    const double* p = partials + (uint64_t)nodes[nd].dst_slot * tiles * 4u;
+    const double* p = partials + (uint64_t)nodes[nd].dst_slot * part_stride * 4u;
     double acc[4] = {0, 0, 0, 0};
     for (uint32_t t = threadIdx.x; t < tiles; t += 128) {
 #pragma unroll
@@ -620,9 +620,9 @@ inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b
 }  // namespace
 
 // ==================================================================================================== launchers
-void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles, double* P,
-                       cudaStream_t st) {
-    if (n_nodes) node_probs_kernel<<<n_nodes, 128, 0, st>>>(nodes, n_nodes, partials, tiles, P);
+void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t part_stride,
+                       uint32_t n_parts, double* P, cudaStream_t st) {
+    if (n_nodes) node_probs_kernel<<<n_nodes, 128, 0, st>>>(nodes, n_nodes, partials, part_stride, n_parts, P);
 }
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,

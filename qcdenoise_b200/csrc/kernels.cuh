@@ -46,6 +46,7 @@ struct DevProgram {
     const Group* groups;
     const SubSite* subs;
     const double* gdata;
+    const DirectSweep* direct;
 };
 
 constexpr int SWEEP_THREADS = 256;
@@ -59,18 +60,24 @@ struct SweepArgs {
     double* partials;        // [slot][tiles][4]
     double* chunk_sums;      // [slot][2^(n_bits - chunk_log)]
     uint64_t chunk_stride;   // doubles per slot in chunk_sums
-    uint32_t tiles_log2;     // log2(tiles per state)
+    uint32_t tiles_log2;     // log2(tiles per state)      (direct kernel: log2(CTAs per state))
     uint32_t n_items;        // nodes * tiles
+    uint32_t part_stride;    // partials: [slot][part_stride][4]; a launch writes tiles (or CTAs-per-state) of them
+    uint32_t direct_vec;     // direct kernel: every sweep of the launch has index bit 0 as a register bit
 };
 
 template <typename T>
 void launch_sweep(const DevProgram<T>& prog, const SweepArgs& a, int k, cudaStream_t st);
 template <typename T>
 cudaError_t configure_sweep(int k);
+// every node's sweep must have DirectSweep.ok; a.tiles_log2 = log2(CTAs per state), each CTA owns
+// 2^(n_bits - 4 - tiles_log2) >= 256 register groups of 16 amplitudes
+template <typename T>
+void launch_sweep_direct(const DevProgram<T>& prog, const SweepArgs& a, cudaStream_t st);
 
 // ---- decide
-void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t tiles, double* P,
-                       cudaStream_t st);
+void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t part_stride,
+                       uint32_t n_parts, double* P, cudaStream_t st);
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
                         const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st);

@@ -815,7 +815,13 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
             pbs.back().ops.push_back(oi);
         }
         for (PB& pb : pbs) {
-            // pad the register set with the highest free local bits (keeps lane-contiguous smem accesses)
+            if (pbs.size() == 1 && si != 0) {
+                // single-pass sweep -> direct (register-only) kernel: pad with the LOWEST free bits, so that a thread's
+                // 16 amplitudes contain contiguous runs (128-bit accesses) and whole probability chunks
+                for (int b = 0; b < t.k && (int)pb.R.size() < nreg; b++)
+                    if (!pb.R.count(b)) pb.R.insert(b);
+            }
+            // otherwise pad with the highest free local bits (keeps lane-contiguous smem accesses)
             for (int b = t.k - 1; b >= 0 && (int)pb.R.size() < nreg; b--)
                 if (!pb.R.count(b)) pb.R.insert(b);
             Pass ps;

@@ -73,6 +73,21 @@ struct Group {
     uint32_t sub_begin, sub_end;
 };
 
+// Fully resolved description of a sweep that consists of ONE pass over <= 4 register bits: executed by the direct
+// (register-only, no shared-memory tile) kernel.  ok == 0: the sweep needs the tiled kernel.
+constexpr int MAX_DIRECT_OPS = 12;
+struct DirectSweep {
+    uint8_t ok;
+    uint8_t n_bits;
+    uint8_t nreg;
+    uint8_t nops;
+    uint8_t rbit[REG_BITS];     // GLOBAL bit of register bit i, ascending
+    int8_t red_q[2];
+    uint8_t flags;
+    uint8_t pad[5];
+    KOp ops[MAX_DIRECT_OPS];
+};
+
 struct CircuitInfo {
     uint32_t sweep_begin, sweep_end;   // range in sweeps[]
     uint32_t n_sites;

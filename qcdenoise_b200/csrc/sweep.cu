@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, Tr<T>::MINB) sweep_kernel(DevPr
         if (tid < 4) {
             double acc = 0;
             for (int w = 0; w < SWEEP_THREADS / 32; w++) acc += s_red[w][tid];
-            args.partials[(((uint64_t)N.dst_slot << args.tiles_log2) + tau) * 4u + tid] = acc;
+            args.partials[((uint64_t)N.dst_slot * args.part_stride + tau) * 4u + tid] = acc;
         }
     }
 }
