@@ -43,6 +43,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src + ".o")
         cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd += os.environ.get("QCD_NVCC_EXTRA", "").split()       # tuning experiments only (e.g. -DDIRECT_MINB=3)
         if src.endswith(".cpp"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")

@@ -172,11 +172,16 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n, uint32_t start) {
 //                 NodeRec (children are therefore ordered by parent, then branch word -- deterministic)
 //   scatter     : shots_out[offs[idx] + (--table[idx])] = shot   (leaves the table all-zero for the next use)
 __global__ void count_keys_kernel(const uint64_t* keys, uint32_t n_traj, int gbits, uint32_t* table) {
+    // warp-aggregated: trajectories of one node mostly draw the same branch word, so the lanes of a warp collapse
+    // to a handful of distinct table entries -- one atomic per distinct entry instead of one per trajectory
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_traj) return;
-    const uint64_t key = keys[i];
-    if (key == ~0ull) return;
-    atomicAdd(table + (((uint64_t)(key >> 32) << gbits) | (uint32_t)key), 1u);
+    const uint64_t key = i < n_traj ? keys[i] : ~0ull;
+    const bool live = key != ~0ull;
+    const uint32_t active = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    const uint32_t idx = (uint32_t)(((uint64_t)(key >> 32) << gbits) | (uint32_t)key);
+    const uint32_t peers = __match_any_sync(active, idx);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(table + idx, (uint32_t)__popc(peers));
 }
 
 // exclusive scan of up to 1024 (count, flag) pairs by 256 threads (4 consecutive each); returns block totals
@@ -290,12 +295,20 @@ __global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, co
 __global__ void scatter_kernel(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits,
                                const uint32_t* offs, uint32_t* table, uint32_t* shots_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_traj) return;
-    const uint64_t key = keys[i];
-    if (key == ~0ull) return;
-    const uint64_t idx = ((uint64_t)(key >> 32) << gbits) | (uint32_t)key;
-    const uint32_t pos = offs[idx] + atomicSub(table + idx, 1u) - 1u;
-    shots_out[pos] = shots_in[i];
+    const uint64_t key = i < n_traj ? keys[i] : ~0ull;
+    const bool live = key != ~0ull;
+    const uint32_t active = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    const uint32_t idx = (uint32_t)(((uint64_t)(key >> 32) << gbits) | (uint32_t)key);
+    const uint32_t peers = __match_any_sync(active, idx);
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicSub(table + idx, (uint32_t)__popc(peers));   // old count
+    base = __shfl_sync(peers, base, leader);
+    // the group takes slots [old - popc, old); this lane's rank inside its group picks one
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    shots_out[offs[idx] + base - (uint32_t)__popc(peers) + rank] = shots_in[i];
 }
 
 // virtual root parents: node.pad = first shot of the node's range

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int DT = 256;  // threads per CTA
 #ifndef DIRECT_MINB
-#define DIRECT_MINB 2
+#define DIRECT_MINB 3
 #endif
 
 template <typename T> struct Cx;
