@@ -693,7 +693,12 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     for (size_t si = 0; si < sw.size(); si++) {
         SweepB& s = sw[si];
         Tile t;
-        if (!choose_tile(s.active, nb, P.k_max, t)) {
+        // the qubits whose populations this sweep reduces are welcome in the tile (they can then become register
+        // bits of a single-pass sweep: cheapest reduction); never at the price of not fitting
+        std::set<int> wanted = s.active;
+        for (int h = 0; h < 2; h++)
+            if (s.red_q[h] >= 0) wanted.insert(s.red_q[h]);
+        if (!choose_tile(wanted, nb, P.k_max, t) && !choose_tile(s.active, nb, P.k_max, t)) {
             err = "an operator does not fit a " + std::to_string(P.k_max) + "-bit tile (tile_bits too small)";
             return QCD_E_UNSUPPORTED;
         }
@@ -818,6 +823,10 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
             if (pbs.size() == 1 && si != 0) {
                 // single-pass sweep -> direct (register-only) kernel: pad with the LOWEST free bits, so that a thread's
                 // 16 amplitudes contain contiguous runs (128-bit accesses) and whole probability chunks
+                for (int h = 0; h < 2; h++) {
+                    const int lb = s.red_q[h] >= 0 ? local_bit(t, s.red_q[h]) : -1;
+                    if (lb >= 0 && (int)pb.R.size() < nreg) pb.R.insert(lb);
+                }
                 for (int b = 0; b < t.k && (int)pb.R.size() < nreg; b++)
                     if (!pb.R.count(b)) pb.R.insert(b);
             }

@@ -76,6 +76,42 @@ __device__ __forceinline__ void m2(C (&a)[16], const C* m) {
     }
 }
 
+// real-coefficient variants (H, Pauli X/Z, damping Kraus, Ry, ...): half the multiplies
+template <int TB, typename C>
+__device__ __forceinline__ void m1r(C (&a)[16], const C* m) {
+    const auto m00 = m[0].x, m01 = m[1].x, m10 = m[2].x, m11 = m[3].x;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        if (s & (1 << TB)) continue;
+        const C x0 = a[s], x1 = a[s | (1 << TB)];
+        C y0, y1;
+        y0.x = m00 * x0.x + m01 * x1.x;
+        y0.y = m00 * x0.y + m01 * x1.y;
+        y1.x = m10 * x0.x + m11 * x1.x;
+        y1.y = m10 * x0.y + m11 * x1.y;
+        a[s] = y0;
+        a[s | (1 << TB)] = y1;
+    }
+}
+template <int T0, int T1, typename C>
+__device__ __forceinline__ void m2r(C (&a)[16], const C* m) {
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        if (s & ((1 << T0) | (1 << T1))) continue;
+        const C x[4] = {a[s], a[s | (1 << T0)], a[s | (1 << T1)], a[s | (1 << T0) | (1 << T1)]};
+        C y[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            y[r].x = m[r * 4].x * x[0].x + m[r * 4 + 1].x * x[1].x + m[r * 4 + 2].x * x[2].x + m[r * 4 + 3].x * x[3].x;
+            y[r].y = m[r * 4].x * x[0].y + m[r * 4 + 1].x * x[1].y + m[r * 4 + 2].x * x[2].y + m[r * 4 + 3].x * x[3].y;
+        }
+        a[s] = y[0];
+        a[s | (1 << T0)] = y[1];
+        a[s | (1 << T1)] = y[2];
+        a[s | (1 << T0) | (1 << T1)] = y[3];
+    }
+}
+
 __device__ __forceinline__ void ldv(const float2* p, float2& a, float2& b) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     a = make_float2(v.x, v.y);
@@ -103,6 +139,8 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
     __shared__ uint32_t s_sign_base[MAX_SIGNS];
     __shared__ uint32_t s_sign_pat[MAX_SIGNS];
     __shared__ double s_red[DT / 32][4];
+    __shared__ uint32_t s_real[MAX_DIRECT_OPS];   // matrix op o has purely real coefficients
+    __shared__ int s_scale_op;                    // matrix op that carries the node's rescale factor (-1: none)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t node_idx = blockIdx.x >> args.tiles_log2;
@@ -143,10 +181,33 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
             if (tid < cnt) s_mats[o][tid] = m[tid];
         }
     }
+    if (tid == 0) {
+        int so = -1;
+        for (int o = 0; o < nops && so < 0; o++)
+            if (D.ops[o].kind == K_M1 || D.ops[o].kind == K_M2) so = o;
+        s_scale_op = so;
+    }
+    __syncthreads();
+    if ((int)tid < nops) {
+        // classify the staged matrix; the first matrix op absorbs the node's 1/sqrt(p) rescale
+        const int kind = D.ops[tid].kind;
+        const int cnt = kind == K_M1 ? 4 : (kind == K_M2 ? 16 : (kind == K_D1 ? 2 : 0));
+        const T f = ((int)tid == s_scale_op) ? (T)N.scale : (T)1;
+        bool real = true;
+        for (int e = 0; e < cnt; e++) {
+            C v = s_mats[tid][e];
+            v.x *= f;
+            v.y *= f;
+            s_mats[tid][e] = v;
+            real = real && v.y == (T)0;
+        }
+        s_real[tid] = real ? 1u : 0u;
+    }
     __syncthreads();
 
     const C* src = reinterpret_cast<const C*>(args.states) + (uint64_t)N.src_slot * args.slot_stride;
     C* dst = reinterpret_cast<C*>(args.states) + (uint64_t)N.dst_slot * args.slot_stride;
+    const bool need_scale = s_scale_op < 0;
     const T sc = (T)N.scale;
     const uint32_t groups_per_cta = 1u << (n_bits - 4 - (int)args.tiles_log2);
     const uint32_t grp0 = part * groups_per_cta;
@@ -158,6 +219,23 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
     for (int i = 0; i < 4; i++) r_low += (D.rbit[i] < CHUNK_LOG) ? 1 : 0;
     double* csum = args.chunk_sums + (uint64_t)N.dst_slot * args.chunk_stride;
     T p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // joint populations P[b(rq0) + 2 b(rq1)]
+    // Fast reduction: when every reduced bit is a register bit or constant over this thread's iterations, the bin of
+    // value s is fixed per thread -> accumulate per-s sums in the loop and bin them once at the end.
+    bool red_fast = true;
+    {
+        const int gl = n_bits - 4 - (int)args.tiles_log2;     // log2(register groups per CTA)
+        const int rq[2] = {rq0, rq1};
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (rq[j] < 0 || ((regmask >> rq[j]) & 1u)) continue;
+            const int cp = rq[j] - __popc(regmask & ((1u << rq[j]) - 1u));   // bit position in the group index
+            if (cp >= 8 && cp < gl) red_fast = false;
+        }
+    }
+    T acc[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) acc[s] = 0;
+    uint32_t gb_last = 0;
 
     for (uint32_t it = tid; it < groups_per_cta; it += DT) {
         uint32_t gb = grp0 + it;
@@ -181,30 +259,52 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
                 a[s] = src[g];
             }
         }
+        if (need_scale) {
 #pragma unroll
-        for (int s = 0; s < 16; s++) {
-            a[s].x *= sc;
-            a[s].y *= sc;
+            for (int s = 0; s < 16; s++) {
+                a[s].x *= sc;
+                a[s].y *= sc;
+            }
         }
         for (int o = 0; o < nops; o++) {
             const KOp op = D.ops[o];
             switch (op.kind) {
                 case K_M1:
-                    switch (op.t0) {
-                        case 0: m1<0>(a, s_mats[o]); break;
-                        case 1: m1<1>(a, s_mats[o]); break;
-                        case 2: m1<2>(a, s_mats[o]); break;
-                        default: m1<3>(a, s_mats[o]); break;
+                    if (s_real[o]) {
+                        switch (op.t0) {
+                            case 0: m1r<0>(a, s_mats[o]); break;
+                            case 1: m1r<1>(a, s_mats[o]); break;
+                            case 2: m1r<2>(a, s_mats[o]); break;
+                            default: m1r<3>(a, s_mats[o]); break;
+                        }
+                    } else {
+                        switch (op.t0) {
+                            case 0: m1<0>(a, s_mats[o]); break;
+                            case 1: m1<1>(a, s_mats[o]); break;
+                            case 2: m1<2>(a, s_mats[o]); break;
+                            default: m1<3>(a, s_mats[o]); break;
+                        }
                     }
                     break;
                 case K_M2:
-                    switch (op.t0 * 4 + op.t1) {
-                        case 1: m2<0, 1>(a, s_mats[o]); break;
-                        case 2: m2<0, 2>(a, s_mats[o]); break;
-                        case 3: m2<0, 3>(a, s_mats[o]); break;
-                        case 6: m2<1, 2>(a, s_mats[o]); break;
-                        case 7: m2<1, 3>(a, s_mats[o]); break;
-                        default: m2<2, 3>(a, s_mats[o]); break;
+                    if (s_real[o]) {
+                        switch (op.t0 * 4 + op.t1) {
+                            case 1: m2r<0, 1>(a, s_mats[o]); break;
+                            case 2: m2r<0, 2>(a, s_mats[o]); break;
+                            case 3: m2r<0, 3>(a, s_mats[o]); break;
+                            case 6: m2r<1, 2>(a, s_mats[o]); break;
+                            case 7: m2r<1, 3>(a, s_mats[o]); break;
+                            default: m2r<2, 3>(a, s_mats[o]); break;
+                        }
+                    } else {
+                        switch (op.t0 * 4 + op.t1) {
+                            case 1: m2<0, 1>(a, s_mats[o]); break;
+                            case 2: m2<0, 2>(a, s_mats[o]); break;
+                            case 3: m2<0, 3>(a, s_mats[o]); break;
+                            case 6: m2<1, 2>(a, s_mats[o]); break;
+                            case 7: m2<1, 3>(a, s_mats[o]); break;
+                            default: m2<2, 3>(a, s_mats[o]); break;
+                        }
                     }
                     break;
                 case K_SIGNS: {
@@ -251,7 +351,11 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
             T w[16];
 #pragma unroll
             for (int s = 0; s < 16; s++) w[s] = a[s].x * a[s].x + a[s].y * a[s].y;
-            if (do_red) {
+            gb_last = gb;
+            if (do_red && red_fast) {
+#pragma unroll
+                for (int s = 0; s < 16; s++) acc[s] += w[s];
+            } else if (do_red) {
 #pragma unroll
                 for (int s = 0; s < 16; s++) {
                     const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
@@ -291,6 +395,18 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
         }
     }
     if (do_red) {
+        if (red_fast) {
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                const uint32_t g = gb_last | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
+                                   ((s & 8) ? go[3] : 0u);
+                const uint32_t bin = ((g >> rq0) & 1u) | (rq1 >= 0 ? (((g >> rq1) & 1u) << 1) : 0u);
+                p0 += bin == 0 ? acc[s] : (T)0;
+                p1 += bin == 1 ? acc[s] : (T)0;
+                p2 += bin == 2 ? acc[s] : (T)0;
+                p3 += bin == 3 ? acc[s] : (T)0;
+            }
+        }
         double d[4] = {(double)p0, (double)p1, (double)p2, (double)p3};
 #pragma unroll
         for (int b = 0; b < 4; b++)
