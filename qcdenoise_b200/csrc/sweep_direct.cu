@@ -18,9 +18,12 @@
 namespace qcd {
 namespace {
 
-constexpr int DT = 256;  // threads per CTA
+#ifndef DIRECT_DT
+#define DIRECT_DT 128
+#endif
+constexpr int DT = DIRECT_DT;  // threads per CTA
 #ifndef DIRECT_MINB
-#define DIRECT_MINB 3
+#define DIRECT_MINB 8
 #endif
 
 template <typename T> struct Cx;
@@ -132,7 +135,7 @@ __device__ __forceinline__ void stv(double2* p, double2 a, double2 b) {
 constexpr int MAX_SIGNS = 48;  // sign masks staged per sweep (more: the sweep is not direct-eligible)
 
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgram<T> prog, SweepArgs args) {
+__global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB / 2) sweep_direct_kernel(DevProgram<T> prog, SweepArgs args) {
     typedef typename Cx<T>::C C;
     __shared__ DirectSweep D;
     __shared__ C s_mats[MAX_DIRECT_OPS][16];   // the selected variant of every matrix op
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(DT, DIRECT_MINB) sweep_direct_kernel(DevProgra
         for (int j = 0; j < 2; j++) {
             if (rq[j] < 0 || ((regmask >> rq[j]) & 1u)) continue;
             const int cp = rq[j] - __popc(regmask & ((1u << rq[j]) - 1u));   // bit position in the group index
-            if (cp >= 8 && cp < gl) red_fast = false;
+            if (cp >= (DT == 256 ? 8 : 7) && cp < gl) red_fast = false;
         }
     }
     T acc[16];
