@@ -690,6 +690,49 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     ci.n_sites = (uint32_t)lw.sites.size();
     uint32_t prep_off = (uint32_t)P.pool.size();
     P.pool.insert(P.pool.end(), prep.begin(), prep.end());
+    // ---- late peephole inside each sweep: a per-branch 1q matrix and a plain 1q matrix on the same bit, with nothing
+    // touching that bit in between, become one per-branch matrix (e.g. Kraus variant followed by the H that closes the
+    // CX).  Safe here and not in fuse(): segmentation is done and the decide step never looks at these matrices.
+    for (SweepB& s : sw) {
+        for (size_t j = 0; j < s.ops.size(); j++) {
+            LOp& x = ops[s.ops[j]];
+            if (x.dead || x.kind != LOp::M1) continue;
+            int prev = -1;
+            for (int i = (int)j - 1; i >= 0; i--) {
+                const LOp& o = ops[s.ops[i]];
+                if (!o.dead && touches(o, x.q[0])) {
+                    prev = i;
+                    break;
+                }
+            }
+            if (prev < 0) continue;
+            LOp& p = ops[s.ops[prev]];
+            if (p.kind != LOp::M1 || (p.nvar > 1 && x.nvar > 1)) continue;
+            const int nv = std::max(p.nvar, x.nvar);
+            std::vector<cd> m;
+            for (int v = 0; v < nv; v++) {
+                std::vector<cd> xv(x.mats.begin() + (x.nvar == 1 ? 0 : v * 4), x.mats.begin() + (x.nvar == 1 ? 0 : v * 4) + 4);
+                std::vector<cd> pv(p.mats.begin() + (p.nvar == 1 ? 0 : v * 4), p.mats.begin() + (p.nvar == 1 ? 0 : v * 4) + 4);
+                std::vector<cd> r = matmul(xv, pv, 2);   // x after p
+                m.insert(m.end(), r.begin(), r.end());
+            }
+            // keep the merged op at the LATER position (everything between commutes with it: it does not touch the bit)
+            if (p.nvar > 1) {
+                x.site = p.site;
+                x.fshift = p.fshift;
+                x.fmask = p.fmask;
+            }
+            x.nvar = nv;
+            x.mats = m;
+            p.dead = true;
+            if (nv == 1 && is_identity(x.mats, 2)) x.dead = true;
+        }
+        std::vector<int> live;
+        for (int oi : s.ops)
+            if (!ops[oi].dead) live.push_back(oi);
+        s.ops.swap(live);
+    }
+
     for (size_t si = 0; si < sw.size(); si++) {
         SweepB& s = sw[si];
         Tile t;

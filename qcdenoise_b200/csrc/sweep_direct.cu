@@ -79,6 +79,17 @@ __device__ __forceinline__ void m2(C (&a)[16], const C* m) {
     }
 }
 
+// real diagonal (no-jump damping Kraus, Z-like): two multipliers
+template <int TB, typename C>
+__device__ __forceinline__ void m1d(C (&a)[16], const C* m) {
+    const auto d0 = m[0].x, d1 = m[3].x;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const auto d = (s & (1 << TB)) ? d1 : d0;
+        a[s].x *= d;
+        a[s].y *= d;
+    }
+}
 // real-coefficient variants (H, Pauli X/Z, damping Kraus, Ry, ...): half the multiplies
 template <int TB, typename C>
 __device__ __forceinline__ void m1r(C (&a)[16], const C* m) {
@@ -204,7 +215,8 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
             s_mats[tid][e] = v;
             real = real && v.y == (T)0;
         }
-        s_real[tid] = real ? 1u : 0u;
+        const bool diag = real && kind == K_M1 && s_mats[tid][1].x == (T)0 && s_mats[tid][2].x == (T)0;
+        s_real[tid] = diag ? 2u : (real ? 1u : 0u);
     }
     __syncthreads();
 
@@ -273,7 +285,14 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
             const KOp op = D.ops[o];
             switch (op.kind) {
                 case K_M1:
-                    if (s_real[o]) {
+                    if (s_real[o] == 2u) {
+                        switch (op.t0) {
+                            case 0: m1d<0>(a, s_mats[o]); break;
+                            case 1: m1d<1>(a, s_mats[o]); break;
+                            case 2: m1d<2>(a, s_mats[o]); break;
+                            default: m1d<3>(a, s_mats[o]); break;
+                        }
+                    } else if (s_real[o]) {
                         switch (op.t0) {
                             case 0: m1r<0>(a, s_mats[o]); break;
                             case 1: m1r<1>(a, s_mats[o]); break;
@@ -386,8 +405,9 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
 #pragma unroll
                 for (int s = 0; s < 16; s++) {
                     if (s & ((1 << r_low) - 1)) continue;
-                    double v = (double)w[s];
-                    for (int o = 1; o < (1 << lane_bits); o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    T vt = w[s];   // <= 32 terms: accumulate in the state's own precision, store as double
+                    for (int o = 1; o < (1 << lane_bits); o <<= 1) vt += __shfl_xor_sync(0xffffffffu, vt, o);
+                    const double v = (double)vt;
                     if ((tid & ((1u << lane_bits) - 1u)) == 0) {
                         const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
                                            ((s & 8) ? go[3] : 0u);
