@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--literal", action="store_true", help="one state per shot (no trajectory-tree sharing)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-chunk", type=int, default=0, help="engine option max_chunk (trajectories per tree); 0 = default")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +200,8 @@ def main():
     eng = qcd.get_engine(local)
     eng.upload(work["programs"])
     eng.set_option("time_sweeps", 1)
+    if args.max_chunk:
+        eng.set_option("max_chunk", args.max_chunk)
     hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
     if world > 1:
         gathered_rows = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(world)]

@@ -75,7 +75,7 @@ struct qcd_ctx {
     // options
     bool time_sweeps = false;
     int tile_bits = 0;           // 0 = default for the precision
-    uint64_t max_chunk = 1u << 20;
+    uint64_t max_chunk = 1u << 25;
     int table_cap_log2 = 22;
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
     bool use_direct = true;      // register-only kernel for single-pass sweeps
@@ -458,7 +458,10 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     if (((uint64_t)1 << R.gbits) > R.table_cap) R.table_cap = (uint64_t)1 << R.gbits;
 
     const uint64_t total = shot_end - shot_begin;
-    const uint64_t T_chunk = std::min<uint64_t>(total, ctx->max_chunk);
+    // trajectories per tree: as many WHOLE circuits as fit max_chunk (a circuit split over two trees loses the
+    // sharing between its halves); a single circuit larger than max_chunk is split
+    uint64_t T_chunk = std::min<uint64_t>(total, ctx->max_chunk);
+    if (spc <= T_chunk) T_chunk = (T_chunk / spc) * spc;
     const bool no_dedup = (flags & QCD_RUN_NO_DEDUP) != 0;
 
     // ---- state slots
@@ -503,8 +506,13 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     }
 
     // ---- outer loop over trajectory chunks of the flattened [circuit][shot] space
-    for (uint64_t g0 = shot_begin; g0 < shot_end; g0 += T_chunk) {
-        const uint64_t g1 = std::min(shot_end, g0 + T_chunk);
+    for (uint64_t g0 = shot_begin; g0 < shot_end;) {
+        // chunk boundaries on circuit boundaries whenever a chunk holds whole circuits
+        uint64_t g1 = std::min(shot_end, g0 + T_chunk);
+        if (spc <= T_chunk && g1 < shot_end) {
+            const uint64_t aligned = (g1 / spc) * spc;
+            if (aligned > g0) g1 = aligned;
+        }
         std::vector<NodeRec> roots;
         uint32_t off = 0;
         for (uint64_t c = g0 / spc; c <= (g1 - 1) / spc; c++) {
@@ -534,6 +542,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
         int rc = R.process(0, roots, 0, roots.size(), true, 1);
         if (rc) return rc;
         ctx->stats.trajectories += g1 - g0;
+        g0 = g1;
     }
     CU(cudaStreamSynchronize(st));
     return finish_timing(ctx);

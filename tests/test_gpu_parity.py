@@ -26,7 +26,7 @@ def _circ(n, ops):
 
 
 def _reset_opts(eng):
-    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 20)):
+    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25)):
         eng.set_option(k, v)
 
 
