@@ -53,6 +53,7 @@ struct DevBuf {
 
 struct DevProg {
     bool valid = false;
+    bool host_ready = false;   // P was lowered at upload time (device copies still to be made)
     Program P;
     DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits, direct;
     std::vector<DirectSweep> direct_host;
@@ -62,6 +63,7 @@ struct DevProg {
         sweeps.release(); passes.release(); kops.release(); pool.release(); masks.release();
         groups.release(); subs.release(); gdata.release(); circuits.release();
         valid = false;
+        host_ready = false;
         P = Program();
     }
 };
@@ -127,19 +129,23 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         *out = &dp;
         return QCD_OK;
     }
-    dp.release();
+    const bool reuse = dp.host_ready && dp.P.k_max == kb && dp.P.mode == mode;
+    if (!reuse) dp.release();
     Program& P = dp.P;
-    P.n_qubits = ctx->n_qubits;
-    P.mode = mode;
-    P.n_bits = mode == MODE_DM ? 2 * ctx->n_qubits : ctx->n_qubits;
-    P.k_max = kb;
-    if (P.n_bits > 30) return fail(ctx, QCD_E_UNSUPPORTED, "state of more than 30 index bits");
-    for (int c = 0; c < ctx->n_circuits; c++) {
-        std::string err;
-        uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
-        int rc = compile_circuit(P, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
-        if (rc != QCD_OK) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+    if (!reuse) {
+        P.n_qubits = ctx->n_qubits;
+        P.mode = mode;
+        P.n_bits = mode == MODE_DM ? 2 * ctx->n_qubits : ctx->n_qubits;
+        P.k_max = kb;
+        if (P.n_bits > 30) return fail(ctx, QCD_E_UNSUPPORTED, "state of more than 30 index bits");
+        for (int c = 0; c < ctx->n_circuits; c++) {
+            std::string err;
+            uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
+            int rc = compile_circuit(P, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
+            if (rc != QCD_OK) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+        }
     }
+    dp.host_ready = false;
     int rc;
     if ((rc = upload_vec(ctx, dp.sweeps, P.sweeps))) return rc;
     if ((rc = upload_vec(ctx, dp.passes, P.passes))) return rc;
@@ -739,17 +745,21 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     if (n_params && !params) return fail(ctx, QCD_E_INVALID, "params is NULL");
     for (int c = 0; c < n_circuits; c++)
         if (op_offsets[c] > op_offsets[c + 1]) return fail(ctx, QCD_E_INVALID, "op_offsets must be non-decreasing");
-    // validate by lowering one mode now, so that malformed programs fail at upload time
-    {
-        Program P;
-        P.n_qubits = n_qubits;
-        P.mode = MODE_DM;
-        P.n_bits = 2 * n_qubits;
-        P.k_max = 13;
-        for (int c = 0; c < n_circuits; c++) {
-            std::string err;
-            int rc = compile_circuit(P, ops + op_offsets[c], op_offsets[c + 1] - op_offsets[c], params, n_params, err);
-            if (rc == QCD_E_INVALID) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+    // validate by lowering now (statevector mode, complex64 tile), so that malformed programs fail at upload time; the
+    // result is kept as the host half of that program so the first run does not lower again
+    Program P;
+    P.n_qubits = n_qubits;
+    P.mode = MODE_SV;
+    P.n_bits = n_qubits;
+    P.k_max = ctx->tile_bits > 0 ? ctx->tile_bits : default_tile_bits(32);
+    bool keep = true;
+    for (int c = 0; c < n_circuits; c++) {
+        std::string err;
+        int rc = compile_circuit(P, ops + op_offsets[c], op_offsets[c + 1] - op_offsets[c], params, n_params, err);
+        if (rc == QCD_E_INVALID) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+        if (rc != QCD_OK) {   // valid but not runnable in this mode (e.g. needs the density-matrix mode): reported at run time
+            keep = false;
+            break;
         }
     }
     cudaSetDevice(ctx->device);
@@ -760,6 +770,10 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     ctx->n_qubits = n_qubits;
     for (int m = 0; m < 2; m++)
         for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
+    if (keep) {
+        ctx->prog[MODE_SV][0].P = std::move(P);
+        ctx->prog[MODE_SV][0].host_ready = true;
+    }
     return QCD_OK;
 }
 

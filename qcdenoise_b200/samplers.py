@@ -39,6 +39,15 @@ def get_engine(device=None):
     return _ENGINES[device]
 
 
+def _to_host(t):
+    """Device tensor -> numpy through a pinned staging buffer (pageable cudaMemcpy is ~3x slower for the 4 MiB-per-
+    circuit histograms of a 20-qubit run)."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
 @dataclass(init=True)
 class NoiseSpec:
     """Noise-model specification (same container as the reference's, samplers.py:205-209)."""
@@ -246,7 +255,7 @@ class CircuitSampler:
         else:
             self.last_probs = None
             hist, _ = eng.run_trajectories(self.n_shots, seed=seed, precision=self.precision, readout=readout)
-        h = hist.cpu().numpy()
+        h = _to_host(hist)
         out = [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(circs))]
         return out[0] if single else out
 

@@ -160,7 +160,7 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
 
 def _batched_counts(sampler: CircuitSampler, circuits, models):
     """Instantiate each circuit with ITS noise model and simulate the whole batch at once."""
-    from .samplers import Counts, NoiseModel
+    from .samplers import Counts, NoiseModel, _to_host
     inst = [(m if m is not None else NoiseModel()).instantiate(c) for c, m in zip(circuits, models)]
     progs = [c for c, _ in inst]
     n = progs[0].n_qubits
@@ -177,5 +177,5 @@ def _batched_counts(sampler: CircuitSampler, circuits, models):
         hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
     else:
         hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
-    h = hist.cpu().numpy()
+    h = _to_host(hist)
     return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
