@@ -13,3 +13,5 @@ from .samplers import *  # noqa: E402,F401,F403
 from .stabilizers import *  # noqa: E402,F401,F403
 from .witnesses import *  # noqa: E402,F401,F403
 from .simulate import *  # noqa: E402,F401,F403
+from .dataset import *  # noqa: E402,F401,F403
+from . import channels, distributed  # noqa: E402,F401

@@ -47,6 +47,7 @@ class AdjTensorSpecs:
     tensor_shape: tuple
     fixed_size: bool = True
     directed: bool = False
+    encoding: dict = None     # gate name -> code; None: the gate names that occur, enumerated from 1
 
 
 @dataclass(init=True)
@@ -96,9 +97,8 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
         raise AssertionError("sampler_specs must be an instance of SamplingSpecs")
     if not isinstance(graph_specs, GraphSpecs):
         raise AssertionError("graph_specs must be an instance of GraphSpecs")
-    if adj_tensor_specs is not None:
-        raise NotImplementedError("adjacency tensors need the qiskit transpiler DAG (reference simulate.py:105-134); "
-                                  "out of this engine's scope")
+    if adj_tensor_specs is not None and not isinstance(adj_tensor_specs, AdjTensorSpecs):
+        raise AssertionError("adj_tensor_specs must be an instance of AdjTensorSpecs")
     if entangle_specs is not None and not isinstance(entangle_specs, EntanglementSpecs):
         raise AssertionError("entangle_specs must be an instance of EntanglementSpecs")
     n = sim_specs.n_qubits
@@ -126,6 +126,17 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
         graphs.append(graph)
         circuits.append(cd["circuit"])
         models.append(deepcopy(sampler.noise_model))
+
+    if adj_tensor_specs is not None:
+        # gate-list walk (no transpiler DAG); codes enumerate the gate names that occur, from 1 (0 = empty slot)
+        from .dataset import generate_adjacency_tensor
+        enc = adj_tensor_specs.encoding
+        if enc is None:
+            names = sorted({op[0] for c in circuits for op in c.ops if op[0] not in ("barrier", "measure_all")})
+            enc = {nm: i + 1 for i, nm in enumerate(names)}
+        for num in range(sim_specs.n_circuits):
+            results[num]["adj_tensor"] = generate_adjacency_tensor(
+                circuits[num], enc, adj_tensor_specs.tensor_shape, adj_tensor_specs.fixed_size, adj_tensor_specs.directed)
 
     # ---- stage 1: all noisy circuits in one engine call
     prob_vecs = _batched_counts(sampler, circuits, models)

@@ -121,3 +121,38 @@ def test_simulate(qcd, with_witness):
         assert r["prob_vec"].shape == (16,) and abs(r["prob_vec"].sum() - 1) < 1e-12 and r["graph_data"]
         if with_witness:
             assert r["entanglement"]["value"] == -1.0        # stabilizer settings are ideal (reference quirk Q7)
+
+
+def test_dataset_rows_noisy_ideal(qcd):
+    """(N, 2^n, 2) rows: column 1 (ideal) of a CX graph circuit is the uniform |amplitude|^2 = 2^-n support of the
+    graph state; column 0 differs by the drawn damping noise; both are normalised histograms."""
+    import torch
+    n = 5
+    np.random.seed(4)
+    builder = qcd.CXGateCircuit(n_qubits=n, stochastic=True)
+    cds = [builder.build(_graph(n, s, qcd)) for s in range(6)]
+    sampler = qcd.UnitaryNoiseSampler(None, n_shots=8192, noise_specs=qcd.NoiseSpec(
+        specs={"type": "amplitude_damping_error", "max_prob": 0.3}), seed=2)
+    rows = qcd.sample_prob_rows(cds, sampler)
+    assert rows.shape == (6, 2 ** n, 2) and rows.dtype == torch.float32 and rows.is_cuda
+    r = rows.cpu().numpy()
+    np.testing.assert_allclose(r.sum(axis=1), 1.0, atol=1e-6)
+    for i, cd in enumerate(cds):
+        p_ideal = np.abs(sim.ideal_statevector(cd["circuit"].ops, n)) ** 2
+        assert 0.5 * np.abs(r[i, :, 1] - p_ideal).sum() < 0.06
+        if cd["ops"]:
+            assert 0.5 * np.abs(r[i, :, 0] - p_ideal).sum() > 0.01
+    adj = qcd.adjacency_tensors(cds, {"h": 1, "cx": 2, "unitary": 3}, tensor_shape=(16, n, n))
+    assert adj.shape == (6, 16, n, n)
+
+
+def test_simulate_with_adjacency_tensor(qcd):
+    random.seed(0)
+    np.random.seed(0)
+    sim_specs = qcd.SimulationSpecs(n_qubits=4, n_circuits=3, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=True))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.UnitaryNoiseSampler, noise_specs=qcd.unitary_noise_spec, n_shots=256)
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4),
+                       adj_tensor_specs=qcd.AdjTensorSpecs(tensor_shape=(16, 32, 32)))
+    for r in res.values():
+        assert r["adj_tensor"].shape == (16, 32, 32) and r["adj_tensor"].any()       # reference test: (16, 32, 32)

@@ -181,3 +181,22 @@ def test_counts_mapping_and_prob_vector():
     np.testing.assert_array_equal(qcd.convert_to_prob_vector(c, 3, 10), h / 10)
     np.testing.assert_array_equal(qcd.convert_to_prob_vector(dict(c), 3, 10), ref_glue.convert_to_prob_vector(dict(c), 3, 10))
     assert qcd.generate_binary_strings(3) == ref_glue.generate_binary_strings(3)
+
+
+def test_adjacency_tensor_gate_list_walk():
+    """Same integer scatter as the reference's DAG walk (samplers.py:119-192), on the gate list as written."""
+    c = qcd.Circuit(3).h(0).h(1).h(0).cx(0, 1).cx(0, 1).cx(1, 2)
+    enc = {"h": 1, "cx": 2}
+    a = qcd.generate_adjacency_tensor(c, enc, tensor_shape=(4, 3, 3))
+    assert a.shape == (4, 3, 3)
+    assert a[0, 0, 0] == 1 and a[1, 0, 0] == 1 and a[2, 0, 0] == 0          # two h on qubit 0 stack in planes
+    assert a[0, 1, 1] == 1 and a[1, 1, 1] == 0
+    assert a[0, 0, 1] == 2 and a[0, 1, 0] == 2 and a[1, 0, 1] == 2 and a[1, 1, 0] == 2
+    assert a[0, 1, 2] == 2 and a[0, 2, 1] == 2
+    d = qcd.generate_adjacency_tensor(c, enc, tensor_shape=(4, 3, 3), directed=True)
+    assert d[0, 0, 1] == 2 and d[0, 1, 0] == 0
+    t = qcd.generate_adjacency_tensor(c, enc, tensor_shape=(4, 3, 3), fixed_size=False)
+    assert t.shape == (2, 3, 3)
+    assert qcd.encode_basis_gates(["id", "u1", "cx"]) == {"id": 0, "u1": 1, "cx": 2}
+    with pytest.raises(KeyError):
+        qcd.generate_adjacency_tensor(c, {"h": 1}, tensor_shape=(4, 3, 3))
