@@ -18,8 +18,10 @@ bytes moved by the state-sweep kernel / its CUDA-event time, against the measure
 `cpu_baseline` / `--impl reference` = the compiled CPU port of the qiskit-Aer statevector-trajectory algorithm
 (oracle/cpu_sim.c, OpenMP over shots) on a bounded number of shots of the same noisy circuit.
 
-N > 1 (torchrun): every rank simulates its own graph (same per-GPU work: weak scaling, circuits partitioned by
-rank index, no data-path collective); one NCCL all_gather assembles the dataset histograms and parity sums.
+N > 1 (torchrun): the job is the same 22 circuits with N x 1M shots each; rank r simulates its own 1M-shot slice of
+every circuit (independent Philox streams: seed + r), so per-GPU work is fixed (weak scaling) and there is no
+data-path communication; ONE NCCL all_reduce(SUM) assembles the 22 dataset histograms (92 MB), after which the
+stabilizer parity sums are taken on the assembled counts.
 """
 import argparse
 import json
@@ -194,7 +196,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    work = build_workload(rank, args.shots)
+    work = build_workload(0, args.shots)
     B = len(work["programs"])
     N = 2 ** N_QUBITS
     eng = qcd.get_engine(local)
@@ -203,18 +205,13 @@ def main():
     if args.max_chunk:
         eng.set_option("max_chunk", args.max_chunk)
     hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
-    if world > 1:
-        gathered_rows = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(world)]
-        gathered_sums = [torch.empty((B,), dtype=torch.int64, device=dev) for _ in range(world)]
-
     def step():
         hist.zero_()
-        eng.run_trajectories(args.shots, seed=SEED, precision=32, hist=hist, dedup=not args.literal)
+        eng.run_trajectories(args.shots, seed=SEED + rank, precision=32, hist=hist, dedup=not args.literal)
         st = eng.stats()
+        if world > 1:   # assemble the dataset histograms: counts are additive over the ranks' shot slices
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
         ss, tot = eng.parity_counts(hist, work["masks"])
-        if world > 1:   # assemble the dataset rows (noisy histogram of each rank's graph circuit) and the <S> sums
-            dist.all_gather(gathered_rows, hist[0])
-            dist.all_gather(gathered_sums, ss[:, 0].contiguous())
         return st, ss, tot
 
     def barrier():
@@ -241,7 +238,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    assert tot.cpu().tolist() == [args.shots] * B, "histograms do not hold every shot"
+    assert tot.cpu().tolist() == [args.shots * world] * B, "histograms do not hold every shot"
     shots_per_step = B * args.shots * world
     value = shots_per_step * args.steps / (ms * 1e-3)
 
@@ -249,11 +246,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         g, cd, stab = work["graph"], work["circuit_dict"], work["stab"]
-        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=32, seed=SEED)
-        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=32, seed=SEED + 1)
+        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=32,
+                                          seed=SEED + 100 * rank)
+        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=32,
+                                     seed=SEED + 100 * rank + 1)
 
         def e2e_step():
-            np.random.seed(SEED + rank)
+            np.random.seed(SEED)
             p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
             counts = ssam.sample(stab, cd["circuit"], noise_model=sampler.noise_model)   # 21 Counts (host histograms)
             w = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
