@@ -166,29 +166,26 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     if ((rc = upload_vec(ctx, dp.subs, P.subs))) return rc;
     if ((rc = upload_vec(ctx, dp.gdata, P.gdata))) return rc;
     if ((rc = upload_vec(ctx, dp.circuits, P.circuits))) return rc;
-    // direct (register-only) descriptors for single-pass sweeps
-    dp.direct_host.assign(P.sweeps.size(), DirectSweep());
-    for (size_t si = 0; si < P.sweeps.size(); si++) {
-        const Sweep& S = P.sweeps[si];
-        DirectSweep& D = dp.direct_host[si];
-        memset(&D, 0, sizeof(D));
-        if ((S.flags & SW_PREP) || S.pass_end - S.pass_begin != 1 || S.n_bits < 13) continue;
-        const Pass& ps = P.passes[S.pass_begin];
+    // direct (register-only) descriptors: entry si for single-pass sweep si, entry n_sweeps + pi for pass pi run as a
+    // sweep of its own (density-matrix mode launches multi-pass sweeps pass by pass on the register-only kernel)
+    dp.direct_host.assign(P.sweeps.size() + P.passes.size(), DirectSweep());
+    for (DirectSweep& D : dp.direct_host) memset(&D, 0, sizeof(D));
+    auto describe = [&](DirectSweep& D, const Sweep& S, uint32_t pi, uint8_t flags, bool reduce) {
+        if (S.n_bits < 13) return;
+        const Pass& ps = P.passes[pi];
         const uint32_t nops = ps.op_end - ps.op_begin;
-        if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) continue;
+        if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) return;
         uint32_t n_signs = 0;
-        bool ok = true;
         for (uint32_t o = 0; o < nops; o++) {
             KOp op = P.kops[ps.op_begin + o];
             if (op.kind == K_SIGNS) {
-                if (n_signs + op.count > 48 || n_signs > 255) ok = false;
+                if (n_signs + op.count > 48) return;
                 op.t1 = (uint8_t)n_signs;
                 n_signs += op.count;
             }
-            if (op.kind == K_M4) ok = false;  // 16x16 superoperators stay on the tiled kernel
+            if (op.kind == K_M4) return;  // 16x16 superoperators stay on the tiled kernel
             D.ops[o] = op;
         }
-        if (!ok) continue;
         D.ok = 1;
         D.n_bits = S.n_bits;
         D.nreg = ps.nreg;
@@ -197,9 +194,20 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             const int b = ps.rbits[i];
             D.rbit[i] = (uint8_t)(b < S.L ? b : S.high[b - S.L]);
         }
-        D.red_q[0] = S.red_q[0];
-        D.red_q[1] = S.red_q[1];
-        D.flags = S.flags;
+        D.red_q[0] = reduce ? S.red_q[0] : -1;
+        D.red_q[1] = reduce ? S.red_q[1] : -1;
+        D.flags = flags;
+        D.prep_off = S.prep_off;
+    };
+    for (size_t si = 0; si < P.sweeps.size(); si++) {
+        const Sweep& S = P.sweeps[si];
+        if (S.pass_end - S.pass_begin == 1) describe(dp.direct_host[si], S, S.pass_begin, S.flags, true);
+        for (uint32_t pi = S.pass_begin; pi < S.pass_end; pi++) {
+            uint8_t fl = 0;
+            if (pi == S.pass_begin) fl |= S.flags & SW_PREP;
+            if (pi + 1 == S.pass_end) fl |= S.flags & SW_FINAL;
+            describe(dp.direct_host[P.sweeps.size() + pi], S, pi, fl, pi + 1 == S.pass_end);
+        }
     }
     if ((rc = upload_vec(ctx, dp.direct, dp.direct_host))) return rc;
     int k = std::min(P.k_max, P.n_bits);
@@ -299,6 +307,7 @@ struct SvRunner {
         a.n_items = n_nodes * tiles;
         a.part_stride = part_stride;
         a.direct_vec = 0;
+        a.desc_from_pad = 0;
         return a;
     }
 
@@ -575,6 +584,78 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
     T* out = reinterpret_cast<T*>(probs_out);
     for (int c0 = cb; c0 < ce; c0 += (int)n_slots) {
         const int c1 = (int)std::min<uint64_t>((uint64_t)ce, (uint64_t)c0 + n_slots);
+        // Register-only path: every pass of every circuit of the chunk becomes a launch level of its own on the direct
+        // kernel (more state passes than the tiled kernel's one-per-sweep, each at streaming speed).
+        bool all_direct = ctx->use_direct && nb >= 13;
+        for (int c = c0; c < c1 && all_direct; c++) {
+            const CircuitInfo& ci = P.circuits[c];
+            for (uint32_t si = ci.sweep_begin; si < ci.sweep_end && all_direct; si++) {
+                if (P.sweeps[si].pass_begin == P.sweeps[si].pass_end) all_direct = false;   // op-less sweep
+                for (uint32_t pi = P.sweeps[si].pass_begin; pi < P.sweeps[si].pass_end; pi++)
+                    all_direct = all_direct && dp->direct_host[P.sweeps.size() + pi].ok;
+            }
+        }
+        if (all_direct) {
+            std::vector<std::vector<uint32_t>> pass_list(c1 - c0);
+            size_t max_p = 0;
+            for (int c = c0; c < c1; c++) {
+                const CircuitInfo& ci = P.circuits[c];
+                for (uint32_t si = ci.sweep_begin; si < ci.sweep_end; si++)
+                    for (uint32_t pi = P.sweeps[si].pass_begin; pi < P.sweeps[si].pass_end; pi++)
+                        pass_list[c - c0].push_back(pi);
+                max_p = std::max(max_p, pass_list[c - c0].size());
+            }
+            std::vector<NodeRec> recs;
+            std::vector<size_t> lvl_off;
+            std::vector<char> lvl_vec, lvl_prep;
+            for (size_t l = 0; l < max_p; l++) {
+                lvl_off.push_back(recs.size());
+                bool vec = true, prep = true;
+                for (int c = c0; c < c1; c++) {
+                    if (pass_list[c - c0].size() <= l) continue;
+                    NodeRec r;
+                    memset(&r, 0, sizeof(r));
+                    r.src_slot = r.dst_slot = (uint32_t)(c - c0);
+                    r.scale = 1.0;
+                    r.circuit = (uint32_t)c;
+                    r.pad = (uint32_t)(P.sweeps.size() + pass_list[c - c0][l]);
+                    const DirectSweep& D = dp->direct_host[r.pad];
+                    vec = vec && D.rbit[0] == 0;
+                    prep = prep && (D.flags & SW_PREP);
+                    recs.push_back(r);
+                }
+                lvl_vec.push_back(vec);
+                lvl_prep.push_back(prep);
+            }
+            lvl_off.push_back(recs.size());
+            CU(ctx->children.ensure(recs.size() * sizeof(NodeRec)));
+            CU(cudaMemcpyAsync(ctx->children.p, recs.data(), recs.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+            for (size_t l = 0; l < max_p; l++) {
+                const uint64_t cnt = lvl_off[l + 1] - lvl_off[l];
+                int pl = std::max(0, nb - 4 - 8 - 3);
+                while (pl < nb - 4 - 8 && (cnt << pl) < 1184) pl++;
+                while ((cnt << pl) > 0x7fffffffull) pl--;
+                SweepArgs a;
+                a.nodes = ctx->children.as<NodeRec>() + lvl_off[l];
+                a.states = ctx->states.p;
+                a.slot_stride = slot_stride;
+                a.partials = nullptr;
+                a.chunk_sums = nullptr;
+                a.chunk_stride = 0;
+                a.tiles_log2 = (uint32_t)pl;
+                a.n_items = (uint32_t)(cnt << pl);
+                a.part_stride = 1;
+                a.direct_vec = lvl_vec[l] ? 1 : 0;
+                a.desc_from_pad = 1;
+                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                launch_sweep_direct<T>(prog, a, st);
+                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                CU(cudaGetLastError());
+                ctx->stats.sweep_launches++;
+                ctx->stats.node_sweeps += cnt;
+                ctx->stats.sweep_bytes += cnt * slot_bytes * (lvl_prep[l] ? 1 : 2);
+            }
+        } else {
         // one NodeRec per (circuit, sweep), grouped by sweep ordinal; the sweep works in place (src == dst)
         std::vector<NodeRec> recs;
         std::vector<size_t> lvl_off;
@@ -610,6 +691,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             a.n_items = cnt * tiles;
             a.part_stride = tiles;
             a.direct_vec = 0;
+            a.desc_from_pad = 0;
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
             launch_sweep<T>(prog, a, k, st);
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -617,6 +699,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             ctx->stats.sweep_launches++;
             ctx->stats.node_sweeps += cnt;
             ctx->stats.sweep_bytes += (uint64_t)cnt * slot_bytes * (l == 0 ? 1 : 2);
+        }
         }
         std::vector<uint32_t> slots(c1 - c0);
         for (int i = 0; i < c1 - c0; i++) slots[i] = (uint32_t)i;

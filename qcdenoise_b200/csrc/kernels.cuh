@@ -64,6 +64,7 @@ struct SweepArgs {
     uint32_t n_items;        // nodes * tiles
     uint32_t part_stride;    // partials: [slot][part_stride][4]; a launch writes tiles (or CTAs-per-state) of them
     uint32_t direct_vec;     // direct kernel: every sweep of the launch has index bit 0 as a register bit
+    uint32_t desc_from_pad;  // direct kernel: descriptor index = node.pad (per-pass launches) instead of node.sweep
 };
 
 template <typename T>

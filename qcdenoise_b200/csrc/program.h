@@ -83,8 +83,9 @@ struct DirectSweep {
     uint8_t nops;
     uint8_t rbit[REG_BITS];     // GLOBAL bit of register bit i, ascending
     int8_t red_q[2];
-    uint8_t flags;
-    uint8_t pad[5];
+    uint8_t flags;              // SW_PREP: the source is the product state at prep_off (no read)
+    uint8_t pad;
+    uint32_t prep_off;
     KOp ops[MAX_DIRECT_OPS];
 };
 

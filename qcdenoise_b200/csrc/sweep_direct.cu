@@ -155,13 +155,15 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
     __shared__ double s_red[DT / 32][4];
     __shared__ uint32_t s_real[MAX_DIRECT_OPS];   // matrix op o has purely real coefficients
     __shared__ int s_scale_op;                    // matrix op that carries the node's rescale factor (-1: none)
+    __shared__ C s_prep[64];                      // prep sweeps: (alpha, beta) per index bit
+    __shared__ C s_prep_reg[16];                  // ... and the 16 products over the register bits
 
     const uint32_t tid = threadIdx.x;
     const uint32_t node_idx = blockIdx.x >> args.tiles_log2;
     const uint32_t part = blockIdx.x & ((1u << args.tiles_log2) - 1u);
     const NodeRec N = args.nodes[node_idx];
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(prog.direct + N.sweep);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prog.direct + (args.desc_from_pad ? N.pad : N.sweep));
         uint32_t* dst = reinterpret_cast<uint32_t*>(&D);
         if (tid < sizeof(DirectSweep) / 4) dst[tid] = src[tid];
     }
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
             if (tid < cnt) s_mats[o][tid] = m[tid];
         }
     }
+    const bool is_prep = (D.flags & SW_PREP) != 0;
+    if (is_prep && tid < 2u * (uint32_t)n_bits) s_prep[tid] = prog.pool[D.prep_off + tid];
     if (tid == 0) {
         int so = -1;
         for (int o = 0; o < nops && so < 0; o++)
@@ -217,6 +221,15 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
         }
         const bool diag = real && kind == K_M1 && s_mats[tid][1].x == (T)0 && s_mats[tid][2].x == (T)0;
         s_real[tid] = diag ? 2u : (real ? 1u : 0u);
+    }
+    if (is_prep && tid >= 32 && tid < 48) {
+        const int sidx = (int)tid - 32;
+        C v;
+        v.x = 1;
+        v.y = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) v = cmul(v, s_prep[2 * D.rbit[i] + ((sidx >> i) & 1)]);
+        s_prep_reg[sidx] = v;
     }
     __syncthreads();
 
@@ -260,7 +273,15 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
             gb = ((gb >> b) << (b + 1)) | (gb & ((1u << b) - 1u));
         }
         C a[16];
-        if (VEC) {
+        if (is_prep) {
+            C base;
+            base.x = 1;
+            base.y = 0;
+            for (int b = 0; b < n_bits; b++)
+                if (!((regmask >> b) & 1u)) base = cmul(base, s_prep[2 * b + ((gb >> b) & 1u)]);
+#pragma unroll
+            for (int s = 0; s < 16; s++) a[s] = cmul(base, s_prep_reg[s]);
+        } else if (VEC) {
 #pragma unroll
             for (int s = 0; s < 16; s += 2) {
                 const uint32_t g = gb | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) | ((s & 8) ? go[3] : 0u);
