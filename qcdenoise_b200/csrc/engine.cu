@@ -10,9 +10,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qcdsim.h"
@@ -138,12 +140,41 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         P.n_bits = mode == MODE_DM ? 2 * ctx->n_qubits : ctx->n_qubits;
         P.k_max = kb;
         if (P.n_bits > 30) return fail(ctx, QCD_E_UNSUPPORTED, "state of more than 30 index bits");
-        for (int c = 0; c < ctx->n_circuits; c++) {
-            std::string err;
-            uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
-            int rc = compile_circuit(P, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
-            if (rc != QCD_OK) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
+        // lower on several host threads: contiguous blocks of circuits into private Programs, merged in order
+        const int nc = ctx->n_circuits;
+        int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        n_thr = std::max(1, std::min(n_thr, nc / 32));
+        std::vector<Program> parts(n_thr);
+        std::vector<int> part_rc(n_thr, QCD_OK);
+        std::vector<std::string> part_err(n_thr);
+        auto work = [&](int t) {
+            Program& Q = parts[t];
+            Q.n_qubits = P.n_qubits;
+            Q.mode = P.mode;
+            Q.n_bits = P.n_bits;
+            Q.k_max = P.k_max;
+            const int c_lo = (int)((long long)nc * t / n_thr), c_hi = (int)((long long)nc * (t + 1) / n_thr);
+            for (int c = c_lo; c < c_hi; c++) {
+                std::string err;
+                uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
+                int rc = compile_circuit(Q, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
+                if (rc != QCD_OK) {
+                    part_rc[t] = rc;
+                    part_err[t] = "circuit " + std::to_string(c) + ": " + err;
+                    return;
+                }
+            }
+        };
+        if (n_thr == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; t++) pool.emplace_back(work, t);
+            for (std::thread& th : pool) th.join();
         }
+        for (int t = 0; t < n_thr; t++)
+            if (part_rc[t] != QCD_OK) return fail(ctx, part_rc[t], part_err[t]);
+        for (int t = 0; t < n_thr; t++) merge_program(P, parts[t]);
     }
     dp.host_ready = false;
     int rc;
@@ -828,21 +859,44 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     if (n_params && !params) return fail(ctx, QCD_E_INVALID, "params is NULL");
     for (int c = 0; c < n_circuits; c++)
         if (op_offsets[c] > op_offsets[c + 1]) return fail(ctx, QCD_E_INVALID, "op_offsets must be non-decreasing");
-    // validate by lowering now (statevector mode, complex64 tile), so that malformed programs fail at upload time; the
-    // result is kept as the host half of that program so the first run does not lower again
-    Program P;
-    P.n_qubits = n_qubits;
-    P.mode = MODE_SV;
-    P.n_bits = n_qubits;
-    P.k_max = ctx->tile_bits > 0 ? ctx->tile_bits : default_tile_bits(32);
-    bool keep = true;
+    // structural validation now (cheap, O(ops)), so that malformed programs fail at upload time; lowering happens
+    // once per (mode, precision) at the first run
     for (int c = 0; c < n_circuits; c++) {
-        std::string err;
-        int rc = compile_circuit(P, ops + op_offsets[c], op_offsets[c + 1] - op_offsets[c], params, n_params, err);
-        if (rc == QCD_E_INVALID) return fail(ctx, rc, "circuit " + std::to_string(c) + ": " + err);
-        if (rc != QCD_OK) {   // valid but not runnable in this mode (e.g. needs the density-matrix mode): reported at run time
-            keep = false;
-            break;
+        for (uint32_t i = op_offsets[c]; i < op_offsets[c + 1]; i++) {
+            const qcd_op& op = ops[i];
+            const std::string where = "circuit " + std::to_string(c) + ", op " + std::to_string(i - op_offsets[c]) + ": ";
+            if (op.opcode >= QCD_OP_COUNT) return fail(ctx, QCD_E_INVALID, where + "unknown opcode");
+            bool two = false;
+            size_t need = 0;
+            switch (op.opcode) {
+                case QCD_OP_CX: case QCD_OP_CZ: case QCD_OP_SWAP: two = true; break;
+                case QCD_OP_U2Q: two = true; need = 32; break;
+                case QCD_OP_KRAUS2Q: two = true; need = 1; break;
+                case QCD_OP_PAULI2Q: two = true; need = 16; break;
+                case QCD_OP_RX: case QCD_OP_RY: case QCD_OP_RZ: need = 1; break;
+                case QCD_OP_U1Q: need = 8; break;
+                case QCD_OP_KRAUS1Q: need = 1; break;
+                case QCD_OP_PAULI1Q: need = 4; break;
+                default: break;
+            }
+            if (op.q0 >= n_qubits || (two && (op.q1 >= n_qubits || op.q1 == op.q0)))
+                return fail(ctx, QCD_E_INVALID, where + "qubit index out of range");
+            if (need && (size_t)op.param_off + need > n_params)
+                return fail(ctx, QCD_E_INVALID, where + "op parameters run past params[]");
+            if (op.opcode == QCD_OP_KRAUS1Q || op.opcode == QCD_OP_KRAUS2Q) {
+                const double m = params[op.param_off];
+                const size_t per = op.opcode == QCD_OP_KRAUS1Q ? 8 : 32;
+                if (!(m >= 1 && m <= 64) || (size_t)op.param_off + 1 + (size_t)m * per > n_params)
+                    return fail(ctx, QCD_E_INVALID, where + "bad Kraus operator count");
+            }
+            if (op.opcode == QCD_OP_PAULI1Q || op.opcode == QCD_OP_PAULI2Q) {
+                double tot = 0;
+                for (size_t j = 0; j < need; j++) {
+                    if (params[op.param_off + j] < 0) return fail(ctx, QCD_E_INVALID, where + "negative Pauli probability");
+                    tot += params[op.param_off + j];
+                }
+                if (std::abs(tot - 1.0) > 1e-9) return fail(ctx, QCD_E_INVALID, where + "Pauli probabilities do not sum to 1");
+            }
         }
     }
     cudaSetDevice(ctx->device);
@@ -853,10 +907,6 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     ctx->n_qubits = n_qubits;
     for (int m = 0; m < 2; m++)
         for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
-    if (keep) {
-        ctx->prog[MODE_SV][0].P = std::move(P);
-        ctx->prog[MODE_SV][0].host_ready = true;
-    }
     return QCD_OK;
 }
 

@@ -960,6 +960,48 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     return QCD_OK;
 }
 
+void merge_program(Program& dst, const Program& src) {
+    const uint32_t sweep0 = (uint32_t)dst.sweeps.size(), pass0 = (uint32_t)dst.passes.size();
+    const uint32_t kop0 = (uint32_t)dst.kops.size(), pool0 = (uint32_t)dst.pool.size();
+    const uint32_t mask0 = (uint32_t)dst.masks.size(), group0 = (uint32_t)dst.groups.size();
+    const uint32_t sub0 = (uint32_t)dst.subs.size(), gdata0 = (uint32_t)dst.gdata.size();
+    for (Sweep s : src.sweeps) {
+        s.pass_begin += pass0;
+        s.pass_end += pass0;
+        s.prep_off += pool0;
+        if (s.group >= 0) s.group += (int32_t)group0;
+        dst.sweeps.push_back(s);
+    }
+    for (Pass p : src.passes) {
+        p.op_begin += kop0;
+        p.op_end += kop0;
+        dst.passes.push_back(p);
+    }
+    for (KOp k : src.kops) {
+        k.off += k.kind == K_SIGNS ? mask0 : pool0;
+        dst.kops.push_back(k);
+    }
+    dst.pool.insert(dst.pool.end(), src.pool.begin(), src.pool.end());
+    dst.masks.insert(dst.masks.end(), src.masks.begin(), src.masks.end());
+    for (Group g : src.groups) {
+        g.sub_begin += sub0;
+        g.sub_end += sub0;
+        dst.groups.push_back(g);
+    }
+    for (SubSite ss : src.subs) {
+        ss.data_off += gdata0;
+        dst.subs.push_back(ss);
+    }
+    dst.gdata.insert(dst.gdata.end(), src.gdata.begin(), src.gdata.end());
+    for (CircuitInfo ci : src.circuits) {
+        ci.sweep_begin += sweep0;
+        ci.sweep_end += sweep0;
+        dst.circuits.push_back(ci);
+    }
+    dst.max_group_bits = std::max(dst.max_group_bits, src.max_group_bits);
+    dst.max_sweeps = std::max(dst.max_sweeps, src.max_sweeps);
+}
+
 std::string program_to_json(const Program& P, int c) {
     std::ostringstream o;
     o.precision(17);

@@ -35,6 +35,10 @@ struct Program {
 int compile_circuit(Program& P, const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params,
                     std::string& err);
 
+// Appends every circuit of `src` (compiled separately with the same n_qubits / mode / k_max) to `dst`, re-basing all
+// offsets.  Used to lower large batches on several host threads.
+void merge_program(Program& dst, const Program& src);
+
 // JSON description of circuit `c` of P (for the CPU-side schedule interpreter in tests/).
 std::string program_to_json(const Program& P, int c);
 

@@ -145,10 +145,21 @@ def encode_programs(circuits):
     n = None
     recs, offsets, params = [], [0], []
 
+    memo = {}      # id(payload object) -> param offset: a noise model attaches the SAME channel object many times
+
     def put(vals):
         off = len(params)
-        params.extend(float(v) for v in vals)
+        params.extend(np.asarray(vals, dtype=np.float64).ravel().tolist())
         return off
+
+    def put_once(obj, make):
+        key = id(obj)
+        if key not in memo:
+            memo[key] = (put(make(obj)), obj)      # keep obj alive so the id stays unique
+        return memo[key][0]
+
+    def kraus_flat(ks):
+        return np.concatenate([[float(len(ks))]] + [cflat(k) for k in ks])
 
     def cflat(m):
         m = np.asarray(m, dtype=np.complex128).reshape(-1)
@@ -176,19 +187,15 @@ def encode_programs(circuits):
                 recs.append((OPCODES[name], qs[0], qs[1], 0))
             elif name == "unitary":
                 if len(qs) == 1:
-                    recs.append((OPCODES["u1q"], qs[0], 0xFF, put(cflat(op[2]))))
+                    recs.append((OPCODES["u1q"], qs[0], 0xFF, put_once(op[2], cflat)))
                 else:
-                    recs.append((OPCODES["u2q"], qs[0], qs[1], put(cflat(op[2]))))
+                    recs.append((OPCODES["u2q"], qs[0], qs[1], put_once(op[2], cflat)))
             elif name == "kraus":
-                ks = op[2]
-                off = put([len(ks)])
-                for k in ks:
-                    put(cflat(k))
                 recs.append((OPCODES["kraus1q" if len(qs) == 1 else "kraus2q"], qs[0],
-                             qs[1] if len(qs) > 1 else 0xFF, off))
+                             qs[1] if len(qs) > 1 else 0xFF, put_once(op[2], kraus_flat)))
             elif name == "pauli":
                 recs.append((OPCODES["pauli1q" if len(qs) == 1 else "pauli2q"], qs[0],
-                             qs[1] if len(qs) > 1 else 0xFF, put(op[2])))
+                             qs[1] if len(qs) > 1 else 0xFF, put_once(op[2], lambda p: p)))
             elif name == "reset":
                 recs.append((OPCODES["reset"], qs[0], 0xFF, 0))
             else:

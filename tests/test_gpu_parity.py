@@ -314,3 +314,27 @@ def test_n20_ideal_graph_state_stabilizers(eng):
     ss, tot = eng.parity_counts(hist, masks)
     assert tot.cpu().tolist() == [4096] * len(settings)
     assert ss.cpu().numpy()[:, 0].tolist() == [4096] * len(settings)
+
+
+def test_large_batch_parallel_lowering_matches_single_uploads(eng):
+    """>= 64 circuits are lowered on several host threads and merged; results must equal one-circuit uploads."""
+    _reset_opts(eng)
+    n = 5
+    rng = np.random.default_rng(77)
+    batch = []
+    for i in range(96):
+        kind = i % 3
+        if kind == 0:
+            batch.append(circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, i), rng, max_prob=0.3))
+        elif kind == 1:
+            batch.append(circuits.device_noise_circuit(n, circuits.ref_graph(n, i), rng)[0])
+        else:
+            batch.append(circuits.random_circuit(n, 25, rng))
+    eng.upload([_circ(n, ops) for ops in batch])
+    probs = eng.run_density_matrix(64).cpu().numpy()
+    _, out = eng.run_trajectories(64, seed=5, precision=64, want_outcomes=True)
+    out = out.cpu().numpy().reshape(96, 64)
+    for i in (0, 1, 2, 31, 32, 33, 64, 65, 95):
+        np.testing.assert_allclose(probs[i], sim.density_matrix_probs(batch[i], n), atol=1e-10, rtol=0)
+        want = sim.run_trajectories(batch[i], n, 64, 5, circuit=i)
+        assert np.array_equal(out[i], want.astype(np.int64))
