@@ -433,6 +433,20 @@ __device__ __forceinline__ uint32_t readout_flips(uint32_t x, int n, const doubl
     return x;
 }
 
+// Warp-cooperative inverse CDF inside one probability chunk: every lane holds one element's weight (0 beyond len);
+// inclusive warp-shuffle prefix sum in double, ballot of (prefix > target), first set lane wins (last element if none).
+__device__ __forceinline__ uint32_t warp_pick(double w, double target, uint32_t len) {
+    const uint32_t lane = threadIdx.x & 31u;
+    double acc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double nb = __shfl_up_sync(0xffffffffu, acc, o);
+        if (lane >= (uint32_t)o) acc += nb;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, acc > target && lane < len);
+    return hit ? (uint32_t)(__ffs(hit) - 1) : len - 1u;
+}
+
 template <typename T>
 __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_t slot_stride, const double* chunk_sums,
                               uint64_t chunk_stride, const double* block_sums, uint64_t block_stride, uint32_t n_chunks,
@@ -441,35 +455,51 @@ __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_
                               uint64_t shot_begin) {
     typedef typename Cplx<T>::type C;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_traj) return;
-    const NodeRec nd = leaves[owner[i]];
-    if (!(nd.flags & NODE_LEAF)) return;
-    const uint64_t shot = shots[i];
-    const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
-    const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
-    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
-    const double tot = bs[n_blocks - 1];
-    double target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * tot;
-    const uint32_t b = upper_search(bs, 0, n_blocks, target);
-    if (b > 0) target -= bs[b - 1];
-    const uint32_t cbeg = b << SCAN_BLOCK_LOG;
-    const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
-    const uint32_t c = upper_search(cs, cbeg, cend, target);
-    if (c > cbeg) target -= cs[c - 1];
-    const int chunk_log = n_bits < CHUNK_LOG ? n_bits : CHUNK_LOG;
-    const C* amp = reinterpret_cast<const C*>(states) + (uint64_t)nd.dst_slot * slot_stride + ((uint64_t)c << chunk_log);
-    const uint32_t len = 1u << chunk_log;
-    uint32_t e_sel = len - 1;
-    double acc = 0.0;
-    for (uint32_t e = 0; e < len; e++) {
-        const C a = amp[e];
-        const T w = a.x * a.x + a.y * a.y;
-        acc += (double)w;
-        if (acc > target) {
-            e_sel = e;
-            break;
-        }
+    const uint32_t lane = threadIdx.x & 31u;
+    // phase 1 (per thread): locate the trajectory's chunk by two binary searches over the scanned sums
+    bool live = i < n_traj;
+    NodeRec nd;
+    uint64_t shot = 0;
+    uint32_t c = 0;
+    double target = 0.0;
+    if (live) {
+        nd = leaves[owner[i]];
+        live = (nd.flags & NODE_LEAF) != 0;
     }
+    if (live) {
+        shot = shots[i];
+        const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
+        const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
+        const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+        target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+        const uint32_t b = upper_search(bs, 0, n_blocks, target);
+        if (b > 0) target -= bs[b - 1];
+        const uint32_t cbeg = b << SCAN_BLOCK_LOG;
+        const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
+        c = upper_search(cs, cbeg, cend, target);
+        if (c > cbeg) target -= cs[c - 1];
+    }
+    // phase 2 (per warp): for each live trajectory of the warp, all lanes read its chunk (one coalesced request) and
+    // pick the element by a warp-shuffle prefix sum
+    const int chunk_log = n_bits < CHUNK_LOG ? n_bits : CHUNK_LOG;
+    const uint32_t len = 1u << chunk_log;
+    uint32_t todo = __ballot_sync(0xffffffffu, live);
+    uint32_t e_sel = 0;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t slot_j = __shfl_sync(0xffffffffu, nd.dst_slot, src);
+        const uint32_t c_j = __shfl_sync(0xffffffffu, c, src);
+        const double t_j = __shfl_sync(0xffffffffu, target, src);
+        double w = 0.0;
+        if (lane < len) {
+            const C a = reinterpret_cast<const C*>(states)[(uint64_t)slot_j * slot_stride + ((uint64_t)c_j << chunk_log) + lane];
+            w = (double)(a.x * a.x + a.y * a.y);
+        }
+        const uint32_t pick = warp_pick(w, t_j, len);
+        if ((int)lane == src) e_sel = pick;
+    }
+    if (!live) return;
     uint32_t x = (c << chunk_log) + e_sel;
     if (flip) x = readout_flips(x, n_bits, flip + (uint64_t)nd.circuit * n_bits * 2u, seed, nd.circuit, shot);
     if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
@@ -521,31 +551,38 @@ __global__ void sample_probs_kernel(const T* probs, int n, const double* chunk_s
                                     const double* flip, uint32_t* hist) {
     const uint32_t v = blockIdx.y;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_shots) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool live = i < n_shots;
     const uint64_t shot = shot_begin + i;
     const uint32_t circuit = first_circuit + v;
-    const double* cs = chunk_sums + (uint64_t)v * chunk_stride;
-    const double* bs = block_sums + (uint64_t)v * block_stride;
-    const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
-    double target = u53(draw(seed, circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
-    const uint32_t b = upper_search(bs, 0, n_blocks, target);
-    if (b > 0) target -= bs[b - 1];
-    const uint32_t cbeg = b << SCAN_BLOCK_LOG;
-    const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
-    const uint32_t c = upper_search(cs, cbeg, cend, target);
-    if (c > cbeg) target -= cs[c - 1];
     const int chunk_log = n < CHUNK_LOG ? n : CHUNK_LOG;
-    const T* p = probs + ((uint64_t)v << n) + ((uint64_t)c << chunk_log);
     const uint32_t len = 1u << chunk_log;
-    uint32_t e_sel = len - 1;
-    double acc = 0.0;
-    for (uint32_t e = 0; e < len; e++) {
-        acc += (double)p[e];
-        if (acc > target) {
-            e_sel = e;
-            break;
-        }
+    uint32_t c = 0;
+    double target = 0.0;
+    if (live) {
+        const double* cs = chunk_sums + (uint64_t)v * chunk_stride;
+        const double* bs = block_sums + (uint64_t)v * block_stride;
+        const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+        target = u53(draw(seed, circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+        const uint32_t b = upper_search(bs, 0, n_blocks, target);
+        if (b > 0) target -= bs[b - 1];
+        const uint32_t cbeg = b << SCAN_BLOCK_LOG;
+        const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
+        c = upper_search(cs, cbeg, cend, target);
+        if (c > cbeg) target -= cs[c - 1];
     }
+    uint32_t todo = __ballot_sync(0xffffffffu, live);
+    uint32_t e_sel = 0;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t c_j = __shfl_sync(0xffffffffu, c, src);
+        const double t_j = __shfl_sync(0xffffffffu, target, src);
+        const double w = lane < len ? (double)probs[((uint64_t)v << n) + ((uint64_t)c_j << chunk_log) + lane] : 0.0;
+        const uint32_t pick = warp_pick(w, t_j, len);
+        if ((int)lane == src) e_sel = pick;
+    }
+    if (!live) return;
     uint32_t x = (c << chunk_log) + e_sel;
     if (flip) x = readout_flips(x, n, flip + (uint64_t)v * n * 2u, seed, circuit, shot);
     atomicAdd(hist + ((uint64_t)v << n) + x, 1u);
