@@ -26,7 +26,7 @@ def _circ(n, ops):
 
 
 def _reset_opts(eng):
-    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25)):
+    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1)):
         eng.set_option(k, v)
 
 
@@ -338,3 +338,50 @@ def test_large_batch_parallel_lowering_matches_single_uploads(eng):
         np.testing.assert_allclose(probs[i], sim.density_matrix_probs(batch[i], n), atol=1e-10, rtol=0)
         want = sim.run_trajectories(batch[i], n, 64, 5, circuit=i)
         assert np.array_equal(out[i], want.astype(np.int64))
+
+
+@pytest.mark.parametrize("n", [13, 14, 16])
+def test_midsize_trajectories_match_compiled_oracle(eng, n):
+    """n >= 13: single-pass sweeps run on the register-only kernel, multi-pass ones on the tile kernel.  complex128
+    outcomes must equal the compiled CPU oracle (oracle/cpu_sim.c, itself pinned to the numpy oracle) shot for shot;
+    complex64 may differ only where a draw lands within float rounding of a CDF boundary."""
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    _reset_opts(eng)
+    rng = np.random.default_rng(1000 + n)
+    base = circuits.ref_graph(14 if n >= 14 else 10, 1)
+    extra = [(i, i + 1) for i in range(max(a for e in base for a in e), n - 1)]
+    g = base + extra
+    batch = [circuits.graph_circuit_amp_damp(n, g, rng, max_prob=0.3, all_sites=True),
+             circuits.graph_circuit_amp_damp(n, g, rng, max_prob=0.2, builder="cz"),
+             circuits.device_noise_circuit(n, g[:8], rng, gate_error=0.05)[0],
+             circuits.random_circuit(n, 40, rng)]
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 160, 21
+    _, o64 = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
+    _, o32 = eng.run_trajectories(shots, seed=seed, precision=32, want_outcomes=True)
+    o64 = o64.cpu().numpy().reshape(len(batch), shots)
+    o32 = o32.cpu().numpy().reshape(len(batch), shots)
+    for c, ops in enumerate(batch):
+        want = cpu_build.run_trajectories(encode_programs([_circ(n, ops)]), shots, seed, circuit=c).astype(np.int64)
+        assert np.array_equal(o64[c], want), f"circuit {c}: {np.count_nonzero(o64[c] != want)} outcomes differ"
+        assert np.count_nonzero(o32[c] != want) <= 3
+    # the tile kernel alone (register-only kernel switched off) gives the same complex128 outcomes
+    eng.set_option("use_direct", 0)
+    _, t64 = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
+    eng.set_option("use_direct", 1)
+    assert np.array_equal(t64.cpu().numpy().reshape(len(batch), shots), o64)
+
+
+def test_dm_direct_and_tile_kernels_agree(eng):
+    _reset_opts(eng)
+    n = 8
+    rng = np.random.default_rng(5)
+    batch = [circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, i), rng, max_prob=0.3) for i in range(3)]
+    eng.upload([_circ(n, ops) for ops in batch])
+    a = eng.run_density_matrix(64).cpu().numpy()
+    eng.set_option("use_direct", 0)
+    b = eng.run_density_matrix(64).cpu().numpy()
+    eng.set_option("use_direct", 1)
+    np.testing.assert_allclose(a, b, atol=1e-13, rtol=0)
+    np.testing.assert_allclose(a[0], sim.density_matrix_probs(batch[0], n), atol=1e-10, rtol=0)
