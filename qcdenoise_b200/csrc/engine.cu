@@ -83,6 +83,7 @@ struct qcd_ctx {
     int table_cap_log2 = 22;
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
     bool use_direct = true;      // register-only kernel for single-pass sweeps
+    uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
     // programs (host copy of the IR; compiled lazily per (mode, precision))
     int n_qubits = 0, n_circuits = 0;
     std::vector<qcd_op> ops;
@@ -339,18 +340,66 @@ struct SvRunner {
         a.part_stride = part_stride;
         a.direct_vec = 0;
         a.desc_from_pad = 0;
+        a.direct_kind = 3;
         return a;
+    }
+
+    // Measurement sampling of every leaf of nodes[begin, end) (the WHOLE batch, before anything below it is swept:
+    // NODE_NOSTORE leaves read their parent's slot, which the host may already have returned to the free list).
+    int sample_leaves(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end) {
+        bool any_leaf = false, any_nostore = false, any_stored = false;
+        for (size_t i = begin; i < end; i++)
+            if (nodes[i].flags & NODE_LEAF) {
+                any_leaf = true;
+                if (nodes[i].flags & NODE_NOSTORE) any_nostore = true;
+                else any_stored = true;
+            }
+        if (!any_leaf) return QCD_OK;
+        const size_t n_nodes = end - begin;
+        const uint32_t t0 = nodes[begin].traj_off;
+        const uint32_t tc = nodes[end - 1].traj_off + nodes[end - 1].traj_cnt - t0;
+        const NodeRec* ndev = ctx->level_nodes[d].as<NodeRec>() + begin;
+        uint32_t* shots_d = ctx->level_shots[d].as<uint32_t>() + t0;
+        uint32_t* owner = ctx->owner.as<uint32_t>();
+        launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
+        launch_scan_chunks(ndev, (uint32_t)n_nodes, ctx->chunk_sums.as<double>(), n_chunks,
+                           ctx->block_sums.as<double>(), n_blocks, n_chunks, st);
+        ctx->stats.aux_launches += 3;
+        if (any_stored) {
+            launch_sample<T>(ndev, (uint32_t)n_nodes, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(), n_chunks,
+                             ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed, flip_dev,
+                             hist, outcomes, spc, shot_begin, st);
+            ctx->stats.aux_launches++;
+        }
+        if (any_nostore) {
+            launch_sample_nostore<T>(prog, ndev, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(), n_chunks,
+                                     ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed,
+                                     flip_dev, hist, outcomes, spc, shot_begin, st);
+            ctx->stats.aux_launches++;
+        }
+        CU(cudaGetLastError());
+        for (size_t i = begin; i < end; i++)
+            if (nodes[i].flags & NODE_LEAF) {
+                free_slot(nodes[i].dst_slot);
+                ctx->stats.leaves++;
+            }
+        return QCD_OK;
     }
 
     // nodes[begin, end) at depth d have executed their sweep (d == 0: virtual roots); their device copy is
     // level_nodes[d] + begin and their trajectories are level_shots[d][traj_off ...).
-    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root, uint32_t n_parts) {
+    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root, uint32_t n_parts,
+                bool leaves_done = false) {
         const size_t n_nodes = end - begin;
         if (n_nodes == 0) return QCD_OK;
+        if (!is_root && !leaves_done) {
+            int rc = sample_leaves(d, nodes, begin, end);
+            if (rc) return rc;
+        }
         if (((uint64_t)n_nodes << gbits) > table_cap && n_nodes > 1) {
             const size_t piece = std::max<uint64_t>(1, table_cap >> gbits);
             for (size_t b = begin; b < end; b += piece) {
-                int rc = process(d, nodes, b, std::min(end, b + piece), is_root, n_parts);
+                int rc = process(d, nodes, b, std::min(end, b + piece), is_root, n_parts, true);
                 if (rc) return rc;
             }
             return QCD_OK;
@@ -366,30 +415,14 @@ struct SvRunner {
 
         launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
         ctx->stats.aux_launches++;
-        bool any_leaf = false, any_inner = false;
         if (is_root) {
             launch_root_shots(ndev, owner, shots_d, tc, st);
             launch_fill_root_probs(P, (uint32_t)n_nodes, st);
             ctx->stats.aux_launches += 2;
-            any_inner = true;
         } else {
-            for (size_t i = begin; i < end; i++) {
-                if (nodes[i].flags & NODE_LEAF) any_leaf = true;
-                else any_inner = true;
-            }
-            if (any_leaf) {
-                launch_scan_chunks(ndev, (uint32_t)n_nodes, ctx->chunk_sums.as<double>(), n_chunks,
-                                   ctx->block_sums.as<double>(), n_blocks, n_chunks, st);
-                launch_sample<T>(ndev, (uint32_t)n_nodes, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(),
-                                 n_chunks, ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed,
-                                 flip_dev, hist, outcomes, spc, shot_begin, st);
-                ctx->stats.aux_launches += 3;
-                for (size_t i = begin; i < end; i++)
-                    if (nodes[i].flags & NODE_LEAF) {
-                        free_slot(nodes[i].dst_slot);
-                        ctx->stats.leaves++;
-                    }
-            }
+            bool any_inner = false;
+            for (size_t i = begin; i < end; i++)
+                if (!(nodes[i].flags & NODE_LEAF)) any_inner = true;
             if (!any_inner) return QCD_OK;
             launch_node_probs(ndev, (uint32_t)n_nodes, ctx->partials.as<double>(), part_stride, n_parts, P, st);
             ctx->stats.aux_launches++;
@@ -432,14 +465,25 @@ struct SvRunner {
             for (NodeRec& r : chunk) r.dst_slot = alloc_slot();
             CU(ctx->level_nodes[d + 1].ensure(c * sizeof(NodeRec)));
             NodeRec* cdev = ctx->level_nodes[d + 1].as<NodeRec>();
-            CU(cudaMemcpyAsync(cdev, chunk.data(), c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
             // single-pass sweeps run on the register-only kernel; anything else on the shared-memory tile kernel
-            bool direct = ctx->use_direct, vec = true;
+            bool direct = ctx->use_direct, vec = true, need_red = false, need_chunks = false, need_prep = false;
             for (const NodeRec& r : chunk) {
                 const DirectSweep& D = dp->direct_host[r.sweep];
                 direct = direct && D.ok;
                 vec = vec && D.rbit[0] == 0;
+                need_red = need_red || D.red_q[0] >= 0;
+                need_chunks = need_chunks || (D.flags & SW_FINAL);
+                need_prep = need_prep || (D.flags & SW_PREP);
             }
+            uint64_t n_nostore = 0;
+            if (direct && !is_root && ctx->nostore_max > 0) {
+                for (NodeRec& r : chunk)
+                    if ((r.flags & NODE_LEAF) && r.traj_cnt <= ctx->nostore_max) {
+                        r.flags |= NODE_NOSTORE;
+                        n_nostore++;
+                    }
+            }
+            CU(cudaMemcpyAsync(cdev, chunk.data(), c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
             SweepArgs sa = sweep_args(cdev, (uint32_t)c);
             uint32_t parts_used = tiles;
             if (direct) {
@@ -450,6 +494,8 @@ struct SvRunner {
                 sa.tiles_log2 = (uint32_t)pl;
                 sa.n_items = (uint32_t)(c << pl);
                 sa.direct_vec = vec ? 1 : 0;
+                sa.direct_kind = (!need_red && !need_chunks) ? 0u : ((need_prep || (need_red && need_chunks)) ? 3u
+                                                                     : (need_red ? 1u : 2u));
                 parts_used = 1u << pl;
             }
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -459,7 +505,7 @@ struct SvRunner {
             CU(cudaGetLastError());
             ctx->stats.sweep_launches++;
             ctx->stats.node_sweeps += c;
-            ctx->stats.sweep_bytes += (uint64_t)c * slot_stride * sizeof(C) * (is_root ? 1 : 2);
+            ctx->stats.sweep_bytes += ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C);
             pos += c;
             if (!is_root) {
                 const size_t done_to = pos == n_children ? n_nodes : ch[pos].parent;
@@ -678,6 +724,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
                 a.part_stride = 1;
                 a.direct_vec = lvl_vec[l] ? 1 : 0;
                 a.desc_from_pad = 1;
+                a.direct_kind = 0;
                 if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
                 launch_sweep_direct<T>(prog, a, st);
                 if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -723,6 +770,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             a.part_stride = tiles;
             a.direct_vec = 0;
             a.desc_from_pad = 0;
+            a.direct_kind = 3;
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
             launch_sweep<T>(prog, a, k, st);
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -839,6 +887,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
         ctx->table_cap_log2 = (int)value;
     } else if (k == "max_slots") ctx->max_slots = (uint64_t)value;
     else if (k == "use_direct") ctx->use_direct = value != 0;
+    else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }

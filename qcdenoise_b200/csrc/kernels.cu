@@ -464,7 +464,7 @@ __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_
     double target = 0.0;
     if (live) {
         nd = leaves[owner[i]];
-        live = (nd.flags & NODE_LEAF) != 0;
+        live = (nd.flags & NODE_LEAF) != 0 && !(nd.flags & NODE_NOSTORE);
     }
     if (live) {
         shot = shots[i];

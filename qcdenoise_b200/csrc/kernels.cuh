@@ -31,6 +31,7 @@ struct NodeRec {
     uint32_t pad;
 };
 constexpr uint32_t NODE_LEAF = 1;
+constexpr uint32_t NODE_NOSTORE = 2;   // leaf whose state is not written: sampled by recomputing chunks from the parent
 
 template <typename T> struct Cplx;
 template <> struct Cplx<float> { typedef float2 type; };
@@ -65,6 +66,7 @@ struct SweepArgs {
     uint32_t part_stride;    // partials: [slot][part_stride][4]; a launch writes tiles (or CTAs-per-state) of them
     uint32_t direct_vec;     // direct kernel: every sweep of the launch has index bit 0 as a register bit
     uint32_t desc_from_pad;  // direct kernel: descriptor index = node.pad (per-pass launches) instead of node.sweep
+    uint32_t direct_kind;    // direct kernel variant: 0 plain (+prep), 1 inner (reduction), 2 final (chunk sums), 3 generic
 };
 
 template <typename T>
@@ -75,6 +77,13 @@ cudaError_t configure_sweep(int k);
 // 2^(n_bits - 4 - tiles_log2) >= 256 register groups of 16 amplitudes
 template <typename T>
 void launch_sweep_direct(const DevProgram<T>& prog, const SweepArgs& a, cudaStream_t st);
+
+template <typename T>
+void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, const void* states, uint64_t slot_stride,
+                           const double* chunk_sums, uint64_t chunk_stride, const double* block_sums,
+                           uint64_t block_stride, uint32_t n_chunks, int n_bits, const uint32_t* owner,
+                           const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
+                           uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin, cudaStream_t st);
 
 // ---- decide
 void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t part_stride,

@@ -1,5 +1,6 @@
 // sweep_direct.cu -- register-only state sweep for sweeps that consist of ONE pass over <= 4 register bits (the common
-// case in trajectory mode: the Kraus variants of one site group + the few gates up to the next site).
+// case in trajectory mode: the Kraus variants of one site group + the few gates up to the next site; in
+// density-matrix mode every pass of a multi-pass sweep is launched as such a sweep).
 //
 // No shared-memory tile: a thread owns one "register group" = the 16 amplitudes that differ only in the pass's 4
 // register bits, loads them straight from global memory (128-bit loads when index bit 0 is a register bit, otherwise
@@ -13,7 +14,13 @@
 //     values (register bits below 5) and by xor-shuffles over the lanes that hold the other low index bits.
 // The sweep's description (register bits, ops, the matrices of this node's branch) is staged once per CTA in shared
 // memory: three dependent global reads (node -> descriptor -> matrices), then the streaming loop.
+//
+// Leaf states that only a few trajectories sample from are NOT written (NODE_NOSTORE): the final sweep then only emits
+// the chunk sums, and sample_nostore_kernel recomputes the one 32-amplitude chunk each trajectory lands in from the
+// parent state with the same staging + apply code (identical arithmetic).
 #include "kernels.cuh"
+
+#include "../../include/qcdsim.h"
 
 namespace qcd {
 namespace {
@@ -25,6 +32,7 @@ constexpr int DT = DIRECT_DT;  // threads per CTA
 #ifndef DIRECT_MINB
 #define DIRECT_MINB 8
 #endif
+constexpr int MAX_SIGNS = 48;  // sign masks staged per sweep (more: the sweep is not direct-eligible)
 
 template <typename T> struct Cx;
 template <> struct Cx<float> { typedef float2 C; };
@@ -78,7 +86,6 @@ __device__ __forceinline__ void m2(C (&a)[16], const C* m) {
         a[s | (1 << T0) | (1 << T1)] = y[3];
     }
 }
-
 // real diagonal (no-jump damping Kraus, Z-like): two multipliers
 template <int TB, typename C>
 __device__ __forceinline__ void m1d(C (&a)[16], const C* m) {
@@ -143,42 +150,64 @@ __device__ __forceinline__ void stv(double2* p, double2 a, double2 b) {
     p[1] = b;
 }
 
-constexpr int MAX_SIGNS = 48;  // sign masks staged per sweep (more: the sweep is not direct-eligible)
+// ---------------------------------------------------------------------------------------------------------------
+// pre-decoded op codes (low 8 bits; K_SIGNS: count in bits 8..15, slot offset in bits 16..23; K_D1: global bit in 8..15)
+enum : uint32_t {
+    C_M1D = 0,    // +t0   real diagonal 2x2
+    C_M1R = 4,    // +t0   real 2x2
+    C_M1C = 8,    // +t0   complex 2x2
+    C_M2R = 12,   // +pair real 4x4, pair index: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    C_M2C = 18,   // +pair complex 4x4
+    C_SIGNS = 24,
+    C_D1 = 25
+};
+__device__ __forceinline__ uint32_t pair_index(int t0, int t1) {
+    return t0 == 0 ? (uint32_t)(t1 - 1) : (t0 == 1 ? (uint32_t)(t1 + 1) : 5u);
+}
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB / 2) sweep_direct_kernel(DevProgram<T> prog, SweepArgs args) {
+// Per-sweep staging area (one per CTA in the sweep kernel, one per warp in the recompute-sampling kernel)
+template <typename T>
+struct Staged {
     typedef typename Cx<T>::C C;
-    __shared__ DirectSweep D;
-    __shared__ C s_mats[MAX_DIRECT_OPS][16];   // the selected variant of every matrix op
-    __shared__ uint32_t s_sign_base[MAX_SIGNS];
-    __shared__ uint32_t s_sign_pat[MAX_SIGNS];
-    __shared__ double s_red[DT / 32][4];
-    __shared__ uint32_t s_real[MAX_DIRECT_OPS];   // matrix op o has purely real coefficients
-    __shared__ int s_scale_op;                    // matrix op that carries the node's rescale factor (-1: none)
-    __shared__ C s_prep[64];                      // prep sweeps: (alpha, beta) per index bit
-    __shared__ C s_prep_reg[16];                  // ... and the 16 products over the register bits
+    DirectSweep D;
+    C mats[MAX_DIRECT_OPS][16];      // the selected variant of every matrix op
+    uint32_t sign_base[MAX_SIGNS];   // part of each sign mask outside the register bits
+    uint32_t sign_pat[MAX_SIGNS];    // per-value pattern of the part inside the register bits
+    uint32_t kind_flags[MAX_DIRECT_OPS];  // 0 complex, 1 real, 2 real diagonal
+    uint32_t code[MAX_DIRECT_OPS];        // pre-decoded op: one jump-table dispatch per op in the streaming loop
+    int scale_op;                    // matrix op that carries the node's rescale factor (-1: none)
+    C prep[64];                      // prep sweeps: (alpha, beta) per index bit
+    C prep_reg[16];                  // ... and the 16 products over the register bits
+};
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t node_idx = blockIdx.x >> args.tiles_log2;
-    const uint32_t part = blockIdx.x & ((1u << args.tiles_log2) - 1u);
-    const NodeRec N = args.nodes[node_idx];
+template <bool WARP>
+__device__ __forceinline__ void group_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+// Stage descriptor `desc`, the matrices of branch word `branch` (rescale folded into the first matrix op) and the
+// sign masks.  Executed by NT cooperating threads (tid in [0, NT)).
+template <typename T, int NT, bool WARP>
+__device__ __forceinline__ void stage_sweep(Staged<T>& S, const DevProgram<T>& prog, uint32_t desc, uint32_t branch,
+                                            double scale, uint32_t tid) {
+    typedef typename Cx<T>::C C;
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(prog.direct + (args.desc_from_pad ? N.pad : N.sweep));
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&D);
-        if (tid < sizeof(DirectSweep) / 4) dst[tid] = src[tid];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prog.direct + desc);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&S.D);
+        for (uint32_t e = tid; e < sizeof(DirectSweep) / 4; e += NT) dst[e] = src[e];
     }
-    __syncthreads();
-    const int n_bits = D.n_bits, nops = D.nops;
-    uint32_t go[4];  // global offset of register bit i
+    group_sync<WARP>();
+    const int nops = S.D.nops, n_bits = S.D.n_bits;
+    uint32_t go[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) go[i] = 1u << D.rbit[i];
+    for (int i = 0; i < 4; i++) go[i] = 1u << S.D.rbit[i];
     const uint32_t regmask = go[0] | go[1] | go[2] | go[3];
-    // stage matrices of this node's branch + sign masks
     for (int o = 0; o < nops; o++) {
-        const KOp op = D.ops[o];
+        const KOp op = S.D.ops[o];
         if (op.kind == K_SIGNS) {
-            if (tid < op.count) {
-                const uint32_t mk = prog.masks[op.off + tid];
+            for (uint32_t e = tid; e < op.count; e += NT) {
+                const uint32_t mk = prog.masks[op.off + e];
                 const uint32_t mr = mk & regmask;
                 uint32_t pat = 0;
 #pragma unroll
@@ -188,206 +217,277 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
                     pat |= ((g & mr) == mr ? 1u : 0u) << s;
                 }
                 // K_SIGNS ops of one sweep share the staging arrays: `t1` carries the op's slot offset (see host)
-                s_sign_base[op.t1 + tid] = mk & ~regmask;
-                s_sign_pat[op.t1 + tid] = pat;
+                S.sign_base[op.t1 + e] = mk & ~regmask;
+                S.sign_pat[op.t1 + e] = pat;
             }
         } else {
-            const C* m = prog.pool + op.off + ((N.branch >> op.sel_shift) & op.sel_mask) * op.stride;
+            const C* m = prog.pool + op.off + ((branch >> op.sel_shift) & op.sel_mask) * op.stride;
             const uint32_t cnt = op.kind == K_M1 ? 4u : (op.kind == K_M2 ? 16u : 2u);
-            if (tid < cnt) s_mats[o][tid] = m[tid];
+            for (uint32_t e = tid; e < cnt; e += NT) S.mats[o][e] = m[e];
         }
     }
-    const bool is_prep = (D.flags & SW_PREP) != 0;
-    if (is_prep && tid < 2u * (uint32_t)n_bits) s_prep[tid] = prog.pool[D.prep_off + tid];
+    const bool is_prep = (S.D.flags & SW_PREP) != 0;
+    if (is_prep)
+        for (uint32_t e = tid; e < 2u * (uint32_t)n_bits; e += NT) S.prep[e] = prog.pool[S.D.prep_off + e];
     if (tid == 0) {
         int so = -1;
         for (int o = 0; o < nops && so < 0; o++)
-            if (D.ops[o].kind == K_M1 || D.ops[o].kind == K_M2) so = o;
-        s_scale_op = so;
+            if (S.D.ops[o].kind == K_M1 || S.D.ops[o].kind == K_M2) so = o;
+        S.scale_op = so;
     }
-    __syncthreads();
-    if ((int)tid < nops) {
+    group_sync<WARP>();
+    for (uint32_t o = tid; o < (uint32_t)nops; o += NT) {
         // classify the staged matrix; the first matrix op absorbs the node's 1/sqrt(p) rescale
-        const int kind = D.ops[tid].kind;
+        const int kind = S.D.ops[o].kind;
         const int cnt = kind == K_M1 ? 4 : (kind == K_M2 ? 16 : (kind == K_D1 ? 2 : 0));
-        const T f = ((int)tid == s_scale_op) ? (T)N.scale : (T)1;
+        const T f = ((int)o == S.scale_op) ? (T)scale : (T)1;
         bool real = true;
         for (int e = 0; e < cnt; e++) {
-            C v = s_mats[tid][e];
+            C v = S.mats[o][e];
             v.x *= f;
             v.y *= f;
-            s_mats[tid][e] = v;
+            S.mats[o][e] = v;
             real = real && v.y == (T)0;
         }
-        const bool diag = real && kind == K_M1 && s_mats[tid][1].x == (T)0 && s_mats[tid][2].x == (T)0;
-        s_real[tid] = diag ? 2u : (real ? 1u : 0u);
+        const bool diag = real && kind == K_M1 && S.mats[o][1].x == (T)0 && S.mats[o][2].x == (T)0;
+        S.kind_flags[o] = diag ? 2u : (real ? 1u : 0u);
+        const KOp op = S.D.ops[o];
+        uint32_t code;
+        if (kind == K_M1) code = (diag ? C_M1D : (real ? C_M1R : C_M1C)) + op.t0;
+        else if (kind == K_M2) code = (real ? C_M2R : C_M2C) + pair_index(op.t0, op.t1);
+        else if (kind == K_SIGNS) code = C_SIGNS | ((uint32_t)op.count << 8) | ((uint32_t)op.t1 << 16);
+        else code = C_D1 | ((uint32_t)op.gbit << 8);
+        S.code[o] = code;
     }
-    if (is_prep && tid >= 32 && tid < 48) {
-        const int sidx = (int)tid - 32;
-        C v;
-        v.x = 1;
-        v.y = 0;
+    if (is_prep) {
+        for (uint32_t sidx = tid; sidx < 16; sidx += NT) {
+            C v;
+            v.x = 1;
+            v.y = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) v = cmul(v, s_prep[2 * D.rbit[i] + ((sidx >> i) & 1)]);
-        s_prep_reg[sidx] = v;
+            for (int i = 0; i < 4; i++) v = cmul(v, S.prep[2 * S.D.rbit[i] + ((sidx >> i) & 1)]);
+            S.prep_reg[sidx] = v;
+        }
     }
-    __syncthreads();
+    group_sync<WARP>();
+}
+
+// All fused ops of the sweep on one register group (gb = its base index, register bits clear).
+template <typename T>
+__device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const Staged<T>& S, int nops, uint32_t gb,
+                                            const uint32_t (&go)[4]) {
+    typedef typename Cx<T>::C C;
+    for (int o = 0; o < nops; o++) {
+        const uint32_t code = S.code[o];
+        const C* mt = S.mats[o];
+        switch (code & 0xffu) {
+            case C_M1D + 0: m1d<0>(a, mt); break;
+            case C_M1D + 1: m1d<1>(a, mt); break;
+            case C_M1D + 2: m1d<2>(a, mt); break;
+            case C_M1D + 3: m1d<3>(a, mt); break;
+            case C_M1R + 0: m1r<0>(a, mt); break;
+            case C_M1R + 1: m1r<1>(a, mt); break;
+            case C_M1R + 2: m1r<2>(a, mt); break;
+            case C_M1R + 3: m1r<3>(a, mt); break;
+            case C_M1C + 0: m1<0>(a, mt); break;
+            case C_M1C + 1: m1<1>(a, mt); break;
+            case C_M1C + 2: m1<2>(a, mt); break;
+            case C_M1C + 3: m1<3>(a, mt); break;
+            case C_M2R + 0: m2r<0, 1>(a, mt); break;
+            case C_M2R + 1: m2r<0, 2>(a, mt); break;
+            case C_M2R + 2: m2r<0, 3>(a, mt); break;
+            case C_M2R + 3: m2r<1, 2>(a, mt); break;
+            case C_M2R + 4: m2r<1, 3>(a, mt); break;
+            case C_M2R + 5: m2r<2, 3>(a, mt); break;
+            case C_M2C + 0: m2<0, 1>(a, mt); break;
+            case C_M2C + 1: m2<0, 2>(a, mt); break;
+            case C_M2C + 2: m2<0, 3>(a, mt); break;
+            case C_M2C + 3: m2<1, 2>(a, mt); break;
+            case C_M2C + 4: m2<1, 3>(a, mt); break;
+            case C_M2C + 5: m2<2, 3>(a, mt); break;
+            case C_SIGNS: {
+                const uint32_t cnt = (code >> 8) & 0xffu, off = code >> 16;
+                uint32_t par = 0;
+                for (uint32_t t = 0; t < cnt; t++) {
+                    const uint32_t mb = S.sign_base[off + t];
+                    par ^= ((gb & mb) == mb) ? S.sign_pat[off + t] : 0u;
+                }
+#pragma unroll
+                for (int s = 0; s < 16; s++)
+                    if ((par >> s) & 1u) {
+                        a[s].x = -a[s].x;
+                        a[s].y = -a[s].y;
+                    }
+                break;
+            }
+            default: {  // C_D1
+                const C d0 = mt[0], d1 = mt[1];
+                const uint32_t gbit = (code >> 8) & 0xffu;
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
+                                       ((s & 8) ? go[3] : 0u);
+                    a[s] = cmul(a[s], ((g >> gbit) & 1u) ? d1 : d0);
+                }
+                break;
+            }
+        }
+    }
+}
+
+// The 16 amplitudes of register group gb BEFORE the sweep's ops: product state (prep sweeps) or the parent state.
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_group(typename Cx<T>::C (&a)[16], const Staged<T>& S,
+                                           const typename Cx<T>::C* src, uint32_t gb, const uint32_t (&go)[4],
+                                           uint32_t regmask, T sc, bool is_prep, bool need_scale) {
+    typedef typename Cx<T>::C C;
+    if (is_prep) {
+        C base;
+        base.x = 1;
+        base.y = 0;
+        for (int b = 0; b < S.D.n_bits; b++)
+            if (!((regmask >> b) & 1u)) base = cmul(base, S.prep[2 * b + ((gb >> b) & 1u)]);
+#pragma unroll
+        for (int s = 0; s < 16; s++) a[s] = cmul(base, S.prep_reg[s]);
+    } else if (VEC) {
+#pragma unroll
+        for (int s = 0; s < 16; s += 2) {
+            const uint32_t g = gb | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) | ((s & 8) ? go[3] : 0u);
+            ldv(src + g, a[s], a[s + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
+                               ((s & 8) ? go[3] : 0u);
+            a[s] = src[g];
+        }
+    }
+    if (need_scale) {   // no matrix op to carry the rescale factor
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            a[s].x *= sc;
+            a[s].y *= sc;
+        }
+    }
+}
+
+// r[(bit I0 of s) | (bit I1 of s) << 1] += w[s]   (I = 4: that reduced bit is not a register bit -> contributes 0)
+template <int I0, int I1, typename T>
+__device__ __forceinline__ void rel_accumulate(T (&r)[4], const T (&w)[16]) {
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int b0 = I0 < 4 ? ((s >> I0) & 1) : 0;
+        const int b1 = I1 < 4 ? ((s >> I1) & 1) : 0;
+        r[b0 | (b1 << 1)] += w[s];
+    }
+}
+template <typename T>
+__device__ __forceinline__ void rel_accumulate_dyn(T (&r)[4], const T (&w)[16], int red_case) {
+    switch (red_case) {
+#define RC(i0, i1) case (i0) * 5 + (i1): rel_accumulate<i0, i1>(r, w); break;
+        RC(0, 1) RC(0, 2) RC(0, 3) RC(0, 4) RC(1, 0) RC(1, 2) RC(1, 3) RC(1, 4) RC(2, 0) RC(2, 1) RC(2, 3) RC(2, 4)
+        RC(3, 0) RC(3, 1) RC(3, 2) RC(3, 4) RC(4, 0) RC(4, 1) RC(4, 2) RC(4, 3)
+#undef RC
+        default: rel_accumulate<4, 4>(r, w); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KIND selects which epilogues / sources are compiled in (dead paths cost registers in this kernel):
+//   0 PLAIN   no reduction, no chunk sums; product-state source allowed      (density-matrix passes, prep sweeps)
+//   1 INNER   population reduction                                           (inner tree levels)
+//   2 FINAL   chunk sums                                                     (leaf level)
+//   3 GENERIC everything                                                     (mixed launches)
+template <typename T, bool VEC, int KIND>
+__global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB / 2)
+    sweep_direct_kernel(DevProgram<T> prog, SweepArgs args) {
+    typedef typename Cx<T>::C C;
+    constexpr bool HAS_RED = KIND == 1 || KIND == 3, HAS_CHUNKS = KIND == 2 || KIND == 3,
+                   HAS_PREP = KIND == 0 || KIND == 3;
+    __shared__ Staged<T> S;
+    __shared__ double s_red[DT / 32][4];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t node_idx = blockIdx.x >> args.tiles_log2;
+    const uint32_t part = blockIdx.x & ((1u << args.tiles_log2) - 1u);
+    const NodeRec N = args.nodes[node_idx];
+    stage_sweep<T, DT, false>(S, prog, args.desc_from_pad ? N.pad : N.sweep, N.branch, N.scale, tid);
+    const DirectSweep& D = S.D;
+    const int n_bits = D.n_bits;
+    uint32_t go[4];  // global offset of register bit i
+#pragma unroll
+    for (int i = 0; i < 4; i++) go[i] = 1u << D.rbit[i];
+    const uint32_t regmask = go[0] | go[1] | go[2] | go[3];
 
     const C* src = reinterpret_cast<const C*>(args.states) + (uint64_t)N.src_slot * args.slot_stride;
     C* dst = reinterpret_cast<C*>(args.states) + (uint64_t)N.dst_slot * args.slot_stride;
-    const bool need_scale = s_scale_op < 0;
+    const bool store = !(N.flags & NODE_NOSTORE);
     const T sc = (T)N.scale;
+    const bool is_prep = HAS_PREP && (D.flags & SW_PREP) != 0, need_scale = S.scale_op < 0;
+    const int nops = D.nops;
     const uint32_t groups_per_cta = 1u << (n_bits - 4 - (int)args.tiles_log2);
     const uint32_t grp0 = part * groups_per_cta;
     const int rq0 = D.red_q[0], rq1 = D.red_q[1];
-    const bool do_red = rq0 >= 0;
-    const bool do_chunks = (D.flags & SW_FINAL) != 0 && args.chunk_sums != nullptr;
+    const bool do_red = HAS_RED && rq0 >= 0;
+    const bool do_chunks = HAS_CHUNKS && (D.flags & SW_FINAL) != 0 && args.chunk_sums != nullptr;
     int r_low = 0;  // register bits below the chunk size
 #pragma unroll
     for (int i = 0; i < 4; i++) r_low += (D.rbit[i] < CHUNK_LOG) ? 1 : 0;
     double* csum = args.chunk_sums + (uint64_t)N.dst_slot * args.chunk_stride;
-    T p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // joint populations P[b(rq0) + 2 b(rq1)]
-    // Fast reduction: when every reduced bit is a register bit or constant over this thread's iterations, the bin of
-    // value s is fixed per thread -> accumulate per-s sums in the loop and bin them once at the end.
+    // Population reduction: value s falls into bin (bit rq0) | (bit rq1) << 1 of its global index.  A reduced bit that
+    // is a register bit depends on s only ("relative bin", compile-time selected by red_case); one that is not
+    // contributes a base bin that is constant per thread (red_fast) or changes per iteration.
+    T rel[4] = {0, 0, 0, 0};   // red_fast: accumulated over all iterations;  else: per iteration
+    T p[4] = {0, 0, 0, 0};
     bool red_fast = true;
-    {
+    int red_case = 24;
+    uint32_t base_mask0 = 0, base_mask1 = 0;   // global-index masks of the reduced bits that are NOT register bits
+    if (do_red) {
         const int gl = n_bits - 4 - (int)args.tiles_log2;     // log2(register groups per CTA)
         const int rq[2] = {rq0, rq1};
+        int idx[2] = {4, 4};
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            if (rq[j] < 0 || ((regmask >> rq[j]) & 1u)) continue;
+            if (rq[j] < 0) continue;
+            if ((regmask >> rq[j]) & 1u) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if ((int)D.rbit[i] == rq[j]) idx[j] = i;
+                continue;
+            }
+            if (j == 0) base_mask0 = 1u << rq[j];
+            else base_mask1 = 1u << rq[j];
             const int cp = rq[j] - __popc(regmask & ((1u << rq[j]) - 1u));   // bit position in the group index
             if (cp >= (DT == 256 ? 8 : 7) && cp < gl) red_fast = false;
         }
+        red_case = idx[0] * 5 + idx[1];
     }
-    T acc[16];
-#pragma unroll
-    for (int s = 0; s < 16; s++) acc[s] = 0;
     uint32_t gb_last = 0;
 
     for (uint32_t it = tid; it < groups_per_cta; it += DT) {
-        uint32_t gb = grp0 + it;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t b = D.rbit[i];
-            gb = ((gb >> b) << (b + 1)) | (gb & ((1u << b) - 1u));
-        }
+        uint32_t gb = grp0 + it;   // insert a zero at every register bit (ascending)
+        gb = ((gb & ~(go[0] - 1u)) << 1) | (gb & (go[0] - 1u));
+        gb = ((gb & ~(go[1] - 1u)) << 1) | (gb & (go[1] - 1u));
+        gb = ((gb & ~(go[2] - 1u)) << 1) | (gb & (go[2] - 1u));
+        gb = ((gb & ~(go[3] - 1u)) << 1) | (gb & (go[3] - 1u));
         C a[16];
-        if (is_prep) {
-            C base;
-            base.x = 1;
-            base.y = 0;
-            for (int b = 0; b < n_bits; b++)
-                if (!((regmask >> b) & 1u)) base = cmul(base, s_prep[2 * b + ((gb >> b) & 1u)]);
+        load_group<T, VEC>(a, S, src, gb, go, regmask, sc, is_prep, need_scale);
+        apply_sweep<T>(a, S, nops, gb, go);
+        if (store) {
+            if (VEC) {
 #pragma unroll
-            for (int s = 0; s < 16; s++) a[s] = cmul(base, s_prep_reg[s]);
-        } else if (VEC) {
-#pragma unroll
-            for (int s = 0; s < 16; s += 2) {
-                const uint32_t g = gb | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) | ((s & 8) ? go[3] : 0u);
-                ldv(src + g, a[s], a[s + 1]);
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < 16; s++) {
-                const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                   ((s & 8) ? go[3] : 0u);
-                a[s] = src[g];
-            }
-        }
-        if (need_scale) {
-#pragma unroll
-            for (int s = 0; s < 16; s++) {
-                a[s].x *= sc;
-                a[s].y *= sc;
-            }
-        }
-        for (int o = 0; o < nops; o++) {
-            const KOp op = D.ops[o];
-            switch (op.kind) {
-                case K_M1:
-                    if (s_real[o] == 2u) {
-                        switch (op.t0) {
-                            case 0: m1d<0>(a, s_mats[o]); break;
-                            case 1: m1d<1>(a, s_mats[o]); break;
-                            case 2: m1d<2>(a, s_mats[o]); break;
-                            default: m1d<3>(a, s_mats[o]); break;
-                        }
-                    } else if (s_real[o]) {
-                        switch (op.t0) {
-                            case 0: m1r<0>(a, s_mats[o]); break;
-                            case 1: m1r<1>(a, s_mats[o]); break;
-                            case 2: m1r<2>(a, s_mats[o]); break;
-                            default: m1r<3>(a, s_mats[o]); break;
-                        }
-                    } else {
-                        switch (op.t0) {
-                            case 0: m1<0>(a, s_mats[o]); break;
-                            case 1: m1<1>(a, s_mats[o]); break;
-                            case 2: m1<2>(a, s_mats[o]); break;
-                            default: m1<3>(a, s_mats[o]); break;
-                        }
-                    }
-                    break;
-                case K_M2:
-                    if (s_real[o]) {
-                        switch (op.t0 * 4 + op.t1) {
-                            case 1: m2r<0, 1>(a, s_mats[o]); break;
-                            case 2: m2r<0, 2>(a, s_mats[o]); break;
-                            case 3: m2r<0, 3>(a, s_mats[o]); break;
-                            case 6: m2r<1, 2>(a, s_mats[o]); break;
-                            case 7: m2r<1, 3>(a, s_mats[o]); break;
-                            default: m2r<2, 3>(a, s_mats[o]); break;
-                        }
-                    } else {
-                        switch (op.t0 * 4 + op.t1) {
-                            case 1: m2<0, 1>(a, s_mats[o]); break;
-                            case 2: m2<0, 2>(a, s_mats[o]); break;
-                            case 3: m2<0, 3>(a, s_mats[o]); break;
-                            case 6: m2<1, 2>(a, s_mats[o]); break;
-                            case 7: m2<1, 3>(a, s_mats[o]); break;
-                            default: m2<2, 3>(a, s_mats[o]); break;
-                        }
-                    }
-                    break;
-                case K_SIGNS: {
-                    uint32_t par = 0;
-                    for (uint32_t t = 0; t < op.count; t++) {
-                        const uint32_t mb = s_sign_base[op.t1 + t];
-                        par ^= ((gb & mb) == mb) ? s_sign_pat[op.t1 + t] : 0u;
-                    }
-#pragma unroll
-                    for (int s = 0; s < 16; s++)
-                        if ((par >> s) & 1u) {
-                            a[s].x = -a[s].x;
-                            a[s].y = -a[s].y;
-                        }
-                    break;
+                for (int s = 0; s < 16; s += 2) {
+                    const uint32_t g = gb | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) | ((s & 8) ? go[3] : 0u);
+                    stv(dst + g, a[s], a[s + 1]);
                 }
-                default: {  // K_D1
-                    const C d0 = s_mats[o][0], d1 = s_mats[o][1];
+            } else {
 #pragma unroll
-                    for (int s = 0; s < 16; s++) {
-                        const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                           ((s & 8) ? go[3] : 0u);
-                        a[s] = cmul(a[s], ((g >> op.gbit) & 1u) ? d1 : d0);
-                    }
-                    break;
+                for (int s = 0; s < 16; s++) {
+                    const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
+                                       ((s & 8) ? go[3] : 0u);
+                    dst[g] = a[s];
                 }
-            }
-        }
-        if (VEC) {
-#pragma unroll
-            for (int s = 0; s < 16; s += 2) {
-                const uint32_t g = gb | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) | ((s & 8) ? go[3] : 0u);
-                stv(dst + g, a[s], a[s + 1]);
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < 16; s++) {
-                const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                   ((s & 8) ? go[3] : 0u);
-                dst[g] = a[s];
             }
         }
         if (do_red || do_chunks) {
@@ -395,19 +495,16 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
 #pragma unroll
             for (int s = 0; s < 16; s++) w[s] = a[s].x * a[s].x + a[s].y * a[s].y;
             gb_last = gb;
-            if (do_red && red_fast) {
+            if (do_red) {
+                rel_accumulate_dyn<T>(rel, w, red_case);
+                if (!red_fast) {   // base bin changes with the iteration: fold the relative bins now
+                    const uint32_t bb = ((gb & base_mask0) ? 1u : 0u) | ((gb & base_mask1) ? 2u : 0u);
 #pragma unroll
-                for (int s = 0; s < 16; s++) acc[s] += w[s];
-            } else if (do_red) {
+                    for (int j = 0; j < 4; j++) {
 #pragma unroll
-                for (int s = 0; s < 16; s++) {
-                    const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                       ((s & 8) ? go[3] : 0u);
-                    const uint32_t bin = ((g >> rq0) & 1u) | (rq1 >= 0 ? (((g >> rq1) & 1u) << 1) : 0u);
-                    p0 += bin == 0 ? w[s] : (T)0;
-                    p1 += bin == 1 ? w[s] : (T)0;
-                    p2 += bin == 2 ? w[s] : (T)0;
-                    p3 += bin == 3 ? w[s] : (T)0;
+                        for (int b = 0; b < 4; b++) p[b] += ((j | bb) == (uint32_t)b) ? rel[j] : (T)0;
+                        rel[j] = 0;
+                    }
                 }
             }
             if (do_chunks) {
@@ -440,18 +537,14 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
     }
     if (do_red) {
         if (red_fast) {
+            const uint32_t bb = ((gb_last & base_mask0) ? 1u : 0u) | ((gb_last & base_mask1) ? 2u : 0u);
 #pragma unroll
-            for (int s = 0; s < 16; s++) {
-                const uint32_t g = gb_last | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                   ((s & 8) ? go[3] : 0u);
-                const uint32_t bin = ((g >> rq0) & 1u) | (rq1 >= 0 ? (((g >> rq1) & 1u) << 1) : 0u);
-                p0 += bin == 0 ? acc[s] : (T)0;
-                p1 += bin == 1 ? acc[s] : (T)0;
-                p2 += bin == 2 ? acc[s] : (T)0;
-                p3 += bin == 3 ? acc[s] : (T)0;
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) p[b] += ((j | bb) == (uint32_t)b) ? rel[j] : (T)0;
             }
         }
-        double d[4] = {(double)p0, (double)p1, (double)p2, (double)p3};
+        double d[4] = {(double)p[0], (double)p[1], (double)p[2], (double)p[3]};
 #pragma unroll
         for (int b = 0; b < 4; b++)
             for (int o = 16; o > 0; o >>= 1) d[b] += __shfl_down_sync(0xffffffffu, d[b], o);
@@ -461,24 +554,204 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
         }
         __syncthreads();
         if (tid < 4) {
-            double acc = 0;
-            for (int w = 0; w < DT / 32; w++) acc += s_red[w][tid];
-            args.partials[((uint64_t)N.dst_slot * args.part_stride + part) * 4u + tid] = acc;
+            double accd = 0;
+            for (int w = 0; w < DT / 32; w++) accd += s_red[w][tid];
+            args.partials[((uint64_t)N.dst_slot * args.part_stride + part) * 4u + tid] = accd;
         }
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (same stream convention as kernels.cu / include/qcdsim.h)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 draw(uint64_t seed, uint32_t circuit, uint64_t shot, uint32_t stream) {
+    return philox4x32_10(make_uint4((uint32_t)shot, (uint32_t)(shot >> 32), stream, circuit),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ double u53(uint4 w) {
+    const uint64_t x = ((uint64_t)w.y << 32) | (uint64_t)w.x;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ uint32_t upper_search(const double* arr, uint32_t lo, uint32_t hi, double target) {
+    uint32_t a = lo, b = hi;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (arr[mid] > target) b = mid;
+        else a = mid + 1;
+    }
+    return a < hi ? a : hi - 1;
+}
+
+constexpr int SN_WARPS = 4;
+
+// Measurement sampling for NODE_NOSTORE leaves.  Phase 1 (per thread): locate the trajectory's chunk from the scanned
+// chunk sums the final sweep wrote.  Phase 2 (per warp, one trajectory at a time): stage the leaf's sweep, let lane g
+// recompute register group g of that chunk from the PARENT state, scatter the |amplitude|^2 of the chunk's 32 elements
+// into shared memory in index order, warp-shuffle prefix sum, ballot pick.
+template <typename T>
+__global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
+    DevProgram<T> prog, const NodeRec* leaves, const void* states, uint64_t slot_stride, const double* chunk_sums,
+    uint64_t chunk_stride, const double* block_sums, uint64_t block_stride, uint32_t n_chunks, int n_bits,
+    const uint32_t* owner, const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
+    uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin) {
+    typedef typename Cx<T>::C C;
+    __shared__ Staged<T> S_all[SN_WARPS];
+    __shared__ double s_w[SN_WARPS][32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    Staged<T>& S = S_all[wid];
+
+    bool live = i < n_traj;
+    NodeRec nd;
+    memset(&nd, 0, sizeof(nd));
+    uint64_t shot = 0;
+    uint32_t c = 0;
+    double target = 0.0;
+    if (live) {
+        nd = leaves[owner[i]];
+        live = (nd.flags & NODE_LEAF) && (nd.flags & NODE_NOSTORE);
+    }
+    if (live) {
+        shot = shots[i];
+        const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
+        const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
+        const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
+        target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+        const uint32_t b = upper_search(bs, 0, n_blocks, target);
+        if (b > 0) target -= bs[b - 1];
+        const uint32_t cbeg = b << SCAN_BLOCK_LOG;
+        const uint32_t cend = min(cbeg + (1u << SCAN_BLOCK_LOG), n_chunks);
+        c = upper_search(cs, cbeg, cend, target);
+        if (c > cbeg) target -= cs[c - 1];
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, live);
+    uint32_t e_sel = 0;
+    while (todo) {
+        const int srcl = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t sweep_j = __shfl_sync(0xffffffffu, nd.sweep, srcl);
+        const uint32_t branch_j = __shfl_sync(0xffffffffu, nd.branch, srcl);
+        const double scale_j = __shfl_sync(0xffffffffu, nd.scale, srcl);
+        const uint32_t pslot_j = __shfl_sync(0xffffffffu, nd.src_slot, srcl);
+        const uint32_t c_j = __shfl_sync(0xffffffffu, c, srcl);
+        const double t_j = __shfl_sync(0xffffffffu, target, srcl);
+        __syncwarp();
+        stage_sweep<T, 32, true>(S, prog, sweep_j, branch_j, scale_j, lane);
+        uint32_t go[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) go[k] = 1u << S.D.rbit[k];
+        const uint32_t regmask = go[0] | go[1] | go[2] | go[3];
+        int r_low = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) r_low += (S.D.rbit[k] < CHUNK_LOG) ? 1 : 0;
+        const uint32_t n_groups = 1u << (CHUNK_LOG - r_low);
+        const uint32_t chunk_base = c_j << CHUNK_LOG;
+        if (lane < n_groups) {
+            // group base: chunk base with the register bits cleared, lane bits deposited on the non-register low bits
+            uint32_t low = 0, lb = lane;
+            for (int b = 0; b < CHUNK_LOG; b++)
+                if (!((regmask >> b) & 1u)) {
+                    low |= (lb & 1u) << b;
+                    lb >>= 1;
+                }
+            const uint32_t gb = (chunk_base & ~regmask) | low;
+            const C* src = reinterpret_cast<const C*>(states) + (uint64_t)pslot_j * slot_stride;
+            C a[16];
+            load_group<T, false>(a, S, src, gb, go, regmask, (T)scale_j, (S.D.flags & SW_PREP) != 0, S.scale_op < 0);
+            apply_sweep<T>(a, S, S.D.nops, gb, go);
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
+                                   ((s & 8) ? go[3] : 0u);
+                if ((g >> CHUNK_LOG) == c_j) s_w[wid][g & 31u] = (double)(a[s].x * a[s].x + a[s].y * a[s].y);
+            }
+        }
+        __syncwarp();
+        // inclusive prefix over the chunk in index order
+        double acc = s_w[wid][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double nb = __shfl_up_sync(0xffffffffu, acc, o);
+            if (lane >= (uint32_t)o) acc += nb;
+        }
+        const uint32_t hit = __ballot_sync(0xffffffffu, acc > t_j);
+        const uint32_t pick = hit ? (uint32_t)(__ffs(hit) - 1) : 31u;
+        if ((int)lane == srcl) e_sel = pick;
+    }
+    if (!live) return;
+    uint32_t x = (c << CHUNK_LOG) + e_sel;
+    if (flip) {
+        const double* fc = flip + (uint64_t)nd.circuit * n_bits * 2u;
+        for (int blk = 0; blk * 4 < n_bits; blk++) {
+            const uint4 w = draw(seed, nd.circuit, shot, QCD_STREAM_READOUT + blk);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = blk * 4 + j;
+                if (q < n_bits) {
+                    const uint32_t bit = (x >> q) & 1u;
+                    if ((double)ww[j] * (1.0 / 4294967296.0) < fc[q * 2 + bit]) x ^= 1u << q;
+                }
+            }
+        }
+    }
+    if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
+    if (outcomes) outcomes[(uint64_t)nd.circuit * shots_per_circuit + shot - shot_begin] = x;
+}
+
 }  // namespace
+
+template <typename T, bool VEC>
+static void launch_kind(const DevProgram<T>& prog, const SweepArgs& a, cudaStream_t st) {
+    switch (a.direct_kind) {
+        case 0: sweep_direct_kernel<T, VEC, 0><<<a.n_items, DT, 0, st>>>(prog, a); break;
+        case 1: sweep_direct_kernel<T, VEC, 1><<<a.n_items, DT, 0, st>>>(prog, a); break;
+        case 2: sweep_direct_kernel<T, VEC, 2><<<a.n_items, DT, 0, st>>>(prog, a); break;
+        default: sweep_direct_kernel<T, VEC, 3><<<a.n_items, DT, 0, st>>>(prog, a); break;
+    }
+}
 
 template <typename T>
 void launch_sweep_direct(const DevProgram<T>& prog, const SweepArgs& a, cudaStream_t st) {
     // direct_vec: index bit 0 is a register bit of EVERY sweep in this launch (128-bit accesses); the scalar variant
-    // is correct for any sweep
-    if (a.direct_vec) sweep_direct_kernel<T, true><<<a.n_items, DT, 0, st>>>(prog, a);
-    else sweep_direct_kernel<T, false><<<a.n_items, DT, 0, st>>>(prog, a);
+    // is correct for any sweep.  direct_kind: see sweep_direct_kernel.
+    if (a.direct_vec) launch_kind<T, true>(prog, a, st);
+    else launch_kind<T, false>(prog, a, st);
+}
+
+template <typename T>
+void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, const void* states, uint64_t slot_stride,
+                           const double* chunk_sums, uint64_t chunk_stride, const double* block_sums,
+                           uint64_t block_stride, uint32_t n_chunks, int n_bits, const uint32_t* owner,
+                           const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
+                           uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin, cudaStream_t st) {
+    if (!n_traj) return;
+    const uint32_t bs = 32 * SN_WARPS;
+    sample_nostore_kernel<T><<<(n_traj + bs - 1) / bs, bs, 0, st>>>(prog, leaves, states, slot_stride, chunk_sums,
+                                                                    chunk_stride, block_sums, block_stride, n_chunks,
+                                                                    n_bits, owner, shots, n_traj, seed, flip, hist,
+                                                                    outcomes, shots_per_circuit, shot_begin);
 }
 
 template void launch_sweep_direct<float>(const DevProgram<float>&, const SweepArgs&, cudaStream_t);
 template void launch_sweep_direct<double>(const DevProgram<double>&, const SweepArgs&, cudaStream_t);
+template void launch_sample_nostore<float>(const DevProgram<float>&, const NodeRec*, const void*, uint64_t, const double*,
+                                           uint64_t, const double*, uint64_t, uint32_t, int, const uint32_t*,
+                                           const uint32_t*, uint32_t, uint64_t, const double*, uint32_t*, uint32_t*,
+                                           uint64_t, uint64_t, cudaStream_t);
+template void launch_sample_nostore<double>(const DevProgram<double>&, const NodeRec*, const void*, uint64_t,
+                                            const double*, uint64_t, const double*, uint64_t, uint32_t, int,
+                                            const uint32_t*, const uint32_t*, uint32_t, uint64_t, const double*,
+                                            uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);
 
 }  // namespace qcd
