@@ -313,11 +313,11 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
                     par ^= ((gb & mb) == mb) ? S.sign_pat[off + t] : 0u;
                 }
 #pragma unroll
-                for (int s = 0; s < 16; s++)
-                    if ((par >> s) & 1u) {
-                        a[s].x = -a[s].x;
-                        a[s].y = -a[s].y;
-                    }
+                for (int s = 0; s < 16; s++) {   // branch-free: a select + two multiplies per value
+                    const auto sg = ((par >> s) & 1u) ? (decltype(a[s].x))-1 : (decltype(a[s].x))1;
+                    a[s].x *= sg;
+                    a[s].y *= sg;
+                }
                 break;
             }
             default: {  // C_D1
@@ -368,6 +368,64 @@ __device__ __forceinline__ void load_group(typename Cx<T>::C (&a)[16], const Sta
         for (int s = 0; s < 16; s++) {
             a[s].x *= sc;
             a[s].y *= sc;
+        }
+    }
+}
+
+// Probability chunk sums of one warp-iteration.  w[s] = |amplitude|^2 of this thread's 16 values.  The 32-element chunk
+// bits are R_LOW register bits (the lowest register indices) + the lowest (5 - R_LOW) lane bits.
+//   (1) fold the R_LOW register bits in-thread: L = 16 >> R_LOW live partial sums per thread (distinct chunks);
+//   (2) butterfly reduce-scatter over the G = 5 - R_LOW lane bits: while more than one value is live, lane bit k decides
+//       which half of the values a lane keeps (it adds its partner's copy of that half) -- L-1 shuffles instead of
+//       L*G; remaining lane bits are plain xor-reductions;
+//   (3) every lane ends up owning max(1, L >> G) chunk sums and stores them (lanes whose unused bits are 0).
+template <int R_LOW, typename T>
+__device__ __forceinline__ void chunk_sums(T (&w)[16], double* csum, uint32_t gb, const uint32_t (&go)[4], uint32_t lane) {
+#pragma unroll
+    for (int i = 0; i < R_LOW; i++) {
+#pragma unroll
+        for (int s = 0; s < 16; s++)
+            if (!(s & (1 << i))) w[s] += w[s | (1 << i)];
+    }
+    constexpr int L = 16 >> R_LOW;       // live values: s = j << R_LOW
+    constexpr int G = CHUNK_LOG - R_LOW;  // lane bits inside the chunk
+    T v[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) v[j] = w[j << R_LOW];
+    int cur = L;          // compile-time after unrolling
+    uint32_t sel = 0;     // which original live index this lane's v[0..cur) block starts at
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        const bool up = (lane >> k) & 1u;
+        if (cur > 1) {
+            const int half = cur >> 1;
+#pragma unroll
+            for (int j = 0; j < L / 2; j++) {
+                if (j < half) {
+                    const T send = up ? v[j] : v[j + half];
+                    const T recv = __shfl_xor_sync(0xffffffffu, send, 1 << k);
+                    const T keep = up ? v[j + half] : v[j];
+                    v[j] = keep + recv;
+                }
+            }
+            sel += up ? (uint32_t)half : 0u;
+            cur = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1 << k);
+        }
+    }
+    // lane bits consumed by plain reductions (k >= log2 L) must be zero for the writer
+    constexpr int LOG_L = L == 16 ? 4 : (L == 8 ? 3 : (L == 4 ? 2 : (L == 2 ? 1 : 0)));
+    constexpr uint32_t plain_mask = G > LOG_L ? (((1u << G) - 1u) & ~((1u << LOG_L) - 1u)) : 0u;
+    if ((lane & plain_mask) == 0) {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            if (j < cur) {
+                const uint32_t sidx = (sel + (uint32_t)j) << R_LOW;   // original value index (low R_LOW bits clear)
+                const uint32_t g = (gb & ~((1u << CHUNK_LOG) - 1u)) | ((sidx & 1u) ? go[0] : 0u) | ((sidx & 2u) ? go[1] : 0u) |
+                                   ((sidx & 4u) ? go[2] : 0u) | ((sidx & 8u) ? go[3] : 0u);
+                csum[g >> CHUNK_LOG] = (double)v[j];
+            }
         }
     }
 }
@@ -508,29 +566,12 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
                 }
             }
             if (do_chunks) {
-                // (1) fold the register bits that lie inside the 32-amplitude chunk (they are the lowest register
-                //     indices: rbit is ascending); live values afterwards: s with the low r_low bits clear
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < r_low) {
-#pragma unroll
-                        for (int s = 0; s < 16; s++)
-                            if (!(s & (1 << i))) w[s] += w[s | (1 << i)];
-                    }
-                }
-                // (2) the other chunk bits are the lowest (5 - r_low) lane bits
-                const int lane_bits = CHUNK_LOG - r_low;
-#pragma unroll
-                for (int s = 0; s < 16; s++) {
-                    if (s & ((1 << r_low) - 1)) continue;
-                    T vt = w[s];   // <= 32 terms: accumulate in the state's own precision, store as double
-                    for (int o = 1; o < (1 << lane_bits); o <<= 1) vt += __shfl_xor_sync(0xffffffffu, vt, o);
-                    const double v = (double)vt;
-                    if ((tid & ((1u << lane_bits) - 1u)) == 0) {
-                        const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
-                                           ((s & 8) ? go[3] : 0u);
-                        csum[g >> CHUNK_LOG] = v;
-                    }
+                switch (r_low) {
+                    case 0: chunk_sums<0, T>(w, csum, gb, go, tid & 31u); break;
+                    case 1: chunk_sums<1, T>(w, csum, gb, go, tid & 31u); break;
+                    case 2: chunk_sums<2, T>(w, csum, gb, go, tid & 31u); break;
+                    case 3: chunk_sums<3, T>(w, csum, gb, go, tid & 31u); break;
+                    default: chunk_sums<4, T>(w, csum, gb, go, tid & 31u); break;
                 }
             }
         }
