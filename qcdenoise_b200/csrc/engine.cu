@@ -83,6 +83,7 @@ struct qcd_ctx {
     int table_cap_log2 = 22;
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
     bool use_direct = true;      // register-only kernel for single-pass sweeps
+    bool no_slots = false;
     uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
     // programs (host copy of the IR; compiled lazily per (mode, precision))
     int n_qubits = 0, n_circuits = 0;
@@ -341,6 +342,7 @@ struct SvRunner {
         a.direct_vec = 0;
         a.desc_from_pad = 0;
         a.direct_kind = 3;
+        a.no_slots = ctx->no_slots ? 1 : 0;
         return a;
     }
 
@@ -725,6 +727,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
                 a.direct_vec = lvl_vec[l] ? 1 : 0;
                 a.desc_from_pad = 1;
                 a.direct_kind = 0;
+                a.no_slots = ctx->no_slots ? 1 : 0;
                 if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
                 launch_sweep_direct<T>(prog, a, st);
                 if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -771,6 +774,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             a.direct_vec = 0;
             a.desc_from_pad = 0;
             a.direct_kind = 3;
+            a.no_slots = 0;
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
             launch_sweep<T>(prog, a, k, st);
             if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
@@ -888,6 +892,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     } else if (k == "max_slots") ctx->max_slots = (uint64_t)value;
     else if (k == "use_direct") ctx->use_direct = value != 0;
     else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
+    else if (k == "no_slots") ctx->no_slots = value != 0;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }

@@ -66,6 +66,7 @@ struct SweepArgs {
     uint32_t part_stride;    // partials: [slot][part_stride][4]; a launch writes tiles (or CTAs-per-state) of them
     uint32_t direct_vec;     // direct kernel: every sweep of the launch has index bit 0 as a register bit
     uint32_t desc_from_pad;  // direct kernel: descriptor index = node.pad (per-pass launches) instead of node.sweep
+    uint32_t no_slots;       // direct kernel: disable the slotted fast path (tuning / A-B only)
     uint32_t direct_kind;    // direct kernel variant: 0 plain (+prep), 1 inner (reduction), 2 final (chunk sums), 3 generic
 };
 

@@ -176,6 +176,9 @@ struct Staged {
     uint32_t kind_flags[MAX_DIRECT_OPS];  // 0 complex, 1 real, 2 real diagonal
     uint32_t code[MAX_DIRECT_OPS];        // pre-decoded op: one jump-table dispatch per op in the streaming loop
     int scale_op;                    // matrix op that carries the node's rescale factor (-1: none)
+    uint32_t slots;                  // slotted fast path: 8 nibbles = op index of the real 2x2 on register bit r before
+                                     // (nibbles 0..3) / after (4..7) the sign layer, 0xF = none;  0 = shape not slotted
+    uint32_t sign_code;              // code word of the sign layer of the slotted shape (0: none)
     C prep[64];                      // prep sweeps: (alpha, beta) per index bit
     C prep_reg[16];                  // ... and the 16 products over the register bits
 };
@@ -259,6 +262,31 @@ __device__ __forceinline__ void stage_sweep(Staged<T>& S, const DevProgram<T>& p
         else code = C_D1 | ((uint32_t)op.gbit << 8);
         S.code[o] = code;
     }
+    group_sync<WARP>();
+    if (tid == 0) {
+        // Slotted shape: [real 2x2 ops on DISTINCT register bits] [one sign layer] [real 2x2 ops on distinct register
+        // bits].  The ops of one side commute, so the streaming loop can run them in register-bit order with a
+        // uniform predicate per slot instead of a jump-table dispatch per op.
+        uint32_t slots = 0xFFFFFFFFu, sign_code = 0;
+        bool ok = true;
+        int phase = 0;
+        for (int o = 0; o < nops && ok; o++) {
+            const uint32_t code = S.code[o] & 0xffu;
+            if (code == C_SIGNS) {
+                if (phase == 1) ok = false;
+                phase = 1;
+                sign_code = S.code[o];
+            } else if (code < C_M1C) {   // real diagonal or real 2x2
+                const int slot = phase * 4 + (int)(code & 3u);
+                if (((slots >> (4 * slot)) & 0xFu) != 0xFu) ok = false;
+                slots = (slots & ~(0xFu << (4 * slot))) | ((uint32_t)o << (4 * slot));
+            } else {
+                ok = false;
+            }
+        }
+        S.slots = ok ? slots : 0u;
+        S.sign_code = ok ? sign_code : 0u;
+    }
     if (is_prep) {
         for (uint32_t sidx = tid; sidx < 16; sidx += NT) {
             C v;
@@ -270,6 +298,22 @@ __device__ __forceinline__ void stage_sweep(Staged<T>& S, const DevProgram<T>& p
         }
     }
     group_sync<WARP>();
+}
+
+template <typename T>
+__device__ __forceinline__ void apply_signs(typename Cx<T>::C (&a)[16], const Staged<T>& S, uint32_t code, uint32_t gb) {
+    const uint32_t cnt = (code >> 8) & 0xffu, off = code >> 16;
+    uint32_t par = 0;
+    for (uint32_t t = 0; t < cnt; t++) {
+        const uint32_t mb = S.sign_base[off + t];
+        par ^= ((gb & mb) == mb) ? S.sign_pat[off + t] : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const auto sg = ((par >> s) & 1u) ? (decltype(a[s].x))-1 : (decltype(a[s].x))1;
+        a[s].x *= sg;
+        a[s].y *= sg;
+    }
 }
 
 // All fused ops of the sweep on one register group (gb = its base index, register bits clear).
@@ -305,21 +349,9 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
             case C_M2C + 3: m2<1, 2>(a, mt); break;
             case C_M2C + 4: m2<1, 3>(a, mt); break;
             case C_M2C + 5: m2<2, 3>(a, mt); break;
-            case C_SIGNS: {
-                const uint32_t cnt = (code >> 8) & 0xffu, off = code >> 16;
-                uint32_t par = 0;
-                for (uint32_t t = 0; t < cnt; t++) {
-                    const uint32_t mb = S.sign_base[off + t];
-                    par ^= ((gb & mb) == mb) ? S.sign_pat[off + t] : 0u;
-                }
-#pragma unroll
-                for (int s = 0; s < 16; s++) {   // branch-free: a select + two multiplies per value
-                    const auto sg = ((par >> s) & 1u) ? (decltype(a[s].x))-1 : (decltype(a[s].x))1;
-                    a[s].x *= sg;
-                    a[s].y *= sg;
-                }
+            case C_SIGNS:
+                apply_signs<T>(a, S, code, gb);
                 break;
-            }
             default: {  // C_D1
                 const C d0 = mt[0], d1 = mt[1];
                 const uint32_t gbit = (code >> 8) & 0xffu;
@@ -333,6 +365,22 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
             }
         }
     }
+}
+
+// Slotted fast path (see stage_sweep): `slots` != 0.
+template <typename T>
+__device__ __forceinline__ void apply_slotted(typename Cx<T>::C (&a)[16], const Staged<T>& S, uint32_t slots,
+                                              uint32_t sign_code, uint32_t gb) {
+    uint32_t o;
+    o = slots & 0xFu;          if (o != 0xFu) m1r<0>(a, S.mats[o]);
+    o = (slots >> 4) & 0xFu;   if (o != 0xFu) m1r<1>(a, S.mats[o]);
+    o = (slots >> 8) & 0xFu;   if (o != 0xFu) m1r<2>(a, S.mats[o]);
+    o = (slots >> 12) & 0xFu;  if (o != 0xFu) m1r<3>(a, S.mats[o]);
+    if (sign_code) apply_signs<T>(a, S, sign_code, gb);
+    o = (slots >> 16) & 0xFu;  if (o != 0xFu) m1r<0>(a, S.mats[o]);
+    o = (slots >> 20) & 0xFu;  if (o != 0xFu) m1r<1>(a, S.mats[o]);
+    o = (slots >> 24) & 0xFu;  if (o != 0xFu) m1r<2>(a, S.mats[o]);
+    o = (slots >> 28) & 0xFu;  if (o != 0xFu) m1r<3>(a, S.mats[o]);
 }
 
 // The 16 amplitudes of register group gb BEFORE the sweep's ops: product state (prep sweeps) or the parent state.
@@ -484,6 +532,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
     const T sc = (T)N.scale;
     const bool is_prep = HAS_PREP && (D.flags & SW_PREP) != 0, need_scale = S.scale_op < 0;
     const int nops = D.nops;
+    const uint32_t slots = args.no_slots ? 0u : S.slots, sign_code = S.sign_code;
     const uint32_t groups_per_cta = 1u << (n_bits - 4 - (int)args.tiles_log2);
     const uint32_t grp0 = part * groups_per_cta;
     const int rq0 = D.red_q[0], rq1 = D.red_q[1];
@@ -531,7 +580,8 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
         gb = ((gb & ~(go[3] - 1u)) << 1) | (gb & (go[3] - 1u));
         C a[16];
         load_group<T, VEC>(a, S, src, gb, go, regmask, sc, is_prep, need_scale);
-        apply_sweep<T>(a, S, nops, gb, go);
+        if (slots) apply_slotted<T>(a, S, slots, sign_code, gb);
+        else apply_sweep<T>(a, S, nops, gb, go);
         if (store) {
             if (VEC) {
 #pragma unroll
@@ -709,7 +759,8 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
             const C* src = reinterpret_cast<const C*>(states) + (uint64_t)pslot_j * slot_stride;
             C a[16];
             load_group<T, false>(a, S, src, gb, go, regmask, (T)scale_j, (S.D.flags & SW_PREP) != 0, S.scale_op < 0);
-            apply_sweep<T>(a, S, S.D.nops, gb, go);
+            if (S.slots) apply_slotted<T>(a, S, S.slots, S.sign_code, gb);
+            else apply_sweep<T>(a, S, S.D.nops, gb, go);
 #pragma unroll
             for (int s = 0; s < 16; s++) {
                 const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
