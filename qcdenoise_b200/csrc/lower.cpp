@@ -866,6 +866,7 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
             if (pbs.size() == 1 && si != 0) {
                 // single-pass sweep -> direct (register-only) kernel: pad with the LOWEST free bits, so that a thread's
                 // 16 amplitudes contain contiguous runs (128-bit accesses) and whole probability chunks
+                if ((int)pb.R.size() < nreg) pb.R.insert(0);   // index bit 0 first: 128-bit accesses
                 for (int h = 0; h < 2; h++) {
                     const int lb = s.red_q[h] >= 0 ? local_bit(t, s.red_q[h]) : -1;
                     if (lb >= 0 && (int)pb.R.size() < nreg) pb.R.insert(lb);
