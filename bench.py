@@ -290,12 +290,12 @@ def main():
     peak, peak_src = measured_hbm_peak()
     achieved = agg["sweep_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9 if agg["sweep_ms"] > 0 else None
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01j_traffic.json")
     if os.path.exists(tp):   # DRAM bytes per algorithmic byte of this kernel, from the committed ncu --set full capture
         with open(tp) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_per_algorithmic_byte"] * agg["sweep_bytes"] / max(agg["sweep_launches"], 1)
-        traffic_src = "profiles/r01g_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per algorithmic byte) x bytes_per_launch"
+        traffic_src = "profiles/r01j_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per algorithmic byte) x bytes_per_launch"
     roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (+ qcd::sweep_kernel<float> for prep sweeps)",
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,13 @@ using namespace qcd;
 namespace {
 
 thread_local std::string g_create_error;
+
+struct Trace {
+    bool on = getenv("QCD_TRACE") != nullptr;
+    double t_sync = 0, t_h2d = 0, t_total = 0;
+    int n_sync = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} g_trace;
 
 struct DevBuf {
     void* p = nullptr;
@@ -446,13 +454,17 @@ struct SvRunner {
         launch_child_scale<T>(prog, ctx->children.as<NodeRec>(), max_children, ctx->counter.as<uint32_t>() + 1, P, st);
         ctx->stats.aux_launches += 7;
         uint32_t totals[2] = {0, 0};
+        double tt0 = g_trace.on ? Trace::now() : 0;
         CU(cudaMemcpyAsync(totals, ctx->counter.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (g_trace.on) { g_trace.t_sync += Trace::now() - tt0; g_trace.n_sync++; }
         const uint32_t n_children = totals[1];
         if (n_children == 0) return fail(ctx, QCD_E_CUDA, "internal: inner nodes produced no children");
         std::vector<NodeRec> ch(n_children);
+        tt0 = g_trace.on ? Trace::now() : 0;
         CU(cudaMemcpyAsync(ch.data(), ctx->children.p, (size_t)n_children * sizeof(NodeRec), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (g_trace.on) g_trace.t_h2d += Trace::now() - tt0;
 
         // ---- sweep the children in chunks; finish each chunk's subtree before the next
         size_t pos = 0;
@@ -638,7 +650,14 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
         ctx->stats.trajectories += g1 - g0;
         g0 = g1;
     }
+    double tt1 = g_trace.on ? Trace::now() : 0;
     CU(cudaStreamSynchronize(st));
+    if (g_trace.on) {
+        fprintf(stderr, "[qcd trace] run_sv: wait-for-decide %.2f ms in %d syncs, child readback %.2f ms, final drain %.2f ms\n",
+                g_trace.t_sync * 1e3, g_trace.n_sync, g_trace.t_h2d * 1e3, (Trace::now() - tt1) * 1e3);
+        g_trace.t_sync = g_trace.t_h2d = 0;
+        g_trace.n_sync = 0;
+    }
     return finish_timing(ctx);
 }
 
