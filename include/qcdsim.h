@@ -155,6 +155,14 @@ QCD_API int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs
 QCD_API int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_qubits, const uint32_t* masks,
                       int n_masks, int per_vector_masks, int64_t* signed_sums, int64_t* totals, void* stream);
 
+/* Same reduction on per-shot outcome lists (the sparse form used when 2^n histograms are too large, n > 26):
+ *   outcomes [dev] [n_vectors][shots_per_vector] uint32 basis indices (as written by qcd_run_sv_trajectories) ->
+ *   signed_sums [dev] [n_vectors][n_masks] int64 = sum_shots (-1)^popcount(x & mask);  mean = signed / shots.
+ * Replaces witnesses.py:40-67 where the reference would need 2^n-entry diagonals.  Asynchronous. */
+QCD_API int qcd_parity_outcomes(qcd_ctx* ctx, const uint32_t* outcomes, int n_vectors, uint64_t shots_per_vector,
+                                const uint32_t* masks, int n_masks, int per_vector_masks, int64_t* signed_sums,
+                                void* stream);
+
 /* Same reduction on exact probabilities (float/double by precision): expvals [dev] [n_vectors][n_masks] double =
  * sum_x p[x] D_mask[x], accumulated in double with a fixed reduction order (deterministic). Asynchronous. */
 QCD_API int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,

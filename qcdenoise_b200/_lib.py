@@ -55,6 +55,7 @@ _PROTOS = {
                                              ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, _P, _P, _P]),
     "qcd_parity_counts": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P,
                                          _P]),
+    "qcd_parity_outcomes": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_uint64, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_parity_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int,
                                         ctypes.c_int, _P, _P]),
     "qcd_debug_schedule_json": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
@@ -66,12 +67,12 @@ _lib = None
 
 
 def load():
-    """Load libqcdsim.so (once).  Raises if it has not been built: run `python -m qcdenoise_b200.build`."""
+    """Load libqcdsim.so (once).  Raises if it has not been built: run `python qcdenoise_b200/build.py`."""
     global _lib
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} not found: build the CUDA engine first (python -m qcdenoise_b200.build); "
+        raise ImportError(f"{LIB_PATH} not found: build the CUDA engine first (python qcdenoise_b200/build.py); "
                           "qcdenoise_b200 has no CPU fallback")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _PROTOS.items():

@@ -1,7 +1,7 @@
 """Build libqcdsim.so (the C-ABI engine) in-tree with nvcc for sm_100a.  No JIT cache: the .so sits next to the
 sources so that it travels to the GPU box with the repository snapshot.
 
-    python -m qcdenoise_b200.build [--force]
+    python qcdenoise_b200/build.py [--force]
 """
 import os
 import subprocess

@@ -1102,6 +1102,26 @@ int qcd_parity_counts(qcd_ctx* ctx, const uint32_t* hist, int n_vectors, int n_q
     return QCD_OK;
 }
 
+int qcd_parity_outcomes(qcd_ctx* ctx, const uint32_t* outcomes, int n_vectors, uint64_t shots_per_vector,
+                        const uint32_t* masks, int n_masks, int per_vector_masks, int64_t* signed_sums, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (!outcomes || !masks || !signed_sums || n_vectors < 0 || n_masks < 1 || shots_per_vector > 0x7fffffffull)
+        return fail(ctx, QCD_E_INVALID, "bad arguments to qcd_parity_outcomes");
+    if (n_vectors == 0) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nm = (size_t)n_masks * (per_vector_masks ? n_vectors : 1);
+    std::vector<uint32_t> mk(masks, masks + nm);
+    int rc = upload_vec(ctx, ctx->masks, mk);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(signed_sums, 0, (size_t)n_vectors * n_masks * 8, st));
+    if (shots_per_vector)
+        launch_parity_outcomes(outcomes, n_vectors, shots_per_vector, ctx->masks.as<uint32_t>(), n_masks,
+                               per_vector_masks, (long long*)signed_sums, st);
+    CU(cudaGetLastError());
+    return QCD_OK;
+}
+
 int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
                      const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream) {
     if (!ctx) return QCD_E_INVALID;

@@ -629,6 +629,36 @@ __global__ void parity_counts_kernel(const uint32_t* hist, int n, const uint32_t
     }
 }
 
+// signed_sums[v][m] = sum over the shots of vector v of (-1)^popc(outcome & mask[m])   (sparse form of parity_counts)
+__global__ void parity_outcomes_kernel(const uint32_t* outcomes, uint64_t shots, const uint32_t* masks, int n_masks,
+                                       int per_vec, long long* signed_sums) {
+    const uint32_t v = blockIdx.y;
+    const uint32_t* o = outcomes + (uint64_t)v * shots;
+    const uint32_t* mk = masks + (per_vec ? (uint64_t)v * n_masks : 0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int m0 = 0; m0 < n_masks; m0 += PAR_GROUP) {
+        uint32_t mm[PAR_GROUP];
+        int acc[PAR_GROUP];
+#pragma unroll
+        for (int j = 0; j < PAR_GROUP; j++) {
+            mm[j] = (m0 + j < n_masks) ? mk[m0 + j] : 0u;
+            acc[j] = 0;
+        }
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < shots; i += stride) {
+            const uint32_t x = o[i];
+#pragma unroll
+            for (int j = 0; j < PAR_GROUP; j++) acc[j] += 1 - 2 * (__popc(x & mm[j]) & 1);
+        }
+#pragma unroll
+        for (int j = 0; j < PAR_GROUP; j++) {
+            int a = acc[j];
+            for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+            if ((threadIdx.x & 31) == 0 && m0 + j < n_masks && a != 0)
+                atomicAdd((unsigned long long*)(signed_sums + (uint64_t)v * n_masks + m0 + j), (unsigned long long)(long long)a);
+        }
+    }
+}
+
 // expvals from exact probabilities: per-CTA partial sums (fixed order), then a second kernel adds the partials in order
 template <typename T>
 __global__ void parity_probs_kernel(const T* probs, int n, const uint32_t* masks, int n_masks, int per_vec,
@@ -795,6 +825,18 @@ void launch_parity_counts(const uint32_t* hist, uint32_t n_vec, int n, const uin
         parity_counts_kernel<<<dim3(gx, ny), 256, 0, st>>>(hist + ((uint64_t)y0 << n), n,
                                                           masks + (per_vec ? (uint64_t)y0 * n_masks : 0), n_masks,
                                                           per_vec, signed_sums + (uint64_t)y0 * n_masks, totals + y0);
+    }
+}
+void launch_parity_outcomes(const uint32_t* outcomes, uint32_t n_vec, uint64_t shots, const uint32_t* masks, int n_masks,
+                            int per_vec, long long* signed_sums, cudaStream_t st) {
+    uint32_t gx = cdiv(shots, 256 * 4);
+    if (gx > 1184) gx = 1184;
+    if (gx < 1) gx = 1;
+    for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
+        uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
+        parity_outcomes_kernel<<<dim3(gx, ny), 256, 0, st>>>(outcomes + (uint64_t)y0 * shots, shots,
+                                                            masks + (per_vec ? (uint64_t)y0 * n_masks : 0), n_masks,
+                                                            per_vec, signed_sums + (uint64_t)y0 * n_masks);
     }
 }
 template <typename T>

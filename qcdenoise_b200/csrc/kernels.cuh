@@ -138,6 +138,8 @@ void launch_scan_vectors(uint32_t n_vec, double* chunk_sums, uint64_t chunk_stri
 // ---- parity
 void launch_parity_counts(const uint32_t* hist, uint32_t n_vec, int n, const uint32_t* masks, int n_masks,
                           int per_vec, long long* signed_sums, long long* totals, cudaStream_t st);
+void launch_parity_outcomes(const uint32_t* outcomes, uint32_t n_vec, uint64_t shots, const uint32_t* masks, int n_masks,
+                            int per_vec, long long* signed_sums, cudaStream_t st);
 template <typename T>
 void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* masks, int n_masks, int per_vec,
                          double* partial, uint32_t n_part, double* expvals, cudaStream_t st);

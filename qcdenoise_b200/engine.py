@@ -161,6 +161,17 @@ class Engine:
                                                    _ptr(tot), self._stream()))
         return ss, tot
 
+    def parity_outcomes(self, outcomes, masks):
+        """outcomes: int32 tensor [B, shots] of basis indices -> signed_sums int64 [B, M] (sparse form of
+        parity_counts for registers too wide for dense histograms)."""
+        n_vec, shots = outcomes.shape
+        m, n_masks, per = self._masks(masks, n_vec)
+        with torch.cuda.device(self.device):
+            ss = torch.empty((n_vec, n_masks), dtype=torch.int64, device=self.device)
+            self._check(self.lib.qcd_parity_outcomes(self._h, _ptr(outcomes), n_vec, shots, _ptr(m), n_masks, per,
+                                                     _ptr(ss), self._stream()))
+        return ss
+
     def parity_probs(self, probs, masks):
         n_vec, N = probs.shape
         n = N.bit_length() - 1

@@ -385,3 +385,15 @@ def test_dm_direct_and_tile_kernels_agree(eng):
     eng.set_option("use_direct", 1)
     np.testing.assert_allclose(a, b, atol=1e-13, rtol=0)
     np.testing.assert_allclose(a[0], sim.density_matrix_probs(batch[0], n), atol=1e-10, rtol=0)
+
+
+def test_parity_outcomes_matches_parity_counts(eng):
+    import torch
+    n = 12
+    rng = np.random.default_rng(3)
+    out = rng.integers(0, 2 ** n, size=(3, 5000)).astype(np.int32)
+    masks = rng.integers(0, 2 ** n, size=(3, 13)).astype(np.uint32)
+    ss = eng.parity_outcomes(torch.tensor(out, device="cuda"), masks).cpu().numpy()
+    hist = np.stack([np.bincount(o, minlength=2 ** n) for o in out]).astype(np.int32)
+    ref, tot = eng.parity_counts(torch.tensor(hist, device="cuda"), masks)
+    assert np.array_equal(ss, ref.cpu().numpy()) and tot.cpu().tolist() == [5000] * 3
