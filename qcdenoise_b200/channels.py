@@ -75,10 +75,10 @@ def thermal_relaxation_kraus(t1, t2, duration, p_excited=0.0):
     return ops
 
 
-def _avg_fidelity(kraus):
+def _process_fidelity(kraus):
     d = kraus[0].shape[0]
-    f_pro = sum(abs(np.trace(k)) ** 2 for k in kraus) / d ** 2
-    return (d * f_pro + 1.0) / (d + 1.0)
+    return sum(abs(k[0, 0] + k[1, 1]) ** 2 for k in kraus) / d ** 2 if d == 2 else \
+        sum(abs(np.trace(k)) ** 2 for k in kraus) / d ** 2
 
 
 def device_gate_error(n_gate_qubits, gate_error, gate_length_ns, t1_us, t2_us):
@@ -91,8 +91,12 @@ def device_gate_error(n_gate_qubits, gate_error, gate_length_ns, t1_us, t2_us):
         for t1, t2 in zip(t1_us, t2_us):
             t1n = t1 * 1e3
             relax.append(thermal_relaxation_kraus(t1n, min(t2 * 1e3, 2 * t1n), gate_length_ns))
-        joint = relax[0] if n_gate_qubits == 1 else [np.kron(b, a) for b in relax[1] for a in relax[0]]
-        f_relax = _avg_fidelity(joint)
+        # process fidelity of a tensor product of channels is the product of the factors' (tr(A (x) B) = tr A tr B)
+        f_pro = 1.0
+        for ks in relax:
+            f_pro *= _process_fidelity(ks)
+        dim_all = 2 ** n_gate_qubits
+        f_relax = (dim_all * f_pro + 1.0) / (dim_all + 1.0)
     probs = None
     if gate_error and gate_error > 0:
         dim = 2 ** n_gate_qubits

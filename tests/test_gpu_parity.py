@@ -397,3 +397,19 @@ def test_parity_outcomes_matches_parity_counts(eng):
     hist = np.stack([np.bincount(o, minlength=2 ** n) for o in out]).astype(np.int32)
     ref, tot = eng.parity_counts(torch.tensor(hist, device="cuda"), masks)
     assert np.array_equal(ss, ref.cpu().numpy()) and tot.cpu().tolist() == [5000] * 3
+
+
+def test_n28_ghz_outcomes_are_all_zero_or_all_one(eng):
+    """Maximum size of the BASELINE configs (n = 28, 2 GiB complex64 state): a GHZ ladder -- the legacy reference
+    circuit (circuit_constructors.py:1169-1192) -- may only produce 00...0 and 11...1; exercises 2^28 index
+    arithmetic, scattered high tile bits and multi-pass sweeps without a CPU oracle of that size."""
+    _reset_opts(eng)
+    n = 28
+    ops = [("h", (0,))] + [("cx", (q, q + 1)) for q in range(n - 1)]
+    eng.upload([_circ(n, ops)])
+    _, out = eng.run_trajectories(256, seed=3, precision=32, want_outcomes=True)
+    vals, counts = np.unique(out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, return_counts=True)
+    assert set(vals.tolist()) == {0, 2 ** n - 1}
+    assert abs(int(counts[0]) - 128) < 60          # a fair coin over 256 shots
+    ss = eng.parity_outcomes(out.reshape(1, -1), np.array([3, 2 ** n - 1, 1 | (1 << 27)], dtype=np.uint32)).cpu().numpy()[0]
+    assert ss[0] == 256 and ss[1] == 256 and ss[2] == 256      # Z_i Z_j = +1 for every pair, even-weight parity too
