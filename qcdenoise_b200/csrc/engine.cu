@@ -216,7 +216,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         const Pass& ps = P.passes[pi];
         const uint32_t nops = ps.op_end - ps.op_begin;
         if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) return;
-        uint32_t n_signs = 0;
+        uint32_t n_signs = 0, n_m4 = 0;
         for (uint32_t o = 0; o < nops; o++) {
             KOp op = P.kops[ps.op_begin + o];
             if (op.kind == K_SIGNS) {
@@ -224,7 +224,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
                 op.t1 = (uint8_t)n_signs;
                 n_signs += op.count;
             }
-            if (op.kind == K_M4) return;  // 16x16 superoperators stay on the tiled kernel
+            if (op.kind == K_M4 && (++n_m4 > 1 || op.sel_mask != 0)) return;  // one plain 16x16 superoperator per pass
             D.ops[o] = op;
         }
         D.ok = 1;
@@ -488,6 +488,7 @@ struct SvRunner {
                 need_red = need_red || D.red_q[0] >= 0;
                 need_chunks = need_chunks || (D.flags & SW_FINAL);
                 need_prep = need_prep || (D.flags & SW_PREP);
+                for (int o = 0; o < D.nops; o++) need_prep = need_prep || D.ops[o].kind == K_M4;   // forces the generic kind
             }
             uint64_t n_nostore = 0;
             if (direct && !is_root && ctx->nostore_max > 0) {

@@ -159,7 +159,8 @@ enum : uint32_t {
     C_M2R = 12,   // +pair real 4x4, pair index: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
     C_M2C = 18,   // +pair complex 4x4
     C_SIGNS = 24,
-    C_D1 = 25
+    C_D1 = 25,
+    C_M4 = 26     // 16x16 on the 4 register bits (density-matrix superoperators); bit 8: real coefficients
 };
 __device__ __forceinline__ uint32_t pair_index(int t0, int t1) {
     return t0 == 0 ? (uint32_t)(t1 - 1) : (t0 == 1 ? (uint32_t)(t1 + 1) : 5u);
@@ -171,6 +172,7 @@ struct Staged {
     typedef typename Cx<T>::C C;
     DirectSweep D;
     C mats[MAX_DIRECT_OPS][16];      // the selected variant of every matrix op
+    C m4[256];                       // the (single) 16x16 op of the pass, row-major
     uint32_t sign_base[MAX_SIGNS];   // part of each sign mask outside the register bits
     uint32_t sign_pat[MAX_SIGNS];    // per-value pattern of the part inside the register bits
     uint32_t kind_flags[MAX_DIRECT_OPS];  // 0 complex, 1 real, 2 real diagonal
@@ -225,8 +227,12 @@ __device__ __forceinline__ void stage_sweep(Staged<T>& S, const DevProgram<T>& p
             }
         } else {
             const C* m = prog.pool + op.off + ((branch >> op.sel_shift) & op.sel_mask) * op.stride;
-            const uint32_t cnt = op.kind == K_M1 ? 4u : (op.kind == K_M2 ? 16u : 2u);
-            for (uint32_t e = tid; e < cnt; e += NT) S.mats[o][e] = m[e];
+            if (op.kind == K_M4) {
+                for (uint32_t e = tid; e < 256u; e += NT) S.m4[e] = m[e];
+            } else {
+                const uint32_t cnt = op.kind == K_M1 ? 4u : (op.kind == K_M2 ? 16u : 2u);
+                for (uint32_t e = tid; e < cnt; e += NT) S.mats[o][e] = m[e];
+            }
         }
     }
     const bool is_prep = (S.D.flags & SW_PREP) != 0;
@@ -259,7 +265,11 @@ __device__ __forceinline__ void stage_sweep(Staged<T>& S, const DevProgram<T>& p
         if (kind == K_M1) code = (diag ? C_M1D : (real ? C_M1R : C_M1C)) + op.t0;
         else if (kind == K_M2) code = (real ? C_M2R : C_M2C) + pair_index(op.t0, op.t1);
         else if (kind == K_SIGNS) code = C_SIGNS | ((uint32_t)op.count << 8) | ((uint32_t)op.t1 << 16);
-        else code = C_D1 | ((uint32_t)op.gbit << 8);
+        else if (kind == K_M4) {
+            bool r4 = true;
+            for (int e = 0; e < 256; e++) r4 = r4 && S.m4[e].y == (T)0;
+            code = C_M4 | (r4 ? 0x100u : 0u);
+        } else code = C_D1 | ((uint32_t)op.gbit << 8);
         S.code[o] = code;
     }
     group_sync<WARP>();
@@ -319,7 +329,8 @@ __device__ __forceinline__ void apply_signs(typename Cx<T>::C (&a)[16], const St
 // All fused ops of the sweep on one register group (gb = its base index, register bits clear).
 template <typename T>
 __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const Staged<T>& S, int nops, uint32_t gb,
-                                            const uint32_t (&go)[4]) {
+                                            const uint32_t (&go)[4], typename Cx<T>::C* ybuf /*[16][stride] or null*/,
+                                            uint32_t ystride, uint32_t ytid) {
     typedef typename Cx<T>::C C;
     for (int o = 0; o < nops; o++) {
         const uint32_t code = S.code[o];
@@ -352,6 +363,33 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
             case C_SIGNS:
                 apply_signs<T>(a, S, code, gb);
                 break;
+            case C_M4: {
+                // y = M a with M 16x16: rows one at a time, results parked in this thread's private shared-memory
+                // column (dynamic row index), then read back into the registers
+                if (ybuf) {
+                    const bool r4 = (code & 0x100u) != 0;
+                    for (int r = 0; r < 16; r++) {
+                        const C* row = S.m4 + r * 16;
+                        C acc;
+                        acc.x = 0;
+                        acc.y = 0;
+                        if (r4) {
+#pragma unroll
+                            for (int c = 0; c < 16; c++) {
+                                acc.x += row[c].x * a[c].x;
+                                acc.y += row[c].x * a[c].y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 16; c++) cfma(acc, row[c], a[c]);
+                        }
+                        ybuf[r * ystride + ytid] = acc;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; c++) a[c] = ybuf[c * ystride + ytid];
+                }
+                break;
+            }
             default: {  // C_D1
                 const C d0 = mt[0], d1 = mt[1];
                 const uint32_t gbit = (code >> 8) & 0xffu;
@@ -513,6 +551,8 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
                    HAS_PREP = KIND == 0 || KIND == 3;
     __shared__ Staged<T> S;
     __shared__ double s_red[DT / 32][4];
+    constexpr bool HAS_M4 = KIND == 0 || KIND == 3;
+    __shared__ C s_ybuf[HAS_M4 ? 16 : 1][DT];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t node_idx = blockIdx.x >> args.tiles_log2;
@@ -581,7 +621,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
         C a[16];
         load_group<T, VEC>(a, S, src, gb, go, regmask, sc, is_prep, need_scale);
         if (slots) apply_slotted<T>(a, S, slots, sign_code, gb);
-        else apply_sweep<T>(a, S, nops, gb, go);
+        else apply_sweep<T>(a, S, nops, gb, go, HAS_M4 ? &s_ybuf[0][0] : nullptr, DT, tid);
         if (store) {
             if (VEC) {
 #pragma unroll
@@ -760,7 +800,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
             C a[16];
             load_group<T, false>(a, S, src, gb, go, regmask, (T)scale_j, (S.D.flags & SW_PREP) != 0, S.scale_op < 0);
             if (S.slots) apply_slotted<T>(a, S, S.slots, S.sign_code, gb);
-            else apply_sweep<T>(a, S, S.D.nops, gb, go);
+            else apply_sweep<T>(a, S, S.D.nops, gb, go, nullptr, 0, 0);
 #pragma unroll
             for (int s = 0; s < 16; s++) {
                 const uint32_t g = gb | ((s & 1) ? go[0] : 0u) | ((s & 2) ? go[1] : 0u) | ((s & 4) ? go[2] : 0u) |
