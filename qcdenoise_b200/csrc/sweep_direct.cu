@@ -409,16 +409,19 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
 template <typename T>
 __device__ __forceinline__ void apply_slotted(typename Cx<T>::C (&a)[16], const Staged<T>& S, uint32_t slots,
                                               uint32_t sign_code, uint32_t gb) {
-    uint32_t o;
-    o = slots & 0xFu;          if (o != 0xFu) m1r<0>(a, S.mats[o]);
-    o = (slots >> 4) & 0xFu;   if (o != 0xFu) m1r<1>(a, S.mats[o]);
-    o = (slots >> 8) & 0xFu;   if (o != 0xFu) m1r<2>(a, S.mats[o]);
-    o = (slots >> 12) & 0xFu;  if (o != 0xFu) m1r<3>(a, S.mats[o]);
+    // the pre-sign slots hold the Kraus variants: the no-jump operators are diagonal (two multipliers per pair)
+#define QCD_SLOT(shift, r)                                                   \
+    {                                                                        \
+        const uint32_t o = (slots >> (shift)) & 0xFu;                        \
+        if (o != 0xFu) {                                                     \
+            if (S.kind_flags[o] == 2u) m1d<r>(a, S.mats[o]);                 \
+            else m1r<r>(a, S.mats[o]);                                       \
+        }                                                                    \
+    }
+    QCD_SLOT(0, 0) QCD_SLOT(4, 1) QCD_SLOT(8, 2) QCD_SLOT(12, 3)
     if (sign_code) apply_signs<T>(a, S, sign_code, gb);
-    o = (slots >> 16) & 0xFu;  if (o != 0xFu) m1r<0>(a, S.mats[o]);
-    o = (slots >> 20) & 0xFu;  if (o != 0xFu) m1r<1>(a, S.mats[o]);
-    o = (slots >> 24) & 0xFu;  if (o != 0xFu) m1r<2>(a, S.mats[o]);
-    o = (slots >> 28) & 0xFu;  if (o != 0xFu) m1r<3>(a, S.mats[o]);
+    QCD_SLOT(16, 0) QCD_SLOT(20, 1) QCD_SLOT(24, 2) QCD_SLOT(28, 3)
+#undef QCD_SLOT
 }
 
 // The 16 amplitudes of register group gb BEFORE the sweep's ops: product state (prep sweeps) or the parent state.
