@@ -103,7 +103,16 @@ QCD_API int qcd_abi_version(void);
 QCD_API int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out);
 QCD_API void qcd_destroy(qcd_ctx* ctx);
 QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of the last failed qcd_create */
-QCD_API int qcd_set_option(qcd_ctx* ctx, const char* key, double value); /* "time_sweeps" 0/1, "tile_bits", "max_chunk" */
+/* Options (all optional; defaults in parentheses):
+ *   "time_sweeps" 0/1 (0)   record CUDA events around every sweep launch -> qcd_stats.sweep_ms
+ *   "tile_bits" 0|5..13 (0 = 13 complex64 / 12 complex128)   index bits of a shared-memory tile
+ *   "max_chunk" (2^25)      trajectories per tree; whole circuits are kept together when they fit
+ *   "max_slots" (0 = memory budget)   cap on resident states (exercises the depth-first schedule)
+ *   "table_cap_log2" (22)   size of the trajectory-grouping table
+ *   "use_direct" 0/1 (1)    register-only kernel for single-pass sweeps / density-matrix passes
+ *   "nostore_max" (8)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
+ *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements) */
+QCD_API int qcd_set_option(qcd_ctx* ctx, const char* key, double value);
 QCD_API int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
 
 /* Replaces: building `circuit` + `noise_model` and handing them to qk.execute (samplers.py:322-324).

@@ -180,7 +180,9 @@ __global__ void count_keys_kernel(const uint64_t* keys, uint32_t n_traj, int gbi
     const uint32_t active = __ballot_sync(0xffffffffu, live);
     if (!live) return;
     const uint32_t idx = (uint32_t)(((uint64_t)(key >> 32) << gbits) | (uint32_t)key);
-    const uint32_t peers = __match_any_sync(active, idx);
+    // common case: the whole warp sits in one node and drew the same word -> no match instruction needed
+    const uint32_t first = __shfl_sync(active, idx, __ffs(active) - 1);
+    const uint32_t peers = __all_sync(active, idx == first) ? active : __match_any_sync(active, idx);
     if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(table + idx, (uint32_t)__popc(peers));
 }
 
@@ -300,7 +302,8 @@ __global__ void scatter_kernel(const uint64_t* keys, const uint32_t* shots_in, u
     const uint32_t active = __ballot_sync(0xffffffffu, live);
     if (!live) return;
     const uint32_t idx = (uint32_t)(((uint64_t)(key >> 32) << gbits) | (uint32_t)key);
-    const uint32_t peers = __match_any_sync(active, idx);
+    const uint32_t first = __shfl_sync(active, idx, __ffs(active) - 1);
+    const uint32_t peers = __all_sync(active, idx == first) ? active : __match_any_sync(active, idx);
     const uint32_t lane = threadIdx.x & 31u;
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
