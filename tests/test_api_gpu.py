@@ -156,3 +156,28 @@ def test_simulate_with_adjacency_tensor(qcd):
                        adj_tensor_specs=qcd.AdjTensorSpecs(tensor_shape=(16, 32, 32)))
     for r in res.values():
         assert r["adj_tensor"].shape == (16, 32, 32) and r["adj_tensor"].any()       # reference test: (16, 32, 32)
+
+
+def test_simulate_device_noise_sampler(qcd):
+    """Reference tests/test_simulate.py configuration: DeviceNoiseSampler, non-stochastic CX circuits, 4 qubits."""
+    random.seed(1)
+    np.random.seed(1)
+    sim_specs = qcd.SimulationSpecs(n_qubits=4, n_circuits=10, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 100.0, "readout_error": 0.05, "prob_meas0_prep1": 0.05,
+                                          "prob_meas1_prep0": 0.05},
+                                "cx": {"gate_error": 0.1, "gate_length": 400.0},
+                                "h": {"gate_error": 0.01, "gate_length": 50.0}})
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=1024)
+    ent = qcd.EntanglementSpecs(witness=qcd.BiSeparableWitness, stabilizer=qcd.TothStabilizer, n_shots=512, noisy=True)
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), entangle_specs=ent)
+    assert sorted(res) == list(range(10))
+    for r in res.values():
+        assert r["prob_vec"].shape == (16,) and abs(r["prob_vec"].sum() - 1) < 1e-12
+        assert len(r["entanglement"]["value"]) == len(r["graph_data"])
+        assert all(-1.0 <= v <= 1.0 for v in r["entanglement"]["value"])
+        assert any(v > -1.0 for v in r["entanglement"]["value"])       # noisy settings: no longer the ideal -1
+    with pytest.raises(AssertionError):
+        qcd.simulate(qcd.SimulationSpecs(n_qubits=4, n_circuits=1, data=qcd.GraphData(),
+                                         circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=True)),
+                     sampler_specs, qcd.GraphSpecs(max_num_edges=4))
