@@ -153,7 +153,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         // lower on several host threads: contiguous blocks of circuits into private Programs, merged in order
         const int nc = ctx->n_circuits;
         int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-        n_thr = std::max(1, std::min(n_thr, nc / 32));
+        n_thr = std::max(1, std::min(n_thr, nc / 2));   // a 20-qubit circuit lowers in ~1 ms: threads pay off early
         std::vector<Program> parts(n_thr);
         std::vector<int> part_rc(n_thr, QCD_OK);
         std::vector<std::string> part_err(n_thr);
