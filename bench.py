@@ -114,13 +114,21 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm wants)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_arm(work, n_shots, threads=0):
     """Literal one-trajectory-per-shot CPU port on the noisy graph circuit.  Returns (shots/s, seconds, threads)."""
     from oracle import cpu_build
     from qcdenoise_b200.ir import encode_programs
     enc = encode_programs([work["programs"][0]])
-    cores = threads or cpu_build.max_threads()
+    cores = threads or host_threads()
     t0 = time.perf_counter()
     cpu_build.run_trajectories(enc, n_shots, SEED, circuit=0, n_threads=cores)
     dt = time.perf_counter() - t0
@@ -130,9 +138,8 @@ def cpu_arm(work, n_shots, threads=0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import cpu_build
     work = build_workload(0, args.shots)
-    cores = cpu_build.max_threads()
+    cores = host_threads()
     per_step = max(4 * cores, 8)
     for _ in range(args.warmup):
         cpu_arm(work, max(cores // 4, 2))
@@ -306,9 +313,8 @@ def main():
                 "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep]; "
                                      "one sweep per state-dependent noise-site group"}
     cpu = None
-    if not args.no_cpu:
-        from oracle import cpu_build
-        cores = cpu_build.max_threads()
+    if not args.no_cpu and world == 1:      # reported at N = 1 only
+        cores = host_threads()
         n_cpu = max(16 * cores, 16)
         v, dt_cpu, cores = cpu_arm(work, n_cpu)
         cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
