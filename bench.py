@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--literal", action="store_true", help="one state per shot (no trajectory-tree sharing)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64], help="32 = complex64 (default), 64 = complex128")
     ap.add_argument("--max-chunk", type=int, default=0, help="engine option max_chunk (trajectories per tree); 0 = default")
     args = ap.parse_args()
 
@@ -217,7 +218,7 @@ def main():
     hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
     def step():
         hist.zero_()
-        eng.run_trajectories(args.shots, seed=SEED + rank, precision=32, hist=hist, dedup=not args.literal)
+        eng.run_trajectories(args.shots, seed=SEED + rank, precision=args.precision, hist=hist, dedup=not args.literal)
         st = eng.stats()
         if world > 1:   # assemble the dataset histograms: counts are additive over the ranks' shot slices
             dist.all_reduce(hist, op=dist.ReduceOp.SUM)
@@ -256,9 +257,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         g, cd, stab = work["graph"], work["circuit_dict"], work["stab"]
-        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=32,
+        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=args.precision,
                                           seed=SEED + 100 * rank)
-        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=32,
+        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=args.precision,
                                      seed=SEED + 100 * rank + 1)
 
         def e2e_step():
@@ -323,7 +324,8 @@ def main():
     line = {"metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
             "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "c64", "data": "synthetic", "config": workload_config(work, args.shots),
+            "dtype": "c64" if args.precision == 32 else "c128", "data": "synthetic",
+            "config": workload_config(work, args.shots),
             "circuits_per_s": B * world * args.steps / (ms * 1e-3),
             "trajectory_sharing": not args.literal,
             "states_swept_per_step": agg["node_sweeps"] / args.steps, "leaf_states_per_step": agg["leaves"] / args.steps,
