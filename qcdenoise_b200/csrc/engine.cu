@@ -513,14 +513,77 @@ struct SvRunner {
                                                                      : (need_red ? 1u : 2u));
                 parts_used = 1u << pl;
             }
-            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
-            if (direct) launch_sweep_direct<T>(prog, sa, st);
-            else launch_sweep<T>(prog, sa, k, st);
-            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
-            CU(cudaGetLastError());
-            ctx->stats.sweep_launches++;
-            ctx->stats.node_sweeps += c;
-            ctx->stats.sweep_bytes += ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C);
+            // Sweeps of up to 3 passes run pass by pass on the register-only kernel (each pass a streaming read + write:
+            // cheaper than one trip through the shared-memory tile kernel); longer ones stay on the tile kernel.
+            size_t max_passes = 0;
+            bool by_pass = !direct && ctx->use_direct && n >= 13;
+            if (by_pass) {
+                const size_t n_sw = dp->P.sweeps.size();
+                for (const NodeRec& r : chunk) {
+                    const Sweep& S = dp->P.sweeps[r.sweep];
+                    const size_t np = S.pass_end - S.pass_begin;
+                    if (np == 0 || np > 3) by_pass = false;
+                    max_passes = std::max(max_passes, np);
+                    for (uint32_t pi = S.pass_begin; pi < S.pass_end && by_pass; pi++)
+                        by_pass = by_pass && dp->direct_host[n_sw + pi].ok;
+                    if (!by_pass) break;
+                }
+            }
+            if (by_pass) {
+                const size_t n_sw = dp->P.sweeps.size();
+                int pl = std::max(0, n - 4 - 8 - 3);
+                while (pl < n - 4 - 8 && ((uint64_t)c << pl) < 1184) pl++;
+                while (((uint64_t)c << pl) > 0x7fffffffull) pl--;
+                parts_used = 1u << pl;     // the same split at every pass level: node_probs reads parts_used partials
+                std::vector<NodeRec> recs;
+                std::vector<size_t> lvl_off;
+                std::vector<char> lvl_vec;
+                for (size_t l = 0; l < max_passes; l++) {
+                    lvl_off.push_back(recs.size());
+                    bool v = true;
+                    for (const NodeRec& r0 : chunk) {
+                        const Sweep& S = dp->P.sweeps[r0.sweep];
+                        if (S.pass_end - S.pass_begin <= l) continue;
+                        NodeRec r = r0;
+                        r.pad = (uint32_t)(n_sw + S.pass_begin + l);
+                        if (l > 0) {
+                            r.src_slot = r.dst_slot;   // later passes work in place
+                            r.scale = 1.0;
+                        }
+                        v = v && dp->direct_host[r.pad].rbit[0] == 0;
+                        recs.push_back(r);
+                    }
+                    lvl_vec.push_back(v);
+                }
+                lvl_off.push_back(recs.size());
+                CU(ctx->children.ensure(recs.size() * sizeof(NodeRec)));
+                CU(cudaMemcpyAsync(ctx->children.p, recs.data(), recs.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+                for (size_t l = 0; l < max_passes; l++) {
+                    const uint64_t cnt = lvl_off[l + 1] - lvl_off[l];
+                    SweepArgs pa = sweep_args(ctx->children.as<NodeRec>() + lvl_off[l], (uint32_t)cnt);
+                    pa.tiles_log2 = (uint32_t)pl;
+                    pa.n_items = (uint32_t)(cnt << pl);
+                    pa.direct_vec = lvl_vec[l] ? 1 : 0;
+                    pa.direct_kind = 3;
+                    pa.desc_from_pad = 1;
+                    if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                    launch_sweep_direct<T>(prog, pa, st);
+                    if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                    CU(cudaGetLastError());
+                    ctx->stats.sweep_launches++;
+                    ctx->stats.sweep_bytes += cnt * ((is_root && l == 0) ? 1 : 2) * slot_stride * sizeof(C);
+                }
+                ctx->stats.node_sweeps += c;
+            } else {
+                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                if (direct) launch_sweep_direct<T>(prog, sa, st);
+                else launch_sweep<T>(prog, sa, k, st);
+                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                CU(cudaGetLastError());
+                ctx->stats.sweep_launches++;
+                ctx->stats.node_sweeps += c;
+                ctx->stats.sweep_bytes += ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C);
+            }
             pos += c;
             if (!is_root) {
                 const size_t done_to = pos == n_children ? n_nodes : ch[pos].parent;
