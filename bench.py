@@ -13,7 +13,8 @@ complex64 amplitudes.
 One step = one pass of that path.  `value` = noisy shots/s with the lowered programs resident on the GPU (timed with
 CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API (UnitaryNoiseSampler.sample
 + StabilizerSampler.sample + GenuineWitness.estimate) from host gate lists to host numpy results, every step
-including encode, upload + lowering, and the device->host copies of all 22 histograms.  `roofline` = algorithmic
+including encode, upload + lowering, the device->host copy of the dataset histogram and of the 21 parity sums (the
+stabilizer histograms stay on the GPU until somebody reads `Counts.hist`).  `roofline` = algorithmic
 bytes moved by the state-sweep kernel / its CUDA-event time, against the measured HBM copy bandwidth.
 `cpu_baseline` / `--impl reference` = the compiled CPU port of the qiskit-Aer statevector-trajectory algorithm
 (oracle/cpu_sim.c, OpenMP over shots) on a bounded number of shots of the same noisy circuit.
@@ -285,7 +286,7 @@ def main():
         from qcdenoise_b200.ir import encode_programs
         enc = encode_programs(work["programs"])
         h2d = int(enc[0].nbytes + enc[1].nbytes + enc[2].nbytes)
-        d2h = int(B * N * 4 + (B - 1) * 16)
+        d2h = int(N * 4 + (B - 1) * 16)     # the dataset row; the 21 stabilizer histograms stay on the GPU (lazy Counts)
         e2e = {"value": shots_per_step * k_e2e / dt, "unit": "shots/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e, "witness_value": float(w.value),
                "api": "UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate"}

@@ -72,10 +72,17 @@ class Counts(Mapping):
     the engine produced; the Python dict is only materialised if somebody iterates it."""
 
     def __init__(self, hist, n_qubits, device_hist=None):
-        self.hist = np.asarray(hist)
+        self._hist = None if hist is None else np.asarray(hist)
         self.n_qubits = n_qubits
-        self.device_hist = device_hist
+        self.device_hist = device_hist      # [1, 2^n] int32 view of the engine's output (stays on the GPU)
         self._d = None
+
+    @property
+    def hist(self):
+        """Dense host histogram; copied from the device the first time somebody asks for it."""
+        if self._hist is None:
+            self._hist = _to_host(self.device_hist)[0]
+        return self._hist
 
     @classmethod
     def from_dict(cls, d, n_qubits=None):
@@ -255,8 +262,7 @@ class CircuitSampler:
         else:
             self.last_probs = None
             hist, _ = eng.run_trajectories(self.n_shots, seed=seed, precision=self.precision, readout=readout)
-        h = _to_host(hist)
-        out = [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(circs))]
+        out = [Counts(None, n, device_hist=hist[i:i + 1]) for i in range(len(circs))]
         return out[0] if single else out
 
 

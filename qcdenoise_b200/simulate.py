@@ -139,7 +139,7 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
                 circuits[num], enc, adj_tensor_specs.tensor_shape, adj_tensor_specs.fixed_size, adj_tensor_specs.directed)
 
     # ---- stage 1: all noisy circuits in one engine call
-    prob_vecs = _batched_counts(sampler, circuits, models)
+    prob_vecs = _batched_counts(sampler, circuits, models, fetch=True)
     for num in range(sim_specs.n_circuits):
         results[num]["prob_vec"] = prob_vecs[num].hist.astype(np.float64) / sampler_specs.n_shots
 
@@ -169,9 +169,9 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
     return results
 
 
-def _batched_counts(sampler: CircuitSampler, circuits, models):
+def _batched_counts(sampler: CircuitSampler, circuits, models, fetch=False):
     """Instantiate each circuit with ITS noise model and simulate the whole batch at once."""
-    from .samplers import Counts, NoiseModel, _to_host
+    from .samplers import Counts, NoiseModel
     inst = [(m if m is not None else NoiseModel()).instantiate(c) for c, m in zip(circuits, models)]
     progs = [c for c, _ in inst]
     n = progs[0].n_qubits
@@ -188,5 +188,8 @@ def _batched_counts(sampler: CircuitSampler, circuits, models):
         hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
     else:
         hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
-    h = _to_host(hist)
-    return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
+    if fetch:       # one batched device->host copy (the caller reads every histogram)
+        from .samplers import _to_host
+        h = _to_host(hist)
+        return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
+    return [Counts(None, n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
