@@ -318,10 +318,13 @@ def main():
     if not args.no_cpu and world == 1:      # reported at N = 1 only
         cores = host_threads()
         n_cpu = max(16 * cores, 16)
-        v, dt_cpu, cores = cpu_arm(work, n_cpu)
-        cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} shots of the noisy 20-qubit graph circuit (circuit 0 of the step), one trajectory "
-                         f"per shot, complex128, {dt_cpu:.1f} s"}
+        try:
+            v, dt_cpu, cores = cpu_arm(work, n_cpu)
+            cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu} shots of the noisy 20-qubit graph circuit (circuit 0 of the step), one "
+                             f"trajectory per shot, complex128, {dt_cpu:.1f} s"}
+        except Exception as exc:     # a CPU-baseline problem must not lose the GPU measurement
+            cpu = {"value": None, "unit": "shots/s", "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
     line = {"metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
             "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -13,17 +13,30 @@ LIB = os.path.join(OUT_DIR, "libcpusim.so")
 _lib = None
 
 
+def _host_has_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = f.read()
+        return all(w in flags for w in (" avx2", " fma", " bmi2"))
+    except OSError:
+        return False
+
+
 def build(force=False):
+    """The AVX2 build (x86-64-v3) is made in the build container and travels to the GPU box; a host without AVX2 gets
+    a generic build compiled on the spot (separate file name, so the two never overwrite each other)."""
     hdr = os.path.join(HERE, "..", "include", "qcdsim.h")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
-        return LIB
+    avx2 = _host_has_avx2()
+    lib = LIB if avx2 else os.path.join(OUT_DIR, "libcpusim_generic.so")
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        return lib
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["gcc", "-O3", "-march=x86-64-v3", "-ffast-math", "-fno-finite-math-only", "-fopenmp", "-shared", "-fPIC",
-           "-std=c11", SRC, "-o", LIB, "-lm"]
+    cmd = ["gcc", "-O3"] + (["-march=x86-64-v3"] if avx2 else []) + \
+          ["-ffast-math", "-fno-finite-math-only", "-fopenmp", "-shared", "-fPIC", "-std=c11", SRC, "-o", lib, "-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("gcc failed:\n" + r.stdout)
-    return LIB
+    return lib
 
 
 def load():
