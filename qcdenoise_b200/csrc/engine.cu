@@ -212,7 +212,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     dp.direct_host.assign(P.sweeps.size() + P.passes.size(), DirectSweep());
     for (DirectSweep& D : dp.direct_host) memset(&D, 0, sizeof(D));
     auto describe = [&](DirectSweep& D, const Sweep& S, uint32_t pi, uint8_t flags, bool reduce) {
-        if (S.n_bits < 13) return;
+        // (states below 13 index bits still get descriptors: the tile kernel stages its passes from them)
         const Pass& ps = P.passes[pi];
         const uint32_t nops = ps.op_end - ps.op_begin;
         if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) return;
@@ -272,6 +272,7 @@ DevProgram<T> dev_view(const DevProg& dp) {
     v.subs = dp.subs.as<SubSite>();
     v.gdata = dp.gdata.as<double>();
     v.direct = dp.direct.as<DirectSweep>();
+    v.n_sweeps = (uint32_t)dp.P.sweeps.size();
     return v;
 }
 
@@ -480,7 +481,7 @@ struct SvRunner {
             CU(ctx->level_nodes[d + 1].ensure(c * sizeof(NodeRec)));
             NodeRec* cdev = ctx->level_nodes[d + 1].as<NodeRec>();
             // single-pass sweeps run on the register-only kernel; anything else on the shared-memory tile kernel
-            bool direct = ctx->use_direct, vec = true, need_red = false, need_chunks = false, need_prep = false;
+            bool direct = ctx->use_direct && n >= 13, vec = true, need_red = false, need_chunks = false, need_prep = false;
             for (const NodeRec& r : chunk) {
                 const DirectSweep& D = dp->direct_host[r.sweep];
                 direct = direct && D.ok;

@@ -47,7 +47,8 @@ struct DevProgram {
     const Group* groups;
     const SubSite* subs;
     const double* gdata;
-    const DirectSweep* direct;
+    const DirectSweep* direct;   // [n_sweeps] per single-pass sweep, then [n_passes] per pass
+    uint32_t n_sweeps;
 };
 
 constexpr int SWEEP_THREADS = 256;

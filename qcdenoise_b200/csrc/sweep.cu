@@ -14,7 +14,7 @@
 //
 // Shared-memory layout: element i of the tile lives at i ^ fold(i >> W) (W = log2(128 B / sizeof(amp))), which spreads
 // any 5 varying index bits of a warp over all banks for both the strided pass accesses and the linear load/store.
-#include "kernels.cuh"
+#include "direct_ops.cuh"
 
 namespace qcd {
 namespace {
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, Tr<T>::MINB) sweep_kernel(DevPr
     __shared__ C s_prep[64];
     __shared__ C s_prep_base;
     __shared__ double s_red[SWEEP_THREADS / 32][4];
+    __shared__ dops::Staged<T> St;   // the current pass, staged (matrices of this node's branch, decoded ops, sign patterns)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t item = blockIdx.x;
@@ -255,6 +256,38 @@ __global__ void __launch_bounds__(SWEEP_THREADS, Tr<T>::MINB) sweep_kernel(DevPr
         }
         const uint32_t ngroups = 1u << (k - nreg);
         const uint32_t nval = 1u << nreg;
+        // Fast path: the pass has a staged descriptor (<= 12 ops, <= 48 sign masks, no 16x16 op): ops come from shared
+        // memory, pre-decoded, with real / real-diagonal / slotted paths -- the same code the register-only kernel runs.
+        // The rescale factor was applied while loading the tile, so the staging gets scale = 1.
+        dops::stage_sweep<T, SWEEP_THREADS, false>(St, prog, prog.n_sweeps + pi, N.branch, 1.0, tid);
+        if (St.D.ok && !St.has_m4 && nreg == REG_BITS) {
+            const int nops_s = St.D.nops;
+            const uint32_t slots = St.slots, sign_code = St.sign_code;
+            for (uint32_t grp = tid; grp < ngroups; grp += SWEEP_THREADS) {
+                uint32_t base = grp;
+#pragma unroll
+                for (int i = 0; i < REG_BITS; i++) {
+                    const uint32_t b = ps.rbits[i];
+                    base = ((base >> b) << (b + 1)) | (base & ((1u << b) - 1u));
+                }
+                C a[16];
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const uint32_t off = ((s & 1) ? lo[0] : 0u) | ((s & 2) ? lo[1] : 0u) | ((s & 4) ? lo[2] : 0u) | ((s & 8) ? lo[3] : 0u);
+                    a[s] = tile[swz<W>(base | off)];
+                }
+                const uint32_t gb = gidx(base);
+                if (slots) dops::apply_slotted<T>(a, St, slots, sign_code, gb);
+                else dops::apply_sweep<T>(a, St, nops_s, gb, go, nullptr, 0, 0);
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const uint32_t off = ((s & 1) ? lo[0] : 0u) | ((s & 2) ? lo[1] : 0u) | ((s & 4) ? lo[2] : 0u) | ((s & 8) ? lo[3] : 0u);
+                    tile[swz<W>(base | off)] = a[s];
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         for (uint32_t grp = tid; grp < ngroups; grp += SWEEP_THREADS) {
             uint32_t base = grp;
 #pragma unroll
