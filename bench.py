@@ -213,7 +213,7 @@ def main():
     eng.set_option("time_sweeps", 1)
     if args.max_chunk:
         eng.set_option("max_chunk", args.max_chunk)
-    for key in ("nostore_max", "use_direct", "no_slots"):        # tuning experiments only
+    for key in ("nostore_max", "use_direct", "no_slots", "tile_bits"):        # tuning experiments only
         if os.environ.get("QCD_" + key.upper()):
             eng.set_option(key, float(os.environ["QCD_" + key.upper()]))
     hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
