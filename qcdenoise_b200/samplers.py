@@ -25,7 +25,7 @@ from .ir import Circuit
 
 __all__ = ["NoiseSpec", "unitary_noise_spec", "device_noise_spec", "NoiseModel", "Counts", "CircuitSampler",
            "UnitaryNoiseSampler", "DeviceNoiseSampler", "convert_to_prob_vector", "generate_binary_strings",
-           "get_engine"]
+           "get_backendProp", "get_engine"]
 
 _ENGINES = {}
 
@@ -60,6 +60,14 @@ device_noise_spec = NoiseSpec(specs={
     "qubit": {"T1": 0.5, "T2": 0.5, "frequency": 0.5, "readout_error": 0.5, "prob_meas0_prep1": 0.5,
               "prob_meas1_prep0": 0.5},
     "cx": dict(_GATE), "id": dict(_GATE), "u1": dict(_GATE), "u2": dict(_GATE), "u3": dict(_GATE)})
+
+
+def get_backendProp(backend_dict):
+    """The reference wraps its random properties dict in a qiskit `BackendProperties` (samplers.py:94-112); here the
+    plain dict IS the properties object the samplers consume."""
+    if not isinstance(backend_dict, dict) or "qubits" not in backend_dict or "gates" not in backend_dict:
+        raise ValueError("backend properties must be a dict with 'qubits' and 'gates'")
+    return backend_dict
 
 
 def generate_binary_strings(n_qubits):
@@ -342,17 +350,22 @@ class DeviceNoiseSampler(CircuitSampler):
             specs.setdefault(key, {"gate": op[0], "qubits": list(op[1])})
         return specs
 
+    def _generate_qbit_props(self):
+        """One qubit's properties, each ~ U(0, spec) (samplers.py:613-637)."""
+        return {nm: self._get_random_value(nm, "qubit") for nm in self.noise_specs.specs["qubit"].keys()}
+
+    def _generate_gate_props(self, name, specs):
+        """One (gate, qubits) entry; the property names always come from the 'cx' spec (reference quirk Q5,
+        samplers.py:639-659)."""
+        g = {"name": name, "gate": specs["gate"], "qubits": specs["qubits"]}
+        for nm in self.noise_specs.specs["cx"].keys():
+            g[nm] = self._get_random_value(nm, specs["gate"])
+        return g
+
     def _generate_backend_dict(self, n_qubits):
-        qnames = list(self.noise_specs.specs["qubit"].keys())
-        gnames = list(self.noise_specs.specs["cx"].keys())      # reference quirk Q5: always cx's property names
-        qubits = [{nm: self._get_random_value(nm, "qubit") for nm in qnames} for _ in range(n_qubits)]
-        gates = []
-        for key, spec in self._get_gate_specs().items():
-            g = {"name": key, "gate": spec["gate"], "qubits": spec["qubits"]}
-            for nm in gnames:
-                g[nm] = self._get_random_value(nm, spec["gate"])
-            gates.append(g)
-        return {"qubits": qubits, "gates": gates, "backend_name": "qcdenoise-fake-backend"}
+        return {"qubits": [self._generate_qbit_props() for _ in range(n_qubits)],
+                "gates": [self._generate_gate_props(key, spec) for key, spec in self._get_gate_specs().items()],
+                "general": [], "backend_name": "qcdenoise-fake-backend", "backend_version": "0.0.0"}
 
     def build_noise_model(self, n_qubits, user_backend=True):
         self.noise_model = NoiseModel()

@@ -13,7 +13,7 @@ from .stabilizers import StabilizerSampler, TothStabilizer, pauli_mask
 from .witnesses import GenuineWitness
 
 __all__ = ["GraphSpecs", "SamplingSpecs", "CircuitSpecs", "AdjTensorSpecs", "EntanglementSpecs", "SimulationSpecs",
-           "simulate", "circuit_sampling_op", "estimate_entanglement_op"]
+           "simulate", "circuit_sampling_op", "estimate_entanglement_op", "adjacency_tensor_op"]
 
 
 @dataclass(init=True)
@@ -66,6 +66,18 @@ class SimulationSpecs:
     data: Any
     circuit: CircuitSpecs
     backend: Any = None
+
+
+def adjacency_tensor_op(circuit, backend, sampler, sampler_specs, adj_tensor_specs):
+    """Adjacency-tensor encoding of one circuit (reference simulate.py:105-134).  Without a transpiler the walk is
+    over the gate list as written; `adj_tensor_specs.encoding` (or the gate names that occur, from 1) gives the codes."""
+    from .dataset import generate_adjacency_tensor
+    enc = adj_tensor_specs.encoding
+    if enc is None:
+        names = sorted({op[0] for op in circuit.ops if op[0] not in ("barrier", "measure_all")})
+        enc = {nm: i + 1 for i, nm in enumerate(names)}
+    return generate_adjacency_tensor(circuit, enc, adj_tensor_specs.tensor_shape, adj_tensor_specs.fixed_size,
+                                     adj_tensor_specs.directed)
 
 
 def circuit_sampling_op(graph, circ_builder, circ_specs, sampler, sampler_specs) -> Dict:

@@ -413,3 +413,27 @@ def test_n28_ghz_outcomes_are_all_zero_or_all_one(eng):
     assert abs(int(counts[0]) - 128) < 60          # a fair coin over 256 shots
     ss = eng.parity_outcomes(out.reshape(1, -1), np.array([3, 2 ** n - 1, 1 | (1 << 27)], dtype=np.uint32)).cpu().numpy()[0]
     assert ss[0] == 256 and ss[1] == 256 and ss[2] == 256      # Z_i Z_j = +1 for every pair, even-weight parity too
+
+
+def test_two_qubit_kraus_channels(eng):
+    """4x4 Kraus sets (tensor products, as Aer presents `e1.tensor(e2)`): 16x16 superoperators in density-matrix mode,
+    two-qubit per-branch matrices in trajectory mode; n = 7 / 13 also take the register-only kernel."""
+    from tests.test_schedule_cpu import _two_qubit_kraus_circuit
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    _reset_opts(eng)
+    rng = np.random.default_rng(23)
+    for n in (4, 7):
+        ops = _two_qubit_kraus_circuit(n, rng)
+        eng.upload([_circ(n, ops)])
+        want = sim.density_matrix_probs(ops, n)
+        np.testing.assert_allclose(eng.run_density_matrix(64).cpu().numpy()[0], want, atol=1e-10, rtol=0)
+        np.testing.assert_allclose(eng.run_density_matrix(32).cpu().numpy()[0], want, atol=1e-5, rtol=0)
+        _, out = eng.run_trajectories(300, seed=8, precision=64, want_outcomes=True)
+        assert np.array_equal(out.cpu().numpy().astype(np.uint64), sim.run_trajectories(ops, n, 300, 8))
+    n = 13
+    ops = _two_qubit_kraus_circuit(n, rng)
+    eng.upload([_circ(n, ops)])
+    _, out = eng.run_trajectories(200, seed=8, precision=64, want_outcomes=True)
+    want = cpu_build.run_trajectories(encode_programs([_circ(n, ops)]), 200, 8)
+    assert np.array_equal(out.cpu().numpy().astype(np.uint64), want)

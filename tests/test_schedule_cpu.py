@@ -119,3 +119,25 @@ def test_invalid_programs_rejected():
         qb.debug_schedule(qb.Circuit(3, [("pauli", (0,), np.array([0.5, 0.2, 0.2, 0.2]))]))
     with pytest.raises(_lib.QcdError):
         qb.debug_schedule(qb.Circuit(3, [("cx", (0, 5))]))
+
+
+def _two_qubit_kraus_circuit(n, rng):
+    """Two-qubit Kraus channels (tensor products of single-qubit damping / relaxation operators, given as ONE
+    4x4 Kraus set the way Aer's `error1.tensor(error2)` presents them) on several pairs, between entangling gates."""
+    from oracle import noise
+    ops = [("h", (q,)) for q in range(n)]
+    for (a, b) in [(0, 1), (2, 1), (n - 1, 0), (1, n - 2)]:
+        ops.append(("cx", (a, b)))
+        k0 = noise.amplitude_damping_kraus(float(rng.uniform(0.05, 0.4)))
+        k1 = noise.thermal_relaxation_kraus(50.0, 70.0, float(rng.uniform(5, 40)))
+        ops.append(("kraus", (a, b), noise.tensor_kraus(k1, k0)))      # k0 acts on a (LSB), k1 on b
+        ops.append(("h", (b,)))
+    return ops
+
+
+def test_two_qubit_kraus_dm_and_trajectories():
+    rng = np.random.default_rng(17)
+    for n in (4, 5):
+        ops = _two_qubit_kraus_circuit(n, rng)
+        np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
+        _check_trajectories(n, ops, 300, seed=4)
