@@ -121,6 +121,29 @@ QCD_API int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
 QCD_API int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
                         size_t n_params, int n_circuits, int n_qubits);
 
+/* Replaces: NoiseModel.from_backend(backend) (samplers.py:588, :608 -- qiskit-aer's basic_device_gate_errors) and the
+ * attachment of that noise model to the circuit's gates at qk.execute (samplers.py:322-324), for a whole batch and on
+ * native host threads.  ops / op_offsets / params describe NOISE-FREE gate lists as in qcd_upload_programs;
+ *   qubit_t1_t2   [host] [n_circuits][n_qubits][2] doubles: T1, T2 in microseconds (inf = no relaxation);
+ *   op_gate_props [host] [op_offsets[n_circuits]][2] doubles: gate_error, gate_length (ns) of the calibration entry
+ *                 (gate, qubits) the op belongs to; (NaN, NaN) = no entry, the op stays noise-free.
+ * After every op with an entry the library writes PAULI1Q/2Q (depolarizing strength such that depolarizing o
+ * relaxation has average gate infidelity gate_error) and one KRAUS1Q per gate qubit (thermal relaxation over
+ * gate_length; T2 clipped to 2 T1), exactly the program qcdenoise_b200.samplers.DeviceNoiseSampler builds op by op
+ * in Python -- same operator order, hence the same shots -- then keeps it like qcd_upload_programs. */
+QCD_API int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets,
+                                             const double* params, size_t n_params, int n_circuits, int n_qubits,
+                                             const double* qubit_t1_t2, const double* op_gate_props);
+
+/* Host-only (no GPU needed): the expansion qcd_upload_device_noise_programs performs, written to caller buffers
+ * (offsets_out holds n_circuits + 1 entries).  Returns QCD_E_NOMEM when a capacity is too small; the required sizes
+ * are always stored in *ops_needed / *params_needed.  Used by the CPU tests to check the native channel
+ * construction against the Python one and the oracle. */
+QCD_API int qcd_expand_device_noise(const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                                    int n_circuits, int n_qubits, const double* qubit_t1_t2, const double* op_gate_props,
+                                    qcd_op* ops_out, size_t ops_cap, uint32_t* offsets_out, double* params_out,
+                                    size_t params_cap, size_t* ops_needed, size_t* params_needed);
+
 /* Replaces: AerSimulator `statevector` method under a noise model, i.e. execute(...).result().get_counts() for
  * shots <= 2^n or n > ~14 (samplers.py:308-326; stabilizers.py:214).  Global shot index g in
  * [shot_begin, shot_end) of the flattened [n_circuits][shots_per_circuit] space: circuit = g / shots_per_circuit,
@@ -176,6 +199,33 @@ QCD_API int qcd_parity_outcomes(qcd_ctx* ctx, const uint32_t* outcomes, int n_ve
  * sum_x p[x] D_mask[x], accumulated in double with a fixed reduction order (deterministic). Asynchronous. */
 QCD_API int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
                      const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream);
+
+/* Replaces: GraphState.sample (graph_state.py:74-122) with pick_subgraphs (:200-215), combine_subgraphs (:176-198)
+ * and the vertex-cover screen (networkx min_weighted_vertex_cover, :101-106), for n_graphs graphs at once on native
+ * host threads (host-only, no GPU needed).  Undirected graphs.
+ *   library: n_lib connected graphs; graph g has lib_orders[g] vertices numbered in node-iteration order and the
+ *            edges lib_edges[2e], lib_edges[2e+1] (u < v, sorted by u = networkx edges() order),
+ *            e in [lib_edge_offsets[g], lib_edge_offsets[g+1]);
+ *   order_graphs[order_offsets[k] .. order_offsets[k+1]) = library graphs with k vertices, k in [0, max_order];
+ *   combinations: comb_sizes[comb_offsets[c] .. comb_offsets[c+1]) = sub-graph orders adding up to n_qubits.
+ * Graph g (global index first_graph + g) draws from Philox4x32-10 with key = seed, counter = (index lo, index hi,
+ * attempt, block); draw j is word j of that stream mapped to [0, k) by (word * k) >> 32, in the order: combination,
+ * one library graph per block, then per later block one earlier vertex and order(block) connector targets among
+ * the block's first order(block) - 1 vertices.  Up to max(1, max_itr) attempts until cover_size / 2 >=
+ * min_vertex_cover.  edges_out [n_graphs][max_edges][2] (max_edges >= n (n - 1) / 2) in networkx edges() order of
+ * the joined graph, n_edges_out [n_graphs]. */
+QCD_API int qcd_sample_graph_states(const uint8_t* lib_edges, const uint32_t* lib_edge_offsets, const uint8_t* lib_orders,
+                                    int n_lib, const uint32_t* order_offsets, const uint32_t* order_graphs, int max_order,
+                                    const uint8_t* comb_sizes, const uint32_t* comb_offsets, int n_combs, int n_qubits,
+                                    int n_graphs, int min_vertex_cover, int max_itr, uint64_t seed, uint64_t first_graph,
+                                    uint8_t* edges_out, uint32_t max_edges, uint32_t* n_edges_out);
+
+/* Replaces: generate_adjacency_tensor (samplers.py:119-192) for a batch of gate lists (host-only).  Walks each
+ * circuit's gates in order: a 1-qubit gate on q writes codes[opcode] at [p][q][q], a 2-qubit gate on (a, b) at
+ * [p][a][b] (and [p][b][a] unless directed), p = first plane whose [a][b] slot is still 0.  Noise ops are skipped.
+ * codes [QCD_OP_COUNT]; out [host] [n_circuits][planes][rows][cols] doubles, overwritten. */
+QCD_API int qcd_adjacency_tensors(const qcd_op* ops, const uint32_t* op_offsets, int n_circuits, const int32_t* codes,
+                                  int planes, int rows, int cols, int directed, double* out);
 
 /* Host-only introspection (no GPU needed): lower + schedule ONE circuit and write a JSON description of the sweep
  * program (tile bits, passes, fused matrices, sign terms, site groups) into buf.  mode: 0 = statevector

@@ -14,4 +14,4 @@ from .stabilizers import *  # noqa: E402,F401,F403
 from .witnesses import *  # noqa: E402,F401,F403
 from .simulate import *  # noqa: E402,F401,F403
 from .dataset import *  # noqa: E402,F401,F403
-from . import channels, distributed  # noqa: E402,F401
+from . import batch, channels, distributed  # noqa: E402,F401

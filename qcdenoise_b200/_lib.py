@@ -47,6 +47,11 @@ _PROTOS = {
     "qcd_set_option": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_double]),
     "qcd_get_stats": (ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     "qcd_upload_programs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]),
+    "qcd_upload_device_noise_programs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _P,
+                                                        _P]),
+    "qcd_expand_device_noise": (ctypes.c_int, [_P, _P, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _P, _P, _P,
+                                               ctypes.c_size_t, _P, _P, ctypes.c_size_t,
+                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "qcd_run_sv_trajectories": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                                ctypes.c_uint64, _P, _P, _P, ctypes.c_uint32, _P]),
     "qcd_run_density_matrix": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
@@ -58,6 +63,11 @@ _PROTOS = {
     "qcd_parity_outcomes": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_uint64, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_parity_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int,
                                         ctypes.c_int, _P, _P]),
+    "qcd_sample_graph_states": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                                               ctypes.c_uint64, _P, ctypes.c_uint32, _P]),
+    "qcd_adjacency_tensors": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, _P]),
     "qcd_debug_schedule_json": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t,
                                                ctypes.POINTER(ctypes.c_size_t)]),

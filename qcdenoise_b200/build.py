@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqcdsim.so")
-SOURCES = ["engine.cu", "sweep.cu", "sweep_direct.cu", "kernels.cu", "lower.cpp"]
-HEADERS = ["kernels.cuh", "direct_ops.cuh", "program.h", "lower.h", os.path.join("..", "..", "include", "qcdsim.h")]
+SOURCES = ["engine.cu", "sweep.cu", "sweep_direct.cu", "kernels.cu", "lower.cpp", "device_noise.cpp", "host_batch.cpp"]
+HEADERS = ["kernels.cuh", "direct_ops.cuh", "program.h", "lower.h", "device_noise.h", os.path.join("..", "..", "include", "qcdsim.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--use_fast_math=false"]
 

@@ -20,6 +20,7 @@
 
 #include "../../include/qcdsim.h"
 #include "kernels.cuh"
+#include "device_noise.h"
 #include "lower.h"
 
 using namespace qcd;
@@ -987,18 +988,12 @@ int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out) {
     return QCD_OK;
 }
 
-int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
-                        size_t n_params, int n_circuits, int n_qubits) {
-    if (!ctx) return QCD_E_INVALID;
-    if (!op_offsets || n_circuits < 1) return fail(ctx, QCD_E_INVALID, "need at least one circuit");
-    if (n_qubits < 1 || n_qubits > 30) return fail(ctx, QCD_E_INVALID, "n_qubits must be in [1, 30]");
-    const uint32_t n_ops = op_offsets[n_circuits];
-    if (n_ops && !ops) return fail(ctx, QCD_E_INVALID, "ops is NULL");
-    if (n_params && !params) return fail(ctx, QCD_E_INVALID, "params is NULL");
-    for (int c = 0; c < n_circuits; c++)
-        if (op_offsets[c] > op_offsets[c + 1]) return fail(ctx, QCD_E_INVALID, "op_offsets must be non-decreasing");
-    // structural validation now (cheap, O(ops)), so that malformed programs fail at upload time; lowering happens
-    // once per (mode, precision) at the first run
+namespace {
+
+// structural validation (cheap, O(ops)), so that malformed programs fail at upload time; lowering happens once per
+// (mode, precision) at the first run
+int validate_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                      int n_circuits, int n_qubits) {
     for (int c = 0; c < n_circuits; c++) {
         for (uint32_t i = op_offsets[c]; i < op_offsets[c + 1]; i++) {
             const qcd_op& op = ops[i];
@@ -1037,14 +1032,151 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
             }
         }
     }
-    cudaSetDevice(ctx->device);
-    ctx->ops.assign(ops, ops + n_ops);
-    ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
-    ctx->params.assign(params, params + n_params);
+    return QCD_OK;
+}
+
+int check_batch_args(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                     int n_circuits, int n_qubits) {
+    if (!op_offsets || n_circuits < 1) return fail(ctx, QCD_E_INVALID, "need at least one circuit");
+    if (n_qubits < 1 || n_qubits > 30) return fail(ctx, QCD_E_INVALID, "n_qubits must be in [1, 30]");
+    const uint32_t n_ops = op_offsets[n_circuits];
+    if (n_ops && !ops) return fail(ctx, QCD_E_INVALID, "ops is NULL");
+    if (n_params && !params) return fail(ctx, QCD_E_INVALID, "params is NULL");
+    for (int c = 0; c < n_circuits; c++)
+        if (op_offsets[c] > op_offsets[c + 1]) return fail(ctx, QCD_E_INVALID, "op_offsets must be non-decreasing");
+    return QCD_OK;
+}
+
+void adopt_programs(qcd_ctx* ctx, int n_circuits, int n_qubits) {
     ctx->n_circuits = n_circuits;
     ctx->n_qubits = n_qubits;
     for (int m = 0; m < 2; m++)
         for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
+}
+
+// Expands a noise-free batch on several host threads (contiguous blocks of circuits, merged in order).
+int expand_batch(const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params, int n_circuits,
+                 int n_qubits, const double* qubit_t1_t2, const double* op_gate_props, std::vector<qcd_op>& ops_out,
+                 std::vector<uint32_t>& offsets_out, std::vector<double>& params_out, std::string& err) {
+    int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    n_thr = std::max(1, std::min(n_thr, n_circuits / 64));
+    struct Part {
+        std::vector<qcd_op> ops;
+        std::vector<uint32_t> counts;
+        std::vector<double> params;
+        std::string err;
+        int rc = QCD_OK;
+    };
+    std::vector<Part> parts(n_thr);
+    auto work = [&](int t) {
+        Part& p = parts[t];
+        const int c_lo = (int)((long long)n_circuits * t / n_thr), c_hi = (int)((long long)n_circuits * (t + 1) / n_thr);
+        p.rc = expand_device_noise(ops, op_offsets, params, n_params, c_lo, c_hi, n_qubits, qubit_t1_t2, op_gate_props,
+                                   p.ops, p.counts, p.params, p.err);
+    };
+    if (n_thr == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; t++) pool.emplace_back(work, t);
+        for (std::thread& th : pool) th.join();
+    }
+    size_t tot_ops = 0, tot_params = 0;
+    for (const Part& p : parts) {
+        if (p.rc != QCD_OK) {
+            err = p.err;
+            return p.rc;
+        }
+        tot_ops += p.ops.size();
+        tot_params += p.params.size();
+    }
+    if (tot_ops > 0xffffffffull || tot_params > 0xffffffffull) {
+        err = "expanded batch exceeds 2^32 ops or parameters: split the upload";
+        return QCD_E_UNSUPPORTED;
+    }
+    ops_out.clear();
+    params_out.clear();
+    offsets_out.assign(1, 0u);
+    ops_out.reserve(tot_ops);
+    params_out.reserve(tot_params);
+    for (const Part& p : parts) {
+        const uint32_t base = (uint32_t)params_out.size();
+        for (qcd_op op : p.ops) {
+            const bool has_params = (op.opcode >= QCD_OP_RX && op.opcode <= QCD_OP_U1Q) || op.opcode == QCD_OP_U2Q ||
+                                    (op.opcode >= QCD_OP_KRAUS1Q && op.opcode <= QCD_OP_PAULI2Q);
+            if (has_params) op.param_off += base;
+            ops_out.push_back(op);
+        }
+        params_out.insert(params_out.end(), p.params.begin(), p.params.end());
+        for (uint32_t cnt : p.counts) offsets_out.push_back(offsets_out.back() + cnt);
+    }
+    return QCD_OK;
+}
+
+}  // namespace
+
+int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
+                        size_t n_params, int n_circuits, int n_qubits) {
+    if (!ctx) return QCD_E_INVALID;
+    int rc = check_batch_args(ctx, ops, op_offsets, params, n_params, n_circuits, n_qubits);
+    if (rc) return rc;
+    if ((rc = validate_programs(ctx, ops, op_offsets, params, n_params, n_circuits, n_qubits))) return rc;
+    cudaSetDevice(ctx->device);
+    const uint32_t n_ops = op_offsets[n_circuits];
+    ctx->ops.assign(ops, ops + n_ops);
+    ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
+    ctx->params.assign(params, params + n_params);
+    adopt_programs(ctx, n_circuits, n_qubits);
+    return QCD_OK;
+}
+
+int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets, const double* params,
+                                     size_t n_params, int n_circuits, int n_qubits, const double* qubit_t1_t2,
+                                     const double* op_gate_props) {
+    if (!ctx) return QCD_E_INVALID;
+    int rc = check_batch_args(ctx, ops, op_offsets, params, n_params, n_circuits, n_qubits);
+    if (rc) return rc;
+    if (!qubit_t1_t2 || !op_gate_props) return fail(ctx, QCD_E_INVALID, "qubit_t1_t2 / op_gate_props is NULL");
+    std::vector<qcd_op> e_ops;
+    std::vector<uint32_t> e_off;
+    std::vector<double> e_par;
+    std::string err;
+    if ((rc = expand_batch(ops, op_offsets, params, n_params, n_circuits, n_qubits, qubit_t1_t2, op_gate_props, e_ops, e_off,
+                           e_par, err)))
+        return fail(ctx, rc, err);
+    if ((rc = validate_programs(ctx, e_ops.data(), e_off.data(), e_par.data(), e_par.size(), n_circuits, n_qubits))) return rc;
+    cudaSetDevice(ctx->device);
+    ctx->ops.swap(e_ops);
+    ctx->offsets.swap(e_off);
+    ctx->params.swap(e_par);
+    adopt_programs(ctx, n_circuits, n_qubits);
+    return QCD_OK;
+}
+
+int qcd_expand_device_noise(const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                            int n_circuits, int n_qubits, const double* qubit_t1_t2, const double* op_gate_props,
+                            qcd_op* ops_out, size_t ops_cap, uint32_t* offsets_out, double* params_out, size_t params_cap,
+                            size_t* ops_needed, size_t* params_needed) {
+    if (!op_offsets || n_circuits < 1 || n_qubits < 1 || n_qubits > 30 || !qubit_t1_t2 || !op_gate_props) return QCD_E_INVALID;
+    if (op_offsets[n_circuits] && !ops) return QCD_E_INVALID;
+    std::vector<qcd_op> e_ops;
+    std::vector<uint32_t> e_off;
+    std::vector<double> e_par;
+    std::string err;
+    int rc = expand_batch(ops, op_offsets, params, n_params, n_circuits, n_qubits, qubit_t1_t2, op_gate_props, e_ops, e_off,
+                          e_par, err);
+    if (rc) {
+        g_create_error = err;   // readable through qcd_last_error(NULL)
+        return rc;
+    }
+    if (ops_needed) *ops_needed = e_ops.size();
+    if (params_needed) *params_needed = e_par.size();
+    if (e_ops.size() > ops_cap || e_par.size() > params_cap || !offsets_out || (!ops_out && !e_ops.empty()) ||
+        (!params_out && !e_par.empty()))
+        return QCD_E_NOMEM;
+    std::copy(e_ops.begin(), e_ops.end(), ops_out);
+    std::copy(e_off.begin(), e_off.end(), offsets_out);
+    std::copy(e_par.begin(), e_par.end(), params_out);
     return QCD_OK;
 }
 

@@ -75,6 +75,25 @@ class Engine:
         self.n_circuits = len(offsets) - 1
         return self
 
+    def upload_device_noise(self, circuits, qubit_t1_t2, op_gate_props):
+        """Noise-free circuits (list of ir.Circuit or an encode_programs tuple) + calibration numbers; the library
+        writes the device-noise channels after every gate natively (qcd_upload_device_noise_programs).
+        qubit_t1_t2: float64 [B, n, 2] (us); op_gate_props: float64 [total ops, 2] (gate_error, gate_length ns;
+        NaN row = no error on that op)."""
+        enc = circuits if isinstance(circuits, tuple) else encode_programs(circuits)
+        ops, offsets, params, n = enc
+        B = len(offsets) - 1
+        tq = np.ascontiguousarray(qubit_t1_t2, dtype=np.float64)
+        gp = np.ascontiguousarray(op_gate_props, dtype=np.float64)
+        if tq.shape != (B, n, 2) or gp.shape != (len(ops), 2):
+            raise ValueError(f"qubit_t1_t2 must be ({B}, {n}, 2) and op_gate_props ({len(ops)}, 2)")
+        self._check(self.lib.qcd_upload_device_noise_programs(
+            self._h, _ptr(ops) if len(ops) else None, _ptr(offsets), _ptr(params) if len(params) else None,
+            len(params), B, n, _ptr(tq), _ptr(gp)))
+        self.n_qubits = n
+        self.n_circuits = B
+        return self
+
     @staticmethod
     def _readout_array(readout, n_vec, n):
         if readout is None:
@@ -202,3 +221,32 @@ def debug_schedule(circuit, mode=0, precision=32, tile_bits=0):
         if rc:
             raise _lib.QcdError(rc, d.get("error", "schedule failed"))
         return d
+
+
+def expand_device_noise(enc, qubit_t1_t2, op_gate_props):
+    """Host-only: the explicit programs the library builds from noise-free gate lists + calibration numbers
+    (qcd_expand_device_noise) -> (ops, offsets, params, n) like ir.encode_programs.  No GPU needed."""
+    lib = _lib.load()
+    ops, offsets, params, n = enc
+    B = len(offsets) - 1
+    tq = np.ascontiguousarray(qubit_t1_t2, dtype=np.float64)
+    gp = np.ascontiguousarray(op_gate_props, dtype=np.float64)
+    if tq.shape != (B, n, 2) or gp.shape != (len(ops), 2):
+        raise ValueError(f"qubit_t1_t2 must be ({B}, {n}, 2) and op_gate_props ({len(ops)}, 2)")
+    n_ops, n_par = ctypes.c_size_t(), ctypes.c_size_t()
+    out_ops = np.zeros(0, dtype=_lib.OP_DTYPE)
+    out_par = np.zeros(0, dtype=np.float64)
+    out_off = np.zeros(B + 1, dtype=np.uint32)
+    for _ in range(2):
+        rc = lib.qcd_expand_device_noise(_ptr(ops) if len(ops) else None, _ptr(offsets),
+                                         _ptr(params) if len(params) else None, len(params), B, n, _ptr(tq), _ptr(gp),
+                                         _ptr(out_ops) if len(out_ops) else None, len(out_ops), _ptr(out_off),
+                                         _ptr(out_par) if len(out_par) else None, len(out_par),
+                                         ctypes.byref(n_ops), ctypes.byref(n_par))
+        if rc != _lib.QCD_E_NOMEM:
+            break
+        out_ops = np.zeros(n_ops.value, dtype=_lib.OP_DTYPE)
+        out_par = np.zeros(n_par.value, dtype=np.float64)
+    if rc:
+        raise _lib.QcdError(rc, lib.qcd_last_error(None).decode())
+    return out_ops, out_off, out_par, n

@@ -23,7 +23,7 @@ from . import channels
 from .engine import Engine
 from .ir import Circuit
 
-__all__ = ["NoiseSpec", "unitary_noise_spec", "device_noise_spec", "NoiseModel", "Counts", "CircuitSampler",
+__all__ = ["NoiseSpec", "unitary_noise_spec", "device_noise_spec", "NoiseModel", "DeviceNoiseModel", "Counts", "CircuitSampler",
            "UnitaryNoiseSampler", "DeviceNoiseSampler", "convert_to_prob_vector", "generate_binary_strings",
            "get_backendProp", "get_engine"]
 
@@ -190,6 +190,144 @@ class NoiseModel:
         return out, ro
 
 
+class DeviceNoiseModel(NoiseModel):
+    """Noise model given by calibration numbers (`props`: {"qubits": [...], "gates": [...]}, see DeviceNoiseSampler).
+    The channels are built natively, for the whole batch, when the circuits are uploaded
+    (qcd_upload_device_noise_programs).  Reading `gate_errors` / `readout` (or adding errors) materialises the same
+    channels explicitly in Python instead; both routes give the same program, operator for operator."""
+
+    def __init__(self, props):
+        self.props = props
+        self._explicit = False
+        self._gate_errors, self._readout = {}, {}
+        super().__init__()
+        nq = len(props["qubits"])
+        # calibration entry per (gate, qubits); entries that name a qubit without properties are ignored
+        self.gate_table = {(g["gate"], tuple(g["qubits"])): (g.get("gate_error"), g.get("gate_length"))
+                           for g in props["gates"] if all(q < nq for q in g["qubits"])}
+
+    @property
+    def native(self):
+        """True while nothing but the calibration numbers defines this model."""
+        return not (self._explicit or self.label_errors or self.all_qubit_errors)
+
+    def _materialize(self):
+        if self._explicit:
+            return
+        self._explicit = True
+        props = self.props
+        for (gate, qs), (g_err, g_len) in self.gate_table.items():
+            t1 = [max(props["qubits"][q].get("T1", float("inf")), 1e-9) for q in qs]
+            t2 = [max(props["qubits"][q].get("T2", float("inf")), 1e-9) for q in qs]
+            probs, relax = channels.device_gate_error(len(qs), g_err, g_len, t1, t2)
+            err = []
+            if probs is not None:
+                err.append(("pauli", tuple(range(len(qs))), probs))
+            if relax is not None:
+                err += [("kraus", (i,), k) for i, k in enumerate(relax)]
+            if err:
+                self._gate_errors.setdefault((gate, qs), []).append(err)
+        for q, m in enumerate(self.readout_rows()):
+            if m is not None:
+                self._readout[q] = np.array(m, dtype=np.float64)
+
+    def readout_rows(self):
+        """Per qubit: [[1 - p10, p10], [p01, 1 - p01]] or None (no readout entry)."""
+        out = []
+        for qp in self.props["qubits"]:
+            if "prob_meas1_prep0" in qp and "prob_meas0_prep1" in qp:
+                a, b = qp["prob_meas1_prep0"], qp["prob_meas0_prep1"]
+            elif "readout_error" in qp:
+                a = b = qp["readout_error"]
+            else:
+                out.append(None)
+                continue
+            out.append([[1.0 - a, a], [b, 1.0 - b]])
+        return out
+
+    def is_ideal(self):
+        if self.native:
+            return not (self.gate_table or any(m is not None for m in self.readout_rows()))
+        return super().is_ideal()
+
+    gate_errors = property(lambda self: (self._materialize(), self._gate_errors)[1],
+                           lambda self, v: setattr(self, "_gate_errors", v))
+    readout = property(lambda self: (self._materialize(), self._readout)[1],
+                       lambda self, v: setattr(self, "_readout", v))
+
+
+_NAN2 = (float("nan"), float("nan"))
+_NOT_GATES = ("barrier", "measure_all")
+
+
+def device_noise_arrays(circuits, models):
+    """Calibration numbers of a batch as the arrays qcd_upload_device_noise_programs takes:
+    (qubit_t1_t2 [B, n, 2], op_gate_props [total ops, 2], readout [B, n, 2, 2] | None)."""
+    n = circuits[0].n_qubits
+    inf = float("inf")
+    t1t2, gp, ro, any_ro = [], [], [], False
+    eye = [[1.0, 0.0], [0.0, 1.0]]
+    for circ, model in zip(circuits, models):
+        qp = model.props["qubits"]
+        row = [[max(q.get("T1", inf), 1e-9), max(q.get("T2", inf), 1e-9)] for q in qp[:n]]
+        row += [[inf, inf]] * (n - len(row))
+        t1t2.append(row)
+        rr = model.readout_rows()[:n]
+        any_ro = any_ro or any(m is not None for m in rr)
+        rr = [m if m is not None else eye for m in rr]
+        rr += [eye] * (n - len(rr))
+        ro.append(rr)
+        table = model.gate_table
+        for op in circ.ops:
+            name = op[0]
+            if name in _NOT_GATES:
+                continue
+            ent = table.get((name, tuple(op[1])), _NAN2) if name not in ("kraus", "pauli", "reset") else _NAN2
+            gp.append((float("nan") if ent[0] is None else ent[0], float("nan") if ent[1] is None else ent[1]))
+    return (np.array(t1t2, dtype=np.float64).reshape(len(circuits), n, 2),
+            np.array(gp, dtype=np.float64).reshape(-1, 2),
+            np.array(ro, dtype=np.float64) if any_ro else None)
+
+
+def upload_batch(eng, circuits, models):
+    """Upload circuits with THEIR noise models (None = ideal) -> (readout [B, n, 2, 2] | None, noisy)."""
+    from .ir import encode_programs
+    n = circuits[0].n_qubits
+    if models and all(isinstance(m, DeviceNoiseModel) and m.native for m in models):
+        t1t2, gp, readout = device_noise_arrays(circuits, models)
+        eng.upload_device_noise(encode_programs(circuits), t1t2, gp)
+        with np.errstate(invalid="ignore"):
+            noisy = bool((gp > 0).any()) or any(op[0] in ("kraus", "pauli", "reset") for c in circuits for op in c.ops)
+        return readout, noisy
+    inst = [(m if m is not None else NoiseModel()).instantiate(c) for c, m in zip(circuits, models)]
+    progs = [c for c, _ in inst]
+    readout = None
+    if any(r is not None for _, r in inst):
+        readout = np.stack([r if r is not None else np.tile(np.eye(2), (n, 1, 1)) for _, r in inst])
+    noisy = any(op[0] in ("kraus", "pauli", "reset") for c in progs for op in c.ops)
+    eng.upload(progs)
+    return readout, noisy
+
+
+def run_batch(sampler, circuits, models, fetch=False):
+    """Simulate a batch in ONE engine call, every circuit under its own noise model -> list of Counts."""
+    n = circuits[0].n_qubits
+    eng = get_engine(sampler.device)
+    readout, noisy = upload_batch(eng, circuits, models)
+    seed = sampler._next_seed()
+    if sampler._pick_method(n, noisy) == "density_matrix":
+        probs = eng.run_density_matrix(sampler.precision)
+        sampler.last_probs = probs
+        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
+    else:
+        sampler.last_probs = None
+        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
+    if fetch:       # one batched device->host copy (the caller reads every histogram)
+        h = _to_host(hist)
+        return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(circuits))]
+    return [Counts(None, n, device_hist=hist[i:i + 1]) for i in range(len(circuits))]
+
+
 class CircuitSampler:
     """Base class (samplers.py:234-352).  `method`: "automatic" (Aer's rule: noisy and n_shots > 2^n and the
     density matrix fits -> exact density matrix + multinomial sampling, else statevector trajectories),
@@ -252,25 +390,8 @@ class CircuitSampler:
         """circuit | list of circuits -> Counts | list of Counts (samplers.py:308-326)."""
         single = isinstance(circuit, Circuit)
         circs = [circuit] if single else list(circuit)
-        model = self.noise_model if (self.noise_model is not None and self.noisy) else NoiseModel()
-        inst = [model.instantiate(c) for c in circs]
-        progs = [c for c, _ in inst]
-        n = progs[0].n_qubits
-        readout = None
-        if any(r is not None for _, r in inst):
-            readout = np.stack([r if r is not None else np.tile(np.eye(2), (n, 1, 1)) for _, r in inst])
-        noisy = any(op[0] in ("kraus", "pauli", "reset") for c in progs for op in c.ops)
-        eng = get_engine(self.device)
-        eng.upload(progs)
-        seed = self._next_seed()
-        if self._pick_method(n, noisy) == "density_matrix":
-            probs = eng.run_density_matrix(self.precision)
-            self.last_probs = probs
-            hist = eng.sample_from_probs(probs, self.n_shots, seed=seed, readout=readout)
-        else:
-            self.last_probs = None
-            hist, _ = eng.run_trajectories(self.n_shots, seed=seed, precision=self.precision, readout=readout)
-        out = [Counts(None, n, device_hist=hist[i:i + 1]) for i in range(len(circs))]
+        model = self.noise_model if (self.noise_model is not None and self.noisy) else None
+        out = run_batch(self, circs, [model] * len(circs))
         return out[0] if single else out
 
 
@@ -372,29 +493,7 @@ class DeviceNoiseSampler(CircuitSampler):
         if not self.noisy:
             return
         self.backend_props = self.backend if self.backend else self._generate_backend_dict(n_qubits)
-        props = self.backend_props
-        for g in props["gates"]:
-            qs = list(g["qubits"])
-            if any(q >= len(props["qubits"]) for q in qs):
-                continue
-            t1 = [max(props["qubits"][q].get("T1", float("inf")), 1e-9) for q in qs]
-            t2 = [max(props["qubits"][q].get("T2", float("inf")), 1e-9) for q in qs]
-            probs, relax = channels.device_gate_error(len(qs), g.get("gate_error"), g.get("gate_length"), t1, t2)
-            err = []
-            if probs is not None:
-                err.append(("pauli", tuple(range(len(qs))), probs))
-            if relax is not None:
-                err += [("kraus", (i,), k) for i, k in enumerate(relax)]
-            if err:
-                self.noise_model.add_quantum_error(err, g["gate"], qs)
-        for q, qp in enumerate(props["qubits"]):
-            if "prob_meas1_prep0" in qp and "prob_meas0_prep1" in qp:
-                m = channels.readout_matrix(qp["prob_meas1_prep0"], qp["prob_meas0_prep1"])
-            elif "readout_error" in qp:
-                m = channels.readout_matrix(qp["readout_error"], qp["readout_error"])
-            else:
-                continue
-            self.noise_model.add_readout_error(m, q)
+        self.noise_model = DeviceNoiseModel(self.backend_props)
 
     def stateprep_errors(self, circuit, zero_init=True):
         """Reference quirk Q3, reproduced literally (only called when faithful=True): appends reset + |0>/|1>

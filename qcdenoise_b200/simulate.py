@@ -1,12 +1,14 @@
 """Orchestration with the reference's spec dataclasses and `simulate()` signature (qcdenoise/simulate.py:43-326).
 The reference loops over circuits, one qiskit call each; here all circuits of a run are built first and simulated
 in ONE batched engine call per stage (sampling, stabilizer settings)."""
+import random
 from copy import deepcopy
 from dataclasses import dataclass
 from typing import Any, Dict
 
 import numpy as np
 
+from .graph_circuit import CPhaseGateCircuit, CXGateCircuit, CZGateCircuit
 from .graph_state import GraphData, GraphDB, GraphState
 from .samplers import CircuitSampler, DeviceNoiseSampler, NoiseSpec, UnitaryNoiseSampler, get_engine
 from .stabilizers import StabilizerSampler, TothStabilizer, pauli_mask
@@ -101,8 +103,59 @@ def estimate_entanglement_op(graph, graph_circuit, entangle_specs, n_qubits, bac
     return witness.estimate(graph=graph)
 
 
-def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None) -> Dict:
-    """-> {i: {"graph_data": edges, "prob_vec": np.ndarray (2^n,), ["entanglement": {"value", "variance"}]}}."""
+def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
+    """The whole-batch array route (batch.py) covers: random device noise (backend None), the three graph-circuit
+    builders without stochastic sites, undirected graphs, no entanglement stage."""
+    return (isinstance(sampler, DeviceNoiseSampler) and sampler.noisy and sim_specs.backend is None
+            and type(builder) in (CXGateCircuit, CZGateCircuit, CPhaseGateCircuit) and not sim_specs.circuit.stochastic
+            and not graph_specs.directed and entangle_specs is None)
+
+
+def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler):
+    """simulate() without per-circuit Python objects: graphs, gate lists, calibration draws and adjacency tensors are
+    built for the whole batch (natively / in numpy), the noise channels are written natively at upload, one engine
+    call simulates everything.  Draws come from numpy / Philox generators seeded from `random`, so `random.seed()`
+    still fixes the result -- but the stream differs from the object route's."""
+    from . import batch
+    from .samplers import _to_host, get_engine
+    n, B = sim_specs.n_qubits, sim_specs.n_circuits
+    edges, n_edges = graph_state.sample_batch(B, min_vertex_cover=graph_specs.min_vertex_cover,
+                                              max_itr=graph_specs.max_itr)
+    enc = batch.build_gate_lists(builder, edges, n_edges, **(sim_specs.circuit.build_options or {}))
+    props = batch.draw_device_props(sampler.noise_specs, enc, np.random.default_rng(random.getrandbits(63)))
+    t1t2, gp, readout = batch.device_noise_inputs(props)
+    sampler.backend_props = props
+    eng = get_engine(sampler.device)
+    eng.upload_device_noise(enc, t1t2, gp)
+    seed = sampler._next_seed()
+    if sampler._pick_method(n, True) == "density_matrix":
+        probs = eng.run_density_matrix(sampler.precision)
+        sampler.last_probs = probs
+        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
+    else:
+        sampler.last_probs = None
+        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
+    prob = _to_host(hist).astype(np.float64) / sampler_specs.n_shots
+    adj = None
+    if adj_tensor_specs is not None:
+        enc_names = adj_tensor_specs.encoding
+        if enc_names is None:
+            names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"])})
+            enc_names = {nm: i + 1 for i, nm in enumerate(names)}
+        adj = batch.adjacency_tensors_batch(enc, enc_names, adj_tensor_specs.tensor_shape, adj_tensor_specs.directed)
+    results = {}
+    for num, graph_data in enumerate(batch.edge_lists(edges, n_edges)):
+        results[num] = {"graph_data": graph_data, "prob_vec": prob[num]}
+        if adj is not None:
+            a = adj[num]
+            results[num]["adj_tensor"] = a if adj_tensor_specs.fixed_size else a[np.any(a != 0, axis=(1, 2))]
+    return results
+
+
+def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto") -> Dict:
+    """-> {i: {"graph_data": edges, "prob_vec": np.ndarray (2^n,), ["adj_tensor"], ["entanglement": {"value",
+    "variance"}]}}.  route: "auto" (whole-batch array route where it applies, see _array_route_ok) or "objects"
+    (always build a Circuit + NoiseModel per circuit, like the reference's loop, simulate.py:276-322)."""
     if not isinstance(sim_specs, SimulationSpecs):
         raise AssertionError("sim_specs must be an instance of SimulationSpecs")
     if not isinstance(sampler_specs, SamplingSpecs):
@@ -123,6 +176,11 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
     if sim_specs.circuit.stochastic and not isinstance(sampler, UnitaryNoiseSampler):
         raise AssertionError("stochastic gates need sampler=UnitaryNoiseSampler")
 
+    if route not in ("auto", "objects"):
+        raise ValueError("route must be 'auto' or 'objects'")
+    if route == "auto" and _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
+        return _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler)
+
     results = {i: {} for i in range(sim_specs.n_circuits)}
     graphs, circuits, models = [], [], []
     for num in range(sim_specs.n_circuits):
@@ -137,7 +195,7 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
             sampler.build_noise_model(n, **(sampler_specs.sample_options or {}))
         graphs.append(graph)
         circuits.append(cd["circuit"])
-        models.append(deepcopy(sampler.noise_model))
+        models.append(sampler.noise_model)      # a fresh object per build_noise_model call
 
     if adj_tensor_specs is not None:
         # gate-list walk (no transpiler DAG); codes enumerate the gate names that occur, from 1 (0 = empty slot)
@@ -183,25 +241,5 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
 
 def _batched_counts(sampler: CircuitSampler, circuits, models, fetch=False):
     """Instantiate each circuit with ITS noise model and simulate the whole batch at once."""
-    from .samplers import Counts, NoiseModel
-    inst = [(m if m is not None else NoiseModel()).instantiate(c) for c, m in zip(circuits, models)]
-    progs = [c for c, _ in inst]
-    n = progs[0].n_qubits
-    readout = None
-    if any(r is not None for _, r in inst):
-        readout = np.stack([r if r is not None else np.tile(np.eye(2), (n, 1, 1)) for _, r in inst])
-    noisy = any(op[0] in ("kraus", "pauli", "reset") for c in progs for op in c.ops)
-    eng = get_engine(sampler.device)
-    eng.upload(progs)
-    seed = sampler._next_seed()
-    if sampler._pick_method(n, noisy) == "density_matrix":
-        probs = eng.run_density_matrix(sampler.precision)
-        sampler.last_probs = probs
-        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
-    else:
-        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
-    if fetch:       # one batched device->host copy (the caller reads every histogram)
-        from .samplers import _to_host
-        h = _to_host(hist)
-        return [Counts(h[i], n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
-    return [Counts(None, n, device_hist=hist[i:i + 1]) for i in range(len(progs))]
+    from .samplers import run_batch
+    return run_batch(sampler, circuits, models, fetch=fetch)

@@ -181,3 +181,99 @@ def test_simulate_device_noise_sampler(qcd):
         qcd.simulate(qcd.SimulationSpecs(n_qubits=4, n_circuits=1, data=qcd.GraphData(),
                                          circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=True)),
                      sampler_specs, qcd.GraphSpecs(max_num_edges=4))
+
+
+_DEV_SPEC = {"qubit": {"T1": 100.0, "T2": 150.0, "readout_error": 0.05, "prob_meas0_prep1": 0.05, "prob_meas1_prep0": 0.03},
+             "cx": {"gate_error": 0.1, "gate_length": 400.0}, "h": {"gate_error": 0.01, "gate_length": 50.0}}
+
+
+def test_device_noise_native_route_equals_explicit_route(qcd):
+    """Channels written natively at upload (qcd_upload_device_noise_programs) vs. written out in Python and uploaded as
+    an explicit program: same exact distributions, and the same complex128 trajectories shot for shot."""
+    import torch
+    from qcdenoise_b200.samplers import get_engine, upload_batch
+    n = 5
+    random.seed(4)
+    np.random.seed(4)
+    s = qcd.DeviceNoiseSampler(None, n_shots=256, noise_specs=qcd.NoiseSpec(specs=_DEV_SPEC))
+    circuits, models = [], []
+    for i in range(9):
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(_graph(n, 10 + i, qcd))["circuit"]
+        s.transpile_circuit(c)
+        s.build_noise_model(n)
+        circuits.append(c)
+        models.append(s.noise_model)
+    eng = get_engine()
+    assert all(m.native for m in models)
+    ro, noisy = upload_batch(eng, circuits, models)
+    assert noisy and all(m.native for m in models)
+    p_nat = eng.run_density_matrix(64).clone()
+    h_nat, o_nat = eng.run_trajectories(256, seed=77, precision=64, readout=ro, want_outcomes=True)
+    inst = [m.instantiate(c) for m, c in zip(models, circuits)]          # materialises the Python channels
+    assert not any(m.native for m in models)
+    ro2, noisy2 = upload_batch(eng, circuits, models)                     # explicit route now
+    np.testing.assert_array_equal(ro, ro2)
+    p_exp = eng.run_density_matrix(64)
+    h_exp, o_exp = eng.run_trajectories(256, seed=77, precision=64, readout=ro2, want_outcomes=True)
+    assert float((p_nat - p_exp).abs().max()) < 1e-14
+    assert torch.equal(o_nat, o_exp) and torch.equal(h_nat, h_exp)
+    # and both equal the oracle's density matrix on the explicit program
+    for i in (0, 4, 8):
+        np.testing.assert_allclose(p_nat[i].cpu().numpy(), sim.density_matrix_probs(inst[i][0].ops, n), atol=1e-10)
+
+
+def test_simulate_array_route_matches_oracle(qcd):
+    """simulate()'s whole-batch route (native graphs, numpy gate lists and calibration draws, native channels): the
+    exact distributions behind its histograms equal the oracle on the object route's explicit program built from
+    the same numbers; adjacency tensors equal the Python walk."""
+    from qcdenoise_b200 import batch
+    from qcdenoise_b200.samplers import get_engine
+    n, B = 5, 12
+    spec = qcd.NoiseSpec(specs=_DEV_SPEC)
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n, max_num_edges=4)
+    edges, n_edges = gs.sample_batch(B, seed=21)
+    builder = qcd.CXGateCircuit(n_qubits=n, stochastic=False)
+    enc = batch.build_gate_lists(builder, edges, n_edges)
+    props = batch.draw_device_props(spec, enc, np.random.default_rng(3))
+    t1t2, gp, ro = batch.device_noise_inputs(props)
+    eng = get_engine()
+    eng.upload_device_noise(enc, t1t2, gp)
+    probs = eng.apply_readout(eng.run_density_matrix(64).clone(), ro).cpu().numpy()
+    for i in (0, 5, 11):
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from(batch.edge_lists(edges, n_edges)[i])
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)["circuit"]
+        s = qcd.DeviceNoiseSampler(batch.device_props_dict(props, i), n_shots=16, noise_specs=spec)
+        s.transpile_circuit(c)
+        s.build_noise_model(n)
+        inst, ro_i = s.noise_model.instantiate(c)
+        want = sim.apply_readout_to_probs(sim.density_matrix_probs(inst.ops, n), n, ro_i)
+        np.testing.assert_allclose(probs[i], want, atol=1e-10)
+    # the public call
+    random.seed(5)
+    sim_specs = qcd.SimulationSpecs(n_qubits=n, n_circuits=40, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=2048)
+    adj_specs = qcd.AdjTensorSpecs(tensor_shape=(16, 8, 8))
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), adj_tensor_specs=adj_specs)
+    random.seed(5)
+    res2 = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), adj_tensor_specs=adj_specs)
+    assert sorted(res) == list(range(40))
+    for i, r in res.items():
+        assert r["prob_vec"].shape == (2 ** n,) and abs(r["prob_vec"].sum() - 1) < 1e-12
+        assert r["adj_tensor"].shape == (16, 8, 8)
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from(r["graph_data"])
+        assert nx.is_connected(g)
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)["circuit"]
+        np.testing.assert_array_equal(r["adj_tensor"], qcd.generate_adjacency_tensor(c, {"cx": 1, "h": 2}, (16, 8, 8)))
+        assert r["graph_data"] == res2[i]["graph_data"]                  # random.seed() fixes the graphs ...
+        assert abs(r["prob_vec"] - res2[i]["prob_vec"]).sum() < 0.35    # ... and the noise (shots: sampler seed differs)
+    # noise visibly present: the ideal graph state is uniform on its support, these are not
+    assert np.std([r["prob_vec"].max() for r in res.values()]) > 0
+    # forcing the object route still works and has the same shape of results
+    res3 = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), adj_tensor_specs=adj_specs,
+                        route="objects")
+    assert sorted(res3) == list(range(40)) and res3[0]["adj_tensor"].shape == (16, 8, 8)

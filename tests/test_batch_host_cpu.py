@@ -1,0 +1,155 @@
+"""The whole-batch host stages (qcdenoise_b200/batch.py, GraphState.sample_batch -> qcd_sample_graph_states,
+qcd_adjacency_tensors) against the object route they replace.  Host-only: no GPU."""
+import random
+
+import networkx as nx
+import numpy as np
+import pytest
+from networkx.algorithms.approximation import vertex_cover
+
+import qcdenoise_b200 as qcd
+from oracle import philox
+from qcdenoise_b200 import batch
+from qcdenoise_b200.dataset import generate_adjacency_tensor
+from qcdenoise_b200.engine import expand_device_noise
+from qcdenoise_b200.ir import encode_programs
+from qcdenoise_b200.samplers import device_noise_arrays
+
+
+class _Stream:
+    """Word j of Philox4x32-10(key = seed, counter = (graph lo, graph hi, attempt, j // 4)) -- the draw convention of
+    qcd_sample_graph_states (include/qcdsim.h)."""
+
+    def __init__(self, seed, graph, attempt):
+        self.seed, self.graph, self.attempt, self.j = seed, graph, attempt, 0
+
+    def below(self, k):
+        blk = philox.philox4x32_10(self.graph & 0xFFFFFFFF, self.graph >> 32, self.attempt, self.j // 4,
+                                   self.seed & 0xFFFFFFFF, self.seed >> 32)
+        w = int(blk[self.j % 4])
+        self.j += 1
+        return (w * k) >> 32
+
+
+def _model_sample(gs, seed, index, min_vertex_cover, max_itr):
+    """GraphState.sample restated with networkx operations (disjoint_union, add_edge, min_weighted_vertex_cover)
+    and the native sampler's draw order."""
+    g = None
+    for attempt in range(max(1, max_itr)):
+        rng = _Stream(seed, index, attempt)
+        comb = gs.graph_combs[rng.below(len(gs.graph_combs))]
+        subs = [gs.all_graphs[k][rng.below(len(gs.all_graphs[k]))] for k in comb]
+        g = nx.Graph()
+        for sg in subs:
+            have = g.order()
+            if have > 1:
+                first = rng.below(have)
+                targets = [have + rng.below(sg.order() - 1) for _ in range(sg.order())]
+                g = nx.disjoint_union(g, sg)
+                g.add_weighted_edges_from((first, t, 1.0) for t in targets)
+            else:
+                g = nx.disjoint_union(g, sg)
+        if len(vertex_cover.min_weighted_vertex_cover(g, weight="weight")) // 2 >= min_vertex_cover:
+            break
+    return g
+
+
+@pytest.mark.parametrize("n,cover,itr", [(4, 1, 1), (8, 1, 1), (9, 3, 4), (14, 5, 3), (20, 1, 10)])
+def test_native_graph_batch_equals_networkx_model(n, cover, itr):
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n, min_num_edges=2, max_num_edges=7)
+    seed = 0x1234_5678_9ABC_DEF0 >> 1
+    edges, n_edges = gs.sample_batch(40, min_vertex_cover=cover, max_itr=itr, seed=seed, first_graph=3)
+    for i in range(40):
+        g = _model_sample(gs, seed, 3 + i, cover, itr)
+        assert [tuple(e) for e in edges[i, :n_edges[i]].tolist()] == [tuple(e) for e in g.edges()], i
+        assert g.order() == n and nx.is_connected(g)
+    # any split of the batch gives the same graphs
+    e2, k2 = gs.sample_batch(15, min_vertex_cover=cover, max_itr=itr, seed=seed, first_graph=3 + 25)
+    assert np.array_equal(k2, n_edges[25:]) and np.array_equal(e2, edges[25:])
+
+
+def test_graph_batch_statistics_match_object_route():
+    """Same distribution as GraphState.sample (different generator): edge-count statistics agree."""
+    random.seed(3)
+    np.random.seed(3)
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=8)
+    obj = np.array([gs.sample(max_itr=1).number_of_edges() for _ in range(1500)])
+    _, ne = gs.sample_batch(20000, max_itr=1, seed=9)
+    assert abs(obj.mean() - ne.mean()) < 4 * obj.std() / np.sqrt(len(obj))
+    assert abs(obj.std() - ne.std()) < 0.25
+
+
+def _graphs_from(edges, n_edges, n):
+    out = []
+    for rows, k in zip(edges, n_edges):
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from((int(u), int(v)) for u, v in rows[:k])
+        out.append(g)
+    return out
+
+
+@pytest.mark.parametrize("cls,opts", [(qcd.CXGateCircuit, {}), (qcd.CZGateCircuit, {}),
+                                      (qcd.CPhaseGateCircuit, {}), (qcd.CPhaseGateCircuit, {"Lambda": 1.1, "Theta": 0.4})])
+def test_batched_gate_lists_equal_builder(cls, opts):
+    n = 7
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(25, seed=2)
+    builder = cls(n_qubits=n, stochastic=False)
+    ops, off, par, nn = batch.build_gate_lists(builder, edges, n_edges, **opts)
+    want = encode_programs([cls(n_qubits=n, stochastic=False).build(g, **opts)["circuit"]
+                            for g in _graphs_from(edges, n_edges, n)])
+    assert nn == n and np.array_equal(off, want[1]) and len(ops) == len(want[0])
+    for f in ("opcode", "q0", "q1"):
+        assert np.array_equal(ops[f], want[0][f])
+    has_par = ops["opcode"] == qcd._lib.OPCODES["ry"]
+    assert np.array_equal(par[ops["param_off"][has_par]], want[2][want[0]["param_off"][has_par]])
+    with pytest.raises(ValueError):
+        batch.build_gate_lists(cls(n_qubits=n, stochastic=True), edges, n_edges)
+
+
+def test_batched_device_props_feed_the_same_programs_as_the_object_route():
+    n = 6
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 150.0, "readout_error": 0.2, "prob_meas0_prep1": 0.1,
+                                          "prob_meas1_prep0": 0.05},
+                                "cx": {"gate_error": 0.25, "gate_length": 500.0},
+                                "h": {"gate_error": 0.05}})          # h has no gate_length -> 1e-6 (quirk Q4)
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(70, seed=4)
+    enc = batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=False), edges, n_edges)
+    props = batch.draw_device_props(spec, enc, np.random.default_rng(1))
+    t1t2, gp, ro = batch.device_noise_inputs(props)
+    assert (props["gate"]["gate_length"][(props["gate_key"] >> 16) == qcd._lib.OPCODES["h"]] == 1e-6).all()
+    assert (props["qubit"]["T2"] <= 150.0).all() and (props["gate"]["gate_error"] <= 0.25).all()
+    native = expand_device_noise(enc, t1t2, gp)
+    # object route with the same numbers: DeviceNoiseSampler(backend=<dict>) per circuit
+    circuits, models = [], []
+    for i, g in enumerate(_graphs_from(edges, n_edges, n)):
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)["circuit"]
+        s = qcd.DeviceNoiseSampler(batch.device_props_dict(props, i), n_shots=16, noise_specs=spec)
+        s.transpile_circuit(c)
+        s.build_noise_model(n)
+        circuits.append(c)
+        models.append(s.noise_model)
+    t1t2_o, gp_o, ro_o = device_noise_arrays(circuits, models)
+    assert np.array_equal(t1t2, t1t2_o) and np.array_equal(gp, gp_o) and np.array_equal(ro, ro_o)
+    obj = expand_device_noise(encode_programs(circuits), t1t2_o, gp_o)
+    for x, y in zip(native, obj):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_native_adjacency_tensors_equal_python_walk(directed):
+    n = 6
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(70, seed=6)
+    encoding = {"h": 1, "cx": 2}
+    enc = batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=False), edges, n_edges)
+    got = batch.adjacency_tensors_batch(enc, encoding, (9, 8, 8), directed)
+    for i, g in enumerate(_graphs_from(edges, n_edges, n)):
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)["circuit"]
+        assert np.array_equal(got[i], generate_adjacency_tensor(c, encoding, (9, 8, 8), True, directed)), i
+    with pytest.raises(KeyError):
+        batch.adjacency_tensors_batch(enc, {"h": 1}, (9, 8, 8))
+    with pytest.raises(IndexError):
+        batch.adjacency_tensors_batch(enc, encoding, (9, 4, 4))

@@ -117,6 +117,34 @@ def c2(eng, n_circ):
                       "states_swept": st["node_sweeps"], "host_build_s": t_build, "upload_lower_s": t_up}), flush=True)
 
 
+def c2_simulate(n_circ):
+    """C2 end to end through the public call: qcd.simulate() with DeviceNoiseSampler on 8-qubit random graph states,
+    host stages included (graph sampling, gate lists, calibration draws, channel construction, lowering, upload,
+    simulation, histograms back to the host, adjacency tensors)."""
+    import random
+    random.seed(1234)
+    np.random.seed(1234)
+    n = 8
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 100.0, "readout_error": 0.25, "prob_meas0_prep1": 0.1,
+                                          "prob_meas1_prep0": 0.1},
+                                "cx": {"gate_error": 0.25, "gate_length": 500.0},
+                                "h": {"gate_error": 0.05, "gate_length": 50.0}})
+    sim_specs = qcd.SimulationSpecs(n_qubits=n, n_circuits=n_circ, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=1024)
+    adj = qcd.AdjTensorSpecs(tensor_shape=(16, 8, 8))
+    for route, count in (("auto", n_circ), ("auto", n_circ), ("objects", min(n_circ, 1000))):
+        sim_specs.n_circuits = count
+        t0 = time.perf_counter()
+        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), adj_tensor_specs=adj, route=route)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert len(res) == count and abs(res[count - 1]["prob_vec"].sum() - 1) < 1e-9
+        print(json.dumps({"config": f"C2 end to end: simulate() n=8 device noise, {count} circuits x 1024 shots + adjacency "
+                                    f"tensors, route={route}", "s": dt, "value": count / dt, "unit": "circuits/s",
+                          "shots_per_s": 1024 * count / dt}), flush=True)
+
+
 def c3(eng, n_circ):
     """14-qubit density matrix with custom-unitary-noise Kraus channels + witness estimation."""
     n = 14
@@ -186,6 +214,8 @@ if __name__ == "__main__":
         c1(eng)
     if "C2" in which:
         c2(eng, 10000)
+    if "C2" in which:
+        c2_simulate(10000)
     if "C3" in which:
         c3(eng, 16)
     if "C5" in which:
