@@ -22,8 +22,11 @@ _GATE_NAMES[OPCODES["u1q"]] = _GATE_NAMES[OPCODES["u2q"]] = "unitary"
 
 def edge_lists(edges, n_edges):
     """(edges [B, M, 2], n_edges [B]) -> list of B lists of (u, v) tuples (the `graph_data` entry of the results)."""
-    flat = edges.tolist()
-    return [[tuple(e) for e in rows[:k]] for rows, k in zip(flat, n_edges.tolist())]
+    n_edges = np.asarray(n_edges, dtype=np.int64)
+    keep = np.arange(edges.shape[1])[None, :] < n_edges[:, None]
+    pairs = list(zip(edges[..., 0][keep].tolist(), edges[..., 1][keep].tolist()))
+    ends = np.cumsum(n_edges).tolist()
+    return [pairs[e - k:e] for e, k in zip(ends, n_edges.tolist())]
 
 
 def build_gate_lists(builder, edges, n_edges, **build_options):

@@ -150,7 +150,13 @@ int expand_device_noise(const qcd_op* ops, const uint32_t* op_offsets, const dou
         const double* tq = qubit_t1_t2 + (size_t)c * n_qubits * 2;
         for (uint32_t i = op_offsets[c]; i < op_offsets[c + 1]; i++) {
             qcd_op op = ops[i];
-            const std::string where = "circuit " + std::to_string(c) + ", op " + std::to_string(i - op_offsets[c]) + ": ";
+            struct Where {   // built only on error
+                int c;
+                uint32_t i;
+                std::string operator+(const char* m) const {
+                    return "circuit " + std::to_string(c) + ", op " + std::to_string(i) + ": " + m;
+                }
+            } where{c, i - op_offsets[c]};
             if (op.opcode >= QCD_OP_COUNT) { err = where + "unknown opcode"; return QCD_E_INVALID; }
             const bool two = op.opcode == QCD_OP_CX || op.opcode == QCD_OP_CZ || op.opcode == QCD_OP_SWAP ||
                              op.opcode == QCD_OP_U2Q || op.opcode == QCD_OP_KRAUS2Q || op.opcode == QCD_OP_PAULI2Q;

@@ -99,6 +99,10 @@ struct qcd_ctx {
     std::vector<qcd_op> ops;
     std::vector<uint32_t> offsets;
     std::vector<double> params;
+    // device-noise batches keep the noise-free gate lists + calibration numbers; every lowering thread writes a
+    // circuit's channels into a small private buffer right before compiling it (no expanded copy of the batch)
+    bool device_noise = false;
+    std::vector<double> qubit_t1_t2, op_gate_props;
     DevProg prog[2][2];  // [mode][precision == 64]
     int prog_tile_bits[2][2] = {{0, 0}, {0, 0}};
     // arenas / scratch
@@ -165,10 +169,24 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             Q.n_bits = P.n_bits;
             Q.k_max = P.k_max;
             const int c_lo = (int)((long long)nc * t / n_thr), c_hi = (int)((long long)nc * (t + 1) / n_thr);
+            std::vector<qcd_op> x_ops;
+            std::vector<uint32_t> x_cnt;
+            std::vector<double> x_par;
             for (int c = c_lo; c < c_hi; c++) {
                 std::string err;
                 uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
-                int rc = compile_circuit(Q, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
+                int rc;
+                if (ctx->device_noise) {
+                    x_ops.clear();
+                    x_cnt.clear();
+                    x_par.clear();
+                    rc = expand_device_noise(ctx->ops.data(), ctx->offsets.data(), ctx->params.data(), ctx->params.size(), c,
+                                             c + 1, ctx->n_qubits, ctx->qubit_t1_t2.data(), ctx->op_gate_props.data(), x_ops,
+                                             x_cnt, x_par, err);
+                    if (rc == QCD_OK) rc = compile_circuit(Q, x_ops.data(), (uint32_t)x_ops.size(), x_par.data(), x_par.size(), err);
+                } else {
+                    rc = compile_circuit(Q, ctx->ops.data() + b, e - b, ctx->params.data(), ctx->params.size(), err);
+                }
                 if (rc != QCD_OK) {
                     part_rc[t] = rc;
                     part_err[t] = "circuit " + std::to_string(c) + ": " + err;
@@ -997,7 +1015,14 @@ int validate_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offset
     for (int c = 0; c < n_circuits; c++) {
         for (uint32_t i = op_offsets[c]; i < op_offsets[c + 1]; i++) {
             const qcd_op& op = ops[i];
-            const std::string where = "circuit " + std::to_string(c) + ", op " + std::to_string(i - op_offsets[c]) + ": ";
+            // the position string is only built when something is wrong (this loop sees millions of ops)
+            struct Where {
+                int c;
+                uint32_t i;
+                std::string operator+(const char* m) const {
+                    return "circuit " + std::to_string(c) + ", op " + std::to_string(i) + ": " + m;
+                }
+            } where{c, i - op_offsets[c]};
             if (op.opcode >= QCD_OP_COUNT) return fail(ctx, QCD_E_INVALID, where + "unknown opcode");
             bool two = false;
             size_t need = 0;
@@ -1126,6 +1151,9 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     ctx->ops.assign(ops, ops + n_ops);
     ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
     ctx->params.assign(params, params + n_params);
+    ctx->device_noise = false;
+    ctx->qubit_t1_t2.clear();
+    ctx->op_gate_props.clear();
     adopt_programs(ctx, n_circuits, n_qubits);
     return QCD_OK;
 }
@@ -1137,18 +1165,24 @@ int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint
     int rc = check_batch_args(ctx, ops, op_offsets, params, n_params, n_circuits, n_qubits);
     if (rc) return rc;
     if (!qubit_t1_t2 || !op_gate_props) return fail(ctx, QCD_E_INVALID, "qubit_t1_t2 / op_gate_props is NULL");
-    std::vector<qcd_op> e_ops;
-    std::vector<uint32_t> e_off;
-    std::vector<double> e_par;
-    std::string err;
-    if ((rc = expand_batch(ops, op_offsets, params, n_params, n_circuits, n_qubits, qubit_t1_t2, op_gate_props, e_ops, e_off,
-                           e_par, err)))
-        return fail(ctx, rc, err);
-    if ((rc = validate_programs(ctx, e_ops.data(), e_off.data(), e_par.data(), e_par.size(), n_circuits, n_qubits))) return rc;
+    if ((rc = validate_programs(ctx, ops, op_offsets, params, n_params, n_circuits, n_qubits))) return rc;
+    const uint32_t n_ops = op_offsets[n_circuits];
+    // calibration numbers: T1, T2 > 0 (inf allowed); an op with an entry must be a gate
+    for (size_t i = 0; i < (size_t)n_circuits * n_qubits * 2; i++)
+        if (!(qubit_t1_t2[i] == qubit_t1_t2[i]))
+            return fail(ctx, QCD_E_INVALID, "circuit " + std::to_string(i / (2 * n_qubits)) + ": T1 / T2 is NaN");
+    for (uint32_t i = 0; i < n_ops; i++) {
+        const double ge = op_gate_props[2 * (size_t)i], gl = op_gate_props[2 * (size_t)i + 1];
+        if ((ge == ge || gl == gl) && ops[i].opcode >= QCD_OP_KRAUS1Q)
+            return fail(ctx, QCD_E_INVALID, "op " + std::to_string(i) + ": a noise op cannot carry a gate error");
+    }
     cudaSetDevice(ctx->device);
-    ctx->ops.swap(e_ops);
-    ctx->offsets.swap(e_off);
-    ctx->params.swap(e_par);
+    ctx->ops.assign(ops, ops + n_ops);
+    ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
+    ctx->params.assign(params, params + n_params);
+    ctx->device_noise = true;
+    ctx->qubit_t1_t2.assign(qubit_t1_t2, qubit_t1_t2 + (size_t)n_circuits * n_qubits * 2);
+    ctx->op_gate_props.assign(op_gate_props, op_gate_props + (size_t)n_ops * 2);
     adopt_programs(ctx, n_circuits, n_qubits);
     return QCD_OK;
 }

@@ -85,15 +85,16 @@ std::vector<cd> embed1(const cd* m, int slot, int nq) {
 // re-index an operator on bits (q[0..nq)) to the order given by perm: new slot s holds old slot perm[s]
 std::vector<cd> permute_bits(const std::vector<cd>& m, const int* perm, int nq) {
     int d = 1 << nq;
-    auto map = [&](int idx) {
+    int map[16];
+    for (int idx = 0; idx < d; idx++) {
         int o = 0;
         for (int s = 0; s < nq; s++)
             if ((idx >> s) & 1) o |= 1 << perm[s];
-        return o;
-    };
+        map[idx] = o;
+    }
     std::vector<cd> r(d * d);
     for (int i = 0; i < d; i++)
-        for (int j = 0; j < d; j++) r[i * d + j] = m[map(i) * d + map(j)];
+        for (int j = 0; j < d; j++) r[i * d + j] = m[map[i] * d + map[j]];
     return r;
 }
 
@@ -128,14 +129,14 @@ struct Lowerer {
         if ((size_t)off + cnt > n_params) return fail(QCD_E_INVALID, "op parameters run past params[]");
         return true;
     }
-    void push_m(int kind, std::initializer_list<int> qs, const std::vector<cd>& m) {
+    void push_m(int kind, std::initializer_list<int> qs, std::vector<cd> m) {
         LOp o;
         o.kind = (LOp::Kind)kind;
         o.nq = (int)qs.size();
         int i = 0;
         for (int q : qs) o.q[i++] = q;
-        o.mats = m;
-        ops.push_back(o);
+        o.mats = std::move(m);
+        ops.push_back(std::move(o));
     }
     void push_sign(uint64_t mask) {
         LOp o;
@@ -186,9 +187,9 @@ struct Lowerer {
                                 S[(x + d * y) * D + (xp + d * yp)] += a * std::conj(k[y * d + yp]);
                     }
             if (nq == 1)
-                push_m(LOp::M2, {q[0], q[0] + n}, S);
+                push_m(LOp::M2, {q[0], q[0] + n}, std::move(S));
             else
-                push_m(LOp::M4, {q[0], q[1], q[0] + n, q[1] + n}, S);
+                push_m(LOp::M4, {q[0], q[1], q[0] + n, q[1] + n}, std::move(S));
             return true;
         }
         LSite s;
@@ -257,7 +258,7 @@ struct Lowerer {
                 o.site = sidx;
                 o.fshift = 2 * h;
                 o.fmask = 3;
-                ops.push_back(o);
+                ops.push_back(std::move(o));
             }
             return true;
         }
@@ -271,7 +272,7 @@ struct Lowerer {
         o.site = sidx;
         o.fshift = 0;
         o.fmask = (1 << bits) - 1;
-        ops.push_back(o);
+        ops.push_back(std::move(o));
         return true;
     }
 
@@ -422,12 +423,12 @@ struct Lowerer {
                     if (x.nvar > 1) {
                         // keep the variant op AFTER its SITE marker: absorb p into x and emit x here
                         p.dead = true;
-                        x.mats = m;
-                        out.push_back(x);
+                        x.mats = std::move(m);
+                        out.push_back(std::move(x));
                         continue;
                     }
                     p.nvar = nv;
-                    p.mats = m;
+                    p.mats = std::move(m);
                     // the merged op sits at position j: valid because nothing between j and the end touches this bit
                     if (p.nvar == 1 && is_identity(p.mats, 2)) p.dead = true;
                     continue;
@@ -441,7 +442,7 @@ struct Lowerer {
                     continue;
                 }
                 if (x.nvar == 1 && is_identity(x.mats, 2)) continue;
-                out.push_back(x);
+                out.push_back(std::move(x));
                 continue;
             }
             if ((x.kind == LOp::M2 || x.kind == LOp::M4) && x.nvar == 1) {
@@ -470,10 +471,10 @@ struct Lowerer {
                         out[j].dead = true;
                     }
                 }
-                out.push_back(x);
+                out.push_back(std::move(x));
                 continue;
             }
-            out.push_back(x);
+            out.push_back(std::move(x));
         }
         // demote diagonal 1q matrices; drop dead ops
         std::vector<LOp> res;
@@ -494,10 +495,10 @@ struct Lowerer {
                 d.nq = 1;
                 d.q[0] = o.q[0];
                 d.mats = {d0, d1};
-                res.push_back(d);
+                res.push_back(std::move(d));
                 continue;
             }
-            res.push_back(o);
+            res.push_back(std::move(o));
         }
         ops.swap(res);
     }

@@ -22,8 +22,16 @@ class GraphData:
     def __init__(self, data=None):
         self.data = data if data is not None else self._atlas()
 
+    _atlas_cache = {}
+
     @staticmethod
     def _atlas(max_per_order=12):
+        if max_per_order not in GraphData._atlas_cache:
+            GraphData._atlas_cache[max_per_order] = GraphData._scan_atlas(max_per_order)
+        return {k: {"G": list(v["G"])} for k, v in GraphData._atlas_cache[max_per_order].items()}
+
+    @staticmethod
+    def _scan_atlas(max_per_order):
         out, per = {}, {}
         for g in nx.graph_atlas_g():
             k = g.number_of_nodes()

@@ -118,15 +118,28 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     still fixes the result -- but the stream differs from the object route's."""
     from . import batch
     from .samplers import _to_host, get_engine
+    import time
+    timing, t0 = {}, time.perf_counter()
+
+    def lap(name):
+        nonlocal t0
+        t1 = time.perf_counter()
+        timing[name] = timing.get(name, 0.0) + t1 - t0
+        t0 = t1
+
     n, B = sim_specs.n_qubits, sim_specs.n_circuits
     edges, n_edges = graph_state.sample_batch(B, min_vertex_cover=graph_specs.min_vertex_cover,
                                               max_itr=graph_specs.max_itr)
+    lap("graphs")
     enc = batch.build_gate_lists(builder, edges, n_edges, **(sim_specs.circuit.build_options or {}))
+    lap("gate_lists")
     props = batch.draw_device_props(sampler.noise_specs, enc, np.random.default_rng(random.getrandbits(63)))
     t1t2, gp, readout = batch.device_noise_inputs(props)
     sampler.backend_props = props
+    lap("calibration_draws")
     eng = get_engine(sampler.device)
     eng.upload_device_noise(enc, t1t2, gp)
+    lap("upload")
     seed = sampler._next_seed()
     if sampler._pick_method(n, True) == "density_matrix":
         probs = eng.run_density_matrix(sampler.precision)
@@ -135,7 +148,9 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     else:
         sampler.last_probs = None
         hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
+    lap("lower_and_enqueue")       # channels + lowering on host threads, program upload, kernel launches
     prob = _to_host(hist).astype(np.float64) / sampler_specs.n_shots
+    lap("gpu_and_fetch")
     adj = None
     if adj_tensor_specs is not None:
         enc_names = adj_tensor_specs.encoding
@@ -143,13 +158,20 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
             names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"])})
             enc_names = {nm: i + 1 for i, nm in enumerate(names)}
         adj = batch.adjacency_tensors_batch(enc, enc_names, adj_tensor_specs.tensor_shape, adj_tensor_specs.directed)
+        lap("adjacency_tensors")
     results = {}
     for num, graph_data in enumerate(batch.edge_lists(edges, n_edges)):
         results[num] = {"graph_data": graph_data, "prob_vec": prob[num]}
         if adj is not None:
             a = adj[num]
             results[num]["adj_tensor"] = a if adj_tensor_specs.fixed_size else a[np.any(a != 0, axis=(1, 2))]
+    lap("results")
+    global last_timing
+    last_timing = timing
     return results
+
+
+last_timing = {}       # seconds per host stage of the last array-route simulate() call
 
 
 def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto") -> Dict:

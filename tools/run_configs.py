@@ -142,7 +142,9 @@ def c2_simulate(n_circ):
         assert len(res) == count and abs(res[count - 1]["prob_vec"].sum() - 1) < 1e-9
         print(json.dumps({"config": f"C2 end to end: simulate() n=8 device noise, {count} circuits x 1024 shots + adjacency "
                                     f"tensors, route={route}", "s": dt, "value": count / dt, "unit": "circuits/s",
-                          "shots_per_s": 1024 * count / dt}), flush=True)
+                          "shots_per_s": 1024 * count / dt,
+                          "stages_s": {k: round(v, 4) for k, v in qcd.simulate.__globals__["last_timing"].items()}
+                          if route == "auto" else None}), flush=True)
 
 
 def c3(eng, n_circ):
