@@ -149,6 +149,10 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     const bool reuse = dp.host_ready && dp.P.k_max == kb && dp.P.mode == mode;
     if (!reuse) dp.release();
     Program& P = dp.P;
+    // matrix pools stay per lowering thread, already in device precision: no merged host copy of the (large) pool
+    std::vector<std::vector<char>> dev_pools;
+    std::vector<size_t> pool_elems;
+    const double t_begin = Trace::now();
     if (!reuse) {
         P.n_qubits = ctx->n_qubits;
         P.mode = mode;
@@ -160,6 +164,8 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
         n_thr = std::max(1, std::min(n_thr, nc / 2));   // a 20-qubit circuit lowers in ~1 ms: threads pay off early
         std::vector<Program> parts(n_thr);
+        dev_pools.assign(n_thr, std::vector<char>());
+        pool_elems.assign(n_thr, 0);
         std::vector<int> part_rc(n_thr, QCD_OK);
         std::vector<std::string> part_err(n_thr);
         auto work = [&](int t) {
@@ -193,6 +199,18 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
                     return;
                 }
             }
+            const size_t np = Q.pool.size();
+            pool_elems[t] = np;
+            if (precision == 64) {
+                dev_pools[t].resize(np * sizeof(double2));
+                double2* d = reinterpret_cast<double2*>(dev_pools[t].data());
+                for (size_t i = 0; i < np; i++) d[i] = make_double2(Q.pool[i].real(), Q.pool[i].imag());
+            } else {
+                dev_pools[t].resize(np * sizeof(float2));
+                float2* d = reinterpret_cast<float2*>(dev_pools[t].data());
+                for (size_t i = 0; i < np; i++) d[i] = make_float2((float)Q.pool[i].real(), (float)Q.pool[i].imag());
+            }
+            std::vector<cd>().swap(Q.pool);
         };
         if (n_thr == 1) {
             work(0);
@@ -203,21 +221,52 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         }
         for (int t = 0; t < n_thr; t++)
             if (part_rc[t] != QCD_OK) return fail(ctx, part_rc[t], part_err[t]);
-        for (int t = 0; t < n_thr; t++) merge_program(P, parts[t]);
+        {
+            size_t n_sw = 0, n_pa = 0, n_ko = 0, n_ma = 0, n_gr = 0, n_su = 0, n_gd = 0;
+            for (const Program& q : parts) {
+                n_sw += q.sweeps.size(); n_pa += q.passes.size(); n_ko += q.kops.size(); n_ma += q.masks.size();
+                n_gr += q.groups.size(); n_su += q.subs.size(); n_gd += q.gdata.size();
+            }
+            P.sweeps.reserve(n_sw); P.passes.reserve(n_pa); P.kops.reserve(n_ko); P.masks.reserve(n_ma);
+            P.groups.reserve(n_gr); P.subs.reserve(n_su); P.gdata.reserve(n_gd); P.circuits.reserve(nc);
+        }
+        size_t pool_total = 0;
+        for (int t = 0; t < n_thr; t++) {
+            merge_program(P, parts[t], (long long)pool_total);
+            pool_total += pool_elems[t];
+            parts[t] = Program();
+        }
+        if (pool_total > 0xffffffffull) return fail(ctx, QCD_E_UNSUPPORTED, "matrix pool exceeds 2^32 entries: split the upload");
     }
+    const double t_lowered = Trace::now();
     dp.host_ready = false;
     int rc;
     if ((rc = upload_vec(ctx, dp.sweeps, P.sweeps))) return rc;
     if ((rc = upload_vec(ctx, dp.passes, P.passes))) return rc;
     if ((rc = upload_vec(ctx, dp.kops, P.kops))) return rc;
-    if (precision == 64) {
-        std::vector<double2> pool(P.pool.size());
-        for (size_t i = 0; i < pool.size(); i++) pool[i] = make_double2(P.pool[i].real(), P.pool[i].imag());
-        if ((rc = upload_vec(ctx, dp.pool, pool))) return rc;
-    } else {
-        std::vector<float2> pool(P.pool.size());
-        for (size_t i = 0; i < pool.size(); i++) pool[i] = make_float2((float)P.pool[i].real(), (float)P.pool[i].imag());
-        if ((rc = upload_vec(ctx, dp.pool, pool))) return rc;
+    {
+        const size_t elem = precision == 64 ? sizeof(double2) : sizeof(float2);
+        size_t total = 0;
+        for (size_t n_el : pool_elems) total += n_el;
+        CU(dp.pool.ensure(std::max<size_t>(total, 1) * elem));
+        // one copy per lowering thread's pool, issued from parallel host threads (pageable copies are CPU-bound)
+        std::vector<cudaError_t> cp_rc(dev_pools.size(), cudaSuccess);
+        auto copy_part = [&](size_t t, size_t base) {
+            cudaSetDevice(ctx->device);
+            if (pool_elems[t])
+                cp_rc[t] = cudaMemcpy(dp.pool.as<char>() + base * elem, dev_pools[t].data(), pool_elems[t] * elem,
+                                      cudaMemcpyHostToDevice);
+        };
+        std::vector<std::thread> cps;
+        size_t base = 0;
+        for (size_t t = 0; t < dev_pools.size(); t++) {
+            if (dev_pools.size() > 1 && pool_elems[t] * elem > (1u << 20)) cps.emplace_back(copy_part, t, base);
+            else copy_part(t, base);
+            base += pool_elems[t];
+        }
+        for (std::thread& th : cps) th.join();
+        for (cudaError_t e : cp_rc)
+            if (e != cudaSuccess) return fail(ctx, QCD_E_CUDA, std::string("pool upload: ") + cudaGetErrorString(e));
     }
     std::vector<uint32_t> masks(P.masks.size());
     for (size_t i = 0; i < masks.size(); i++) masks[i] = (uint32_t)P.masks[i];
@@ -276,6 +325,10 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     dp.valid = true;
     ctx->prog_tile_bits[mode][pi] = kb;
     *out = &dp;
+    if (g_trace.on)
+        fprintf(stderr, "[qcd] program: %d circuits lowered in %.1f ms, uploaded in %.1f ms (%zu sweeps, %zu passes)\n",
+                ctx->n_circuits, (t_lowered - t_begin) * 1e3, (Trace::now() - t_lowered) * 1e3, P.sweeps.size(),
+                P.passes.size());
     return QCD_OK;
 }
 

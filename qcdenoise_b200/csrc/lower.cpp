@@ -962,9 +962,10 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     return QCD_OK;
 }
 
-void merge_program(Program& dst, const Program& src) {
+void merge_program(Program& dst, const Program& src, long long pool_base) {
     const uint32_t sweep0 = (uint32_t)dst.sweeps.size(), pass0 = (uint32_t)dst.passes.size();
-    const uint32_t kop0 = (uint32_t)dst.kops.size(), pool0 = (uint32_t)dst.pool.size();
+    const uint32_t kop0 = (uint32_t)dst.kops.size();
+    const uint32_t pool0 = pool_base >= 0 ? (uint32_t)pool_base : (uint32_t)dst.pool.size();
     const uint32_t mask0 = (uint32_t)dst.masks.size(), group0 = (uint32_t)dst.groups.size();
     const uint32_t sub0 = (uint32_t)dst.subs.size(), gdata0 = (uint32_t)dst.gdata.size();
     for (Sweep s : src.sweeps) {
@@ -983,7 +984,7 @@ void merge_program(Program& dst, const Program& src) {
         k.off += k.kind == K_SIGNS ? mask0 : pool0;
         dst.kops.push_back(k);
     }
-    dst.pool.insert(dst.pool.end(), src.pool.begin(), src.pool.end());
+    if (pool_base < 0) dst.pool.insert(dst.pool.end(), src.pool.begin(), src.pool.end());
     dst.masks.insert(dst.masks.end(), src.masks.begin(), src.masks.end());
     for (Group g : src.groups) {
         g.sub_begin += sub0;

@@ -37,7 +37,8 @@ int compile_circuit(Program& P, const qcd_op* ops, uint32_t n_ops, const double*
 
 // Appends every circuit of `src` (compiled separately with the same n_qubits / mode / k_max) to `dst`, re-basing all
 // offsets.  Used to lower large batches on several host threads.
-void merge_program(Program& dst, const Program& src);
+// pool_base >= 0: src's matrix pool is NOT copied; its offsets are re-based to pool_base (the caller places the pools).
+void merge_program(Program& dst, const Program& src, long long pool_base = -1);
 
 // JSON description of circuit `c` of P (for the CPU-side schedule interpreter in tests/).
 std::string program_to_json(const Program& P, int c);
