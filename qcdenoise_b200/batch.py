@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import OPCODES, OP_DTYPE
 from .graph_circuit import CPhaseGateCircuit, CXGateCircuit, CZGateCircuit
 
-__all__ = ["build_gate_lists", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
+__all__ = ["build_gate_lists", "sites_per_edge", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
 
 _GATE_NAMES = {OPCODES[nm]: nm for nm in ("id", "h", "x", "y", "z", "s", "sdg", "t", "tdg", "rx", "ry", "rz", "cx", "cz",
                                           "swap")}
@@ -29,13 +29,23 @@ def edge_lists(edges, n_edges):
     return [pairs[e - k:e] for e, k in zip(ends, n_edges.tolist())]
 
 
-def build_gate_lists(builder, edges, n_edges, **build_options):
+def sites_per_edge(builder):
+    """Potential labelled noise sites per edge: 1 for the CX / CZ builders, 2 for CPhase (one after each CX)."""
+    return 2 if isinstance(builder, CPhaseGateCircuit) else 1
+
+
+def build_gate_lists(builder, edges, n_edges, coins=None, gammas=None, **build_options):
     """Gate lists of a batch of graphs, as the encoded arrays `Engine.upload` takes: (ops, offsets, params, n).
-    builder: a CXGateCircuit / CZGateCircuit / CPhaseGateCircuit instance with stochastic=False (noise sites are drawn
-    per circuit by the object route).  Same gates in the same order as builder.build(graph) for a graph whose
-    `edges()` are edges[i, :n_edges[i]] (graph_circuit.py:81-99, :114-130, :151-173)."""
-    if builder.stochastic:
-        raise ValueError("build_gate_lists covers stochastic=False builders; labelled noise sites need the object route")
+    builder: a CXGateCircuit / CZGateCircuit / CPhaseGateCircuit instance.  Same gates in the same order as
+    builder.build(graph) for a graph whose `edges()` are edges[i, :n_edges[i]] (graph_circuit.py:81-99, :114-130,
+    :151-173).
+
+    Stochastic builders: coins uint8 [total edges, sites_per_edge(builder)] says which potential sites exist (the
+    object route's np.random.choice(2) per site, graph_circuit.py:91); gammas float64 [coins.sum(), 2] are the two
+    U(0, max_prob) draws of each site in site order (samplers.py:423-451).  A site is the labelled identity `unitary`
+    followed by the amplitude-damping channels UnitaryNoiseSampler attaches to its label: draw 1 on the first qubit,
+    draw 0 on the second (reference quirk Q1).  Two sites of one CPhase edge share the label `unitary_a_b`, so each
+    instance carries both sites' channels, like the reference's composed label errors."""
     n = builder.n_qubits
     edges = np.asarray(edges, dtype=np.uint8)
     n_edges = np.asarray(n_edges, dtype=np.int64)
@@ -45,55 +55,104 @@ def build_gate_lists(builder, edges, n_edges, **build_options):
     keep = np.arange(edges.shape[1])[None, :] < n_edges[:, None]
     a = edges[..., 0][keep].astype(np.uint8)       # flat, circuit after circuit
     b = edges[..., 1][keep].astype(np.uint8)
-    if len(a) and max(int(a.max()), int(b.max())) >= n:
+    E = len(a)
+    if E and max(int(a.max()), int(b.max())) >= n:
         raise AssertionError(f"n_qubits={n} but an edge names vertex {max(int(a.max()), int(b.max()))}")
-    e_start = np.concatenate([[0], np.cumsum(n_edges)])
-    e_local = np.arange(len(a)) - np.repeat(e_start[:-1], n_edges)
+    S = sites_per_edge(builder)
+    if coins is None:
+        if builder.stochastic:
+            raise ValueError("a stochastic builder needs `coins` (and `gammas`)")
+        coins = np.zeros((E, S), dtype=np.int64)
+    coins = np.asarray(coins).astype(np.int64).reshape(E, S)
+    n_sites = int(coins.sum())
+    if n_sites:
+        gammas = np.asarray(gammas, dtype=np.float64)
+        if gammas.shape != (n_sites, 2):
+            raise ValueError(f"gammas must have shape ({n_sites}, 2)")
+        if (gammas < 0).any() or (gammas > 1).any():
+            raise ValueError("damping parameters out of range")
     circ = np.repeat(np.arange(B), n_edges)
-    params = np.zeros(0, dtype=np.float64)
     H, CX, CZ, RY = OPCODES["h"], OPCODES["cx"], OPCODES["cz"], OPCODES["ry"]
+    U2Q, K1Q = OPCODES["u2q"], OPCODES["kraus1q"]
     if isinstance(builder, (CXGateCircuit, CZGateCircuit)):
-        per_edge, prefix = 3, n
+        n_gates, prefix = 3, n
     elif isinstance(builder, CPhaseGateCircuit):
-        per_edge, prefix = 5, 0
+        n_gates, prefix = 5, 0
     else:
         raise TypeError(f"no batched gate-list builder for {type(builder).__name__}")
-    offsets = np.concatenate([[0], np.cumsum(prefix + per_edge * n_edges)])
+    k_e = coins.sum(axis=1)                         # chosen sites of the edge = channels pairs behind each instance
+    inst_len = 1 + 2 * k_e                          # marker + 2 channels per chosen site of the edge
+    block = coins * inst_len[:, None]               # [E, S] ops of each site instance (0 if not chosen)
+    edge_len = n_gates + block.sum(axis=1)
+    per_circ = np.bincount(circ, weights=edge_len, minlength=B).astype(np.int64) if E else np.zeros(B, dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(prefix + per_circ)])
     if offsets[-1] >= 2 ** 32:
         raise ValueError("batch too large for one upload (2^32 ops)")
     ops = np.zeros(int(offsets[-1]), dtype=OP_DTYPE)
     ops["q1"] = 0xFF
-    base = offsets[:-1][circ] + prefix + per_edge * e_local
+    base = (circ + 1) * prefix + np.concatenate([[0], np.cumsum(edge_len)[:-1]]) if E else np.zeros(0, dtype=np.int64)
+
+    def put(pos, code, q0, q1=None, off=None, sel=None):
+        if sel is not None:
+            pos, q0 = pos[sel], q0[sel]
+            q1 = q1[sel] if q1 is not None else None
+            off = off[sel] if isinstance(off, np.ndarray) else off
+        ops["opcode"][pos] = code
+        ops["q0"][pos] = q0
+        if q1 is not None:
+            ops["q1"][pos] = q1
+        if off is not None:
+            ops["param_off"][pos] = off
+
     if prefix:
         pos = (offsets[:-1][:, None] + np.arange(n)[None, :]).ravel()
-        ops["opcode"][pos] = H
-        ops["q0"][pos] = np.tile(np.arange(n, dtype=np.uint8), B)
-    if isinstance(builder, CXGateCircuit):          # H(b) CX(a, b) H(b)
-        for k in (0, 2):
-            ops["opcode"][base + k] = H
-            ops["q0"][base + k] = b
-        ops["opcode"][base + 1] = CX
-        ops["q0"][base + 1] = a
-        ops["q1"][base + 1] = b
-    elif isinstance(builder, CZGateCircuit):        # H(a) CZ(a, b) H(a)
-        for k in (0, 2):
-            ops["opcode"][base + k] = H
-            ops["q0"][base + k] = a
-        ops["opcode"][base + 1] = CZ
-        ops["q0"][base + 1] = a
-        ops["q1"][base + 1] = b
-    else:                                           # Ry(L/2, b) CX Ry(-T/2, b) CX Ry(L/2, b)
-        lam = build_options.get("Lambda", np.pi)
-        theta = build_options.get("Theta", np.pi / 2)
-        params = np.array([lam / 2, -theta / 2], dtype=np.float64)
-        for k, off in ((0, 0), (2, 1), (4, 0)):
-            ops["opcode"][base + k] = RY
-            ops["q0"][base + k] = b
-            ops["param_off"][base + k] = off
-        for k in (1, 3):
-            ops["opcode"][base + k] = CX
-            ops["q0"][base + k] = a
-            ops["q1"][base + k] = b
+        put(pos, H, np.tile(np.arange(n, dtype=np.uint8), B))
+    # parameters: [builder angles] [I4 of the site markers] [17 doubles per (site, draw): 2, K0, K1]
+    lam = build_options.get("Lambda", np.pi)
+    theta = build_options.get("Theta", np.pi / 2)
+    head = [lam / 2, -theta / 2] if isinstance(builder, CPhaseGateCircuit) else []
+    i4_off = len(head)
+    k_base = i4_off + (32 if n_sites else 0)
+    params = np.zeros(k_base + 34 * n_sites, dtype=np.float64)
+    params[:len(head)] = head
+    if n_sites:
+        params[i4_off + np.arange(4) * 10] = 1.0             # identity 4x4, (re, im) pairs, row-major
+        kb = params[k_base:].reshape(n_sites, 2, 17)
+        kb[..., 0] = 2.0
+        kb[..., 1] = 1.0                                      # K0 = diag(1, sqrt(1 - g))
+        kb[..., 7] = np.sqrt(np.maximum(0.0, 1.0 - gammas))
+        kb[..., 11] = np.sqrt(gammas)                         # K1 = sqrt(g) |0><1|
+        if (np.sqrt(gammas) <= 1e-12).any():
+            raise ValueError("a damping parameter of (numerically) zero: use the object route")
+    site_idx = (np.cumsum(coins.ravel()) - coins.ravel()).reshape(E, S)      # global index of each chosen site
+
+    def site_block(pos, j):
+        """Instance of site j of every edge that has it, starting at pos: marker, then per chosen site jj of the edge
+        K(a, draw 1), K(b, draw 0)."""
+        sel = coins[:, j] == 1
+        put(pos, U2Q, a, b, i4_off, sel)
+        slot = np.ones(E, dtype=np.int64)
+        for jj in range(S):
+            both = sel & (coins[:, jj] == 1)
+            put(pos + slot, K1Q, a, None, k_base + (2 * site_idx[:, jj] + 1) * 17, both)
+            put(pos + slot + 1, K1Q, b, None, k_base + (2 * site_idx[:, jj]) * 17, both)
+            slot = slot + 2 * coins[:, jj]
+
+    if isinstance(builder, (CXGateCircuit, CZGateCircuit)):
+        hq = b if isinstance(builder, CXGateCircuit) else a       # H(b) CX(a, b) [site] H(b)  /  H(a) CZ(a, b) [site] H(a)
+        put(base, H, hq)
+        put(base + 1, CX if isinstance(builder, CXGateCircuit) else CZ, a, b)
+        site_block(base + 2, 0)
+        put(base + 2 + block[:, 0], H, hq)
+    else:                                           # Ry(L/2, b) CX [site] Ry(-T/2, b) CX [site] Ry(L/2, b)
+        put(base, RY, b, None, 0)
+        put(base + 1, CX, a, b)
+        site_block(base + 2, 0)
+        p2 = base + 2 + block[:, 0]
+        put(p2, RY, b, None, 1)
+        put(p2 + 1, CX, a, b)
+        site_block(p2 + 2, 1)
+        put(p2 + 2 + block[:, 1], RY, b, None, 0)
     return ops, offsets.astype(np.uint32), params, n
 
 

@@ -103,12 +103,22 @@ def estimate_entanglement_op(graph, graph_circuit, entangle_specs, n_qubits, bac
     return witness.estimate(graph=graph)
 
 
+_DAMPING_KINDS = ("phase_amplitude_damping_error", "amplitude_damping_error")
+
+
 def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
-    """The whole-batch array route (batch.py) covers: random device noise (backend None), the three graph-circuit
-    builders without stochastic sites, undirected graphs, no entanglement stage."""
-    return (isinstance(sampler, DeviceNoiseSampler) and sampler.noisy and sim_specs.backend is None
-            and type(builder) in (CXGateCircuit, CZGateCircuit, CPhaseGateCircuit) and not sim_specs.circuit.stochastic
-            and not graph_specs.directed and entangle_specs is None)
+    """The whole-batch array route (batch.py) covers the three graph-circuit builders on undirected graphs without
+    an entanglement stage, with either random device noise (DeviceNoiseSampler, backend None, no stochastic sites)
+    or the labelled damping sites of UnitaryNoiseSampler."""
+    if type(builder) not in (CXGateCircuit, CZGateCircuit, CPhaseGateCircuit) or graph_specs.directed \
+            or entangle_specs is not None or not sampler.noisy:
+        return False
+    if isinstance(sampler, DeviceNoiseSampler):
+        return sim_specs.backend is None and not sim_specs.circuit.stochastic
+    if isinstance(sampler, UnitaryNoiseSampler):
+        specs = sampler.noise_specs.specs
+        return specs.get("type", _DAMPING_KINDS[0]) in _DAMPING_KINDS and set(specs) <= {"type", "max_prob"}
+    return False
 
 
 def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler):
@@ -131,17 +141,31 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     edges, n_edges = graph_state.sample_batch(B, min_vertex_cover=graph_specs.min_vertex_cover,
                                               max_itr=graph_specs.max_itr)
     lap("graphs")
-    enc = batch.build_gate_lists(builder, edges, n_edges, **(sim_specs.circuit.build_options or {}))
-    lap("gate_lists")
-    props = batch.draw_device_props(sampler.noise_specs, enc, np.random.default_rng(random.getrandbits(63)))
-    t1t2, gp, readout = batch.device_noise_inputs(props)
-    sampler.backend_props = props
-    lap("calibration_draws")
+    rng = np.random.default_rng(random.getrandbits(63))
     eng = get_engine(sampler.device)
-    eng.upload_device_noise(enc, t1t2, gp)
+    build_options = sim_specs.circuit.build_options or {}
+    if isinstance(sampler, DeviceNoiseSampler):
+        enc = batch.build_gate_lists(builder, edges, n_edges, **build_options)
+        lap("gate_lists")
+        props = batch.draw_device_props(sampler.noise_specs, enc, rng)
+        t1t2, gp, readout = batch.device_noise_inputs(props)
+        sampler.backend_props = props
+        lap("calibration_draws")
+        eng.upload_device_noise(enc, t1t2, gp)
+        noisy = True
+    else:
+        # UnitaryNoiseSampler: a coin per potential site, two U(0, max_prob) damping draws per site
+        n_slots = (int(n_edges.sum()), batch.sites_per_edge(builder))
+        coins = rng.integers(0, 2, size=n_slots) if sim_specs.circuit.stochastic else np.zeros(n_slots, dtype=np.int64)
+        gammas = rng.uniform(0.0, sampler.noise_specs.specs.get("max_prob", 0.1), size=(int(coins.sum()), 2))
+        enc = batch.build_gate_lists(builder, edges, n_edges, coins=coins, gammas=gammas, **build_options)
+        lap("gate_lists")
+        readout = None
+        eng.upload(enc)
+        noisy = bool(coins.any())
     lap("upload")
     seed = sampler._next_seed()
-    if sampler._pick_method(n, True) == "density_matrix":
+    if sampler._pick_method(n, noisy) == "density_matrix":
         probs = eng.run_density_matrix(sampler.precision)
         sampler.last_probs = probs
         hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
@@ -155,7 +179,7 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     if adj_tensor_specs is not None:
         enc_names = adj_tensor_specs.encoding
         if enc_names is None:
-            names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"])})
+            names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"]) if int(c) in batch._GATE_NAMES})
             enc_names = {nm: i + 1 for i, nm in enumerate(names)}
         adj = batch.adjacency_tensors_batch(enc, enc_names, adj_tensor_specs.tensor_shape, adj_tensor_specs.directed)
         lap("adjacency_tensors")

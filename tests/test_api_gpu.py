@@ -277,3 +277,54 @@ def test_simulate_array_route_matches_oracle(qcd):
     res3 = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), adj_tensor_specs=adj_specs,
                         route="objects")
     assert sorted(res3) == list(range(40)) and res3[0]["adj_tensor"].shape == (16, 8, 8)
+
+
+def test_simulate_array_route_unitary_noise_matches_oracle(qcd, monkeypatch):
+    """Array route for stochastic builders + UnitaryNoiseSampler: exact distributions of the batched programs equal
+    the oracle's density matrix on the object route's explicit programs built from the same coins and damping draws."""
+    from qcdenoise_b200 import batch
+    from qcdenoise_b200.samplers import get_engine
+    n, B = 5, 10
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n, max_num_edges=4)
+    edges, n_edges = gs.sample_batch(B, seed=31)
+    rng = np.random.default_rng(8)
+    eng = get_engine()
+    for cls in (qcd.CXGateCircuit, qcd.CPhaseGateCircuit):
+        builder = cls(n_qubits=n, stochastic=True)
+        coins = rng.integers(0, 2, size=(int(n_edges.sum()), batch.sites_per_edge(builder)))
+        gammas = rng.uniform(0, 0.3, size=(int(coins.sum()), 2))
+        eng.upload(batch.build_gate_lists(builder, edges, n_edges, coins=coins, gammas=gammas))
+        probs = eng.run_density_matrix(64).cpu().numpy()
+        hist, _ = eng.run_trajectories(4096, seed=3, precision=32)
+        coin_iter, gamma_iter = iter(coins.ravel().tolist()), iter(gammas)
+        with monkeypatch.context() as mp:
+            mp.setattr(np.random, "choice", lambda k: next(coin_iter))
+            mp.setattr(np.random, "uniform", lambda high, size: next(gamma_iter).copy())
+            s = qcd.UnitaryNoiseSampler(None, n_shots=16, seed=1,
+                                        noise_specs=qcd.NoiseSpec(specs={"type": "amplitude_damping_error", "max_prob": 0.3}))
+            for i, ed in enumerate(batch.edge_lists(edges, n_edges)):
+                g = nx.Graph()
+                g.add_nodes_from(range(n))
+                g.add_edges_from(ed)
+                cd = cls(n_qubits=n, stochastic=True).build(g)
+                s.build_noise_model(cd["ops"])
+                inst, _ = s.noise_model.instantiate(cd["circuit"])
+                want = sim.density_matrix_probs(inst.ops, n)
+                np.testing.assert_allclose(probs[i], want, atol=1e-10)
+                assert 0.5 * np.abs(hist[i].cpu().numpy() / 4096 - want).sum() < 0.08
+    # the public call (reference examples/simulate_example.py: UnitaryNoiseSampler, stochastic CX, adjacency tensors)
+    random.seed(2)
+    sim_specs = qcd.SimulationSpecs(n_qubits=6, n_circuits=30, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=True))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.UnitaryNoiseSampler, noise_specs=qcd.unitary_noise_spec, n_shots=1024)
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=5),
+                       adj_tensor_specs=qcd.AdjTensorSpecs(tensor_shape=(16, 32, 32)))
+    assert sorted(res) == list(range(30))
+    with_sites = 0
+    for r in res.values():
+        assert r["prob_vec"].shape == (64,) and abs(r["prob_vec"].sum() - 1) < 1e-12
+        assert r["adj_tensor"].shape == (16, 32, 32)
+        codes = set(np.unique(r["adj_tensor"]).tolist())
+        assert {0.0, 1.0, 2.0} <= codes <= {0.0, 1.0, 2.0, 3.0}           # cx, h and (where a coin fell) unitary
+        with_sites += 3.0 in codes
+    assert 0 < with_sites <= 30

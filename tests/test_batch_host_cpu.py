@@ -153,3 +153,43 @@ def test_native_adjacency_tensors_equal_python_walk(directed):
         batch.adjacency_tensors_batch(enc, {"h": 1}, (9, 8, 8))
     with pytest.raises(IndexError):
         batch.adjacency_tensors_batch(enc, encoding, (9, 4, 4))
+
+
+@pytest.mark.parametrize("cls,kind", [(qcd.CXGateCircuit, "phase_amplitude_damping_error"),
+                                      (qcd.CZGateCircuit, "amplitude_damping_error"),
+                                      (qcd.CPhaseGateCircuit, "phase_amplitude_damping_error")])
+def test_batched_stochastic_gate_lists_equal_object_route(cls, kind, monkeypatch):
+    """Stochastic builders + UnitaryNoiseSampler: feed the object route the SAME coins and damping draws (by
+    patching np.random.choice / np.random.uniform) and compare the explicit programs op for op."""
+    n = 6
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(30, seed=8)
+    rng = np.random.default_rng(2)
+    builder = cls(n_qubits=n, stochastic=True)
+    S = batch.sites_per_edge(builder)
+    coins = rng.integers(0, 2, size=(int(n_edges.sum()), S))
+    gammas = rng.uniform(0, 0.3, size=(int(coins.sum()), 2))
+    got = batch.build_gate_lists(builder, edges, n_edges, coins=coins, gammas=gammas)
+    coin_iter, gamma_iter = iter(coins.ravel().tolist()), iter(gammas)
+    monkeypatch.setattr(np.random, "choice", lambda k: next(coin_iter))
+    monkeypatch.setattr(np.random, "uniform", lambda high, size: next(gamma_iter).copy())
+    s = qcd.UnitaryNoiseSampler(None, n_shots=16, noise_specs=qcd.NoiseSpec(specs={"type": kind, "max_prob": 0.3}))
+    progs = []
+    for g in _graphs_from(edges, n_edges, n):
+        cd = cls(n_qubits=n, stochastic=True).build(g)
+        s.build_noise_model(cd["ops"])
+        progs.append(s.noise_model.instantiate(cd["circuit"])[0])
+    want = encode_programs(progs)
+    assert next(coin_iter, None) is None and next(gamma_iter, None) is None
+    (ops, off, par, _), (wops, woff, wpar, _) = got, want
+    assert np.array_equal(off, woff)
+    for f in ("opcode", "q0", "q1"):
+        assert np.array_equal(ops[f], wops[f])
+    K, U, RY = (qcd._lib.OPCODES[k] for k in ("kraus1q", "u2q", "ry"))
+    for i in np.nonzero(ops["opcode"] == K)[0]:
+        assert np.array_equal(par[ops["param_off"][i]:ops["param_off"][i] + 17], wpar[wops["param_off"][i]:wops["param_off"][i] + 17])
+    for i in np.nonzero(ops["opcode"] == U)[0]:
+        assert np.array_equal(par[ops["param_off"][i]:ops["param_off"][i] + 32], wpar[wops["param_off"][i]:wops["param_off"][i] + 32])
+    ry = ops["opcode"] == RY
+    assert np.array_equal(par[ops["param_off"][ry]], wpar[wops["param_off"][ry]])
+    assert (ops["opcode"] == K).sum() >= 2 * coins.sum()
