@@ -130,7 +130,9 @@ QCD_API int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t*
  * After every op with an entry the library writes PAULI1Q/2Q (depolarizing strength such that depolarizing o
  * relaxation has average gate infidelity gate_error) and one KRAUS1Q per gate qubit (thermal relaxation over
  * gate_length; T2 clipped to 2 T1), exactly the program qcdenoise_b200.samplers.DeviceNoiseSampler builds op by op
- * in Python -- same operator order, hence the same shots -- then keeps it like qcd_upload_programs. */
+ * in Python -- same operator order, hence the same shots.  The gate lists and the numbers are validated and copied
+ * here; the channels are written circuit by circuit inside the lowering threads at the first run (no expanded copy
+ * of the batch is ever held), so out-of-range T1/T2 surface as an error of that run. */
 QCD_API int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offsets,
                                              const double* params, size_t n_params, int n_circuits, int n_qubits,
                                              const double* qubit_t1_t2, const double* op_gate_props);
