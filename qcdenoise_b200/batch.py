@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import OPCODES, OP_DTYPE
 from .graph_circuit import CPhaseGateCircuit, CXGateCircuit, CZGateCircuit
 
-__all__ = ["build_gate_lists", "sites_per_edge", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
+__all__ = ["build_gate_lists", "sites_per_edge", "slice_programs", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
 
 _GATE_NAMES = {OPCODES[nm]: nm for nm in ("id", "h", "x", "y", "z", "s", "sdg", "t", "tdg", "rx", "ry", "rz", "cx", "cz",
                                           "swap")}
@@ -252,3 +252,11 @@ def adjacency_tensors_batch(enc, encoding, tensor_shape=(32, 32, 32), directed=F
     if rc:
         raise _lib.QcdError(rc, "qcd_adjacency_tensors: invalid arguments")
     return out
+
+
+def slice_programs(enc, lo, hi):
+    """Circuits [lo, hi) of an encoded batch as an encoded batch of their own (the parameter array is shared, so
+    param_off stays valid) -> ((ops, offsets, params, n), (op_lo, op_hi)): one rank's share of a sharded batch."""
+    ops, offsets, params, n = enc
+    o_lo, o_hi = int(offsets[lo]), int(offsets[hi])
+    return (ops[o_lo:o_hi], (offsets[lo:hi + 1].astype(np.int64) - o_lo).astype(np.uint32), params, n), (o_lo, o_hi)

@@ -121,7 +121,8 @@ def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
     return False
 
 
-def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler):
+def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
+                     distributed=False):
     """simulate() without per-circuit Python objects: graphs, gate lists, calibration draws and adjacency tensors are
     built for the whole batch (natively / in numpy), the noise channels are written natively at upload, one engine
     call simulates everything.  Draws come from numpy / Philox generators seeded from `random`, so `random.seed()`
@@ -138,10 +139,20 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         t0 = t1
 
     n, B = sim_specs.n_qubits, sim_specs.n_circuits
+    # Sharded run (one process per GPU): every rank builds the (cheap) host arrays of the WHOLE batch from common
+    # seeds, lowers / simulates only its contiguous slice of circuits, and one all_gather assembles the histograms.
+    # In density-matrix mode the result is independent of the number of ranks, bit for bit.
+    import torch.distributed as dist
+    from . import distributed as qdist
+    world = dist.get_world_size() if (distributed and dist.is_available() and dist.is_initialized()) else 1
+    seeds = [random.getrandbits(63), random.getrandbits(63), sampler._next_seed()]
+    if world > 1:
+        dist.broadcast_object_list(seeds, src=0)
+    lo, hi = qdist.circuit_slice(B) if world > 1 else (0, B)
     edges, n_edges = graph_state.sample_batch(B, min_vertex_cover=graph_specs.min_vertex_cover,
-                                              max_itr=graph_specs.max_itr)
+                                              max_itr=graph_specs.max_itr, seed=seeds[0])
     lap("graphs")
-    rng = np.random.default_rng(random.getrandbits(63))
+    rng = np.random.default_rng(seeds[1])
     eng = get_engine(sampler.device)
     build_options = sim_specs.circuit.build_options or {}
     if isinstance(sampler, DeviceNoiseSampler):
@@ -151,7 +162,9 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         t1t2, gp, readout = batch.device_noise_inputs(props)
         sampler.backend_props = props
         lap("calibration_draws")
-        eng.upload_device_noise(enc, t1t2, gp)
+        mine, (o_lo, o_hi) = batch.slice_programs(enc, lo, hi)
+        eng.upload_device_noise(mine, t1t2[lo:hi], gp[o_lo:o_hi])
+        readout = readout[lo:hi] if readout is not None else None
         noisy = True
     else:
         # UnitaryNoiseSampler: a coin per potential site, two U(0, max_prob) damping draws per site
@@ -161,18 +174,24 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         enc = batch.build_gate_lists(builder, edges, n_edges, coins=coins, gammas=gammas, **build_options)
         lap("gate_lists")
         readout = None
-        eng.upload(enc)
+        eng.upload(batch.slice_programs(enc, lo, hi)[0])
         noisy = bool(coins.any())
     lap("upload")
-    seed = sampler._next_seed()
-    if sampler._pick_method(n, noisy) == "density_matrix":
+    seed = seeds[2]
+    if hi == lo:
+        import torch
+        hist = torch.zeros((0, 2 ** n), dtype=torch.int32, device=eng.device)
+    elif sampler._pick_method(n, noisy) == "density_matrix":
         probs = eng.run_density_matrix(sampler.precision)
         sampler.last_probs = probs
-        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
+        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, first_circuit=lo, readout=readout)
     else:
         sampler.last_probs = None
-        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout)
+        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed + lo, precision=sampler.precision, readout=readout)
     lap("lower_and_enqueue")       # channels + lowering on host threads, program upload, kernel launches
+    if world > 1:
+        hist = qdist.gather_rows(hist.contiguous())
+        lap("all_gather")
     prob = _to_host(hist).astype(np.float64) / sampler_specs.n_shots
     lap("gpu_and_fetch")
     adj = None
@@ -198,10 +217,14 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
 last_timing = {}       # seconds per host stage of the last array-route simulate() call
 
 
-def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto") -> Dict:
+def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto",
+             distributed=False) -> Dict:
     """-> {i: {"graph_data": edges, "prob_vec": np.ndarray (2^n,), ["adj_tensor"], ["entanglement": {"value",
     "variance"}]}}.  route: "auto" (whole-batch array route where it applies, see _array_route_ok) or "objects"
-    (always build a Circuit + NoiseModel per circuit, like the reference's loop, simulate.py:276-322)."""
+    (always build a Circuit + NoiseModel per circuit, like the reference's loop, simulate.py:276-322).
+    distributed=True (array route, torch.distributed initialised, one process per GPU): every rank simulates its
+    contiguous slice of the circuits and all ranks return the complete result (one all_gather) -- the reference's
+    mp.Pool.map + np.concatenate (older_version/circuit_sampling_utils.py:81-89)."""
     if not isinstance(sim_specs, SimulationSpecs):
         raise AssertionError("sim_specs must be an instance of SimulationSpecs")
     if not isinstance(sampler_specs, SamplingSpecs):
@@ -225,7 +248,10 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
     if route not in ("auto", "objects"):
         raise ValueError("route must be 'auto' or 'objects'")
     if route == "auto" and _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
-        return _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler)
+        return _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
+                                distributed=distributed)
+    if distributed:
+        raise NotImplementedError("distributed=True is implemented for the array route (see _array_route_ok)")
 
     results = {i: {} for i in range(sim_specs.n_circuits)}
     graphs, circuits, models = [], [], []

@@ -193,3 +193,17 @@ def test_batched_stochastic_gate_lists_equal_object_route(cls, kind, monkeypatch
     ry = ops["opcode"] == RY
     assert np.array_equal(par[ops["param_off"][ry]], wpar[wops["param_off"][ry]])
     assert (ops["opcode"] == K).sum() >= 2 * coins.sum()
+
+
+def test_slice_programs_is_the_sub_batch():
+    n = 6
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(12, seed=3)
+    builder = qcd.CPhaseGateCircuit(n_qubits=n, stochastic=False)
+    enc = batch.build_gate_lists(builder, edges, n_edges)
+    (ops, off, par, nn), (o_lo, o_hi) = batch.slice_programs(enc, 4, 9)
+    want = batch.build_gate_lists(builder, edges[4:9], n_edges[4:9])
+    assert nn == n and np.array_equal(off, want[1]) and np.array_equal(ops, want[0]) and np.array_equal(par, want[2])
+    assert (o_lo, o_hi) == (int(enc[1][4]), int(enc[1][9]))
+    empty, _ = batch.slice_programs(enc, 5, 5)
+    assert len(empty[0]) == 0 and empty[1].tolist() == [0]
