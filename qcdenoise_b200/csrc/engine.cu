@@ -31,7 +31,7 @@ thread_local std::string g_create_error;
 
 struct Trace {
     bool on = getenv("QCD_TRACE") != nullptr;
-    double t_sync = 0, t_h2d = 0, t_total = 0;
+    double t_sync = 0, t_h2d = 0, t_total = 0, t_prep = 0, t_launch = 0, t_leaves = 0, t_run0 = 0;
     int n_sync = 0;
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 } g_trace;
@@ -62,15 +62,43 @@ struct DevBuf {
     template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
 
+// page-locked host staging (node records travel host <-> device once per tree level)
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes + bytes / 2, (size_t)4096);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
 struct DevProg {
     bool valid = false;
     bool host_ready = false;   // P was lowered at upload time (device copies still to be made)
     Program P;
     DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits, direct;
     std::vector<DirectSweep> direct_host;
+    std::vector<uint8_t> direct_flags;   // per descriptor: DF_* (what a launch holding this sweep must provide)
     void release() {
         direct.release();
         direct_host.clear();
+        direct_flags.clear();
         sweeps.release(); passes.release(); kops.release(); pool.release(); masks.release();
         groups.release(); subs.release(); gdata.release(); circuits.release();
         valid = false;
@@ -78,6 +106,8 @@ struct DevProg {
         P = Program();
     }
 };
+
+enum { DF_OK = 1, DF_VEC = 2, DF_RED = 4, DF_FINAL = 8, DF_PREP = 16 };
 
 }  // namespace
 
@@ -109,6 +139,7 @@ struct qcd_ctx {
     DevBuf states, partials, chunk_sums, block_sums;
     DevBuf owner, keys, probs4, table, offs, children, counter, bsum, flip, masks, scratch, slots;
     std::vector<DevBuf> level_nodes, level_shots;
+    std::vector<PinBuf> host_nodes;   // children read back at depth d (= the nodes of depth d + 1), page-locked
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     qcd_stats stats;
@@ -318,6 +349,19 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             describe(dp.direct_host[P.sweeps.size() + pi], S, pi, fl, pi + 1 == S.pass_end);
         }
     }
+    dp.direct_flags.assign(dp.direct_host.size(), 0);
+    for (size_t i = 0; i < dp.direct_host.size(); i++) {
+        const DirectSweep& D = dp.direct_host[i];
+        uint8_t f = 0;
+        if (D.ok) f |= DF_OK;
+        if (D.rbit[0] == 0) f |= DF_VEC;
+        if (D.red_q[0] >= 0) f |= DF_RED;
+        if (D.flags & SW_FINAL) f |= DF_FINAL;
+        if (D.flags & SW_PREP) f |= DF_PREP;
+        for (int o = 0; o < D.nops; o++)
+            if (D.ops[o].kind == K_M4) f |= DF_PREP;   // a 16x16 superoperator forces the generic launch kind
+        dp.direct_flags[i] = f;
+    }
     if ((rc = upload_vec(ctx, dp.direct, dp.direct_host))) return rc;
     int k = std::min(P.k_max, P.n_bits);
     if (precision == 64) CU(configure_sweep<double>(k));
@@ -429,7 +473,7 @@ struct SvRunner {
 
     // Measurement sampling of every leaf of nodes[begin, end) (the WHOLE batch, before anything below it is swept:
     // NODE_NOSTORE leaves read their parent's slot, which the host may already have returned to the free list).
-    int sample_leaves(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end) {
+    int sample_leaves(int d, const NodeRec* nodes, size_t begin, size_t end) {
         bool any_leaf = false, any_nostore = false, any_stored = false;
         for (size_t i = begin; i < end; i++)
             if (nodes[i].flags & NODE_LEAF) {
@@ -471,14 +515,16 @@ struct SvRunner {
 
     // nodes[begin, end) at depth d have executed their sweep (d == 0: virtual roots); their device copy is
     // level_nodes[d] + begin and their trajectories are level_shots[d][traj_off ...).
-    int process(int d, const std::vector<NodeRec>& nodes, size_t begin, size_t end, bool is_root, uint32_t n_parts,
+    int process(int d, const NodeRec* nodes, size_t begin, size_t end, bool is_root, uint32_t n_parts,
                 bool leaves_done = false) {
         const size_t n_nodes = end - begin;
         if (n_nodes == 0) return QCD_OK;
+        double tp0 = g_trace.on ? Trace::now() : 0;
         if (!is_root && !leaves_done) {
             int rc = sample_leaves(d, nodes, begin, end);
             if (rc) return rc;
         }
+        if (g_trace.on) { g_trace.t_leaves += Trace::now() - tp0; tp0 = Trace::now(); }
         if (((uint64_t)n_nodes << gbits) > table_cap && n_nodes > 1) {
             const size_t piece = std::max<uint64_t>(1, table_cap >> gbits);
             for (size_t b = begin; b < end; b += piece) {
@@ -528,16 +574,19 @@ struct SvRunner {
         ctx->stats.aux_launches += 7;
         uint32_t totals[2] = {0, 0};
         double tt0 = g_trace.on ? Trace::now() : 0;
+        if (g_trace.on) g_trace.t_launch += tt0 - tp0;
         CU(cudaMemcpyAsync(totals, ctx->counter.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (g_trace.on) { g_trace.t_sync += Trace::now() - tt0; g_trace.n_sync++; }
         const uint32_t n_children = totals[1];
         if (n_children == 0) return fail(ctx, QCD_E_CUDA, "internal: inner nodes produced no children");
-        std::vector<NodeRec> ch(n_children);
+        if ((int)ctx->host_nodes.size() <= d) ctx->host_nodes.resize(d + 1);
+        CU(ctx->host_nodes[d].ensure((size_t)n_children * sizeof(NodeRec)));
+        NodeRec* ch = ctx->host_nodes[d].as<NodeRec>();   // stable while this call's subtree runs: deeper levels use their own
         tt0 = g_trace.on ? Trace::now() : 0;
-        CU(cudaMemcpyAsync(ch.data(), ctx->children.p, (size_t)n_children * sizeof(NodeRec), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ch, ctx->children.p, (size_t)n_children * sizeof(NodeRec), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (g_trace.on) g_trace.t_h2d += Trace::now() - tt0;
+        if (g_trace.on) { g_trace.t_h2d += Trace::now() - tt0; tt0 = Trace::now(); }
 
         // ---- sweep the children in chunks; finish each chunk's subtree before the next
         size_t pos = 0;
@@ -548,30 +597,33 @@ struct SvRunner {
             if (avail < 1)
                 return fail(ctx, QCD_E_NOMEM, "not enough state slots for this circuit depth (raise the memory budget)");
             const size_t c = (size_t)std::min<long long>((long long)(n_children - pos), avail);
-            std::vector<NodeRec> chunk(ch.begin() + pos, ch.begin() + pos + c);
-            for (NodeRec& r : chunk) r.dst_slot = alloc_slot();
+            // the chunk is edited in place in the page-locked readback buffer and goes back to the device from there
+            NodeRec* chunk = ch + pos;
+            NodeRec* const chunk_end = chunk + c;
             CU(ctx->level_nodes[d + 1].ensure(c * sizeof(NodeRec)));
             NodeRec* cdev = ctx->level_nodes[d + 1].as<NodeRec>();
             // single-pass sweeps run on the register-only kernel; anything else on the shared-memory tile kernel
-            bool direct = ctx->use_direct && n >= 13, vec = true, need_red = false, need_chunks = false, need_prep = false;
-            for (const NodeRec& r : chunk) {
-                const DirectSweep& D = dp->direct_host[r.sweep];
-                direct = direct && D.ok;
-                vec = vec && D.rbit[0] == 0;
-                need_red = need_red || D.red_q[0] >= 0;
-                need_chunks = need_chunks || (D.flags & SW_FINAL);
-                need_prep = need_prep || (D.flags & SW_PREP);
-                for (int o = 0; o < D.nops; o++) need_prep = need_prep || D.ops[o].kind == K_M4;   // forces the generic kind
+            uint8_t f_and = 0xFF, f_or = 0;
+            const uint8_t* dflags = dp->direct_flags.data();
+            for (NodeRec* r = chunk; r != chunk_end; ++r) {
+                r->dst_slot = alloc_slot();
+                const uint8_t f = dflags[r->sweep];
+                f_and &= f;
+                f_or |= f;
             }
+            const bool direct = ctx->use_direct && n >= 13 && (f_and & DF_OK);
+            const bool vec = (f_and & DF_VEC) != 0, need_red = (f_or & DF_RED) != 0, need_chunks = (f_or & DF_FINAL) != 0,
+                       need_prep = (f_or & DF_PREP) != 0;
             uint64_t n_nostore = 0;
             if (direct && !is_root && ctx->nostore_max > 0) {
-                for (NodeRec& r : chunk)
-                    if ((r.flags & NODE_LEAF) && r.traj_cnt <= ctx->nostore_max) {
-                        r.flags |= NODE_NOSTORE;
+                const uint32_t lim = ctx->nostore_max;
+                for (NodeRec* r = chunk; r != chunk_end; ++r)
+                    if ((r->flags & NODE_LEAF) && r->traj_cnt <= lim) {
+                        r->flags |= NODE_NOSTORE;
                         n_nostore++;
                     }
             }
-            CU(cudaMemcpyAsync(cdev, chunk.data(), c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(cdev, chunk, c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
             SweepArgs sa = sweep_args(cdev, (uint32_t)c);
             uint32_t parts_used = tiles;
             if (direct) {
@@ -592,7 +644,8 @@ struct SvRunner {
             bool by_pass = !direct && ctx->use_direct && n >= 13;
             if (by_pass) {
                 const size_t n_sw = dp->P.sweeps.size();
-                for (const NodeRec& r : chunk) {
+                for (const NodeRec* rp = chunk; rp != chunk_end; ++rp) {
+                    const NodeRec& r = *rp;
                     const Sweep& S = dp->P.sweeps[r.sweep];
                     const size_t np = S.pass_end - S.pass_begin;
                     if (np == 0 || np > 3) by_pass = false;
@@ -614,7 +667,8 @@ struct SvRunner {
                 for (size_t l = 0; l < max_passes; l++) {
                     lvl_off.push_back(recs.size());
                     bool v = true;
-                    for (const NodeRec& r0 : chunk) {
+                    for (const NodeRec* rp = chunk; rp != chunk_end; ++rp) {
+                        const NodeRec& r0 = *rp;
                         const Sweep& S = dp->P.sweeps[r0.sweep];
                         if (S.pass_end - S.pass_begin <= l) continue;
                         NodeRec r = r0;
@@ -664,8 +718,10 @@ struct SvRunner {
                     if (!(nodes[begin + p].flags & NODE_LEAF)) free_slot(nodes[begin + p].dst_slot);
                 next_parent_to_free = done_to;
             }
+            if (g_trace.on) g_trace.t_prep += Trace::now() - tt0;
             int rc = process(d + 1, chunk, 0, c, false, parts_used);
             if (rc) return rc;
+            tt0 = g_trace.on ? Trace::now() : 0;
         }
         return QCD_OK;
     }
@@ -675,6 +731,7 @@ template <typename T>
 int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot_begin, uint64_t shot_end,
            const double* readout, uint32_t* hist, uint32_t* outcomes, uint32_t flags, cudaStream_t st) {
     typedef typename Cplx<T>::type C;
+    if (g_trace.on) g_trace.t_run0 = Trace::now();
     SvRunner<T> R;
     R.ctx = ctx;
     R.dp = dp;
@@ -782,7 +839,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
         }
         CU(ctx->level_nodes[0].ensure(roots.size() * sizeof(NodeRec)));
         CU(cudaMemcpyAsync(ctx->level_nodes[0].p, roots.data(), roots.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
-        int rc = R.process(0, roots, 0, roots.size(), true, 1);
+        int rc = R.process(0, roots.data(), 0, roots.size(), true, 1);
         if (rc) return rc;
         ctx->stats.trajectories += g1 - g0;
         g0 = g1;
@@ -790,9 +847,11 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     double tt1 = g_trace.on ? Trace::now() : 0;
     CU(cudaStreamSynchronize(st));
     if (g_trace.on) {
-        fprintf(stderr, "[qcd trace] run_sv: wait-for-decide %.2f ms in %d syncs, child readback %.2f ms, final drain %.2f ms\n",
-                g_trace.t_sync * 1e3, g_trace.n_sync, g_trace.t_h2d * 1e3, (Trace::now() - tt1) * 1e3);
-        g_trace.t_sync = g_trace.t_h2d = 0;
+        fprintf(stderr, "[qcd trace] run_sv: wait-for-decide %.2f ms in %d syncs, child readback %.2f ms, final drain %.2f ms; "
+                "host: leaf sampling launches %.2f ms, decide launches %.2f ms, child prep + sweep launch %.2f ms; total %.2f ms\n",
+                g_trace.t_sync * 1e3, g_trace.n_sync, g_trace.t_h2d * 1e3, (Trace::now() - tt1) * 1e3,
+                g_trace.t_leaves * 1e3, g_trace.t_launch * 1e3, g_trace.t_prep * 1e3, (Trace::now() - g_trace.t_run0) * 1e3);
+        g_trace.t_sync = g_trace.t_h2d = g_trace.t_prep = g_trace.t_launch = g_trace.t_leaves = 0;
         g_trace.n_sync = 0;
     }
     return finish_timing(ctx);
@@ -1026,6 +1085,7 @@ void qcd_destroy(qcd_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : ctx->level_nodes) b.release();
     for (DevBuf& b : ctx->level_shots) b.release();
+    for (PinBuf& b : ctx->host_nodes) b.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
