@@ -328,3 +328,46 @@ def test_simulate_array_route_unitary_noise_matches_oracle(qcd, monkeypatch):
         assert {0.0, 1.0, 2.0} <= codes <= {0.0, 1.0, 2.0, 3.0}           # cx, h and (where a coin fell) unitary
         with_sites += 3.0 in codes
     assert 0 < with_sites <= 30
+
+
+def test_c2_full_size_properties(qcd):
+    """BASELINE config C2 at full size (8 qubits, 10 000 circuits, 1024 shots, device noise) through the array route,
+    checked with size-independent properties: every histogram holds every shot; with unital gate noise (depolarizing
+    only: T1 = T2 -> infinity) the pre-readout distribution of a graph state is exactly uniform, so the marginal of
+    every measured bit is 1/2 + (p10 - p01) / 2 of ITS circuit's readout draw -- compared over 10.24 M shots; two runs
+    over different circuit partitions give identical histograms."""
+    import torch
+    from qcdenoise_b200 import batch
+    from qcdenoise_b200.samplers import get_engine
+    n, B, shots = 8, 10000, 1024
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 1e15, "T2": 1e15, "prob_meas0_prep1": 0.3, "prob_meas1_prep0": 0.1},
+                                "cx": {"gate_error": 0.25, "gate_length": 500.0}, "h": {"gate_error": 0.05, "gate_length": 50.0}})
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n, max_num_edges=7)
+    edges, n_edges = gs.sample_batch(B, seed=77)
+    enc = batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=False), edges, n_edges)
+    props = batch.draw_device_props(spec, enc, np.random.default_rng(5))
+    props["qubit"]["T1"][:] = 1e15        # U(0, 1e15) draws can be small: pin both to "no relaxation"
+    props["qubit"]["T2"][:] = 1e15
+    t1t2, gp, ro = batch.device_noise_inputs(props)
+    eng = get_engine()
+    eng.upload_device_noise(enc, t1t2, gp)
+    probs = eng.run_density_matrix(32)
+    assert float((probs - 1.0 / 2 ** n).abs().max()) < 2e-6                     # unital noise keeps the uniform distribution
+    hist = eng.sample_from_probs(probs, shots, seed=11, readout=ro)
+    h = hist.cpu().numpy().astype(np.int64)
+    assert (h.sum(axis=1) == shots).all()
+    x = np.arange(2 ** n)
+    p10, p01 = props["qubit"]["prob_meas1_prep0"], props["qubit"]["prob_meas0_prep1"]
+    for q in range(n):
+        ones = int(h[:, ((x >> q) & 1) == 1].sum())
+        pq = 0.5 + 0.5 * (p10[:, q] - p01[:, q])                                # per circuit
+        mean, var = shots * pq.sum(), shots * (pq * (1 - pq)).sum()
+        assert abs(ones - mean) < 5 * np.sqrt(var), (q, ones, mean)
+    # partition invariance: circuits [0, 4000) and [4000, 10000) uploaded separately give the same rows
+    parts = []
+    for lo, hi in ((0, 4000), (4000, B)):
+        mine, (o_lo, o_hi) = batch.slice_programs(enc, lo, hi)
+        eng.upload_device_noise(mine, t1t2[lo:hi], gp[o_lo:o_hi])
+        pr = eng.run_density_matrix(32)
+        parts.append(eng.sample_from_probs(pr, shots, seed=11, first_circuit=lo, readout=ro[lo:hi]))
+    assert torch.equal(torch.cat(parts, dim=0), hist)
