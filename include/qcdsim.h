@@ -166,6 +166,20 @@ QCD_API int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_
 QCD_API int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,
                            void* stream);
 
+/* Replaces: StabilizerSampler.sample re-simulating the whole graph circuit once per measurement setting
+ * (stabilizers.py:183-215: `graph_circuit + stab_gate + measure_all` for each of the n + 1 Toth settings).  In
+ * density-matrix mode a setting that differs from the uploaded circuit by ONE final single-qubit step (the basis
+ * change of the generator's vertex, X -> H, Y -> H.Sdg, followed by that gate's own noise channel if any) is read
+ * off the circuit's density matrix: p_s[x] = Re sum_{a,b} S_s[(x_q, x_q), (a, b)] rho[x|q=a, x|q=b].
+ *   setting_qubits   [host] [count][n_settings] : qubit of the final step, 0xFF = measure as is;
+ *   setting_superops [host] [count][n_settings][16] complex (re, im): 4x4 superoperator of the step on (ket, bra) of
+ *                    that qubit, row-major, index = ket + 2 * bra  (S = sum_j conj(K_j) (x) K_j; ignored for 0xFF);
+ *   probs_out [dev]  [count][n_settings][2^n] float / double, count = circuit_end - circuit_begin.
+ * One density-matrix simulation per circuit instead of n_settings.  Complete on return (synchronises `stream`). */
+QCD_API int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end,
+                                            int n_settings, const uint8_t* setting_qubits,
+                                            const double* setting_superops, void* probs_out, void* stream);
+
 /* Classical readout error applied to probability vectors, in place: probs [dev] [n_vectors][2^n] (float/double by
  * precision), readout [host] [n_vectors][n][2][2].  Replaces Aer's ReadoutError on `measure` in distribution. */
 QCD_API int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,

@@ -55,6 +55,8 @@ _PROTOS = {
     "qcd_run_sv_trajectories": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                                ctypes.c_uint64, _P, _P, _P, ctypes.c_uint32, _P]),
     "qcd_run_density_matrix": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
+    "qcd_run_density_matrix_settings": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P,
+                                                       _P, _P, _P]),
     "qcd_apply_readout_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_sample_from_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                              ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, _P, _P, _P]),

@@ -859,7 +859,8 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
 
 // ============================================================================================ density matrix
 template <typename T>
-int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStream_t st) {
+int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStream_t st, int n_settings = 0,
+           const uint8_t* setting_qubits = nullptr, const double* setting_superops = nullptr) {
     typedef typename Cplx<T>::type C;
     const Program& P = dp->P;
     const int nb = P.n_bits, n = P.n_qubits;
@@ -1003,8 +1004,21 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
         for (int i = 0; i < c1 - c0; i++) slots[i] = (uint32_t)i;
         CU(ctx->slots.ensure(slots.size() * 4));
         CU(cudaMemcpyAsync(ctx->slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
-        launch_extract_diag<T>(ctx->states.p, slot_stride, ctx->slots.as<uint32_t>(), (uint32_t)(c1 - c0), n,
-                               out + ((size_t)(c0 - cb) << n), st);
+        if (n_settings > 0) {
+            // measurement settings of this batch's density matrices (slot i holds circuit c0 + i)
+            const size_t cnt = (size_t)(c1 - c0) * n_settings;
+            CU(ctx->scratch.ensure(cnt * (16 * sizeof(double2) + 1)));
+            double2* sops_dev = ctx->scratch.as<double2>();
+            uint8_t* q_dev = reinterpret_cast<uint8_t*>(sops_dev + cnt * 16);
+            CU(cudaMemcpyAsync(sops_dev, setting_superops + (size_t)(c0 - cb) * n_settings * 32, cnt * 16 * sizeof(double2),
+                               cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(q_dev, setting_qubits + (size_t)(c0 - cb) * n_settings, cnt, cudaMemcpyHostToDevice, st));
+            launch_setting_probs<T>(ctx->states.p, slot_stride, (uint32_t)(c1 - c0), n, n_settings, q_dev, sops_dev,
+                                    out + (((size_t)(c0 - cb) * n_settings) << n), st);
+        } else {
+            launch_extract_diag<T>(ctx->states.p, slot_stride, ctx->slots.as<uint32_t>(), (uint32_t)(c1 - c0), n,
+                                   out + ((size_t)(c0 - cb) << n), st);
+        }
         CU(cudaGetLastError());
         ctx->stats.aux_launches++;
         ctx->stats.leaves += c1 - c0;
@@ -1370,6 +1384,39 @@ int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int c
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == 64) return run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
     return run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
+}
+
+int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, int n_settings,
+                                    const uint8_t* setting_qubits, const double* setting_superops, void* probs_out,
+                                    void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
+    if (circuit_begin < 0 || circuit_begin > circuit_end || circuit_end > ctx->n_circuits)
+        return fail(ctx, QCD_E_INVALID, "circuit range outside [0, n_circuits]");
+    if (n_settings < 1 || n_settings > 4096) return fail(ctx, QCD_E_INVALID, "n_settings must be in [1, 4096]");
+    if (!probs_out || !setting_qubits || !setting_superops) return fail(ctx, QCD_E_INVALID, "NULL argument");
+    if (ctx->n_qubits > 15) return fail(ctx, QCD_E_UNSUPPORTED, "density-matrix mode supports at most 15 qubits");
+    const size_t cnt = (size_t)(circuit_end - circuit_begin) * n_settings;
+    for (size_t i = 0; i < cnt; i++)
+        if (setting_qubits[i] != 0xFF && setting_qubits[i] >= ctx->n_qubits)
+            return fail(ctx, QCD_E_INVALID, "setting " + std::to_string(i) + ": qubit index out of range");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->ev_used = 0;
+    if (circuit_begin == circuit_end) return QCD_OK;
+    DevProg* dp = nullptr;
+    int rc = get_program(ctx, MODE_DM, precision, &dp);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the per-batch host -> device copies of the setting tables read caller memory asynchronously: drain before returning
+    if (precision == 64)
+        rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
+    else
+        rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    return QCD_OK;
 }
 
 int qcd_apply_readout_probs(qcd_ctx* ctx, int precision, void* probs, int n_vectors, int n_qubits,

@@ -520,6 +520,39 @@ __global__ void extract_diag_kernel(const void* states, uint64_t slot_stride, co
     probs[((uint64_t)v << n) + x] = st[(uint64_t)x * ((1ull << n) + 1ull)].x;
 }
 
+// Outcome distributions of several measurement SETTINGS of one density matrix.  Setting s of vector v applies one
+// final single-qubit step (a 4x4 superoperator on (bit q, bit q + n), index = ket + 2 * bra) and measures; its
+// distribution only needs the 2x2 block of rho in qubit q at equal other bits:
+//   p_s[x] = Re sum_{a,b} S[(x_q, x_q), (a, b)] rho[x with bit q = a, x with bit q = b].        q = 0xFF: plain diagonal.
+template <typename T>
+__global__ void setting_probs_kernel(const void* states, uint64_t slot_stride, uint32_t first_slot, int n, int n_settings,
+                                     const uint8_t* qubits, const double2* sops, T* probs) {
+    typedef typename Cplx<T>::type C;
+    const uint32_t vs = blockIdx.y;                      // (vector, setting) flattened
+    const uint32_t v = vs / (uint32_t)n_settings;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (1u << n)) return;
+    const C* st = reinterpret_cast<const C*>(states) + (uint64_t)(first_slot + v) * slot_stride;
+    const uint32_t q = qubits[vs];
+    const uint64_t N = 1ull << n;
+    double p;
+    if (q == 0xFFu) {
+        p = (double)st[(uint64_t)x * (N + 1ull)].x;
+    } else {
+        const double2* S = sops + (uint64_t)vs * 16u;
+        const uint32_t xq = (x >> q) & 1u, x0 = x & ~(1u << q);
+        const double2* row = S + (xq + 2u * xq) * 4u;
+        p = 0.0;
+#pragma unroll
+        for (uint32_t ab = 0; ab < 4u; ab++) {
+            const uint32_t a = ab & 1u, b = ab >> 1;
+            const C r = st[(uint64_t)(x0 | (a << q)) + N * (uint64_t)(x0 | (b << q))];
+            p += row[ab].x * (double)r.x - row[ab].y * (double)r.y;     // Re(S * rho)
+        }
+    }
+    probs[((uint64_t)vs << n) + x] = (T)p;
+}
+
 template <typename T>
 __global__ void readout_probs_kernel(T* probs, int n, int q, const double* conf) {
     // pairs (x with bit q = 0, x | 1<<q): p0' = c00 p0 + c10 p1 ; p1' = c01 p0 + c11 p1   (row = true, col = measured)
@@ -787,6 +820,17 @@ void launch_extract_diag(const void* states, uint64_t slot_stride, const uint32_
     }
 }
 template <typename T>
+void launch_setting_probs(const void* states, uint64_t slot_stride, uint32_t n_vec, int n, int n_settings,
+                          const uint8_t* qubits, const double2* sops, T* probs, cudaStream_t st) {
+    const uint32_t per = 32768u / (uint32_t)n_settings > 0 ? 32768u / (uint32_t)n_settings : 1u;   // vectors per launch
+    for (uint32_t v0 = 0; v0 < n_vec; v0 += per) {
+        const uint32_t nv = n_vec - v0 < per ? n_vec - v0 : per;
+        setting_probs_kernel<T><<<dim3(cdiv(1ull << n, 256), nv * n_settings), 256, 0, st>>>(
+            states, slot_stride, v0, n, n_settings, qubits + (uint64_t)v0 * n_settings,
+            sops + (uint64_t)v0 * n_settings * 16u, probs + (((uint64_t)v0 * n_settings) << n));
+    }
+}
+template <typename T>
 void launch_readout_probs(T* probs, uint32_t n_vec, int n, const double* conf, cudaStream_t st) {
     for (int q = 0; q < n; q++)
         for (uint32_t y0 = 0; y0 < n_vec; y0 += 32768) {
@@ -863,6 +907,8 @@ void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* 
                                    const double*, uint64_t, uint32_t, int, const uint32_t*, const uint32_t*, uint32_t, \
                                    uint64_t, const double*, uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);  \
     template void launch_extract_diag<T>(const void*, uint64_t, const uint32_t*, uint32_t, int, T*, cudaStream_t);    \
+    template void launch_setting_probs<T>(const void*, uint64_t, uint32_t, int, int, const uint8_t*, const double2*,  \
+                                          T*, cudaStream_t);                                                          \
     template void launch_readout_probs<T>(T*, uint32_t, int, const double*, cudaStream_t);                            \
     template void launch_prob_chunks<T>(const T*, uint32_t, int, double*, uint64_t, cudaStream_t);                    \
     template void launch_sample_probs<T>(const T*, uint32_t, int, const double*, uint64_t, const double*, uint64_t,   \

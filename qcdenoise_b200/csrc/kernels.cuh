@@ -121,6 +121,9 @@ void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states,
 
 // ---- density-matrix helpers / probability vectors
 template <typename T>
+void launch_setting_probs(const void* states, uint64_t slot_stride, uint32_t n_vec, int n, int n_settings,
+                          const uint8_t* qubits, const double2* sops, T* probs, cudaStream_t st);
+template <typename T>
 void launch_extract_diag(const void* states, uint64_t slot_stride, const uint32_t* slots, uint32_t n_vec, int n,
                          T* probs, cudaStream_t st);
 template <typename T>

@@ -136,6 +136,25 @@ class Engine:
             self._check(self.lib.qcd_run_density_matrix(self._h, precision, cb, ce, _ptr(out), self._stream()))
         return out
 
+    def run_density_matrix_settings(self, setting_qubits, setting_superops, precision=32, circuit_range=None):
+        """Outcome distributions of several measurement settings per circuit from ONE density-matrix simulation each
+        (qcd_run_density_matrix_settings).  setting_qubits: uint8 [count, S] (0xFF = measure as is);
+        setting_superops: complex128 [count, S, 4, 4], the final single-qubit step of each setting as a superoperator
+        on (ket, bra), index = ket + 2 * bra.  -> tensor [count, S, 2^n] float32 / float64."""
+        n, B = self.n_qubits, self.n_circuits
+        cb, ce = circuit_range if circuit_range is not None else (0, B)
+        q = np.ascontiguousarray(setting_qubits, dtype=np.uint8)
+        sop = np.ascontiguousarray(setting_superops, dtype=np.complex128)
+        if q.ndim != 2 or q.shape[0] != ce - cb or sop.shape != q.shape + (4, 4):
+            raise ValueError(f"setting_qubits must be ({ce - cb}, S) and setting_superops ({ce - cb}, S, 4, 4)")
+        S = q.shape[1]
+        dt = torch.float64 if precision == 64 else torch.float32
+        with torch.cuda.device(self.device):
+            out = torch.empty((ce - cb, S, 2 ** n), dtype=dt, device=self.device)
+            self._check(self.lib.qcd_run_density_matrix_settings(self._h, precision, cb, ce, S, _ptr(q),
+                                                                 _ptr(sop.view(np.float64)), _ptr(out), self._stream()))
+        return out
+
     def apply_readout(self, probs, readout):
         n_vec, N = probs.shape
         n = N.bit_length() - 1

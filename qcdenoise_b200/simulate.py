@@ -297,7 +297,16 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
                 all_circs.append(circuits[num].copy(name=name).compose(sc))
                 all_models.append(models[num] if entangle_specs.noisy else None)
         stab_sampler.noisy = entangle_specs.noisy
-        counts = _batched_counts(stab_sampler, all_circs, all_models)
+        counts = None
+        if entangle_specs.noisy and stab_sampler.settings_from_one_state and \
+                stab_sampler._pick_method(n, True) == "density_matrix":
+            # density-matrix route: one simulation per circuit, all its settings read off the density matrix
+            from .stabilizers import run_settings_batch, single_qubit_settings
+            settings = [single_qubit_settings(sd, m, n) for sd, m in zip(stab_dicts, models)]
+            if all(st is not None for st in settings) and len({len(st[0]) for st in settings}) == 1:
+                counts = [c for per in run_settings_batch(stab_sampler, circuits, models, settings) for c in per]
+        if counts is None:
+            counts = _batched_counts(stab_sampler, all_circs, all_models)
         for num in range(sim_specs.n_circuits):
             lo, hi = spans[num]
             wit = entangle_specs.witness(n_qubits=n, stabilizer_circuits=stab_dicts[num],

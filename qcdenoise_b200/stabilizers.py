@@ -6,12 +6,13 @@ from collections import OrderedDict
 from copy import deepcopy
 
 import networkx as nx
+import numpy as np
 
 from .ir import Circuit
 from .samplers import CircuitSampler, NoiseModel
 
 __all__ = ["TothStabilizer", "JungStabilizer", "StabilizerSampler", "StabilizerCircuit", "get_unique_operators",
-           "sigma_prod", "pauli_mask"]
+           "sigma_prod", "pauli_mask", "single_qubit_settings", "run_settings_batch"]
 
 # single-qubit Pauli products: (a, b) -> (power of i, result) with a.b = i^power * result
 _IDX = {"I": 0, "X": 1, "Y": 2, "Z": 3}
@@ -145,10 +146,101 @@ class JungStabilizer(StabilizerCircuit):
         return deepcopy(out)
 
 
+_SQ2 = 2 ** -0.5
+_GATE_1Q = {"id": np.eye(2, dtype=np.complex128), "h": np.array([[_SQ2, _SQ2], [_SQ2, -_SQ2]], dtype=np.complex128),
+            "s": np.diag([1, 1j]).astype(np.complex128), "sdg": np.diag([1, -1j]).astype(np.complex128),
+            "x": np.array([[0, 1], [1, 0]], dtype=np.complex128), "y": np.array([[0, -1j], [1j, 0]], dtype=np.complex128),
+            "z": np.diag([1, -1]).astype(np.complex128)}
+_PAULIS = [_GATE_1Q["id"], _GATE_1Q["x"], _GATE_1Q["y"], _GATE_1Q["z"]]
+
+
+def _errors_after(model, name, qs):
+    """Channels `model` attaches to an unlabelled gate `name` on qubits `qs` (the rule of NoiseModel.instantiate),
+    without materialising a calibration-defined model."""
+    from . import channels
+    from .samplers import DeviceNoiseModel
+    if model is None:
+        return []
+    if isinstance(model, DeviceNoiseModel) and model.native:
+        ent = model.gate_table.get((name, tuple(qs)))
+        if ent is None:
+            return []
+        props = model.props["qubits"]
+        t1 = [max(props[q].get("T1", float("inf")), 1e-9) for q in qs]
+        t2 = [max(props[q].get("T2", float("inf")), 1e-9) for q in qs]
+        probs, relax = channels.device_gate_error(len(qs), ent[0], ent[1], t1, t2)
+        out = []
+        if probs is not None:
+            out.append(("pauli", tuple(range(len(qs))), probs))
+        if relax is not None:
+            out += [("kraus", (i,), k) for i, k in enumerate(relax)]
+        return out
+    errs = list(model.label_errors.get(name, [])) + list(model.gate_errors.get((name, tuple(qs)), [])) \
+        + list(model.all_qubit_errors.get(name, []))
+    return [ch for err in errs for ch in err]
+
+
+def single_qubit_settings(stabilizer_circuits, model, n_qubits):
+    """If every measurement setting differs from the bare circuit by single-qubit steps on at most ONE qubit (the Toth
+    settings: H on the generator's vertex, identities elsewhere), return (qubits uint8 [S], superops complex [S, 4, 4])
+    for Engine.run_density_matrix_settings; else None.  The superoperator is the ordered product of the setting's
+    gates on that qubit and of the channels `model` attaches to them, S = sum_j conj(K_j) (x) K_j."""
+    qubits, sops = [], []
+    for stab in stabilizer_circuits.values():
+        if stab.n_qubits != n_qubits:
+            return None
+        target, S = None, np.eye(4, dtype=np.complex128)
+        for op in stab.ops:
+            name, qs = op[0], op[1]
+            if name in ("barrier", "measure_all"):
+                continue
+            if name not in _GATE_1Q or len(qs) != 1:
+                return None
+            errs = _errors_after(model, name, qs)
+            if name == "id" and not errs:
+                continue
+            if target is None:
+                target = qs[0]
+            elif target != qs[0]:
+                return None
+            S = np.kron(_GATE_1Q[name].conj(), _GATE_1Q[name]) @ S
+            for ch in errs:
+                if ch[0] == "kraus" and tuple(ch[1]) == (0,):
+                    T = sum(np.kron(np.asarray(k).conj(), np.asarray(k)) for k in ch[2])
+                elif ch[0] == "pauli" and tuple(ch[1]) == (0,):
+                    T = sum(p * np.kron(P.conj(), P) for p, P in zip(ch[2], _PAULIS))
+                else:
+                    return None
+                S = T @ S
+        qubits.append(0xFF if target is None else target)
+        sops.append(S)
+    return np.array(qubits, dtype=np.uint8), np.array(sops, dtype=np.complex128)
+
+
+def run_settings_batch(sampler, circuits, models, settings):
+    """Density-matrix route for measurement settings: ONE simulation per circuit, every setting's distribution read
+    off its density matrix (qcd_run_density_matrix_settings), then sampled.  settings[i] = single_qubit_settings(...)
+    of circuit i (same number of settings for all).  -> list (per circuit) of lists (per setting) of Counts."""
+    from .samplers import Counts, get_engine, upload_batch
+    n = circuits[0].n_qubits
+    eng = get_engine(sampler.device)
+    readout, _ = upload_batch(eng, circuits, models)
+    q = np.stack([s[0] for s in settings])
+    sop = np.stack([s[1] for s in settings])
+    B, S = q.shape
+    probs = eng.run_density_matrix_settings(q, sop, sampler.precision).reshape(B * S, 2 ** n)
+    sampler.last_probs = probs
+    ro = np.repeat(readout, S, axis=0) if readout is not None else None
+    hist = eng.sample_from_probs(probs, sampler.n_shots, seed=sampler._next_seed(), readout=ro)
+    return [[Counts(None, n, device_hist=hist[i * S + j:i * S + j + 1]) for j in range(S)] for i in range(B)]
+
+
 class StabilizerSampler(CircuitSampler):
     """Appends each setting's basis change to the graph circuit and simulates all settings in ONE batched engine
     call (the reference simulates them one after another: stabilizers.py:183-215).  Ideal unless `noise_model` is
     given (reference quirk Q7)."""
+
+    settings_from_one_state = True     # False: always re-simulate the circuit once per setting (A/B, tests)
 
     def __init__(self, backend=None, n_shots=1024, **kw):
         super().__init__(backend=backend, n_shots=n_shots, **kw)
@@ -156,6 +248,14 @@ class StabilizerSampler(CircuitSampler):
     def sample(self, stabilizer_circuits, graph_circuit, execute=False, noise_model=None):
         if not isinstance(graph_circuit, Circuit):
             raise AssertionError("graph_circuit should be an instance of qcdenoise_b200.Circuit")
+        self.build_noise_model(noise_model)
+        if self.noisy and self.settings_from_one_state and \
+                self._pick_method(graph_circuit.n_qubits, True) == "density_matrix":
+            # density-matrix route: simulate the graph circuit ONCE and read every setting off its density matrix
+            settings = single_qubit_settings(stabilizer_circuits, self.noise_model, graph_circuit.n_qubits)
+            if settings is not None:
+                self.transpile_circuit(graph_circuit, {})
+                return run_settings_batch(self, [graph_circuit], [self.noise_model], [settings])[0]
         circuits = []
         for name, stab in stabilizer_circuits.items():
             circ = graph_circuit.copy(name=name)

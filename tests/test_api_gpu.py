@@ -371,3 +371,44 @@ def test_c2_full_size_properties(qcd):
         pr = eng.run_density_matrix(32)
         parts.append(eng.sample_from_probs(pr, shots, seed=11, first_circuit=lo, readout=ro[lo:hi]))
     assert torch.equal(torch.cat(parts, dim=0), hist)
+
+
+@pytest.mark.parametrize("noise", ["unitary", "device"])
+def test_settings_read_off_one_density_matrix_equal_resimulation(qcd, noise):
+    """StabilizerSampler in density-matrix mode simulates the graph circuit once and reads the n + 1 Toth settings off
+    its density matrix (qcd_run_density_matrix_settings); the reference (and the fallback route) re-simulate the whole
+    circuit per setting.  Same exact distributions, to 1e-12 in complex128, and they equal the oracle's."""
+    n = 5
+    g = _graph(n, 3, qcd)
+    np.random.seed(2)
+    random.seed(2)
+    if noise == "unitary":
+        cd = qcd.CXGateCircuit(n_qubits=n, stochastic=True).build(g)
+        s = qcd.UnitaryNoiseSampler(None, n_shots=4096, noise_specs=qcd.NoiseSpec(
+            specs={"type": "amplitude_damping_error", "max_prob": 0.3}))
+        s.build_noise_model(cd["ops"])
+    else:
+        cd = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)
+        s = qcd.DeviceNoiseSampler(None, n_shots=4096, noise_specs=qcd.NoiseSpec(specs=_DEV_SPEC))
+        s.transpile_circuit(cd["circuit"])
+        s.build_noise_model(n)
+    stab = qcd.TothStabilizer(g, n_qubits=n).build()
+    one = qcd.StabilizerSampler(None, n_shots=4096, precision=64, seed=9)
+    c_one = one.sample(stab, cd["circuit"], noise_model=s.noise_model)
+    p_one = one.last_probs.cpu().numpy()
+    assert one._pick_method(n, True) == "density_matrix" and p_one.shape == (n + 1, 2 ** n)
+    many = qcd.StabilizerSampler(None, n_shots=4096, precision=64, seed=9)
+    many.settings_from_one_state = False
+    c_many = many.sample(stab, cd["circuit"], noise_model=s.noise_model)
+    p_many = many.last_probs.cpu().numpy()
+    np.testing.assert_allclose(p_one, p_many, atol=1e-12)
+    # oracle: explicit program of the graph circuit + each setting's sub-circuit
+    for i, (name, sc) in enumerate(stab.items()):
+        inst, _ = s.noise_model.instantiate(cd["circuit"].copy().compose(sc))
+        np.testing.assert_allclose(p_one[i], sim.density_matrix_probs(inst.ops, n), atol=1e-10)
+    # same seeds and (to rounding) the same distributions: the sampled histograms agree almost everywhere
+    diff = sum(int(np.abs(a.hist.astype(np.int64) - b.hist.astype(np.int64)).sum()) for a, b in zip(c_one, c_many))
+    assert diff <= 8
+    w1 = qcd.GenuineWitness(n, stab, c_one).estimate(g)
+    w2 = qcd.GenuineWitness(n, stab, c_many).estimate(g)
+    assert abs(w1.value - w2.value) < 0.02
