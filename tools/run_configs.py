@@ -179,6 +179,51 @@ def c3(eng, n_circ):
                       "sweep_launches": st["sweep_launches"], "states_swept": st["node_sweeps"]}), flush=True)
 
 
+def c3_witness(eng, n_circ):
+    """C3 with its witness estimation: per circuit the 15 Toth settings -> counts -> genuine witness.  Route A reads all
+    settings off ONE density-matrix simulation per circuit (qcd_run_density_matrix_settings); route B re-simulates the
+    circuit once per setting, which is what the reference does (stabilizers.py:183-215)."""
+    from qcdenoise_b200.samplers import run_batch
+    from qcdenoise_b200.stabilizers import run_settings_batch, single_qubit_settings
+    n = 14
+    gs = graphs(n)
+    np.random.seed(1234)
+    sampler = qcd.UnitaryNoiseSampler(None, n_shots=1024, method="density_matrix")
+    gl, circuits, models, stabs = [], [], [], []
+    for i in range(n_circ):
+        g = nxg(n, gs[i % len(gs)])
+        cd = qcd.CXGateCircuit(n_qubits=n, stochastic=True).build(g)
+        sampler.build_noise_model(cd["ops"])
+        gl.append(g)
+        circuits.append(cd["circuit"])
+        models.append(sampler.noise_model)
+        stabs.append(qcd.TothStabilizer(g, n).build())
+    out = {}
+    for route in ("one simulation per circuit", "one simulation per setting"):
+        ssam = qcd.StabilizerSampler(None, n_shots=1024, method="density_matrix", seed=5)
+        ssam.noisy = True
+        for it in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if route.endswith("circuit"):
+                settings = [single_qubit_settings(sd, m, n) for sd, m in zip(stabs, models)]
+                per = run_settings_batch(ssam, circuits, models, settings)
+            else:
+                allc = [c.copy(name=nm).compose(sc) for c, sd in zip(circuits, stabs) for nm, sc in sd.items()]
+                allm = [m for m, sd in zip(models, stabs) for _ in sd]
+                flat = run_batch(ssam, allc, allm)
+                per = [flat[i * (n + 1):(i + 1) * (n + 1)] for i in range(n_circ)]
+            w = [qcd.GenuineWitness(n, sd, cs).estimate(g).value for sd, cs, g in zip(stabs, per, gl)]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[route] = (dt, w)
+        print(json.dumps({"config": f"C3 n=14 density matrix + Toth witnesses, {n_circ} circuits x 15 settings x 1024 "
+                                    f"shots: {route}", "s": dt, "value": n_circ / dt, "unit": "circuits (with witness)/s",
+                          "witness_mean": float(np.mean(w))}), flush=True)
+    a, b = out["one simulation per circuit"][1], out["one simulation per setting"][1]
+    assert max(abs(x - y) for x, y in zip(a, b)) < 0.05, (a, b)
+
+
 def c5(eng, n_circ, shots):
     """28-qubit statevector noisy trajectories (one GPU's share of the 8-GPU configuration)."""
     n = 28
@@ -209,7 +254,7 @@ def c5(eng, n_circ, shots):
 
 
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["C1", "C2", "C3", "C5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["C1", "C2", "C3", "C3W", "C5"]
     eng = qcd.get_engine(0)
     eng.set_option("time_sweeps", 1)
     if "C1" in which:
@@ -220,5 +265,7 @@ if __name__ == "__main__":
         c2_simulate(10000)
     if "C3" in which:
         c3(eng, 16)
+    if "C3W" in which:
+        c3_witness(eng, 8)
     if "C5" in which:
         c5(eng, 8, 8)
