@@ -216,6 +216,14 @@ QCD_API int qcd_parity_outcomes(qcd_ctx* ctx, const uint32_t* outcomes, int n_ve
 QCD_API int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vectors, int n_qubits,
                      const uint32_t* masks, int n_masks, int per_vector_masks, double* expvals, void* stream);
 
+/* Host-only: the 4x4 superoperators (index = ket + 2 * bra, row-major complex as (re, im)) of `count` noisy
+ * single-qubit gates: the gate `unitary` (2x2 complex, shared) followed by the calibration-derived error of entry i
+ * (depolarizing o thermal relaxation as in qcd_upload_device_noise_programs; (NaN, NaN) = no entry).  Feeds
+ * qcd_run_density_matrix_settings with the noisy final basis change of every measurement setting of a batch. */
+QCD_API int qcd_device_gate_superops_1q(int count, const double* unitary, const double* gate_error,
+                                        const double* gate_length_ns, const double* t1_us, const double* t2_us,
+                                        double* superops_out);
+
 /* Replaces: GraphState.sample (graph_state.py:74-122) with pick_subgraphs (:200-215), combine_subgraphs (:176-198)
  * and the vertex-cover screen (networkx min_weighted_vertex_cover, :101-106), for n_graphs graphs at once on native
  * host threads (host-only, no GPU needed).  Undirected graphs.

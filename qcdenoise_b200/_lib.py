@@ -65,6 +65,7 @@ _PROTOS = {
     "qcd_parity_outcomes": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_uint64, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_parity_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int,
                                         ctypes.c_int, _P, _P]),
+    "qcd_device_gate_superops_1q": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P, _P, _P]),
     "qcd_sample_graph_states": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                                ctypes.c_uint64, _P, ctypes.c_uint32, _P]),

@@ -13,7 +13,8 @@ from . import _lib
 from ._lib import OPCODES, OP_DTYPE
 from .graph_circuit import CPhaseGateCircuit, CXGateCircuit, CZGateCircuit
 
-__all__ = ["build_gate_lists", "sites_per_edge", "slice_programs", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
+__all__ = ["build_gate_lists", "sites_per_edge", "slice_programs", "device_gate_superops_1q", "toth_masks",
+           "toth_witnesses", "draw_device_props", "device_props_dict", "adjacency_tensors_batch", "edge_lists"]
 
 _GATE_NAMES = {OPCODES[nm]: nm for nm in ("id", "h", "x", "y", "z", "s", "sdg", "t", "tdg", "rx", "ry", "rz", "cx", "cz",
                                           "swap")}
@@ -260,3 +261,61 @@ def slice_programs(enc, lo, hi):
     ops, offsets, params, n = enc
     o_lo, o_hi = int(offsets[lo]), int(offsets[hi])
     return (ops[o_lo:o_hi], (offsets[lo:hi + 1].astype(np.int64) - o_lo).astype(np.uint32), params, n), (o_lo, o_hi)
+
+
+_H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+
+
+def device_gate_superops_1q(unitary, gate_error, gate_length, t1_us, t2_us):
+    """4x4 superoperators (index = ket + 2 * bra) of a noisy single-qubit gate for a whole batch, natively
+    (qcd_device_gate_superops_1q): `unitary` followed by the calibration-derived error of each entry (NaN, NaN = no
+    error).  gate_error / gate_length / t1_us / t2_us: float64 arrays of one shape -> complex128 [shape + (4, 4)]."""
+    ge = np.ascontiguousarray(gate_error, dtype=np.float64)
+    gl, t1, t2 = (np.ascontiguousarray(np.broadcast_to(a, ge.shape), dtype=np.float64) for a in (gate_length, t1_us, t2_us))
+    u = np.ascontiguousarray(unitary, dtype=np.complex128).reshape(4)
+    out = np.empty(ge.shape + (4, 4), dtype=np.complex128)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)       # noqa: E731
+    rc = _lib.load().qcd_device_gate_superops_1q(ge.size, p(u.view(np.float64)), p(ge), p(gl), p(t1), p(t2),
+                                                 p(out.view(np.float64)))
+    if rc:
+        raise _lib.QcdError(rc, "qcd_device_gate_superops_1q: relaxation parameters out of range")
+    return out
+
+
+def toth_masks(edges, n_edges, n):
+    """Parity masks of the n + 1 Toth settings of every graph: generator k = X on vertex k, Z on its neighbours
+    (stabilizers.py:104-122) -> bit k and the neighbours' bits; identity last (mask 0).  uint32 [B, n + 1]."""
+    B = len(n_edges)
+    keep = np.arange(edges.shape[1])[None, :] < np.asarray(n_edges)[:, None]
+    circ = np.repeat(np.arange(B), n_edges)
+    a = edges[..., 0][keep].astype(np.int64)
+    b = edges[..., 1][keep].astype(np.int64)
+    masks = np.zeros((B, n + 1), dtype=np.uint32)
+    masks[:, :n] = (1 << np.arange(n, dtype=np.uint32))[None, :]
+    np.bitwise_or.at(masks, (circ, a), (1 << b).astype(np.uint32))
+    np.bitwise_or.at(masks, (circ, b), (1 << a).astype(np.uint32))
+    return masks
+
+
+def toth_witnesses(kind, signed, totals, edges, n_edges, n):
+    """Witness values from the settings' parity sums (witnesses.py:59-67, :74-144), for a whole batch.
+    signed, totals: int64 [B, n + 1] (generator settings, identity last).  kind "genuine": W = (n - 1) <I> - sum_k <g_k>,
+    sigma = sqrt(sum std^2) -> (value [B], sigma [B]); "biseparable": per edge (i, j) W_ij = 1 - <g_i> - <g_j>,
+    sigma = sqrt(std_i^2 + std_j^2) -> (list of B value lists, list of B sigma lists), edge order = graph.edges()."""
+    mean = signed / totals
+    std = np.sqrt(np.maximum(0.0, (1.0 - mean * mean) / totals))
+    if kind == "genuine":
+        value = (n - 1) * mean[:, n] - mean[:, :n].sum(axis=1)
+        coef = -np.ones(n + 1)
+        coef[n] = n - 1
+        return value, np.sqrt(((coef[None, :] * std) ** 2).sum(axis=1))
+    keep = np.arange(edges.shape[1])[None, :] < np.asarray(n_edges)[:, None]
+    circ = np.repeat(np.arange(len(n_edges)), n_edges)
+    a = edges[..., 0][keep].astype(np.int64)
+    b = edges[..., 1][keep].astype(np.int64)
+    val = 1.0 - mean[circ, a] - mean[circ, b]
+    sig = np.sqrt(std[circ, a] ** 2 + std[circ, b] ** 2)
+    ends = np.cumsum(n_edges).tolist()
+    val, sig = val.tolist(), sig.tolist()
+    return ([val[e - k:e] for e, k in zip(ends, np.asarray(n_edges).tolist())],
+            [sig[e - k:e] for e, k in zip(ends, np.asarray(n_edges).tolist())])

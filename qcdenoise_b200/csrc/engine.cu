@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -1311,6 +1312,65 @@ int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint
     ctx->qubit_t1_t2.assign(qubit_t1_t2, qubit_t1_t2 + (size_t)n_circuits * n_qubits * 2);
     ctx->op_gate_props.assign(op_gate_props, op_gate_props + (size_t)n_ops * 2);
     adopt_programs(ctx, n_circuits, n_qubits);
+    return QCD_OK;
+}
+
+int qcd_device_gate_superops_1q(int count, const double* unitary, const double* gate_error, const double* gate_length_ns,
+                                const double* t1_us, const double* t2_us, double* superops_out) {
+    if (count < 0 || !unitary || !gate_error || !gate_length_ns || !t1_us || !t2_us || !superops_out) return QCD_E_INVALID;
+    typedef std::complex<double> cdd;
+    cdd U[4];
+    for (int e = 0; e < 4; e++) U[e] = cdd(unitary[2 * e], unitary[2 * e + 1]);
+    // S = sum_j conj(K_j) (x) K_j, index = ket + 2 * bra:  S[(x + 2 y), (x' + 2 y')] = K[x][x'] conj(K[y][y'])
+    auto accumulate = [](cdd* S, const cdd* K, double w) {
+        for (int y = 0; y < 2; y++)
+            for (int x = 0; x < 2; x++)
+                for (int yp = 0; yp < 2; yp++)
+                    for (int xp = 0; xp < 2; xp++)
+                        S[(x + 2 * y) * 4 + (xp + 2 * yp)] += w * K[x * 2 + xp] * std::conj(K[y * 2 + yp]);
+    };
+    auto matmul4 = [](const cdd* A, const cdd* B, cdd* C) {
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+                cdd acc(0, 0);
+                for (int k = 0; k < 4; k++) acc += A[i * 4 + k] * B[k * 4 + j];
+                C[i * 4 + j] = acc;
+            }
+    };
+    static const cdd PA[4][4] = {{1, 0, 0, 1}, {0, 1, 1, 0}, {0, cdd(0, -1), cdd(0, 1), 0}, {1, 0, 0, -1}};
+    cdd SU[16];
+    for (cdd& v : SU) v = 0;
+    accumulate(SU, U, 1.0);
+    GateError ge;
+    for (int i = 0; i < count; i++) {
+        cdd cur[16], tmp[16], T[16];
+        std::copy(SU, SU + 16, cur);
+        const double t1 = std::max(t1_us[i], 1e-9), t2 = std::max(t2_us[i], 1e-9);
+        if (!(gate_error[i] != gate_error[i] && gate_length_ns[i] != gate_length_ns[i])) {   // an entry exists
+            if (!device_gate_error(1, gate_error[i], gate_length_ns[i], &t1, &t2, ge)) return QCD_E_INVALID;
+            if (ge.has_pauli) {
+                for (cdd& v : T) v = 0;
+                for (int p = 0; p < 4; p++) accumulate(T, PA[p], ge.pauli[p]);
+                matmul4(T, cur, tmp);
+                std::copy(tmp, tmp + 16, cur);
+            }
+            if (ge.has_relax) {
+                for (cdd& v : T) v = 0;
+                const int m = (int)ge.kraus[0][0];
+                for (int j = 0; j < m; j++) {
+                    cdd K[4];
+                    for (int e = 0; e < 4; e++) K[e] = cdd(ge.kraus[0][1 + 8 * j + 2 * e], ge.kraus[0][2 + 8 * j + 2 * e]);
+                    accumulate(T, K, 1.0);
+                }
+                matmul4(T, cur, tmp);
+                std::copy(tmp, tmp + 16, cur);
+            }
+        }
+        for (int e = 0; e < 16; e++) {
+            superops_out[(size_t)i * 32 + 2 * e] = cur[e].real();
+            superops_out[(size_t)i * 32 + 2 * e + 1] = cur[e].imag();
+        }
+    }
     return QCD_OK;
 }
 

@@ -107,12 +107,21 @@ _DAMPING_KINDS = ("phase_amplitude_damping_error", "amplitude_damping_error")
 
 
 def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
-    """The whole-batch array route (batch.py) covers the three graph-circuit builders on undirected graphs without
-    an entanglement stage, with either random device noise (DeviceNoiseSampler, backend None, no stochastic sites)
-    or the labelled damping sites of UnitaryNoiseSampler."""
+    """The whole-batch array route (batch.py) covers the three graph-circuit builders on undirected graphs, with either
+    random device noise (DeviceNoiseSampler, backend None, no stochastic sites) or the labelled damping sites of
+    UnitaryNoiseSampler; an entanglement stage if it is Toth settings + genuine / bi-separable witness in the
+    density-matrix regime (n_shots > 2^n, n <= 12)."""
     if type(builder) not in (CXGateCircuit, CZGateCircuit, CPhaseGateCircuit) or graph_specs.directed \
-            or entangle_specs is not None or not sampler.noisy:
+            or not sampler.noisy:
         return False
+    if entangle_specs is not None:
+        # the Toth settings are read off one density-matrix simulation per circuit: needs that method to apply
+        from .witnesses import BiSeparableWitness
+        n = sim_specs.n_qubits
+        if entangle_specs.stabilizer is not TothStabilizer or entangle_specs.stabilizer_sampler is not StabilizerSampler \
+                or entangle_specs.witness not in (GenuineWitness, BiSeparableWitness) \
+                or not (entangle_specs.n_shots > 2 ** n and n <= StabilizerSampler.dm_max_qubits):
+            return False
     if isinstance(sampler, DeviceNoiseSampler):
         return sim_specs.backend is None and not sim_specs.circuit.stochastic
     if isinstance(sampler, UnitaryNoiseSampler):
@@ -122,7 +131,7 @@ def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
 
 
 def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
-                     distributed=False):
+                     distributed=False, entangle_specs=None):
     """simulate() without per-circuit Python objects: graphs, gate lists, calibration draws and adjacency tensors are
     built for the whole batch (natively / in numpy), the noise channels are written natively at upload, one engine
     call simulates everything.  Draws come from numpy / Philox generators seeded from `random`, so `random.seed()`
@@ -192,6 +201,42 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     if world > 1:
         hist = qdist.gather_rows(hist.contiguous())
         lap("all_gather")
+    ent = None
+    if entangle_specs is not None:
+        # ---- stage 2: the n + 1 Toth settings of every circuit, read off ONE density-matrix simulation per circuit
+        import torch
+        S = n + 1
+        stab_sampler = entangle_specs.stabilizer_sampler(n_shots=entangle_specs.n_shots, backend=sim_specs.backend)
+        sop = np.empty((hi - lo, S, 4, 4), dtype=np.complex128)
+        sop[:] = np.kron(batch._H.conj(), batch._H)
+        ro2 = None
+        if not entangle_specs.noisy:      # ideal settings: the noise-free gate lists
+            clean = enc if isinstance(sampler, DeviceNoiseSampler) else batch.build_gate_lists(
+                builder, edges, n_edges, coins=np.zeros(n_slots, dtype=np.int64), **build_options)
+            eng.upload(batch.slice_programs(clean, lo, hi)[0])
+        elif isinstance(sampler, DeviceNoiseSampler):
+            # the final H of generator k carries the error of this circuit's (h, (k,)) calibration entry
+            if not isinstance(builder, CPhaseGateCircuit):          # CX / CZ lists start with H on every qubit
+                first = enc[1][lo:hi].astype(np.int64)[:, None] + np.arange(n)[None, :]
+                sop[:, :n] = batch.device_gate_superops_1q(batch._H, gp[first, 0], gp[first, 1], t1t2[lo:hi, :, 0],
+                                                           t1t2[lo:hi, :, 1])
+            ro2 = np.repeat(readout, S, axis=0) if readout is not None else None
+        if hi > lo:
+            q = np.tile(np.append(np.arange(n, dtype=np.uint8), np.uint8(0xFF)), (hi - lo, 1))
+            sp = eng.run_density_matrix_settings(q, sop, stab_sampler.precision).reshape((hi - lo) * S, 2 ** n)
+            h2 = eng.sample_from_probs(sp, stab_sampler.n_shots, seed=seeds[2] ^ 0x5DEECE66D, first_circuit=lo * S,
+                                       readout=ro2)
+            masks = batch.toth_masks(edges[lo:hi], n_edges[lo:hi], n).reshape(-1, 1)
+            ss, tot = eng.parity_counts(h2, masks)
+            par = torch.stack([ss[:, 0], tot], dim=1).reshape(hi - lo, 2 * S)
+        else:
+            par = torch.zeros((0, 2 * S), dtype=torch.int64, device=eng.device)
+        if world > 1:
+            par = qdist.gather_rows(par.contiguous())
+        par = par.cpu().numpy().reshape(B, S, 2)
+        kind = "genuine" if entangle_specs.witness is GenuineWitness else "biseparable"
+        ent = batch.toth_witnesses(kind, par[..., 0], par[..., 1], edges, n_edges, n)
+        lap("entanglement")
     prob = _to_host(hist).astype(np.float64) / sampler_specs.n_shots
     lap("gpu_and_fetch")
     adj = None
@@ -205,16 +250,24 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     results = {}
     for num, graph_data in enumerate(batch.edge_lists(edges, n_edges)):
         results[num] = {"graph_data": graph_data, "prob_vec": prob[num]}
+        if ent is not None:
+            results[num]["entanglement"] = {"value": ent[0][num], "variance": ent[1][num]}
         if adj is not None:
             a = adj[num]
             results[num]["adj_tensor"] = a if adj_tensor_specs.fixed_size else a[np.any(a != 0, axis=(1, 2))]
     lap("results")
-    global last_timing
+    global last_timing, last_batch
     last_timing = timing
+    last_batch = {"edges": edges, "n_edges": n_edges, "programs": enc}
+    if isinstance(sampler, DeviceNoiseSampler):
+        last_batch["device_props"] = props
+    else:
+        last_batch.update(coins=coins, gammas=gammas)
     return results
 
 
 last_timing = {}       # seconds per host stage of the last array-route simulate() call
+last_batch = {}        # the drawn inputs of that call (graphs, encoded programs, calibration numbers / coins + dampings)
 
 
 def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto",
@@ -249,7 +302,7 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
         raise ValueError("route must be 'auto' or 'objects'")
     if route == "auto" and _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
         return _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
-                                distributed=distributed)
+                                distributed=distributed, entangle_specs=entangle_specs)
     if distributed:
         raise NotImplementedError("distributed=True is implemented for the array route (see _array_route_ok)")
 

@@ -412,3 +412,71 @@ def test_settings_read_off_one_density_matrix_equal_resimulation(qcd, noise):
     w1 = qcd.GenuineWitness(n, stab, c_one).estimate(g)
     w2 = qcd.GenuineWitness(n, stab, c_many).estimate(g)
     assert abs(w1.value - w2.value) < 0.02
+
+
+@pytest.mark.parametrize("kind", ["device-genuine", "unitary-biseparable", "device-ideal-settings"])
+def test_simulate_array_route_with_entanglement_matches_oracle(qcd, kind, monkeypatch):
+    """simulate() with an entanglement stage on the array route (Toth settings read off one density matrix per
+    circuit, parity sums on the device, witnesses vectorised): witness values agree with the exact expectation values
+    the oracle computes from the object route's explicit programs built from the same drawn numbers."""
+    from qcdenoise_b200 import batch
+    n, B, shots = 5, 8, 65536
+    random.seed(13)
+    device = kind.startswith("device")
+    if device:
+        sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=qcd.NoiseSpec(specs=_DEV_SPEC), n_shots=1024)
+    else:
+        sampler_specs = qcd.SamplingSpecs(sampler=qcd.UnitaryNoiseSampler, n_shots=1024, noise_specs=qcd.NoiseSpec(
+            specs={"type": "amplitude_damping_error", "max_prob": 0.3}))
+    sim_specs = qcd.SimulationSpecs(n_qubits=n, n_circuits=B, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=not device))
+    noisy = kind != "device-ideal-settings"
+    wit = qcd.BiSeparableWitness if kind == "unitary-biseparable" else qcd.GenuineWitness
+    ent = qcd.EntanglementSpecs(witness=wit, stabilizer=qcd.TothStabilizer, n_shots=shots, noisy=noisy)
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), entangle_specs=ent)
+    lb = qcd.simulate.__globals__["last_batch"]
+    assert "entanglement" in qcd.simulate.__globals__["last_timing"]          # the array route ran
+    coin_iter = iter(lb["coins"].ravel().tolist()) if not device else None
+    gamma_iter = iter(lb["gammas"]) if not device else None
+    for i, ed in enumerate(batch.edge_lists(lb["edges"], lb["n_edges"])):
+        assert res[i]["graph_data"] == ed
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from(ed)
+        if device:
+            cd = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)
+            s = qcd.DeviceNoiseSampler(batch.device_props_dict(lb["device_props"], i), n_shots=16,
+                                       noise_specs=qcd.NoiseSpec(specs=_DEV_SPEC))
+            s.transpile_circuit(cd["circuit"])
+            s.build_noise_model(n)
+        else:
+            with monkeypatch.context() as mp:
+                mp.setattr(np.random, "choice", lambda k: next(coin_iter))
+                mp.setattr(np.random, "uniform", lambda high, size: next(gamma_iter).copy())
+                cd = qcd.CXGateCircuit(n_qubits=n, stochastic=True).build(g)
+                s = qcd.UnitaryNoiseSampler(None, n_shots=16, noise_specs=sampler_specs.noise_specs)
+                s.build_noise_model(cd["ops"])
+        model = s.noise_model if noisy else qcd.NoiseModel()
+        stab = qcd.TothStabilizer(g, n_qubits=n).build()
+        x = np.arange(2 ** n)
+        means = []
+        for name, sc in stab.items():
+            inst, ro = model.instantiate(cd["circuit"].copy().compose(sc))
+            p = sim.density_matrix_probs(inst.ops, n)
+            if ro is not None:
+                p = sim.apply_readout_to_probs(p, n, ro)
+            sign = 1 - 2 * (np.array([bin(v & qcd.pauli_mask(name)).count("1") for v in x]) & 1)
+            means.append(float((p * sign).sum()))
+        means = np.array(means)
+        tol = 6 * np.sqrt(n / shots) + 1e-9
+        if wit is qcd.GenuineWitness:
+            want = (n - 1) * means[n] - means[:n].sum()
+            assert abs(res[i]["entanglement"]["value"] - want) < tol, (i, res[i]["entanglement"], want)
+            assert 0 <= res[i]["entanglement"]["variance"] < 0.05
+            if not noisy:
+                assert abs(res[i]["entanglement"]["value"] + 1.0) < 1e-12       # ideal graph state: every <g_k> = 1
+        else:
+            vals = res[i]["entanglement"]["value"]
+            assert len(vals) == len(ed) == len(res[i]["entanglement"]["variance"])
+            for (a, b), v in zip(ed, vals):
+                assert abs(v - (1 - means[a] - means[b])) < tol

@@ -207,3 +207,47 @@ def test_slice_programs_is_the_sub_batch():
     assert (o_lo, o_hi) == (int(enc[1][4]), int(enc[1][9]))
     empty, _ = batch.slice_programs(enc, 5, 5)
     assert len(empty[0]) == 0 and empty[1].tolist() == [0]
+
+
+def test_toth_masks_and_noisy_h_superops_equal_object_route():
+    n = 6
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 150.0, "readout_error": 0.1},
+                                "cx": {"gate_error": 0.25, "gate_length": 500.0}, "h": {"gate_error": 0.05, "gate_length": 60.0}})
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(20, seed=12)
+    masks = batch.toth_masks(edges, n_edges, n)
+    enc = batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=False), edges, n_edges)
+    props = batch.draw_device_props(spec, enc, np.random.default_rng(4))
+    t1t2, gp, _ = batch.device_noise_inputs(props)
+    first = enc[1][:-1].astype(np.int64)[:, None] + np.arange(n)[None, :]
+    sops = batch.device_gate_superops_1q(batch._H, gp[first, 0], gp[first, 1], t1t2[..., 0], t1t2[..., 1])
+    assert sops.shape == (20, n, 4, 4)
+    for i, g in enumerate(_graphs_from(edges, n_edges, n)):
+        stab = qcd.TothStabilizer(g, n_qubits=n).build()
+        assert [qcd.pauli_mask(nm) for nm in stab] == masks[i].tolist()
+        c = qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(g)["circuit"]
+        s = qcd.DeviceNoiseSampler(batch.device_props_dict(props, i), n_shots=16, noise_specs=spec)
+        s.transpile_circuit(c)
+        s.build_noise_model(n)
+        q, want = qcd.single_qubit_settings(stab, s.noise_model, n)
+        assert q.tolist() == list(range(n)) + [0xFF]
+        np.testing.assert_allclose(sops[i], want[:n], rtol=0, atol=1e-14)
+        assert s.noise_model.native                       # reading the settings did not materialise the model
+    # no calibration entry -> the bare gate
+    bare = batch.device_gate_superops_1q(batch._H, np.full(3, np.nan), np.full(3, np.nan), np.ones(3), np.ones(3))
+    np.testing.assert_allclose(bare, np.broadcast_to(np.kron(batch._H.conj(), batch._H), (3, 4, 4)), atol=1e-15)
+
+
+def test_toth_witness_formulas():
+    n = 4
+    edges = np.array([[[0, 1], [1, 2], [2, 3], [0, 0], [0, 0], [0, 0]]], dtype=np.uint8)
+    n_edges = np.array([3], dtype=np.uint32)
+    tot = np.full((1, n + 1), 1000, dtype=np.int64)
+    signed = np.array([[800, 600, 900, 1000, 1000]], dtype=np.int64)
+    val, sig = batch.toth_witnesses("genuine", signed, tot, edges, n_edges, n)
+    mean = signed[0] / 1000
+    std = np.sqrt((1 - mean ** 2) / 1000)
+    assert abs(val[0] - (3 * 1.0 - mean[:4].sum())) < 1e-15 and abs(sig[0] - np.sqrt((std[:4] ** 2).sum())) < 1e-15
+    vals, sigs = batch.toth_witnesses("biseparable", signed, tot, edges, n_edges, n)
+    assert len(vals[0]) == 3
+    assert abs(vals[0][1] - (1 - mean[1] - mean[2])) < 1e-15 and abs(sigs[0][2] - np.sqrt(std[2] ** 2 + std[3] ** 2)) < 1e-15
