@@ -133,15 +133,21 @@ def c2_simulate(n_circ):
                                     circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
     sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=1024)
     adj = qcd.AdjTensorSpecs(tensor_shape=(16, 8, 8))
-    for route, count in (("auto", n_circ), ("auto", n_circ), ("objects", min(n_circ, 1000))):
+    ent = qcd.EntanglementSpecs(witness=qcd.GenuineWitness, stabilizer=qcd.TothStabilizer, n_shots=1024, noisy=True)
+    for route, count, with_ent in (("auto", n_circ, False), ("auto", n_circ, False), ("objects", min(n_circ, 1000), False),
+                                   ("auto", n_circ, True), ("auto", n_circ, True), ("objects", min(n_circ, 500), True)):
         sim_specs.n_circuits = count
         t0 = time.perf_counter()
-        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), adj_tensor_specs=adj, route=route)
+        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), adj_tensor_specs=adj, route=route,
+                           entangle_specs=ent if with_ent else None)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert len(res) == count and abs(res[count - 1]["prob_vec"].sum() - 1) < 1e-9
+        if with_ent:
+            assert all(-8.0 <= r["entanglement"]["value"] <= 8.0 for r in res.values())
         print(json.dumps({"config": f"C2 end to end: simulate() n=8 device noise, {count} circuits x 1024 shots + adjacency "
-                                    f"tensors, route={route}", "s": dt, "value": count / dt, "unit": "circuits/s",
+                                    f"tensors{' + 9 Toth settings x 1024 shots + genuine witness' if with_ent else ''}, "
+                                    f"route={route}", "s": dt, "value": count / dt, "unit": "circuits/s",
                           "shots_per_s": 1024 * count / dt,
                           "stages_s": {k: round(v, 4) for k, v in qcd.simulate.__globals__["last_timing"].items()}
                           if route == "auto" else None}), flush=True)
@@ -261,7 +267,7 @@ if __name__ == "__main__":
         c1(eng)
     if "C2" in which:
         c2(eng, 10000)
-    if "C2" in which:
+    if "C2" in which or "C2S" in which:
         c2_simulate(10000)
     if "C3" in which:
         c3(eng, 16)
