@@ -774,6 +774,15 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     const uint64_t wanted = 2 * T_chunk + 8 + (uint64_t)R.max_sweeps;
     n_slots = std::min<uint64_t>(n_slots, wanted);
     if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
+    {
+        // Keep the arena we already hold when it is adequate: the budget follows the device's free memory, which moves
+        // with the caller's own allocations, and re-allocating a ~100 GB arena costs tens of milliseconds per call.
+        const uint64_t have = std::min(std::min<uint64_t>(ctx->states.cap / slot_bytes,
+                                                          ctx->partials.cap / ((size_t)R.part_stride * 32)),
+                                       std::min<uint64_t>(ctx->chunk_sums.cap / ((size_t)R.n_chunks * 8),
+                                                          ctx->block_sums.cap / ((size_t)R.n_blocks * 8)));
+        if (have >= (uint64_t)R.max_sweeps + 1 && have >= n_slots / 2 && !ctx->max_slots) n_slots = std::min(have, wanted);
+    }
     if (n_slots < (uint64_t)R.max_sweeps + 1)
         return fail(ctx, QCD_E_NOMEM,
                     "memory budget holds " + std::to_string(n_slots) + " states; this program needs at least " +
@@ -793,6 +802,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     CU(ctx->owner.ensure(T_chunk * 4));
     CU(ctx->keys.ensure(T_chunk * 8));
     if (ctx->table.p) CU(cudaMemsetAsync(ctx->table.p, 0, ctx->table.cap, st));  // a failed run may have left counts
+    const double t_setup = g_trace.on ? Trace::now() - g_trace.t_run0 : 0;
 
     // ---- readout flip table [circuit][n][2] = P(1|0), P(0|1)
     if (readout) {
@@ -849,8 +859,9 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     CU(cudaStreamSynchronize(st));
     if (g_trace.on) {
         fprintf(stderr, "[qcd trace] run_sv: wait-for-decide %.2f ms in %d syncs, child readback %.2f ms, final drain %.2f ms; "
-                "host: leaf sampling launches %.2f ms, decide launches %.2f ms, child prep + sweep launch %.2f ms; total %.2f ms\n",
-                g_trace.t_sync * 1e3, g_trace.n_sync, g_trace.t_h2d * 1e3, (Trace::now() - tt1) * 1e3,
+                "host: setup %.2f ms, leaf sampling launches %.2f ms, decide launches %.2f ms, child prep + sweep launch %.2f ms; "
+                "total %.2f ms\n",
+                g_trace.t_sync * 1e3, g_trace.n_sync, g_trace.t_h2d * 1e3, (Trace::now() - tt1) * 1e3, t_setup * 1e3,
                 g_trace.t_leaves * 1e3, g_trace.t_launch * 1e3, g_trace.t_prep * 1e3, (Trace::now() - g_trace.t_run0) * 1e3);
         g_trace.t_sync = g_trace.t_h2d = g_trace.t_prep = g_trace.t_launch = g_trace.t_leaves = 0;
         g_trace.n_sync = 0;
