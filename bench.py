@@ -56,6 +56,7 @@ def build_workload(graph_index, shots):
     g.add_edges_from(edges)
     np.random.seed(SEED + graph_index)                       # coins and channel draws of the reference API use np.random
     cd = qcd.CXGateCircuit(n_qubits=N_QUBITS, stochastic=True).build(g)
+    rng_state = np.random.get_state()      # the end-to-end leg re-draws the SAME damping parameters from here
     sampler = qcd.UnitaryNoiseSampler(None, n_shots=shots, noise_specs=qcd.unitary_noise_spec, method="statevector",
                                       precision=32, seed=SEED)
     sampler.build_noise_model(cd["ops"])
@@ -64,7 +65,7 @@ def build_workload(graph_index, shots):
     programs = [sampler.noise_model.instantiate(c)[0] for c in circuits]
     masks = np.array([[0]] + [[qcd.pauli_mask(nm)] for nm in stab], dtype=np.uint32)
     return {"graph": g, "edges": edges, "circuit_dict": cd, "stab": stab, "programs": programs, "masks": masks,
-            "noise_model": sampler.noise_model, "n_sites": len(cd["ops"])}
+            "noise_model": sampler.noise_model, "n_sites": len(cd["ops"]), "rng_state": rng_state}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -296,7 +297,7 @@ def main():
                                      seed=SEED + 100 * rank + 1)
 
         def e2e_step():
-            np.random.seed(SEED)
+            np.random.set_state(work["rng_state"])      # sample() draws its noise model: the device leg's channels
             p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
             counts = ssam.sample(stab, cd["circuit"], noise_model=sampler.noise_model)   # 21 Counts (host histograms)
             w = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
