@@ -8,6 +8,7 @@
 // that (children are swept in chunks, each chunk is finished before the next), so any circuit depth runs in
 // max_sweeps + 1 slots.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -29,6 +30,20 @@ using namespace qcd;
 namespace {
 
 thread_local std::string g_create_error;
+
+// Large host arrays that are written once (the lowering threads' matrix pools): ask for transparent huge pages, the
+// first-touch page faults of 4 KB pages otherwise cost more than computing the matrices.
+void advise_huge(const void* p, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+    const uintptr_t two_mb = (uintptr_t)2 << 20;
+    const uintptr_t a = ((uintptr_t)p + two_mb - 1) & ~(two_mb - 1);
+    const uintptr_t e = ((uintptr_t)p + bytes) & ~(two_mb - 1);
+    if (e > a) madvise(reinterpret_cast<void*>(a), e - a, MADV_HUGEPAGE);   // best effort
+#else
+    (void)p;
+    (void)bytes;
+#endif
+}
 
 struct Trace {
     bool on = getenv("QCD_TRACE") != nullptr;
@@ -230,9 +245,21 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
                     part_err[t] = "circuit " + std::to_string(c) + ": " + err;
                     return;
                 }
+                if (c == c_lo && c_hi - c_lo > 8) {
+                    // circuits of one batch are alike: size the block's arrays from the first one (no re-growth of
+                    // 100 MB vectors, no page faults on the copies)
+                    const size_t cnt = (size_t)(c_hi - c_lo) + 1;
+                    auto grow = [&](auto& v) { v.reserve(v.size() * cnt + v.size() * cnt / 4); };
+                    grow(Q.pool); grow(Q.kops); grow(Q.passes); grow(Q.sweeps); grow(Q.masks); grow(Q.groups);
+                    grow(Q.subs); grow(Q.gdata);
+                    Q.circuits.reserve(cnt);
+                    advise_huge(Q.pool.data(), Q.pool.capacity() * sizeof(cd));
+                }
             }
             const size_t np = Q.pool.size();
             pool_elems[t] = np;
+            dev_pools[t].reserve(np * (precision == 64 ? sizeof(double2) : sizeof(float2)));
+            advise_huge(dev_pools[t].data(), dev_pools[t].capacity());
             if (precision == 64) {
                 dev_pools[t].resize(np * sizeof(double2));
                 double2* d = reinterpret_cast<double2*>(dev_pools[t].data());

@@ -177,15 +177,20 @@ struct Lowerer {
             // superoperator on (q..., q+n...): index = x + d*y ; S[(x,y),(x',y')] = sum_j K[x,x'] conj(K[y,y'])
             int D = d * d;
             std::vector<cd> S(D * D, cd(0, 0));
-            for (const auto& k : K)
-                for (int x = 0; x < d; x++)
-                    for (int xp = 0; xp < d; xp++) {
-                        cd a = k[x * d + xp];
-                        if (a == cd(0, 0)) continue;
-                        for (int y = 0; y < d; y++)
-                            for (int yp = 0; yp < d; yp++)
-                                S[(x + d * y) * D + (xp + d * yp)] += a * std::conj(k[y * d + yp]);
+            for (const auto& k : K) {
+                // Kraus operators are sparse (Paulis, damping operators: <= d non-zeros): visit non-zero pairs only
+                int nz_idx[16], nz = 0;
+                for (int e = 0; e < d * d; e++)
+                    if (k[e] != cd(0, 0)) nz_idx[nz++] = e;
+                for (int i = 0; i < nz; i++) {
+                    const int x = nz_idx[i] / d, xp = nz_idx[i] % d;
+                    const cd a = k[nz_idx[i]];
+                    for (int j = 0; j < nz; j++) {
+                        const int y = nz_idx[j] / d, yp = nz_idx[j] % d;
+                        S[(x + d * y) * D + (xp + d * yp)] += a * std::conj(k[nz_idx[j]]);
                     }
+                }
+            }
             if (nq == 1)
                 push_m(LOp::M2, {q[0], q[0] + n}, std::move(S));
             else
@@ -344,6 +349,36 @@ struct Lowerer {
                     int nq = op.opcode == QCD_OP_PAULI1Q ? 1 : 2, np = nq == 1 ? 4 : 16;
                     if (!need(op.param_off, np)) return false;
                     static const cd PA[4][4] = {{1, 0, 0, 1}, {0, 1, 1, 0}, {0, cd(0, -1), cd(0, 1), 0}, {1, 0, 0, -1}};
+                    if (mode == MODE_DM) {
+                        // Pauli mixture as a superoperator, straight from the monomial form of the Paulis:
+                        // P_j[r, r ^ f_j] = ph_j(r)  =>  S[(x, y), (x ^ f, y ^ f)] += p_j ph_j(x) conj(ph_j(y))
+                        static const int FL[4] = {0, 1, 1, 0};
+                        static const cd PH[4][2] = {{1, 1}, {1, 1}, {cd(0, -1), cd(0, 1)}, {1, -1}};   // P[r][r ^ f]
+                        const int d = 1 << nq, D = d * d;
+                        std::vector<cd> S(D * D, cd(0, 0));
+                        double tot = 0;
+                        for (int j = 0; j < np; j++) {
+                            if (p[j] < 0) return fail(QCD_E_INVALID, "negative Pauli probability");
+                            tot += p[j];
+                            if (p[j] == 0) continue;
+                            const int j0 = j & 3, j1 = j >> 2;
+                            const int f = nq == 1 ? FL[j0] : (FL[j0] | (FL[j1] << 1));
+                            for (int x = 0; x < d; x++) {
+                                const cd px = nq == 1 ? PH[j0][x] : PH[j0][x & 1] * PH[j1][x >> 1];
+                                for (int y = 0; y < d; y++) {
+                                    const cd py = nq == 1 ? PH[j0][y] : PH[j0][y & 1] * PH[j1][y >> 1];
+                                    S[(x + d * y) * D + ((x ^ f) + d * (y ^ f))] += p[j] * px * std::conj(py);
+                                }
+                            }
+                        }
+                        if (std::abs(tot - 1.0) > 1e-9) return fail(QCD_E_INVALID, "Pauli probabilities do not sum to 1");
+                        if (nq == 1)
+                            push_m(LOp::M2, {a, a + n}, std::move(S));
+                        else
+                            push_m(LOp::M4, {a, b, a + n, b + n}, std::move(S));
+                        stream++;
+                        break;
+                    }
                     std::vector<std::vector<cd>> K;
                     double tot = 0;
                     for (int j = 0; j < np; j++) {

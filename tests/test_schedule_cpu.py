@@ -141,3 +141,19 @@ def test_two_qubit_kraus_dm_and_trajectories():
         ops = _two_qubit_kraus_circuit(n, rng)
         np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
         _check_trajectories(n, ops, 300, seed=4)
+
+
+def test_dm_asymmetric_pauli_mixtures():
+    """Density-matrix lowering builds Pauli-mixture superoperators straight from the Paulis' monomial form: check it
+    with probabilities that distinguish X, Y and Z (depolarizing mixtures would not) on 1 and 2 qubits."""
+    rng = np.random.default_rng(17)
+    n = 4
+    for _ in range(4):
+        ops = [("h", (q,)) for q in range(n)] + [("ry", (1,), 0.7), ("rx", (2,), 1.1), ("cx", (0, 1)), ("cz", (2, 3))]
+        p1 = rng.dirichlet(np.ones(4))
+        p2 = rng.dirichlet(np.ones(16))
+        p2[int(rng.integers(1, 16))] = 0.0
+        p2 /= p2.sum()
+        ops += [("pauli", (1,), p1), ("t", (1,)), ("pauli", (3, 0), p2), ("ry", (3,), 0.3), ("s", (0,)), ("h", (0,)),
+                ("pauli", (0, 2), rng.dirichlet(np.ones(16))), ("h", (2,)), ("rx", (3,), 0.9)]
+        np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
