@@ -101,13 +101,13 @@ std::vector<cd> permute_bits(const std::vector<cd>& m, const int* perm, int nq) 
 bool is_identity(const std::vector<cd>& m, int d) {
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++)
-            if (std::abs(m[i * d + j] - (i == j ? cd(1, 0) : cd(0, 0))) > EPS) return false;
+            if (std::norm(m[i * d + j] - (i == j ? cd(1, 0) : cd(0, 0))) > EPS * EPS) return false;   // |z| > EPS, no hypot
     return true;
 }
 bool is_diag(const cd* m, int d) {
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++)
-            if (i != j && std::abs(m[i * d + j]) > EPS) return false;
+            if (i != j && std::norm(m[i * d + j]) > EPS * EPS) return false;
     return true;
 }
 
