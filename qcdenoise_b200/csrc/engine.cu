@@ -336,8 +336,14 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     if ((rc = upload_vec(ctx, dp.circuits, P.circuits))) return rc;
     // direct (register-only) descriptors: entry si for single-pass sweep si, entry n_sweeps + pi for pass pi run as a
     // sweep of its own (density-matrix mode launches multi-pass sweeps pass by pass on the register-only kernel)
-    dp.direct_host.assign(P.sweeps.size() + P.passes.size(), DirectSweep());
-    for (DirectSweep& D : dp.direct_host) memset(&D, 0, sizeof(D));
+    dp.direct_host.clear();
+    dp.direct_host.reserve(P.sweeps.size() + P.passes.size());
+    advise_huge(dp.direct_host.data(), dp.direct_host.capacity() * sizeof(DirectSweep));
+    {
+        DirectSweep zero;
+        memset(&zero, 0, sizeof(zero));
+        dp.direct_host.assign(P.sweeps.size() + P.passes.size(), zero);
+    }
     auto describe = [&](DirectSweep& D, const Sweep& S, uint32_t pi, uint8_t flags, bool reduce) {
         // (states below 13 index bits still get descriptors: the tile kernel stages its passes from them)
         const Pass& ps = P.passes[pi];
@@ -367,18 +373,8 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         D.flags = flags;
         D.prep_off = S.prep_off;
     };
-    for (size_t si = 0; si < P.sweeps.size(); si++) {
-        const Sweep& S = P.sweeps[si];
-        if (S.pass_end - S.pass_begin == 1) describe(dp.direct_host[si], S, S.pass_begin, S.flags, true);
-        for (uint32_t pi = S.pass_begin; pi < S.pass_end; pi++) {
-            uint8_t fl = 0;
-            if (pi == S.pass_begin) fl |= S.flags & SW_PREP;
-            if (pi + 1 == S.pass_end) fl |= S.flags & SW_FINAL;
-            describe(dp.direct_host[P.sweeps.size() + pi], S, pi, fl, pi + 1 == S.pass_end);
-        }
-    }
     dp.direct_flags.assign(dp.direct_host.size(), 0);
-    for (size_t i = 0; i < dp.direct_host.size(); i++) {
+    auto flags_of = [&](size_t i) {
         const DirectSweep& D = dp.direct_host[i];
         uint8_t f = 0;
         if (D.ok) f |= DF_OK;
@@ -389,6 +385,33 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         for (int o = 0; o < D.nops; o++)
             if (D.ops[o].kind == K_M4) f |= DF_PREP;   // a 16x16 superoperator forces the generic launch kind
         dp.direct_flags[i] = f;
+    };
+    // sweeps own disjoint pass ranges: the descriptors of a block of sweeps are written by one host thread
+    auto describe_block = [&](size_t s_lo, size_t s_hi) {
+        for (size_t si = s_lo; si < s_hi; si++) {
+            const Sweep& S = P.sweeps[si];
+            if (S.pass_end - S.pass_begin == 1) describe(dp.direct_host[si], S, S.pass_begin, S.flags, true);
+            flags_of(si);
+            for (uint32_t pi = S.pass_begin; pi < S.pass_end; pi++) {
+                uint8_t fl = 0;
+                if (pi == S.pass_begin) fl |= S.flags & SW_PREP;
+                if (pi + 1 == S.pass_end) fl |= S.flags & SW_FINAL;
+                describe(dp.direct_host[P.sweeps.size() + pi], S, pi, fl, pi + 1 == S.pass_end);
+                flags_of(P.sweeps.size() + pi);
+            }
+        }
+    };
+    {
+        const size_t ns = P.sweeps.size();
+        int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        n_thr = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_thr, ns / 2048));
+        if (n_thr == 1) {
+            describe_block(0, ns);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; t++) pool.emplace_back(describe_block, ns * t / n_thr, ns * (t + 1) / n_thr);
+            for (std::thread& th : pool) th.join();
+        }
     }
     if ((rc = upload_vec(ctx, dp.direct, dp.direct_host))) return rc;
     int k = std::min(P.k_max, P.n_bits);
