@@ -140,6 +140,8 @@ struct qcd_ctx {
     bool use_direct = true;      // register-only kernel for single-pass sweeps
     bool no_slots = false;
     uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
+    size_t cached_budget = 0;    // last usable_budget() answer and how many runs have reused it
+    int budget_age = 0;
     // programs (host copy of the IR; compiled lazily per (mode, precision))
     int n_qubits = 0, n_circuits = 0;
     std::vector<qcd_op> ops;
@@ -524,7 +526,7 @@ struct SvRunner {
 
     // Measurement sampling of every leaf of nodes[begin, end) (the WHOLE batch, before anything below it is swept:
     // NODE_NOSTORE leaves read their parent's slot, which the host may already have returned to the free list).
-    int sample_leaves(int d, const NodeRec* nodes, size_t begin, size_t end) {
+    int sample_leaves(int d, const NodeRec* nodes, size_t begin, size_t end, bool* owner_filled = nullptr) {
         bool any_leaf = false, any_nostore = false, any_stored = false;
         for (size_t i = begin; i < end; i++)
             if (nodes[i].flags & NODE_LEAF) {
@@ -540,6 +542,7 @@ struct SvRunner {
         uint32_t* shots_d = ctx->level_shots[d].as<uint32_t>() + t0;
         uint32_t* owner = ctx->owner.as<uint32_t>();
         launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
+        if (owner_filled) *owner_filled = true;   // same nodes, same trajectory range: the decide step reuses it
         launch_scan_chunks(ndev, (uint32_t)n_nodes, ctx->chunk_sums.as<double>(), n_chunks,
                            ctx->block_sums.as<double>(), n_blocks, n_chunks, st);
         ctx->stats.aux_launches += 3;
@@ -571,8 +574,9 @@ struct SvRunner {
         const size_t n_nodes = end - begin;
         if (n_nodes == 0) return QCD_OK;
         double tp0 = g_trace.on ? Trace::now() : 0;
+        bool owner_filled = false;
         if (!is_root && !leaves_done) {
-            int rc = sample_leaves(d, nodes, begin, end);
+            int rc = sample_leaves(d, nodes, begin, end, &owner_filled);
             if (rc) return rc;
         }
         if (g_trace.on) { g_trace.t_leaves += Trace::now() - tp0; tp0 = Trace::now(); }
@@ -593,8 +597,10 @@ struct SvRunner {
         CU(ctx->probs4.ensure(n_nodes * 4 * sizeof(double)));
         P = ctx->probs4.as<double>();
 
-        launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
-        ctx->stats.aux_launches++;
+        if (!owner_filled) {
+            launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
+            ctx->stats.aux_launches++;
+        }
         if (is_root) {
             launch_root_shots(ndev, owner, shots_d, tc, st);
             launch_fill_root_probs(P, (uint32_t)n_nodes, st);
@@ -609,10 +615,11 @@ struct SvRunner {
         }
         // ---- decide: branch word per trajectory, then group trajectories into children
         uint64_t* keys = ctx->keys.as<uint64_t>();
-        launch_traj_branch<T>(prog, ndev, P, owner, shots_d, tc, seed, keys, st);
         const uint32_t M = (uint32_t)(n_nodes << gbits);
         const uint32_t max_children = (uint32_t)std::min<uint64_t>(tc, M);
         CU(ctx->table.ensure((size_t)M * 4, true));
+        // branch draw + first step of the grouping (key counting) in one pass over the trajectories
+        launch_traj_branch<T>(prog, ndev, P, owner, shots_d, tc, seed, keys, gbits, ctx->table.as<uint32_t>(), st);
         CU(ctx->offs.ensure((size_t)M * 4));
         CU(ctx->bsum.ensure(((size_t)M / 1024 + 2) * sizeof(uint2)));
         CU(ctx->children.ensure((size_t)max_children * sizeof(NodeRec)));
@@ -620,9 +627,9 @@ struct SvRunner {
         uint32_t* shots_next = ctx->level_shots[d + 1].as<uint32_t>() + t0;
         launch_group_children(keys, shots_d, tc, gbits, ctx->table.as<uint32_t>(), M, ctx->bsum.as<uint2>(),
                               ctx->counter.as<uint32_t>(), ndev, dp->circuits.as<CircuitInfo>(), t0,
-                              ctx->offs.as<uint32_t>(), ctx->children.as<NodeRec>(), shots_next, st);
+                              ctx->offs.as<uint32_t>(), ctx->children.as<NodeRec>(), shots_next, true, st);
         launch_child_scale<T>(prog, ctx->children.as<NodeRec>(), max_children, ctx->counter.as<uint32_t>() + 1, P, st);
-        ctx->stats.aux_launches += 7;
+        ctx->stats.aux_launches += 6;
         uint32_t totals[2] = {0, 0};
         double tt0 = g_trace.on ? Trace::now() : 0;
         if (g_trace.on) g_trace.t_launch += tt0 - tp0;
@@ -819,20 +826,28 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     const size_t slot_bytes = R.slot_stride * sizeof(C);
     R.part_stride = std::max<uint32_t>(R.tiles, n >= 12 ? 1u << (n - 12) : 1u);
     const size_t per_slot = slot_bytes + (size_t)R.part_stride * 32 + (size_t)R.n_chunks * 8 + (size_t)R.n_blocks * 8;
-    const size_t budget = usable_budget(ctx);
+    // Keep the arena we already hold when it is adequate: the budget follows the device's free memory, which moves
+    // with the caller's own allocations, and re-allocating a ~100 GB arena costs tens of milliseconds per call.  The
+    // free-memory query itself is not free either: while the arena is adequate it is repeated every 16th run only.
+    const uint64_t have = std::min(std::min<uint64_t>(ctx->states.cap / slot_bytes,
+                                                      ctx->partials.cap / ((size_t)R.part_stride * 32)),
+                                   std::min<uint64_t>(ctx->chunk_sums.cap / ((size_t)R.n_chunks * 8),
+                                                      ctx->block_sums.cap / ((size_t)R.n_blocks * 8)));
+    const bool adequate = have >= (uint64_t)R.max_sweeps + 1 && !ctx->max_slots;
+    size_t budget;
+    if (adequate && ctx->cached_budget && ctx->budget_age < 16) {
+        budget = ctx->cached_budget;
+        ctx->budget_age++;
+    } else {
+        budget = usable_budget(ctx);
+        ctx->cached_budget = budget;
+        ctx->budget_age = 0;
+    }
     uint64_t n_slots = budget / per_slot;
     const uint64_t wanted = 2 * T_chunk + 8 + (uint64_t)R.max_sweeps;
     n_slots = std::min<uint64_t>(n_slots, wanted);
     if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
-    {
-        // Keep the arena we already hold when it is adequate: the budget follows the device's free memory, which moves
-        // with the caller's own allocations, and re-allocating a ~100 GB arena costs tens of milliseconds per call.
-        const uint64_t have = std::min(std::min<uint64_t>(ctx->states.cap / slot_bytes,
-                                                          ctx->partials.cap / ((size_t)R.part_stride * 32)),
-                                       std::min<uint64_t>(ctx->chunk_sums.cap / ((size_t)R.n_chunks * 8),
-                                                          ctx->block_sums.cap / ((size_t)R.n_blocks * 8)));
-        if (have >= (uint64_t)R.max_sweeps + 1 && have >= n_slots / 2 && !ctx->max_slots) n_slots = std::min(have, wanted);
-    }
+    if (adequate && have >= n_slots / 2) n_slots = std::min(have, wanted);
     if (n_slots < (uint64_t)R.max_sweeps + 1)
         return fail(ctx, QCD_E_NOMEM,
                     "memory budget holds " + std::to_string(n_slots) + " states; this program needs at least " +

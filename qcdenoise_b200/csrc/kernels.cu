@@ -115,21 +115,32 @@ __device__ __forceinline__ uint32_t resolve_group(const Group& G, const SubSite*
 
 template <typename T>
 __global__ void traj_branch_kernel(DevProgram<T> prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                                   const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys) {
+                                   const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits,
+                                   uint32_t* table) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_traj) return;
-    const uint32_t o = owner[i];
-    const NodeRec nd = parents[o];
-    if (nd.flags & NODE_LEAF) {  // finished circuit: no next sweep, no children
-        keys[i] = ~0ull;
-        return;
+    uint64_t key = ~0ull;                        // finished circuit (leaf owner) or past the end: no child
+    if (i < n_traj) {
+        const uint32_t o = owner[i];
+        const NodeRec nd = parents[o];
+        if (!(nd.flags & NODE_LEAF)) {
+            const Sweep& S = prog.sweeps[nd.sweep + 1];
+            uint32_t word = 0;
+            if (S.group >= 0)
+                word = resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)o * 4u, seed, nd.circuit,
+                                     shots[i], -1, nullptr);
+            key = ((uint64_t)o << 32) | word;
+        }
+        keys[i] = key;
     }
-    const Sweep& S = prog.sweeps[nd.sweep + 1];
-    uint32_t word = 0;
-    if (S.group >= 0)
-        word = resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)o * 4u, seed, nd.circuit,
-                             shots[i], -1, nullptr);
-    keys[i] = ((uint64_t)o << 32) | word;
+    if (table == nullptr) return;
+    // first step of the grouping, fused here (see count_keys_kernel): table[owner << gbits | word]++, warp-aggregated
+    const bool live = key != ~0ull;
+    const uint32_t active = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    const uint32_t idx = (uint32_t)(((uint64_t)(key >> 32) << gbits) | (uint32_t)key);
+    const uint32_t first = __shfl_sync(active, idx, __ffs(active) - 1);
+    const uint32_t peers = __all_sync(active, idx == first) ? active : __match_any_sync(active, idx);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(table + idx, (uint32_t)__popc(peers));
 }
 
 template <typename T>
@@ -742,8 +753,11 @@ void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* par
 }
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st) {
-    if (n_traj) traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, shots, n_traj, seed, keys);
+                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits, uint32_t* table,
+                        cudaStream_t st) {
+    if (n_traj)
+        traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, shots, n_traj, seed, keys, gbits,
+                                                                 table);
 }
 template <typename T>
 void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
@@ -753,10 +767,10 @@ void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t m
 void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
                            uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
                            const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
-                           uint32_t* shots_out, cudaStream_t st) {
+                           uint32_t* shots_out, bool counted, cudaStream_t st) {
     if (!n_traj || !M) return;
     const uint32_t nb = cdiv(M, 1024);
-    count_keys_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, n_traj, gbits, table);
+    if (!counted) count_keys_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, n_traj, gbits, table);
     group_l1_kernel<<<nb, 256, 0, st>>>(table, M, bsum);
     group_l2_kernel<<<1, 256, 0, st>>>(bsum, nb, totals);
     group_l3_kernel<<<nb, 256, 0, st>>>(table, M, gbits, bsum, parents, circuits, traj_base, offs, children);
@@ -900,7 +914,7 @@ void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* 
 
 #define INST(T)                                                                                                        \
     template void launch_traj_branch<T>(const DevProgram<T>&, const NodeRec*, const double*, const uint32_t*,         \
-                                        const uint32_t*, uint32_t, uint64_t, uint64_t*, cudaStream_t);                \
+                                        const uint32_t*, uint32_t, uint64_t, uint64_t*, int, uint32_t*, cudaStream_t); \
     template void launch_child_scale<T>(const DevProgram<T>&, NodeRec*, uint32_t, const uint32_t*, const double*,    \
                                         cudaStream_t);                                                                \
     template void launch_sample<T>(const NodeRec*, uint32_t, const void*, uint64_t, const double*, uint64_t,          \

@@ -92,7 +92,8 @@ void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* par
                        uint32_t n_parts, double* P, cudaStream_t st);
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, cudaStream_t st);
+                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits, uint32_t* table,
+                        cudaStream_t st);   // table != NULL: also counts the keys into the grouping table
 template <typename T>
 void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
                         const double* P, cudaStream_t st);
@@ -102,7 +103,7 @@ void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t m
 void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
                            uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
                            const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
-                           uint32_t* shots_out, cudaStream_t st);
+                           uint32_t* shots_out, bool counted, cudaStream_t st);   // counted: traj_branch filled the table
 void launch_root_shots(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj, cudaStream_t st);
 void launch_fill_root_probs(double* P, uint32_t n_nodes, cudaStream_t st);
 void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, uint32_t n_traj, cudaStream_t st);

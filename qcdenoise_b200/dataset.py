@@ -9,15 +9,12 @@ import torch
 
 from . import distributed as qdist
 from .ir import Circuit
-from .samplers import NoiseModel, UnitaryNoiseSampler, get_engine
+from .samplers import UnitaryNoiseSampler, get_engine, upload_batch
 
 __all__ = ["sample_prob_rows", "generate_adjacency_tensor", "encode_basis_gates", "adjacency_tensors"]
 
 
-def _run_batch(eng, progs, readout, sampler, seed):
-    n = progs[0].n_qubits
-    noisy = any(op[0] in ("kraus", "pauli", "reset") for c in progs for op in c.ops)
-    eng.upload(progs)
+def _run_uploaded(eng, n, noisy, readout, sampler, seed):
     if sampler._pick_method(n, noisy) == "density_matrix":
         probs = eng.run_density_matrix(sampler.precision)
         return eng.sample_from_probs(probs, sampler.n_shots, seed=seed, readout=readout)
@@ -39,21 +36,18 @@ def sample_prob_rows(circuit_dicts, sampler, ideal=True, distributed=False):
     if not mine:
         rows = torch.zeros((0, 2 ** n * (2 if ideal else 1)), dtype=torch.float32, device=eng.device)
     else:
-        progs, ros = [], []
+        models = []
         for cd in mine:
             if isinstance(sampler, UnitaryNoiseSampler):
                 sampler.build_noise_model(cd["ops"])
-            model = sampler.noise_model if (sampler.noise_model is not None and sampler.noisy) else NoiseModel()
-            p, ro = model.instantiate(cd["circuit"])
-            progs.append(p)
-            ros.append(ro)
-        readout = None
-        if any(r is not None for r in ros):
-            readout = np.stack([r if r is not None else np.tile(np.eye(2), (n, 1, 1)) for r in ros])
-        noisy = _run_batch(eng, progs, readout, sampler, sampler._next_seed()).to(torch.float32) / sampler.n_shots
+            models.append(sampler.noise_model if (sampler.noise_model is not None and sampler.noisy) else None)
+        # every circuit under ITS model in one upload (calibration-defined models: channels written natively)
+        readout, is_noisy = upload_batch(eng, [cd["circuit"] for cd in mine], models)
+        noisy = _run_uploaded(eng, n, is_noisy, readout, sampler, sampler._next_seed()).to(torch.float32) / sampler.n_shots
         if ideal:
             clean = [Circuit(c["circuit"].n_qubits, c["circuit"].ops) for c in mine]
-            ide = _run_batch(eng, clean, None, sampler, sampler._next_seed()).to(torch.float32) / sampler.n_shots
+            eng.upload(clean)
+            ide = _run_uploaded(eng, n, False, None, sampler, sampler._next_seed()).to(torch.float32) / sampler.n_shots
             rows = torch.stack([noisy, ide], dim=-1).reshape(len(mine), -1)
         else:
             rows = noisy
