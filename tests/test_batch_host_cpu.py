@@ -251,3 +251,41 @@ def test_toth_witness_formulas():
     vals, sigs = batch.toth_witnesses("biseparable", signed, tot, edges, n_edges, n)
     assert len(vals[0]) == 3
     assert abs(vals[0][1] - (1 - mean[1] - mean[2])) < 1e-15 and abs(sigs[0][2] - np.sqrt(std[2] ** 2 + std[3] ** 2)) < 1e-15
+
+
+def test_native_batch_entry_points_reject_bad_arguments():
+    import ctypes
+    lib = qcd._lib.load()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)       # noqa: E731
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=6)
+    le, lo, lord, oo, og, cs, co = gs._library_tables()
+    edges = np.zeros((4, 15, 2), dtype=np.uint8)
+    ne = np.zeros(4, dtype=np.uint32)
+
+    def sample(**kw):
+        a = dict(le=le, lo=lo, lord=lord, oo=oo, og=og, cs=cs, co=co, n=6, max_edges=15)
+        a.update(kw)
+        return lib.qcd_sample_graph_states(p(a["le"]), p(a["lo"]), p(a["lord"]), len(a["lord"]), p(a["oo"]), p(a["og"]),
+                                           len(a["oo"]) - 2, p(a["cs"]), p(a["co"]), len(a["co"]) - 1, a["n"], 4, 1, 1, 7, 0,
+                                           p(edges), a["max_edges"], p(ne))
+    assert sample() == 0 and (ne > 0).all()
+    assert sample(max_edges=5) == qcd._lib.QCD_E_INVALID                   # output rows too short for 6 vertices
+    assert sample(n=7) == qcd._lib.QCD_E_INVALID                           # combinations do not add up to n_qubits
+    bad = le.copy()
+    bad[0] = bad[0][::-1]                                                   # an edge with u > v
+    assert sample(le=bad) == qcd._lib.QCD_E_INVALID
+    assert lib.qcd_sample_graph_states(None, p(lo), p(lord), len(lord), p(oo), p(og), len(oo) - 2, p(cs), p(co),
+                                       len(co) - 1, 6, 4, 1, 1, 7, 0, p(edges), 15, p(ne)) == qcd._lib.QCD_E_INVALID
+    # adjacency tensors / superoperators: NULL pointers and bad shapes
+    out = np.zeros((1, 2, 4, 4))
+    codes = np.zeros(len(qcd._lib.OPCODES), dtype=np.int32)
+    off = np.zeros(2, dtype=np.uint32)
+    assert lib.qcd_adjacency_tensors(None, p(off), 1, p(codes), 2, 4, 4, 0, p(out)) == 0      # an empty circuit is fine
+    assert lib.qcd_adjacency_tensors(None, p(off), 1, None, 2, 4, 4, 0, p(out)) == qcd._lib.QCD_E_INVALID
+    assert lib.qcd_adjacency_tensors(None, p(off), 1, p(codes), 0, 4, 4, 0, p(out)) == qcd._lib.QCD_E_INVALID
+    with pytest.raises(qcd._lib.QcdError):
+        batch.device_gate_superops_1q(batch._H, np.array([0.1]), np.array([10.0]), np.array([np.nan]), np.array([1.0]))
+    # T2 > 2 T1 is clipped like the Python route does, not rejected
+    s = batch.device_gate_superops_1q(batch._H, np.array([0.1]), np.array([10.0]), np.array([1.0]), np.array([50.0]))
+    assert np.isfinite(s).all()
+    np.testing.assert_allclose(s[0][0] + s[0][3], [1, 0, 0, 1], atol=1e-12)      # trace preserving: rows (0,0) + (1,1)
