@@ -198,6 +198,17 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         sampler.last_probs = None
         hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed + lo, precision=sampler.precision, readout=readout)
     lap("lower_and_enqueue")       # channels + lowering on host threads, program upload, kernel launches
+    # host-only stages while the GPU works on what was just enqueued
+    adj = None
+    if adj_tensor_specs is not None:
+        enc_names = adj_tensor_specs.encoding
+        if enc_names is None:
+            names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"]) if int(c) in batch._GATE_NAMES})
+            enc_names = {nm: i + 1 for i, nm in enumerate(names)}
+        adj = batch.adjacency_tensors_batch(enc, enc_names, adj_tensor_specs.tensor_shape, adj_tensor_specs.directed)
+        lap("adjacency_tensors")
+    graph_lists = batch.edge_lists(edges, n_edges)
+    lap("graph_lists")
     if world > 1:
         hist = qdist.gather_rows(hist.contiguous())
         lap("all_gather")
@@ -239,16 +250,8 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         lap("entanglement")
     prob = _to_host(hist).astype(np.float64) / sampler_specs.n_shots
     lap("gpu_and_fetch")
-    adj = None
-    if adj_tensor_specs is not None:
-        enc_names = adj_tensor_specs.encoding
-        if enc_names is None:
-            names = sorted({batch._GATE_NAMES[int(c)] for c in np.unique(enc[0]["opcode"]) if int(c) in batch._GATE_NAMES})
-            enc_names = {nm: i + 1 for i, nm in enumerate(names)}
-        adj = batch.adjacency_tensors_batch(enc, enc_names, adj_tensor_specs.tensor_shape, adj_tensor_specs.directed)
-        lap("adjacency_tensors")
     results = {}
-    for num, graph_data in enumerate(batch.edge_lists(edges, n_edges)):
+    for num, graph_data in enumerate(graph_lists):
         results[num] = {"graph_data": graph_data, "prob_vec": prob[num]}
         if ent is not None:
             results[num]["entanglement"] = {"value": ent[0][num], "variance": ent[1][num]}
