@@ -480,3 +480,24 @@ def test_simulate_array_route_with_entanglement_matches_oracle(qcd, kind, monkey
             assert len(vals) == len(ed) == len(res[i]["entanglement"]["variance"])
             for (a, b), v in zip(ed, vals):
                 assert abs(v - (1 - means[a] - means[b])) < tol
+
+
+def test_dataset_rows_device_noise_native_upload(qcd):
+    """sample_prob_rows with a DeviceNoiseSampler: one calibration-defined model for the whole batch, channels written
+    natively at upload; the noisy column follows the oracle's distribution of the explicit program."""
+    n = 5
+    random.seed(8)
+    cds = [qcd.CXGateCircuit(n_qubits=n, stochastic=False).build(_graph(n, 40 + s, qcd)) for s in range(4)]
+    sampler = qcd.DeviceNoiseSampler(None, n_shots=16384, noise_specs=qcd.NoiseSpec(specs=_DEV_SPEC), seed=4)
+    # one backend for all circuits: every (gate, qubits) of the batch gets an entry
+    merged = qcd.Circuit(n, [op for cd in cds for op in cd["circuit"].ops])
+    sampler.transpile_circuit(merged)
+    sampler.build_noise_model(n)
+    assert sampler.noise_model.native
+    rows = qcd.sample_prob_rows(cds, sampler).cpu().numpy()
+    assert sampler.noise_model.native and rows.shape == (4, 2 ** n, 2)
+    for i, cd in enumerate(cds):
+        inst, ro = sampler.noise_model.instantiate(cd["circuit"])
+        want = sim.apply_readout_to_probs(sim.density_matrix_probs(inst.ops, n), n, ro)
+        assert 0.5 * np.abs(rows[i, :, 0] - want).sum() < 0.05
+        assert abs(rows[i, :, 1].sum() - 1) < 1e-6
