@@ -9,9 +9,9 @@ from typing import Any, Dict
 import numpy as np
 
 from .graph_circuit import CPhaseGateCircuit, CXGateCircuit, CZGateCircuit
-from .graph_state import GraphData, GraphDB, GraphState
+from .graph_state import GraphDB, GraphState
 from .samplers import CircuitSampler, DeviceNoiseSampler, NoiseSpec, UnitaryNoiseSampler, get_engine
-from .stabilizers import StabilizerSampler, TothStabilizer, pauli_mask
+from .stabilizers import StabilizerSampler, TothStabilizer
 from .witnesses import GenuineWitness
 
 __all__ = ["GraphSpecs", "SamplingSpecs", "CircuitSpecs", "AdjTensorSpecs", "EntanglementSpecs", "SimulationSpecs",

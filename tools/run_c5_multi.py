@@ -9,7 +9,6 @@ generator parity sums per circuit.
 import json
 import os
 import sys
-import time
 
 import numpy as np
 
