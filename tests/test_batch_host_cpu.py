@@ -289,3 +289,21 @@ def test_native_batch_entry_points_reject_bad_arguments():
     s = batch.device_gate_superops_1q(batch._H, np.array([0.1]), np.array([10.0]), np.array([1.0]), np.array([50.0]))
     assert np.isfinite(s).all()
     np.testing.assert_allclose(s[0][0] + s[0][3], [1, 0, 0, 1], atol=1e-12)      # trace preserving: rows (0,0) + (1,1)
+
+
+def test_stochastic_builder_with_no_coin_set_equals_plain_builder():
+    n = 5
+    gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+    edges, n_edges = gs.sample_batch(9, seed=1)
+    for cls in (qcd.CXGateCircuit, qcd.CZGateCircuit, qcd.CPhaseGateCircuit):
+        sto = cls(n_qubits=n, stochastic=True)
+        zero = np.zeros((int(n_edges.sum()), batch.sites_per_edge(sto)), dtype=np.int64)
+        a = batch.build_gate_lists(sto, edges, n_edges, coins=zero, gammas=np.zeros((0, 2)))
+        b = batch.build_gate_lists(cls(n_qubits=n, stochastic=False), edges, n_edges)
+        assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3]
+    with pytest.raises(ValueError):
+        batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=True), edges, n_edges)       # coins missing
+    with pytest.raises(ValueError):
+        one = np.ones((int(n_edges.sum()), 1), dtype=np.int64)
+        batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=True), edges, n_edges, coins=one,
+                               gammas=np.full((int(one.sum()), 2), 1.5))                             # gamma > 1
