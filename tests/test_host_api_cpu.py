@@ -200,3 +200,33 @@ def test_adjacency_tensor_gate_list_walk():
     assert qcd.encode_basis_gates(["id", "u1", "cx"]) == {"id": 0, "u1": 1, "cx": 2}
     with pytest.raises(KeyError):
         qcd.generate_adjacency_tensor(c, {"h": 1}, tensor_shape=(4, 3, 3))
+
+
+def test_stateprep_errors_quirk_Q3():
+    """DeviceNoiseSampler.stateprep_errors (reference samplers.py:554-575, quirk Q3): per qubit a reset and, with the
+    spec's assignment-error weights, a flip to |1> -- appended AFTER the gates, exactly like the reference."""
+    import random
+    spec = qcd.NoiseSpec(specs={"qubit": {"T1": 1.0, "T2": 1.0, "prob_meas0_prep1": 0.3, "prob_meas1_prep0": 0.4},
+                                "cx": {"gate_error": 0.1, "gate_length": 1.0}})
+    s = qcd.DeviceNoiseSampler(None, n_shots=8, noise_specs=spec)
+    c = qcd.Circuit(6)
+    c.h(0)
+    c.cx(0, 1)
+    random.seed(1)
+    want = [random.choices([[0, 1], [1, 0]], weights=[0.6, 0.4])[0] == [0, 1] for _ in range(6)]
+    random.seed(1)
+    s.stateprep_errors(c)
+    tail = [op for op in c.ops[2:]]
+    assert [op[0] for op in c.ops[:2]] == ["h", "cx"]
+    i = 0
+    for q in range(6):
+        assert tail[i][0] == "reset" and tuple(tail[i][1]) == (q,)
+        i += 1
+        if want[q]:
+            assert tail[i][0] == "x" and tuple(tail[i][1]) == (q,)
+            i += 1
+    assert i == len(tail) and any(want) and not all(want)
+    quiet = qcd.DeviceNoiseSampler(None, n_shots=8, noise_specs=qcd.NoiseSpec(specs=None))
+    c2 = qcd.Circuit(2)
+    quiet.stateprep_errors(c2)
+    assert len(c2.ops) == 0                        # not noisy: nothing appended
