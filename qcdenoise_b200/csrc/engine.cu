@@ -111,6 +111,15 @@ struct DevProg {
     DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits, direct;
     std::vector<DirectSweep> direct_host;
     std::vector<uint8_t> direct_flags;   // per descriptor: DF_* (what a launch holding this sweep must provide)
+    // A new upload invalidates the compiled program but keeps the device buffers: the next program of similar size
+    // reuses them (cudaFree synchronises the whole device and cudaMalloc of hundreds of MB is not free either).
+    void invalidate() {
+        direct_host.clear();
+        direct_flags.clear();
+        valid = false;
+        host_ready = false;
+        P = Program();
+    }
     void release() {
         direct.release();
         direct_host.clear();
@@ -196,7 +205,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         return QCD_OK;
     }
     const bool reuse = dp.host_ready && dp.P.k_max == kb && dp.P.mode == mode;
-    if (!reuse) dp.release();
+    if (!reuse) dp.invalidate();
     Program& P = dp.P;
     // matrix pools stay per lowering thread, already in device precision: no merged host copy of the (large) pool
     std::vector<std::vector<char>> dev_pools;
@@ -301,6 +310,9 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
     }
     const double t_lowered = Trace::now();
     dp.host_ready = false;
+    // The device buffers of the previous program are about to be overwritten: kernels of an earlier asynchronous run
+    // (on any stream) may still read them.  Lowering above ran concurrently with them; wait only now.
+    CU(cudaDeviceSynchronize());
     int rc;
     if ((rc = upload_vec(ctx, dp.sweeps, P.sweeps))) return rc;
     if ((rc = upload_vec(ctx, dp.passes, P.passes))) return rc;
@@ -1280,7 +1292,7 @@ void adopt_programs(qcd_ctx* ctx, int n_circuits, int n_qubits) {
     ctx->n_circuits = n_circuits;
     ctx->n_qubits = n_qubits;
     for (int m = 0; m < 2; m++)
-        for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
+        for (int p = 0; p < 2; p++) ctx->prog[m][p].invalidate();
 }
 
 // Expands a noise-free batch on several host threads (contiguous blocks of circuits, merged in order).

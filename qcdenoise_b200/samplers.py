@@ -30,13 +30,16 @@ __all__ = ["NoiseSpec", "unitary_noise_spec", "device_noise_spec", "NoiseModel",
 _ENGINES = {}
 
 
-def get_engine(device=None):
-    """Process-wide engine per CUDA device (one context per (process, device))."""
+def get_engine(device=None, slot=0):
+    """Process-wide engine per CUDA device (one context per (process, device)).  slot > 0: an additional context on the
+    same device -- simulate() alternates between two so that one lowers the next chunk of a large batch on the host
+    while the other's kernels run."""
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    if device not in _ENGINES:
-        _ENGINES[device] = Engine(device)
-    return _ENGINES[device]
+    key = device if slot == 0 else (device, slot)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device)
+    return _ENGINES[key]
 
 
 def _to_host(t):

@@ -168,12 +168,9 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         enc = batch.build_gate_lists(builder, edges, n_edges, **build_options)
         lap("gate_lists")
         props = batch.draw_device_props(sampler.noise_specs, enc, rng)
-        t1t2, gp, readout = batch.device_noise_inputs(props)
+        t1t2, gp, readout_all = batch.device_noise_inputs(props)
         sampler.backend_props = props
         lap("calibration_draws")
-        mine, (o_lo, o_hi) = batch.slice_programs(enc, lo, hi)
-        eng.upload_device_noise(mine, t1t2[lo:hi], gp[o_lo:o_hi])
-        readout = readout[lo:hi] if readout is not None else None
         noisy = True
     else:
         # UnitaryNoiseSampler: a coin per potential site, two U(0, max_prob) damping draws per site
@@ -182,21 +179,50 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
         gammas = rng.uniform(0.0, sampler.noise_specs.specs.get("max_prob", 0.1), size=(int(coins.sum()), 2))
         enc = batch.build_gate_lists(builder, edges, n_edges, coins=coins, gammas=gammas, **build_options)
         lap("gate_lists")
-        readout = None
-        eng.upload(batch.slice_programs(enc, lo, hi)[0])
+        t1t2 = gp = readout_all = None
         noisy = bool(coins.any())
-    lap("upload")
+
+    def upload_range(e, c0, c1):
+        """Circuits [c0, c1) into engine e -> their readout rows."""
+        mine, (o_lo, o_hi) = batch.slice_programs(enc, c0, c1)
+        if t1t2 is not None:
+            e.upload_device_noise(mine, t1t2[c0:c1], gp[o_lo:o_hi])
+        else:
+            e.upload(mine)
+        return readout_all[c0:c1] if readout_all is not None else None
+
     seed = seeds[2]
+    method = sampler._pick_method(n, noisy)
+    # Large density-matrix batches run in chunks on two alternating contexts: while one chunk's kernels run, the host
+    # lowers the next one (lowering, not the GPU, bounds this path).  Counters use global circuit indices, so the
+    # result does not depend on the chunking.
+    n_chunks = 4 if (method == "density_matrix" and entangle_specs is None and hi - lo >= PIPELINE_MIN) else 1
     if hi == lo:
         import torch
+        readout = None
         hist = torch.zeros((0, 2 ** n), dtype=torch.int32, device=eng.device)
-    elif sampler._pick_method(n, noisy) == "density_matrix":
-        probs = eng.run_density_matrix(sampler.precision)
-        sampler.last_probs = probs
-        hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, first_circuit=lo, readout=readout)
-    else:
+    elif n_chunks > 1:
+        import torch
+        engines = [eng, get_engine(sampler.device, slot=1)]
+        hist = torch.zeros((hi - lo, 2 ** n), dtype=torch.int32, device=eng.device)
         sampler.last_probs = None
-        hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed + lo, precision=sampler.precision, readout=readout)
+        for k in range(n_chunks):
+            c0, c1 = lo + (hi - lo) * k // n_chunks, lo + (hi - lo) * (k + 1) // n_chunks
+            e = engines[k % 2]
+            ro = upload_range(e, c0, c1)
+            probs = e.run_density_matrix(sampler.precision)
+            e.sample_from_probs(probs, sampler.n_shots, seed=seed, first_circuit=c0, readout=ro, hist=hist[c0 - lo:c1 - lo])
+        readout = readout_all[lo:hi] if readout_all is not None else None
+    else:
+        readout = upload_range(eng, lo, hi)
+        lap("upload")
+        if method == "density_matrix":
+            probs = eng.run_density_matrix(sampler.precision)
+            sampler.last_probs = probs
+            hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, first_circuit=lo, readout=readout)
+        else:
+            sampler.last_probs = None
+            hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed + lo, precision=sampler.precision, readout=readout)
     lap("lower_and_enqueue")       # channels + lowering on host threads, program upload, kernel launches
     # host-only stages while the GPU works on what was just enqueued
     adj = None
@@ -269,6 +295,7 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
     return results
 
 
+PIPELINE_MIN = 2048    # density-matrix batches of at least this many circuits run as 4 pipelined chunks
 last_timing = {}       # seconds per host stage of the last array-route simulate() call
 last_batch = {}        # the drawn inputs of that call (graphs, encoded programs, calibration numbers / coins + dampings)
 

@@ -501,3 +501,23 @@ def test_dataset_rows_device_noise_native_upload(qcd):
         want = sim.apply_readout_to_probs(sim.density_matrix_probs(inst.ops, n), n, ro)
         assert 0.5 * np.abs(rows[i, :, 0] - want).sum() < 0.05
         assert abs(rows[i, :, 1].sum() - 1) < 1e-6
+
+
+def test_simulate_pipelined_chunks_equal_single_upload(qcd, monkeypatch):
+    """Large density-matrix batches run as 4 chunks on two alternating contexts (host lowering of chunk k + 1 overlaps
+    the kernels of chunk k).  Same seeds -> bit-identical histograms with and without the chunking."""
+    import qcdenoise_b200.simulate as simmod
+    n, B = 5, 600
+    spec = qcd.NoiseSpec(specs=_DEV_SPEC)
+    sim_specs = qcd.SimulationSpecs(n_qubits=n, n_circuits=B, data=qcd.GraphData(),
+                                    circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
+    sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=512)
+    out = {}
+    for name, threshold in (("chunked", 64), ("single", 10 ** 9)):
+        monkeypatch.setattr(simmod, "PIPELINE_MIN", threshold)
+        random.seed(99)
+        np.random.seed(99)        # the sampler's shot seed comes from np.random
+        out[name] = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4))
+    for i in range(B):
+        assert out["chunked"][i]["graph_data"] == out["single"][i]["graph_data"]
+        np.testing.assert_array_equal(out["chunked"][i]["prob_vec"], out["single"][i]["prob_vec"])
