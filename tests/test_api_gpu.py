@@ -506,7 +506,8 @@ def test_dataset_rows_device_noise_native_upload(qcd):
 def test_simulate_pipelined_chunks_equal_single_upload(qcd, monkeypatch):
     """Large density-matrix batches run as 4 chunks on two alternating contexts (host lowering of chunk k + 1 overlaps
     the kernels of chunk k).  Same seeds -> bit-identical histograms with and without the chunking."""
-    import qcdenoise_b200.simulate as simmod
+    import sys
+    simmod = sys.modules["qcdenoise_b200.simulate"]      # the package attribute `simulate` is the function
     n, B = 5, 600
     spec = qcd.NoiseSpec(specs=_DEV_SPEC)
     sim_specs = qcd.SimulationSpecs(n_qubits=n, n_circuits=B, data=qcd.GraphData(),
