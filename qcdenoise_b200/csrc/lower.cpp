@@ -644,6 +644,10 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     };
     std::vector<SweepB> sw(1);
     auto fits_bits = [&](const SweepB& s, const int* qs, int nq) {
+        // bits that are already active were accepted together before: nothing new to place in the tile
+        bool all_known = !s.active.empty();
+        for (int i = 0; i < nq && all_known; i++) all_known = s.active.count(qs[i]) != 0;
+        if (all_known) return true;
         std::set<int> a = s.active;
         for (int i = 0; i < nq; i++) a.insert(qs[i]);
         Tile t;
