@@ -859,7 +859,15 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     const uint64_t wanted = 2 * T_chunk + 8 + (uint64_t)R.max_sweeps;
     n_slots = std::min<uint64_t>(n_slots, wanted);
     if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
-    if (adequate && have >= n_slots / 2) n_slots = std::min(have, wanted);
+    if (adequate && have >= n_slots / 2) {
+        n_slots = std::min(have, wanted);
+    } else if (ctx->budget_age > 0) {
+        // the arena has to grow: size it from the device's CURRENT free memory, not from a remembered figure
+        budget = usable_budget(ctx);
+        ctx->cached_budget = budget;
+        ctx->budget_age = 0;
+        n_slots = std::min<uint64_t>(budget / per_slot, wanted);
+    }
     if (n_slots < (uint64_t)R.max_sweeps + 1)
         return fail(ctx, QCD_E_NOMEM,
                     "memory budget holds " + std::to_string(n_slots) + " states; this program needs at least " +
