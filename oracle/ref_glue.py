@@ -230,12 +230,10 @@ def genuine_witness(meas, n_nodes, n):
     vals = [m for m, _ in meas.values()]
     stds = [s for _, s in meas.values()]
     w = (n_nodes - 1) * id_val - (sum(vals) - id_val)
-    # literal: `wit_coef[id_idx]` with id_idx = -1 -- the LAST entry of the (un-reordered) measurement
-    # dict gets (ns - 1), whether or not it is the identity (only stabilizer_circuits is move_to_end'ed)
-    ns = len([k for k in meas if k != id_key])
-    coef = -np.ones(len(vals))
-    coef[-1] = ns - 1
-    sigma = math.sqrt(sum((c * s) ** 2 for c, s in zip(coef, stds)))
+    # witnesses.py:136-144: `unumpy.uarray(witness_terms, var_vals).sum()` -- wit_coef multiplies the nominal values
+    # only (witness_terms = wit_coef * meas_vals); the std-devs are var_vals UNSCALED, and uncertainties' linear
+    # propagation of a plain sum of independent terms gives sqrt(sum std_k^2), whatever the order of the dict
+    sigma = math.sqrt(sum(s * s for s in stds))
     return witness_output(W_ij=None, value=w, variance=sigma)
 
 

@@ -306,9 +306,7 @@ def toth_witnesses(kind, signed, totals, edges, n_edges, n):
     std = np.sqrt(np.maximum(0.0, (1.0 - mean * mean) / totals))
     if kind == "genuine":
         value = (n - 1) * mean[:, n] - mean[:, :n].sum(axis=1)
-        coef = -np.ones(n + 1)
-        coef[n] = n - 1
-        return value, np.sqrt(((coef[None, :] * std) ** 2).sum(axis=1))
+        return value, np.sqrt((std ** 2).sum(axis=1))      # std-devs enter unscaled (witnesses.py:136-144)
     keep = np.arange(edges.shape[1])[None, :] < np.asarray(n_edges)[:, None]
     circ = np.repeat(np.arange(len(n_edges)), n_edges)
     a = edges[..., 0][keep].astype(np.int64)

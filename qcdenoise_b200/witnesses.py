@@ -109,8 +109,8 @@ class GenuineWitness(Witness):
         vals = [m for m, _ in meas.values()]
         stds = [s for _, s in meas.values()]
         w = (graph.order() - 1) * id_val - (sum(vals) - id_val)
-        ns = len([k for k in meas if k != id_key])
-        coef = -np.ones(len(vals))
-        coef[-1] = ns - 1          # as in the reference: the LAST measurement carries the identity coefficient
-        sigma = math.sqrt(sum((c * s) ** 2 for c, s in zip(coef, stds)))
+        # reference: unumpy.uarray(wit_coef * meas_vals, var_vals).sum() -- the coefficients scale the NOMINAL values
+        # only, the standard deviations enter unscaled, so sigma = sqrt(sum std_k^2) for every ordering of the
+        # measurements (witnesses.py:136-144)
+        sigma = math.sqrt(sum(s * s for s in stds))
         return witness_output(W_ij=None, value=w, variance=sigma)

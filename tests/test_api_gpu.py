@@ -99,6 +99,14 @@ def test_witnesses_from_recorded_counts_G1_G2_G3(qcd, goldens):
     res = wit.estimate(g)
     assert res.value == goldens["G2"]["genuine"]["value"]
     assert res.variance == pytest.approx(goldens["G2"]["genuine"]["variance"], abs=5e-9)
+    # identity NOT last (the reference's dict is hash-ordered, quirk Q9): sigma = sqrt(sum std_k^2) all the same --
+    # uncertainties' propagation of uarray(coef * means, stds).sum() (witnesses.py:136-144)
+    i = names.index("IIII")
+    order = [i] + [j for j in range(len(names)) if j != i]
+    wit2 = qcd.GenuineWitness(4, OrderedDict((names[j], None) for j in order), [g1["counts"][j] for j in order])
+    res2 = wit2.estimate(g)
+    expected = sum(ms[1] ** 2 for _, ms in g1["stabilizer_measurements"]) ** 0.5
+    assert res2.value == goldens["G2"]["genuine"]["value"] and res2.variance == pytest.approx(expected, rel=1e-13)
     bis = qcd.BiSeparableWitness(4, OrderedDict((nm, None) for nm in names), g1["counts"]).estimate(g)
     for idx, exp in enumerate(goldens["G3"]["bisep"]):
         assert list(bis[idx].W_ij) == exp["W_ij"] and bis[idx].value == exp["value"]

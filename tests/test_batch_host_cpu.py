@@ -243,11 +243,14 @@ def test_toth_witness_formulas():
     edges = np.array([[[0, 1], [1, 2], [2, 3], [0, 0], [0, 0], [0, 0]]], dtype=np.uint8)
     n_edges = np.array([3], dtype=np.uint32)
     tot = np.full((1, n + 1), 1000, dtype=np.int64)
-    signed = np.array([[800, 600, 900, 1000, 1000]], dtype=np.int64)
+    # a (non-physical) last column with a non-zero std: the std-devs enter the genuine witness UNSCALED
+    # (uncertainties' propagation of uarray(coef * means, stds).sum(), witnesses.py:136-144), the (n - 1) coefficient
+    # multiplies the nominal value only
+    signed = np.array([[800, 600, 900, 1000, 980]], dtype=np.int64)
     val, sig = batch.toth_witnesses("genuine", signed, tot, edges, n_edges, n)
     mean = signed[0] / 1000
     std = np.sqrt((1 - mean ** 2) / 1000)
-    assert abs(val[0] - (3 * 1.0 - mean[:4].sum())) < 1e-15 and abs(sig[0] - np.sqrt((std[:4] ** 2).sum())) < 1e-15
+    assert abs(val[0] - (3 * mean[4] - mean[:4].sum())) < 1e-15 and abs(sig[0] - np.sqrt((std ** 2).sum())) < 1e-15
     vals, sigs = batch.toth_witnesses("biseparable", signed, tot, edges, n_edges, n)
     assert len(vals[0]) == 3
     assert abs(vals[0][1] - (1 - mean[1] - mean[2])) < 1e-15 and abs(sigs[0][2] - np.sqrt(std[2] ** 2 + std[3] ** 2)) < 1e-15

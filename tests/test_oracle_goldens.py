@@ -34,6 +34,25 @@ def test_G2_genuine_witness(goldens):
     assert w.variance == pytest.approx(goldens["G2"]["genuine"]["variance"], abs=5e-9)
 
 
+def test_genuine_witness_sigma_identity_not_last(goldens):
+    """witnesses.py:136-144: arr = unumpy.uarray(wit_coef * meas_vals, var_vals); sigma = std_devs(arr.sum()).  The
+    `uncertainties` rule for a plain sum of independent variables x_k +- s_k is sigma = sqrt(sum_k s_k^2): the
+    coefficients were folded into the nominal values, the std-devs enter UNSCALED, so the result cannot depend on
+    where the identity sits in the (hash-ordered, quirk Q9) measurement dict."""
+    g = goldens["G1"]
+    names, counts = list(g["stabilizer_order"]), list(g["counts"])
+    stds = dict((nm, ms[1]) for nm, ms in g["stabilizer_measurements"])
+    expected = sum(s * s for s in stds.values()) ** 0.5          # hand evaluation of the rule above on G1's stds
+    assert expected == pytest.approx(goldens["G2"]["genuine"]["variance"], abs=5e-9)
+    i = names.index("IIII")
+    for order in ([i] + [j for j in range(len(names)) if j != i],            # identity first
+                  [1, i, 0] + [j for j in range(len(names)) if j not in (0, 1, i)]):
+        meas = ref_glue.stabilizer_measurements([names[j] for j in order], [counts[j] for j in order])
+        w = ref_glue.genuine_witness(meas, n_nodes=4, n=4)
+        assert w.value == goldens["G2"]["genuine"]["value"]
+        assert w.variance == pytest.approx(expected, rel=1e-14)
+
+
 def test_G3_biseparable_witness(goldens):
     g = goldens["G1"]
     meas = ref_glue.stabilizer_measurements(g["stabilizer_order"], g["counts"])
