@@ -68,6 +68,32 @@ def build_workload(graph_index, shots):
             "noise_model": sampler.noise_model, "n_sites": len(cd["ops"]), "rng_state": rng_state}
 
 
+def exact_stabilizer_values(work):
+    """CHECKER (oracle/pauli_prop.py, outside every timed region): the exact <S_k> of the step's 21 Toth settings under
+    the step's own noise channels, by Heisenberg-picture Pauli propagation of the measured parity observable through
+    the noisy Clifford gate list.  Order = work["stab"] (identity last)."""
+    import qcdenoise_b200 as qcd
+    from oracle import pauli_prop
+    noisy = work["programs"][0].ops
+    return pauli_prop.toth_expectations(noisy, N_QUBITS, [(sc.ops, qcd.pauli_mask(nm)) for nm, sc in work["stab"].items()])
+
+
+def check_witness(work, signed, totals, label):
+    """The sampled <S_k> (parity sums of the step's histograms) and the genuine witness against the exact values."""
+    exact = np.array(exact_stabilizer_values(work))
+    mean = signed[1:] / totals[1:]
+    sig = np.sqrt(np.maximum(1 - mean ** 2, 0) / totals[1:])
+    worst = float(np.max(np.abs(mean - exact) / np.maximum(sig, 1e-12)))
+    w_gpu = (N_QUBITS - 1) * mean[-1] - mean[:-1].sum()
+    w_exact = (N_QUBITS - 1) * exact[-1] - exact[:-1].sum()
+    w_sig = float(np.sqrt((sig ** 2).sum()))
+    if worst > 6.0 or abs(w_gpu - w_exact) > 6.0 * w_sig:
+        raise AssertionError(f"{label}: sampled stabilizer values disagree with the exact ones (worst {worst:.1f} sigma; "
+                             f"witness {w_gpu:.5f} vs exact {w_exact:.5f} +- {w_sig:.5f})")
+    return {"witness_sampled": float(w_gpu), "witness_exact": float(w_exact), "witness_sigma": w_sig,
+            "worst_setting_sigmas": worst, "checker": "oracle/pauli_prop.py (exact Pauli propagation), outside the timed region"}
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \

@@ -47,19 +47,23 @@ def load():
         lib.cpu_run_trajectories.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                              ctypes.c_void_p, ctypes.c_int]
+        lib.cpu_run_trajectories_wide.restype = ctypes.c_int
+        lib.cpu_run_trajectories_wide.argtypes = lib.cpu_run_trajectories.argtypes
         lib.cpu_max_threads.restype = ctypes.c_int
         _lib = lib
     return _lib
 
 
-def run_trajectories(encoded, shots, seed, circuit=0, shot_begin=0, n_threads=0):
+def run_trajectories(encoded, shots, seed, circuit=0, shot_begin=0, n_threads=0, wide=False):
     """encoded = (ops, offsets, params, n) of ONE circuit in the C-ABI encoding (qcdenoise_b200.ir.encode_programs
-    output format; the encoder itself is pure numpy host code).  Returns outcomes uint64[shots]."""
+    output format; the encoder itself is pure numpy host code).  Returns outcomes uint64[shots].
+    wide=True: shots one after the other, each state's amplitude loops spread over the threads (large n, few shots)."""
     ops, offsets, params, n = encoded
     lib = load()
     out = np.empty(shots, dtype=np.uint64)
     params = np.ascontiguousarray(params if len(params) else np.zeros(1))
-    rc = lib.cpu_run_trajectories(ops.ctypes.data, len(ops), params.ctypes.data, n, shot_begin, shot_begin + shots, seed,
+    fn = lib.cpu_run_trajectories_wide if wide else lib.cpu_run_trajectories
+    rc = fn(ops.ctypes.data, len(ops), params.ctypes.data, n, shot_begin, shot_begin + shots, seed,
                                   circuit, out.ctypes.data, n_threads)
     if rc:
         raise RuntimeError("cpu_run_trajectories failed")

@@ -83,6 +83,70 @@ static double norm_after2(const cd* psi, uint64_t N, int q0, int q1, const cd m[
 static void scale(cd* psi, uint64_t N, double f) {
     for (uint64_t i = 0; i < N; i++) psi[i] *= f;
 }
+
+/* ---- "wide" mode: ONE trajectory at a time, the loops over the amplitudes split over the OpenMP threads.  Used by the
+ * parity tests at n >= 24, where a handful of shots must finish in seconds (the per-shot mode above keeps one state
+ * per thread and is what the timed CPU baseline runs).  Same arithmetic per amplitude; only the association order of
+ * the norm reductions differs. */
+static int g_wide = 0;
+static inline uint64_t spread1(uint64_t k, int q) { return ((k >> q) << (q + 1)) | (k & ((1ull << q) - 1)); }
+static void apply1_wide(cd* psi, uint64_t N, int q, const cd m[4]) {
+    const uint64_t s = 1ull << q;
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)(N >> 1); k++) {
+        const uint64_t i = spread1((uint64_t)k, q);
+        cd a0 = psi[i], a1 = psi[i + s];
+        psi[i] = m[0] * a0 + m[1] * a1;
+        psi[i + s] = m[2] * a0 + m[3] * a1;
+    }
+}
+static void apply2_wide(cd* psi, uint64_t N, int q0, int q1, const cd m[16]) {
+    const uint64_t s0 = 1ull << q0, s1 = 1ull << q1;
+    const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)(N >> 2); k++) {
+        const uint64_t i = spread1(spread1((uint64_t)k, lo), hi);
+        cd a[4] = {psi[i], psi[i | s0], psi[i | s1], psi[i | s0 | s1]}, b[4];
+        for (int r = 0; r < 4; r++) b[r] = m[4 * r] * a[0] + m[4 * r + 1] * a[1] + m[4 * r + 2] * a[2] + m[4 * r + 3] * a[3];
+        psi[i] = b[0]; psi[i | s0] = b[1]; psi[i | s1] = b[2]; psi[i | s0 | s1] = b[3];
+    }
+}
+static double norm_after1_wide(const cd* psi, uint64_t N, int q, const cd m[4]) {
+    const uint64_t s = 1ull << q;
+    double acc = 0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+    for (long long k = 0; k < (long long)(N >> 1); k++) {
+        const uint64_t i = spread1((uint64_t)k, q);
+        cd a0 = psi[i], a1 = psi[i + s];
+        cd b0 = m[0] * a0 + m[1] * a1, b1 = m[2] * a0 + m[3] * a1;
+        acc += creal(b0) * creal(b0) + cimag(b0) * cimag(b0) + creal(b1) * creal(b1) + cimag(b1) * cimag(b1);
+    }
+    return acc;
+}
+static double norm_after2_wide(const cd* psi, uint64_t N, int q0, int q1, const cd m[16]) {
+    const uint64_t s0 = 1ull << q0, s1 = 1ull << q1;
+    const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+    double acc = 0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+    for (long long k = 0; k < (long long)(N >> 2); k++) {
+        const uint64_t i = spread1(spread1((uint64_t)k, lo), hi);
+        cd a[4] = {psi[i], psi[i | s0], psi[i | s1], psi[i | s0 | s1]};
+        for (int r = 0; r < 4; r++) {
+            cd b = m[4 * r] * a[0] + m[4 * r + 1] * a[1] + m[4 * r + 2] * a[2] + m[4 * r + 3] * a[3];
+            acc += creal(b) * creal(b) + cimag(b) * cimag(b);
+        }
+    }
+    return acc;
+}
+static void scale_wide(cd* psi, uint64_t N, double f) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)N; i++) psi[i] *= f;
+}
+#define APPLY1(psi, N, q, m) (g_wide ? apply1_wide(psi, N, q, m) : apply1(psi, N, q, m))
+#define APPLY2(psi, N, a, b, m) (g_wide ? apply2_wide(psi, N, a, b, m) : apply2(psi, N, a, b, m))
+#define NORM1(psi, N, q, m) (g_wide ? norm_after1_wide(psi, N, q, m) : norm_after1(psi, N, q, m))
+#define NORM2(psi, N, a, b, m) (g_wide ? norm_after2_wide(psi, N, a, b, m) : norm_after2(psi, N, a, b, m))
+#define SCALE(psi, N, f) (g_wide ? scale_wide(psi, N, f) : scale(psi, N, f))
 static int pick(const double* p, int m, double u) {
     double tot = 0, cum = 0;
     for (int j = 0; j < m; j++) tot += p[j];
@@ -113,53 +177,53 @@ static uint64_t run_one(cd* psi, const qcd_op* ops, uint32_t n_ops, const double
         cd m[16];
         switch (op.opcode) {
             case QCD_OP_ID: break;
-            case QCD_OP_H: { cd h[4] = {SQ2, SQ2, SQ2, -SQ2}; apply1(psi, N, a, h); break; }
-            case QCD_OP_X: apply1(psi, N, a, PAULI[1]); break;
-            case QCD_OP_Y: apply1(psi, N, a, PAULI[2]); break;
-            case QCD_OP_Z: apply1(psi, N, a, PAULI[3]); break;
-            case QCD_OP_S: { cd g[4] = {1, 0, 0, I}; apply1(psi, N, a, g); break; }
-            case QCD_OP_SDG: { cd g[4] = {1, 0, 0, -I}; apply1(psi, N, a, g); break; }
-            case QCD_OP_T: { cd g[4] = {1, 0, 0, SQ2 + I * SQ2}; apply1(psi, N, a, g); break; }
-            case QCD_OP_TDG: { cd g[4] = {1, 0, 0, SQ2 - I * SQ2}; apply1(psi, N, a, g); break; }
-            case QCD_OP_RX: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c, -I * s, -I * s, c}; apply1(psi, N, a, g); break; }
-            case QCD_OP_RY: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c, -s, s, c}; apply1(psi, N, a, g); break; }
-            case QCD_OP_RZ: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c - I * s, 0, 0, c + I * s}; apply1(psi, N, a, g); break; }
-            case QCD_OP_U1Q: mat_from(p, 4, m); apply1(psi, N, a, m); break;
-            case QCD_OP_CX: { cd g[16] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0}; apply2(psi, N, a, b, g); break; }
-            case QCD_OP_CZ: { cd g[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1}; apply2(psi, N, a, b, g); break; }
-            case QCD_OP_SWAP: { cd g[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1}; apply2(psi, N, a, b, g); break; }
-            case QCD_OP_U2Q: mat_from(p, 16, m); apply2(psi, N, a, b, m); break;
+            case QCD_OP_H: { cd h[4] = {SQ2, SQ2, SQ2, -SQ2}; APPLY1(psi, N, a, h); break; }
+            case QCD_OP_X: APPLY1(psi, N, a, PAULI[1]); break;
+            case QCD_OP_Y: APPLY1(psi, N, a, PAULI[2]); break;
+            case QCD_OP_Z: APPLY1(psi, N, a, PAULI[3]); break;
+            case QCD_OP_S: { cd g[4] = {1, 0, 0, I}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_SDG: { cd g[4] = {1, 0, 0, -I}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_T: { cd g[4] = {1, 0, 0, SQ2 + I * SQ2}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_TDG: { cd g[4] = {1, 0, 0, SQ2 - I * SQ2}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_RX: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c, -I * s, -I * s, c}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_RY: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c, -s, s, c}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_RZ: { double c = cos(p[0] / 2), s = sin(p[0] / 2); cd g[4] = {c - I * s, 0, 0, c + I * s}; APPLY1(psi, N, a, g); break; }
+            case QCD_OP_U1Q: mat_from(p, 4, m); APPLY1(psi, N, a, m); break;
+            case QCD_OP_CX: { cd g[16] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0}; APPLY2(psi, N, a, b, g); break; }
+            case QCD_OP_CZ: { cd g[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1}; APPLY2(psi, N, a, b, g); break; }
+            case QCD_OP_SWAP: { cd g[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1}; APPLY2(psi, N, a, b, g); break; }
+            case QCD_OP_U2Q: mat_from(p, 16, m); APPLY2(psi, N, a, b, m); break;
             case QCD_OP_KRAUS1Q: case QCD_OP_RESET: {
                 double reset_params[17] = {2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0};
                 if (op.opcode == QCD_OP_RESET) p = reset_params;
                 const int cnt = (int)p[0];
                 double pr[64];
-                for (int j = 0; j < cnt; j++) { mat_from(p + 1 + 8 * j, 4, m); pr[j] = norm_after1(psi, N, a, m); }
+                for (int j = 0; j < cnt; j++) { mat_from(p + 1 + 8 * j, 4, m); pr[j] = NORM1(psi, N, a, m); }
                 const int j = pick(pr, cnt, u53(seed, circuit, shot, stream++));
                 mat_from(p + 1 + 8 * j, 4, m);
-                apply1(psi, N, a, m);
-                scale(psi, N, 1.0 / sqrt(pr[j]));
+                APPLY1(psi, N, a, m);
+                SCALE(psi, N, 1.0 / sqrt(pr[j]));
                 break;
             }
             case QCD_OP_KRAUS2Q: {
                 const int cnt = (int)p[0];
                 double pr[64];
-                for (int j = 0; j < cnt; j++) { mat_from(p + 1 + 32 * j, 16, m); pr[j] = norm_after2(psi, N, a, b, m); }
+                for (int j = 0; j < cnt; j++) { mat_from(p + 1 + 32 * j, 16, m); pr[j] = NORM2(psi, N, a, b, m); }
                 const int j = pick(pr, cnt, u53(seed, circuit, shot, stream++));
                 mat_from(p + 1 + 32 * j, 16, m);
-                apply2(psi, N, a, b, m);
-                scale(psi, N, 1.0 / sqrt(pr[j]));
+                APPLY2(psi, N, a, b, m);
+                SCALE(psi, N, 1.0 / sqrt(pr[j]));
                 break;
             }
             case QCD_OP_PAULI1Q: {
                 const int j = pick(p, 4, u53(seed, circuit, shot, stream++));
-                if (j) apply1(psi, N, a, PAULI[j]);
+                if (j) APPLY1(psi, N, a, PAULI[j]);
                 break;
             }
             case QCD_OP_PAULI2Q: {
                 const int j = pick(p, 16, u53(seed, circuit, shot, stream++));
-                if (j & 3) apply1(psi, N, a, PAULI[j & 3]);
-                if (j >> 2) apply1(psi, N, b, PAULI[j >> 2]);
+                if (j & 3) APPLY1(psi, N, a, PAULI[j & 3]);
+                if (j >> 2) APPLY1(psi, N, b, PAULI[j >> 2]);
                 break;
             }
             default: return ~0ull;
@@ -203,6 +267,26 @@ int cpu_run_trajectories(const qcd_op* ops, uint32_t n_ops, const double* params
             free(psi);
         }
     }
+    return bad ? -1 : 0;
+}
+
+/* Same results, shots one after the other with the amplitude loops spread over the threads (n >= ~22, few shots). */
+int cpu_run_trajectories_wide(const qcd_op* ops, uint32_t n_ops, const double* params, int n_qubits, uint64_t shot_begin,
+                              uint64_t shot_end, uint64_t seed, uint32_t circuit, uint64_t* outcomes, int n_threads) {
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    cd* psi = (cd*)malloc(sizeof(cd) << n_qubits);
+    if (!psi) return -1;
+    int bad = 0;
+    g_wide = 1;
+    for (uint64_t s = shot_begin; s < shot_end; s++) {
+        uint64_t x = run_one(psi, ops, n_ops, params, n_qubits, seed, circuit, s);
+        if (x == ~0ull) bad = 1;
+        outcomes[s - shot_begin] = x;
+    }
+    g_wide = 0;
+    free(psi);
     return bad ? -1 : 0;
 }
 
