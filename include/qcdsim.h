@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 1
+#define QCD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define QCD_API __attribute__((visibility("default")))
@@ -95,6 +95,12 @@ typedef struct qcd_stats {
     uint64_t trajectories;     /* trajectories (shots) simulated */
     uint64_t max_live_states;  /* high-water mark of resident states */
     double sweep_ms;           /* CUDA-event time spent inside sweep kernels (only when timing is enabled) */
+    /* the same three figures per KIND of sweep launch: [0] prep (write-only: the first sweep of a circuit / the first
+     * density-matrix pass), [1] inner (every node of the launch has children), [2] leaf (every node is a final state:
+     * probability chunk sums are reduced, small leaves are not written), [3] mixed */
+    uint64_t kind_launches[4];
+    uint64_t kind_bytes[4];
+    double kind_ms[4];
 } qcd_stats;
 
 QCD_API int qcd_abi_version(void);
@@ -111,7 +117,11 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "table_cap_log2" (22)   size of the trajectory-grouping table
  *   "use_direct" 0/1 (1)    register-only kernel for single-pass sweeps / density-matrix passes
  *   "nostore_max" (8)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
- *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements) */
+ *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements)
+ *   "share_prefix" 0/1 (1)  consecutive circuits whose sweeps are identical up to the final one (a graph circuit and
+ *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the
+ *                           parents of the leaves; every draw stays keyed by the trajectory's own (circuit, shot), so
+ *                           results are bit-identical with the option off */
 QCD_API int qcd_set_option(qcd_ctx* ctx, const char* key, double value);
 QCD_API int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
 
@@ -150,14 +160,17 @@ QCD_API int qcd_expand_device_noise(const qcd_op* ops, const uint32_t* op_offset
  * shots <= 2^n or n > ~14 (samplers.py:308-326; stabilizers.py:214).  Global shot index g in
  * [shot_begin, shot_end) of the flattened [n_circuits][shots_per_circuit] space: circuit = g / shots_per_circuit,
  * shot = g % shots_per_circuit  (the multi-GPU partition: rank r takes a contiguous slice).
+ *   first_circuit: index of uploaded circuit 0 in the caller's whole batch; the Philox counters use
+ *                  first_circuit + circuit, so a rank that uploaded only ITS slice of the circuits reproduces the draws
+ *                  of a single-GPU run of the whole batch (mirrors qcd_sample_from_probs).  0 for a whole batch.
  *   precision: 32 (complex64) or 64 (complex128).
  *   readout [host, may be NULL]: [n_circuits][n_qubits][2][2] doubles, row = true bit, col = measured bit.
  *   hist [dev, may be NULL]: [n_circuits][2^n] uint32, ADDED to (caller zeroes).
  *   outcomes [dev, may be NULL]: [shot_end - shot_begin] uint32 basis indices (requires n_qubits <= 32).
  * Synchronises `stream` internally (tree scheduling needs device counts); results are complete on return. */
 QCD_API int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
-                            uint64_t shot_begin, uint64_t shot_end, const double* readout, uint32_t* hist,
-                            uint32_t* outcomes, uint32_t flags, void* stream);
+                            uint64_t shot_begin, uint64_t shot_end, uint32_t first_circuit, const double* readout,
+                            uint32_t* hist, uint32_t* outcomes, uint32_t flags, void* stream);
 
 /* Replaces: AerSimulator `density_matrix` method (what Aer selects for noisy circuits with shots > 2^n), up to
  * the exact outcome distribution.  probs_out [dev]: [n_circuits][2^n] float (precision 32) or double (64): the

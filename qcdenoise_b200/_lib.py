@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libqcdsim.so")
 
-QCD_ABI_VERSION = 1
+QCD_ABI_VERSION = 2
 QCD_OK, QCD_E_INVALID, QCD_E_CUDA, QCD_E_NOMEM, QCD_E_UNSUPPORTED, QCD_E_STATE = range(6)
 QCD_RUN_NO_DEDUP = 1
 _ERR_NAMES = {1: "QCD_E_INVALID", 2: "QCD_E_CUDA", 3: "QCD_E_NOMEM", 4: "QCD_E_UNSUPPORTED", 5: "QCD_E_STATE"}
@@ -32,10 +32,11 @@ class Stats(ctypes.Structure):
     _fields_ = [("sweep_launches", ctypes.c_uint64), ("aux_launches", ctypes.c_uint64),
                 ("node_sweeps", ctypes.c_uint64), ("sweep_bytes", ctypes.c_uint64), ("leaves", ctypes.c_uint64),
                 ("trajectories", ctypes.c_uint64), ("max_live_states", ctypes.c_uint64),
-                ("sweep_ms", ctypes.c_double)]
+                ("sweep_ms", ctypes.c_double), ("kind_launches", ctypes.c_uint64 * 4),
+                ("kind_bytes", ctypes.c_uint64 * 4), ("kind_ms", ctypes.c_double * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k.startswith("kind_") else getattr(self, k)) for k, _ in self._fields_}
 
 
 _P = ctypes.c_void_p
@@ -53,7 +54,7 @@ _PROTOS = {
                                                ctypes.c_size_t, _P, _P, ctypes.c_size_t,
                                                ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "qcd_run_sv_trajectories": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
-                                               ctypes.c_uint64, _P, _P, _P, ctypes.c_uint32, _P]),
+                                               ctypes.c_uint64, ctypes.c_uint32, _P, _P, _P, ctypes.c_uint32, _P]),
     "qcd_run_density_matrix": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_run_density_matrix_settings": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P,
                                                        _P, _P, _P]),

@@ -111,6 +111,7 @@ struct DevProg {
     DevBuf sweeps, passes, kops, pool, masks, groups, subs, gdata, circuits, direct;
     std::vector<DirectSweep> direct_host;
     std::vector<uint8_t> direct_flags;   // per descriptor: DF_* (what a launch holding this sweep must provide)
+    int member_bits = 0;                 // ceil(log2(longest run of circuits sharing a prefix)), statevector mode
     // A new upload invalidates the compiled program but keeps the device buffers: the next program of similar size
     // reuses them (cudaFree synchronises the whole device and cudaMalloc of hundreds of MB is not free either).
     void invalidate() {
@@ -149,6 +150,7 @@ struct qcd_ctx {
     bool use_direct = true;      // register-only kernel for single-pass sweeps
     bool no_slots = false;
     uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
+    bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
     size_t cached_budget = 0;    // last usable_budget() answer and how many runs have reused it
     int budget_age = 0;
     // programs (host copy of the IR; compiled lazily per (mode, precision))
@@ -168,6 +170,7 @@ struct qcd_ctx {
     std::vector<DevBuf> level_nodes, level_shots;
     std::vector<PinBuf> host_nodes;   // children read back at depth d (= the nodes of depth d + 1), page-locked
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<uint8_t> ev_kind;     // kind of the launch bracketed by events (2 i, 2 i + 1)
     size_t ev_used = 0;
     qcd_stats stats;
 };
@@ -307,6 +310,19 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             parts[t] = Program();
         }
         if (pool_total > 0xffffffffull) return fail(ctx, QCD_E_UNSUPPORTED, "matrix pool exceeds 2^32 entries: split the upload");
+        // runs of consecutive circuits whose sweeps are identical up to the final one (a graph circuit followed by its
+        // stabilizer settings): one trajectory tree serves the whole run down to the parents of the leaves
+        size_t longest = 1;
+        for (size_t c = 0; c < P.circuits.size(); c++) {
+            uint32_t lead = (uint32_t)c;
+            if (mode == MODE_SV && c > 0 && P.prefix[c] == P.prefix[c - 1] &&
+                c - P.circuits[c - 1].lead < ((size_t)1 << MAX_MEMBER_BITS))
+                lead = P.circuits[c - 1].lead;
+            P.circuits[c].lead = lead;
+            longest = std::max(longest, c - lead + 1);
+        }
+        dp.member_bits = 0;
+        while (((size_t)1 << dp.member_bits) < longest) dp.member_bits++;
     }
     const double t_lowered = Trace::now();
     dp.host_ready = false;
@@ -475,6 +491,24 @@ cudaEvent_t next_event(qcd_ctx* ctx) {
     return ctx->ev_pool[ctx->ev_used++];
 }
 
+enum { SK_PREP = 0, SK_INNER = 1, SK_LEAF = 2, SK_MIXED = 3 };
+
+// bracket one sweep launch: launch/byte counters always, CUDA events only when "time_sweeps" is on
+void sweep_begin(qcd_ctx* ctx, int kind, uint64_t bytes, cudaStream_t st) {
+    ctx->stats.sweep_launches++;
+    ctx->stats.sweep_bytes += bytes;
+    ctx->stats.kind_launches[kind]++;
+    ctx->stats.kind_bytes[kind] += bytes;
+    if (ctx->time_sweeps) {
+        if (ctx->ev_kind.size() <= ctx->ev_used / 2) ctx->ev_kind.resize(ctx->ev_used / 2 + 1);
+        ctx->ev_kind[ctx->ev_used / 2] = (uint8_t)kind;
+        cudaEventRecord(next_event(ctx), st);
+    }
+}
+void sweep_end(qcd_ctx* ctx, cudaStream_t st) {
+    if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+}
+
 int finish_timing(qcd_ctx* ctx) {
     if (!ctx->time_sweeps) return QCD_OK;
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
@@ -482,6 +516,7 @@ int finish_timing(qcd_ctx* ctx) {
         CU(cudaEventSynchronize(ctx->ev_pool[i + 1]));
         CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
         ctx->stats.sweep_ms += ms;
+        ctx->stats.kind_ms[ctx->ev_kind[i / 2]] += ms;
     }
     ctx->ev_used = 0;
     return QCD_OK;
@@ -499,6 +534,8 @@ struct SvRunner {
     uint32_t tiles_log2 = 0, tiles = 1, n_chunks = 1, n_blocks = 1, part_stride = 1;
     uint64_t slot_stride = 0;
     uint64_t seed = 0, spc = 0, shot_begin = 0;
+    int mbits = 0;           // member bits of the grouping keys (0: no tree sharing between circuits)
+    TrajMap map;             // of the chunk being processed
     const double* flip_dev = nullptr;
     uint32_t* hist = nullptr;
     uint32_t* outcomes = nullptr;
@@ -560,14 +597,14 @@ struct SvRunner {
         ctx->stats.aux_launches += 3;
         if (any_stored) {
             launch_sample<T>(ndev, (uint32_t)n_nodes, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(), n_chunks,
-                             ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed, flip_dev,
-                             hist, outcomes, spc, shot_begin, st);
+                             ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed, map, flip_dev,
+                             hist, outcomes, shot_begin, st);
             ctx->stats.aux_launches++;
         }
         if (any_nostore) {
             launch_sample_nostore<T>(prog, ndev, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(), n_chunks,
-                                     ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed,
-                                     flip_dev, hist, outcomes, spc, shot_begin, st);
+                                     ctx->block_sums.as<double>(), n_blocks, n_chunks, n, owner, shots_d, tc, seed, map,
+                                     flip_dev, hist, outcomes, shot_begin, st);
             ctx->stats.aux_launches++;
         }
         CU(cudaGetLastError());
@@ -592,13 +629,21 @@ struct SvRunner {
             if (rc) return rc;
         }
         if (g_trace.on) { g_trace.t_leaves += Trace::now() - tp0; tp0 = Trace::now(); }
-        if (((uint64_t)n_nodes << gbits) > table_cap && n_nodes > 1) {
-            const size_t piece = std::max<uint64_t>(1, table_cap >> gbits);
-            for (size_t b = begin; b < end; b += piece) {
-                int rc = process(d, nodes, b, std::min(end, b + piece), is_root, n_parts, true);
+        const int gtot = gbits + mbits;
+        if (((uint64_t)n_nodes << gtot) > table_cap && n_nodes > 1) {
+            const size_t piece = std::max<uint64_t>(1, table_cap >> gtot);
+            bool split = false;
+            for (size_t b = begin; b < end;) {
+                size_t e = std::min(end, b + piece);
+                // virtual roots hand their trajectories to the first root of their run: never cut a run
+                while (is_root && e < end && nodes[e].parent != e) e++;
+                if (b == begin && e == end) break;      // one run larger than the table cap: the table grows instead
+                split = true;
+                int rc = process(d, nodes, b, e, is_root, n_parts, true);
                 if (rc) return rc;
+                b = e;
             }
-            return QCD_OK;
+            if (split) return QCD_OK;
         }
         const uint32_t t0 = nodes[begin].traj_off;
         const uint32_t tc = nodes[end - 1].traj_off + nodes[end - 1].traj_cnt - t0;
@@ -627,17 +672,20 @@ struct SvRunner {
         }
         // ---- decide: branch word per trajectory, then group trajectories into children
         uint64_t* keys = ctx->keys.as<uint64_t>();
-        const uint32_t M = (uint32_t)(n_nodes << gbits);
+        if (((uint64_t)n_nodes << gtot) > 0xffffffffull)
+            return fail(ctx, QCD_E_UNSUPPORTED, "trajectory-grouping table exceeds 2^32 entries");
+        const uint32_t M = (uint32_t)(n_nodes << gtot);
         const uint32_t max_children = (uint32_t)std::min<uint64_t>(tc, M);
         CU(ctx->table.ensure((size_t)M * 4, true));
         // branch draw + first step of the grouping (key counting) in one pass over the trajectories
-        launch_traj_branch<T>(prog, ndev, P, owner, shots_d, tc, seed, keys, gbits, ctx->table.as<uint32_t>(), st);
+        launch_traj_branch<T>(prog, ndev, P, owner, shots_d, tc, seed, map, dp->circuits.as<CircuitInfo>(),
+                              is_root ? (long long)begin : -1ll, keys, gbits, mbits, ctx->table.as<uint32_t>(), st);
         CU(ctx->offs.ensure((size_t)M * 4));
         CU(ctx->bsum.ensure(((size_t)M / 1024 + 2) * sizeof(uint2)));
         CU(ctx->children.ensure((size_t)max_children * sizeof(NodeRec)));
         CU(ctx->counter.ensure(2 * sizeof(uint32_t)));
         uint32_t* shots_next = ctx->level_shots[d + 1].as<uint32_t>() + t0;
-        launch_group_children(keys, shots_d, tc, gbits, ctx->table.as<uint32_t>(), M, ctx->bsum.as<uint2>(),
+        launch_group_children(keys, shots_d, tc, gbits, mbits, ctx->table.as<uint32_t>(), M, ctx->bsum.as<uint2>(),
                               ctx->counter.as<uint32_t>(), ndev, dp->circuits.as<CircuitInfo>(), t0,
                               ctx->offs.as<uint32_t>(), ctx->children.as<NodeRec>(), shots_next, true, st);
         launch_child_scale<T>(prog, ctx->children.as<NodeRec>(), max_children, ctx->counter.as<uint32_t>() + 1, P, st);
@@ -684,6 +732,9 @@ struct SvRunner {
             const bool direct = ctx->use_direct && n >= 13 && (f_and & DF_OK);
             const bool vec = (f_and & DF_VEC) != 0, need_red = (f_or & DF_RED) != 0, need_chunks = (f_or & DF_FINAL) != 0,
                        need_prep = (f_or & DF_PREP) != 0;
+            size_t n_leaf_nodes = 0;
+            for (const NodeRec* r = chunk; r != chunk_end; ++r) n_leaf_nodes += (r->flags & NODE_LEAF) ? 1 : 0;
+            const int launch_kind_of = n_leaf_nodes == 0 ? SK_INNER : (n_leaf_nodes == c ? SK_LEAF : SK_MIXED);
             uint64_t n_nostore = 0;
             if (direct && !is_root && ctx->nostore_max > 0) {
                 const uint32_t lim = ctx->nostore_max;
@@ -763,23 +814,21 @@ struct SvRunner {
                     pa.direct_vec = lvl_vec[l] ? 1 : 0;
                     pa.direct_kind = 3;
                     pa.desc_from_pad = 1;
-                    if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                    sweep_begin(ctx, (is_root && l == 0) ? SK_PREP : launch_kind_of,
+                                cnt * ((is_root && l == 0) ? 1 : 2) * slot_stride * sizeof(C), st);
                     launch_sweep_direct<T>(prog, pa, st);
-                    if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                    sweep_end(ctx, st);
                     CU(cudaGetLastError());
-                    ctx->stats.sweep_launches++;
-                    ctx->stats.sweep_bytes += cnt * ((is_root && l == 0) ? 1 : 2) * slot_stride * sizeof(C);
                 }
                 ctx->stats.node_sweeps += c;
             } else {
-                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                sweep_begin(ctx, is_root ? SK_PREP : launch_kind_of,
+                            ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C), st);
                 if (direct) launch_sweep_direct<T>(prog, sa, st);
                 else launch_sweep<T>(prog, sa, k, st);
-                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                sweep_end(ctx, st);
                 CU(cudaGetLastError());
-                ctx->stats.sweep_launches++;
                 ctx->stats.node_sweeps += c;
-                ctx->stats.sweep_bytes += ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C);
             }
             pos += c;
             if (!is_root) {
@@ -799,7 +848,8 @@ struct SvRunner {
 
 template <typename T>
 int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot_begin, uint64_t shot_end,
-           const double* readout, uint32_t* hist, uint32_t* outcomes, uint32_t flags, cudaStream_t st) {
+           uint32_t first_circuit, const double* readout, uint32_t* hist, uint32_t* outcomes, uint32_t flags,
+           cudaStream_t st) {
     typedef typename Cplx<T>::type C;
     if (g_trace.on) g_trace.t_run0 = Trace::now();
     SvRunner<T> R;
@@ -824,15 +874,17 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     R.shot_begin = shot_begin;
     R.hist = hist;
     R.outcomes = outcomes;
+    const bool no_dedup = (flags & QCD_RUN_NO_DEDUP) != 0;
+    const bool share = ctx->share_prefix && !no_dedup && dp->member_bits > 0;
+    R.mbits = share ? dp->member_bits : 0;
     R.table_cap = (uint64_t)1 << ctx->table_cap_log2;
-    if (((uint64_t)1 << R.gbits) > R.table_cap) R.table_cap = (uint64_t)1 << R.gbits;
+    if (((uint64_t)1 << (R.gbits + R.mbits)) > R.table_cap) R.table_cap = (uint64_t)1 << (R.gbits + R.mbits);
 
     const uint64_t total = shot_end - shot_begin;
     // trajectories per tree: as many WHOLE circuits as fit max_chunk (a circuit split over two trees loses the
     // sharing between its halves); a single circuit larger than max_chunk is split
     uint64_t T_chunk = std::min<uint64_t>(total, ctx->max_chunk);
     if (spc <= T_chunk) T_chunk = (T_chunk / spc) * spc;
-    const bool no_dedup = (flags & QCD_RUN_NO_DEDUP) != 0;
 
     // ---- state slots
     const size_t slot_bytes = R.slot_stride * sizeof(C);
@@ -908,10 +960,23 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
         if (spc <= T_chunk && g1 < shot_end) {
             const uint64_t aligned = (g1 / spc) * spc;
             if (aligned > g0) g1 = aligned;
+            // ... and on the boundaries of runs of circuits that share a tree, when a run starts inside the chunk
+            if (share && g1 % spc == 0 && g1 / spc < (uint64_t)ctx->n_circuits) {
+                const uint64_t lead = P.circuits[g1 / spc].lead;
+                if (lead * spc > g0) g1 = std::min(g1, lead * spc);
+            }
         }
+        // trajectory ids of this tree = positions in [g0, g1); virtual roots: one per circuit (one per shot without
+        // de-duplication); node.pad = id of the root's first trajectory
+        const uint64_t c_first = g0 / spc;
+        R.map.spc = spc;
+        R.map.off0 = g0 - c_first * spc;
+        R.map.inv_spc = 1.0 / (double)spc;
+        R.map.c_first = (uint32_t)c_first;
+        R.map.first_circuit = first_circuit;
         std::vector<NodeRec> roots;
         uint32_t off = 0;
-        for (uint64_t c = g0 / spc; c <= (g1 - 1) / spc; c++) {
+        for (uint64_t c = c_first; c <= (g1 - 1) / spc; c++) {
             const uint64_t s0 = std::max(g0, c * spc) - c * spc, s1 = std::min(g1, (c + 1) * spc) - c * spc;
             NodeRec r;
             memset(&r, 0, sizeof(r));
@@ -920,15 +985,20 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
             r.scale = 1.0;
             if (no_dedup) {
                 for (uint64_t s = s0; s < s1; s++) {
-                    r.traj_off = off++;
+                    r.traj_off = off;
                     r.traj_cnt = 1;
-                    r.pad = (uint32_t)s;
+                    r.pad = off;
+                    r.parent = (uint32_t)roots.size();
+                    off++;
                     roots.push_back(r);
                 }
             } else {
                 r.traj_off = off;
                 r.traj_cnt = (uint32_t)(s1 - s0);
-                r.pad = (uint32_t)s0;
+                r.pad = off;
+                // the root that collects this circuit's trajectories: the first circuit of its run inside this chunk
+                const uint64_t lead = share ? std::max<uint64_t>(P.circuits[c].lead, c_first) : c;
+                r.parent = (uint32_t)(lead - c_first);
                 off += r.traj_cnt;
                 roots.push_back(r);
             }
@@ -1041,13 +1111,11 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
                 a.desc_from_pad = 1;
                 a.direct_kind = 0;
                 a.no_slots = ctx->no_slots ? 1 : 0;
-                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                sweep_begin(ctx, lvl_prep[l] ? SK_PREP : SK_INNER, cnt * slot_bytes * (lvl_prep[l] ? 1 : 2), st);
                 launch_sweep_direct<T>(prog, a, st);
-                if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+                sweep_end(ctx, st);
                 CU(cudaGetLastError());
-                ctx->stats.sweep_launches++;
                 ctx->stats.node_sweeps += cnt;
-                ctx->stats.sweep_bytes += cnt * slot_bytes * (lvl_prep[l] ? 1 : 2);
             }
         } else {
         // one NodeRec per (circuit, sweep), grouped by sweep ordinal; the sweep works in place (src == dst)
@@ -1088,13 +1156,11 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             a.desc_from_pad = 0;
             a.direct_kind = 3;
             a.no_slots = 0;
-            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            sweep_begin(ctx, l == 0 ? SK_PREP : SK_INNER, (uint64_t)cnt * slot_bytes * (l == 0 ? 1 : 2), st);
             launch_sweep<T>(prog, a, k, st);
-            if (ctx->time_sweeps) cudaEventRecord(next_event(ctx), st);
+            sweep_end(ctx, st);
             CU(cudaGetLastError());
-            ctx->stats.sweep_launches++;
             ctx->stats.node_sweeps += cnt;
-            ctx->stats.sweep_bytes += (uint64_t)cnt * slot_bytes * (l == 0 ? 1 : 2);
         }
         }
         std::vector<uint32_t> slots(c1 - c0);
@@ -1220,6 +1286,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     else if (k == "use_direct") ctx->use_direct = value != 0;
     else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
     else if (k == "no_slots") ctx->no_slots = value != 0;
+    else if (k == "share_prefix") ctx->share_prefix = value != 0;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }
@@ -1498,8 +1565,8 @@ int qcd_expand_device_noise(const qcd_op* ops, const uint32_t* op_offsets, const
 }
 
 int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circuit, uint64_t seed,
-                            uint64_t shot_begin, uint64_t shot_end, const double* readout, uint32_t* hist,
-                            uint32_t* outcomes, uint32_t flags, void* stream) {
+                            uint64_t shot_begin, uint64_t shot_end, uint32_t first_circuit, const double* readout,
+                            uint32_t* hist, uint32_t* outcomes, uint32_t flags, void* stream) {
     if (!ctx) return QCD_E_INVALID;
     if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
     if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
@@ -1517,8 +1584,10 @@ int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circ
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == 64)
-        return run_sv<double>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, readout, hist, outcomes, flags, st);
-    return run_sv<float>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, readout, hist, outcomes, flags, st);
+        return run_sv<double>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, first_circuit, readout, hist,
+                              outcomes, flags, st);
+    return run_sv<float>(ctx, dp, shots_per_circuit, seed, shot_begin, shot_end, first_circuit, readout, hist, outcomes,
+                         flags, st);
 }
 
 int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, void* probs_out,

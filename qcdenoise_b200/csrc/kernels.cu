@@ -115,20 +115,30 @@ __device__ __forceinline__ uint32_t resolve_group(const Group& G, const SubSite*
 
 template <typename T>
 __global__ void traj_branch_kernel(DevProgram<T> prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                                   const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits,
+                                   const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map,
+                                   const CircuitInfo* circuits, long long root_base, uint64_t* keys, int gbits, int mbits,
                                    uint32_t* table) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t key = ~0ull;                        // finished circuit (leaf owner) or past the end: no child
+    gbits += mbits;                              // table index = parent << (gbits + mbits) | member << gbits | word
     if (i < n_traj) {
         const uint32_t o = owner[i];
         const NodeRec nd = parents[o];
         if (!(nd.flags & NODE_LEAF)) {
+            uint32_t circuit;
+            uint64_t shot;
+            traj_locate(map, tids[i], circuit, shot);
             const Sweep& S = prog.sweeps[nd.sweep + 1];
             uint32_t word = 0;
             if (S.group >= 0)
-                word = resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)o * 4u, seed, nd.circuit,
-                                     shots[i], -1, nullptr);
-            key = ((uint64_t)o << 32) | word;
+                word = resolve_group(prog.groups[S.group], prog.subs, prog.gdata, P + (uint64_t)o * 4u, seed,
+                                     map.first_circuit + circuit, shot, -1, nullptr);
+            // the node may hold trajectories of several circuits that share everything up to their final sweeps:
+            // children that execute a final sweep are per circuit
+            if (mbits > 0 && nd.sweep + 2u == circuits[nd.circuit].sweep_end)
+                word |= (circuit - circuits[circuit].lead) << (gbits - mbits);
+            const uint32_t ko = root_base >= 0 ? (uint32_t)((long long)nd.parent - root_base) : o;
+            key = ((uint64_t)ko << 32) | word;
         }
         keys[i] = key;
     }
@@ -266,8 +276,9 @@ __global__ void group_l2_kernel(uint2* bsum, uint32_t n_blocks, uint32_t* totals
     }
 }
 
-__global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, const uint2* bsum, const NodeRec* parents,
-                                const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children) {
+__global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, int mbits, const uint2* bsum,
+                                const NodeRec* parents, const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs,
+                                NodeRec* children) {
     __shared__ uint2 warp_tot[8];
     const uint32_t base = blockIdx.x * 1024u + threadIdx.x * 4u;
     uint2 v[4];
@@ -286,7 +297,7 @@ __global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, co
         offs[base + e] = excl;
         if (cnt[e]) {
             const uint32_t idx = base + e;
-            const uint32_t par = idx >> gbits;
+            const uint32_t par = idx >> (gbits + mbits);
             const NodeRec pn = parents[par];
             NodeRec c;
             c.src_slot = pn.dst_slot;
@@ -295,10 +306,16 @@ __global__ void group_l3_kernel(const uint32_t* table, uint32_t M, int gbits, co
             c.branch = idx & ((1u << gbits) - 1u);
             c.scale = 1.0;
             c.circuit = pn.circuit;
+            const CircuitInfo pci = circuits[pn.circuit];
+            if (mbits > 0 && pn.sweep + 2u == pci.sweep_end) {
+                // the final sweep belongs to the trajectories' own circuit (member of the parent's run)
+                c.circuit = pci.lead + ((idx >> gbits) & ((1u << mbits) - 1u));
+                c.sweep = circuits[c.circuit].sweep_end - 1u;
+            }
             c.traj_off = traj_base + excl;
             c.traj_cnt = cnt[e];
             c.parent = par;
-            c.flags = (c.sweep + 1u == circuits[pn.circuit].sweep_end) ? NODE_LEAF : 0u;
+            c.flags = (c.sweep + 1u == circuits[c.circuit].sweep_end) ? NODE_LEAF : 0u;
             c.pad = 0;
             children[v[e].y + boff.y] = c;
         }
@@ -464,15 +481,16 @@ __device__ __forceinline__ uint32_t warp_pick(double w, double target, uint32_t 
 template <typename T>
 __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_t slot_stride, const double* chunk_sums,
                               uint64_t chunk_stride, const double* block_sums, uint64_t block_stride, uint32_t n_chunks,
-                              int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj, uint64_t seed,
-                              const double* flip, uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit,
-                              uint64_t shot_begin) {
+                              int n_bits, const uint32_t* owner, const uint32_t* tids, uint32_t n_traj, uint64_t seed,
+                              TrajMap map, const double* flip, uint32_t* hist, uint32_t* outcomes, uint64_t shot_begin) {
     typedef typename Cplx<T>::type C;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     // phase 1 (per thread): locate the trajectory's chunk by two binary searches over the scanned sums
     bool live = i < n_traj;
     NodeRec nd;
+    nd.circuit = 0;
+    nd.dst_slot = 0;
     uint64_t shot = 0;
     uint32_t c = 0;
     double target = 0.0;
@@ -480,12 +498,13 @@ __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_
         nd = leaves[owner[i]];
         live = (nd.flags & NODE_LEAF) != 0 && !(nd.flags & NODE_NOSTORE);
     }
+    const uint32_t pcirc = map.first_circuit + nd.circuit;      // circuit index in the Philox counters
     if (live) {
-        shot = shots[i];
+        shot = traj_shot(map, tids[i], nd.circuit);
         const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
         const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
         const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
-        target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+        target = u53(draw(seed, pcirc, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
         const uint32_t b = upper_search(bs, 0, n_blocks, target);
         if (b > 0) target -= bs[b - 1];
         const uint32_t cbeg = b << SCAN_BLOCK_LOG;
@@ -515,9 +534,9 @@ __global__ void sample_kernel(const NodeRec* leaves, const void* states, uint64_
     }
     if (!live) return;
     uint32_t x = (c << chunk_log) + e_sel;
-    if (flip) x = readout_flips(x, n_bits, flip + (uint64_t)nd.circuit * n_bits * 2u, seed, nd.circuit, shot);
+    if (flip) x = readout_flips(x, n_bits, flip + (uint64_t)nd.circuit * n_bits * 2u, seed, pcirc, shot);
     if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
-    if (outcomes) outcomes[(uint64_t)nd.circuit * shots_per_circuit + shot - shot_begin] = x;
+    if (outcomes) outcomes[(uint64_t)nd.circuit * map.spc + shot - shot_begin] = x;
 }
 
 // ------------------------------------------------------------------------------------------------ DM helpers
@@ -753,28 +772,29 @@ void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* par
 }
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits, uint32_t* table,
-                        cudaStream_t st) {
+                        const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map, const CircuitInfo* circuits,
+                        long long root_base, uint64_t* keys, int gbits, int mbits, uint32_t* table, cudaStream_t st) {
     if (n_traj)
-        traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, shots, n_traj, seed, keys, gbits,
-                                                                 table);
+        traj_branch_kernel<T><<<cdiv(n_traj, 256), 256, 0, st>>>(prog, parents, P, owner, tids, n_traj, seed, map, circuits,
+                                                                 root_base, keys, gbits, mbits, table);
 }
 template <typename T>
 void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
                         const double* P, cudaStream_t st) {
     if (max_children) child_scale_kernel<T><<<cdiv(max_children, 128), 128, 0, st>>>(prog, children, n_children, P);
 }
-void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
-                           uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
+void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, int mbits,
+                           uint32_t* table, uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
                            const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
                            uint32_t* shots_out, bool counted, cudaStream_t st) {
     if (!n_traj || !M) return;
     const uint32_t nb = cdiv(M, 1024);
-    if (!counted) count_keys_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, n_traj, gbits, table);
+    const int gtot = gbits + mbits;
+    if (!counted) count_keys_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, n_traj, gtot, table);
     group_l1_kernel<<<nb, 256, 0, st>>>(table, M, bsum);
     group_l2_kernel<<<1, 256, 0, st>>>(bsum, nb, totals);
-    group_l3_kernel<<<nb, 256, 0, st>>>(table, M, gbits, bsum, parents, circuits, traj_base, offs, children);
-    scatter_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, shots_in, n_traj, gbits, offs, table, shots_out);
+    group_l3_kernel<<<nb, 256, 0, st>>>(table, M, gbits, mbits, bsum, parents, circuits, traj_base, offs, children);
+    scatter_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(keys, shots_in, n_traj, gtot, offs, table, shots_out);
 }
 void launch_root_shots(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj, cudaStream_t st) {
     if (n_traj) root_shots_kernel<<<cdiv(n_traj, 256), 256, 0, st>>>(nodes, owner, shots, n_traj);
@@ -814,15 +834,14 @@ void launch_scan_vectors(uint32_t n_vec, double* chunk_sums, uint64_t chunk_stri
 template <typename T>
 void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states, uint64_t slot_stride,
                    const double* chunk_sums, uint64_t chunk_stride, const double* block_sums, uint64_t block_stride,
-                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj,
-                   uint64_t seed, const double* flip, uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit,
+                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* tids, uint32_t n_traj,
+                   uint64_t seed, TrajMap map, const double* flip, uint32_t* hist, uint32_t* outcomes,
                    uint64_t shot_begin, cudaStream_t st) {
     (void)n_leaves;
     if (n_traj)
         sample_kernel<T><<<cdiv(n_traj, 128), 128, 0, st>>>(leaves, states, slot_stride, chunk_sums, chunk_stride,
-                                                            block_sums, block_stride, n_chunks, n_bits, owner, shots,
-                                                            n_traj, seed, flip, hist, outcomes, shots_per_circuit,
-                                                            shot_begin);
+                                                            block_sums, block_stride, n_chunks, n_bits, owner, tids,
+                                                            n_traj, seed, map, flip, hist, outcomes, shot_begin);
 }
 template <typename T>
 void launch_extract_diag(const void* states, uint64_t slot_stride, const uint32_t* slots, uint32_t n_vec, int n,
@@ -914,12 +933,13 @@ void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* 
 
 #define INST(T)                                                                                                        \
     template void launch_traj_branch<T>(const DevProgram<T>&, const NodeRec*, const double*, const uint32_t*,         \
-                                        const uint32_t*, uint32_t, uint64_t, uint64_t*, int, uint32_t*, cudaStream_t); \
+                                        const uint32_t*, uint32_t, uint64_t, TrajMap, const CircuitInfo*, long long,  \
+                                        uint64_t*, int, int, uint32_t*, cudaStream_t);                                \
     template void launch_child_scale<T>(const DevProgram<T>&, NodeRec*, uint32_t, const uint32_t*, const double*,    \
                                         cudaStream_t);                                                                \
     template void launch_sample<T>(const NodeRec*, uint32_t, const void*, uint64_t, const double*, uint64_t,          \
                                    const double*, uint64_t, uint32_t, int, const uint32_t*, const uint32_t*, uint32_t, \
-                                   uint64_t, const double*, uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);  \
+                                   uint64_t, TrajMap, const double*, uint32_t*, uint32_t*, uint64_t, cudaStream_t);   \
     template void launch_extract_diag<T>(const void*, uint64_t, const uint32_t*, uint32_t, int, T*, cudaStream_t);    \
     template void launch_setting_probs<T>(const void*, uint64_t, uint32_t, int, int, const uint8_t*, const double2*,  \
                                           T*, cudaStream_t);                                                          \

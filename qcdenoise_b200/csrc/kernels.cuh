@@ -26,10 +26,40 @@ struct NodeRec {
     uint32_t circuit;
     uint32_t traj_off;   // trajectories of this node: [traj_off, traj_off + traj_cnt) of the level's array
     uint32_t traj_cnt;
-    uint32_t parent;     // index of the parent in the previous level's node array
+    uint32_t parent;     // index of the parent in the previous level's node array (virtual roots: index of the root
+                         // that collects this circuit's trajectories -- the first circuit of its run in the chunk)
     uint32_t flags;      // NODE_LEAF: `sweep` is the circuit's last sweep
     uint32_t pad;
 };
+// Trajectory ids: a tree works on one chunk [g0, g1) of the flattened [circuit][shot] index space; a trajectory is named
+// by its position in the chunk (32 bits), from which its circuit and shot follow.  (A node shared by several circuits
+// holds trajectories of all of them, so the circuit cannot be read off the node.)
+struct TrajMap {
+    uint64_t spc;            // shots per circuit
+    uint64_t off0;           // shot index of trajectory id 0 inside its circuit
+    double inv_spc;
+    uint32_t c_first;        // circuit (index among the uploaded ones) of trajectory id 0
+    uint32_t first_circuit;  // added to the circuit index in every Philox counter (a rank's slice of a larger batch)
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void traj_locate(const TrajMap& m, uint32_t tid, uint32_t& circuit, uint64_t& shot) {
+    const uint64_t local = (uint64_t)tid + m.off0;
+    uint64_t q = (uint64_t)((double)local * m.inv_spc);      // exact up to +-1 for local < 2^52
+    long long r = (long long)(local - q * m.spc);
+    if (r < 0) {
+        q--;
+        r += (long long)m.spc;
+    } else if (r >= (long long)m.spc) {
+        q++;
+        r -= (long long)m.spc;
+    }
+    circuit = m.c_first + (uint32_t)q;
+    shot = (uint64_t)r;
+}
+__device__ __forceinline__ uint64_t traj_shot(const TrajMap& m, uint32_t tid, uint32_t circuit) {
+    return (uint64_t)tid + m.off0 - (uint64_t)(circuit - m.c_first) * m.spc;
+}
+#endif
 constexpr uint32_t NODE_LEAF = 1;
 constexpr uint32_t NODE_NOSTORE = 2;   // leaf whose state is not written: sampled by recomputing chunks from the parent
 
@@ -84,24 +114,29 @@ template <typename T>
 void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, const void* states, uint64_t slot_stride,
                            const double* chunk_sums, uint64_t chunk_stride, const double* block_sums,
                            uint64_t block_stride, uint32_t n_chunks, int n_bits, const uint32_t* owner,
-                           const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
-                           uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin, cudaStream_t st);
+                           const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map, const double* flip,
+                           uint32_t* hist, uint32_t* outcomes, uint64_t shot_begin, cudaStream_t st);
 
 // ---- decide
 void launch_node_probs(const NodeRec* nodes, uint32_t n_nodes, const double* partials, uint32_t part_stride,
                        uint32_t n_parts, double* P, cudaStream_t st);
+// gbits = branch-word bits, mbits = member bits (children that execute a circuit's FINAL sweep are keyed by the
+// trajectory's own circuit as well: (parent, member, word)); root_base >= 0: the parents are virtual roots, a
+// trajectory is keyed to parents[owner].parent - root_base instead of its owner.
 template <typename T>
 void launch_traj_branch(const DevProgram<T>& prog, const NodeRec* parents, const double* P, const uint32_t* owner,
-                        const uint32_t* shots, uint32_t n_traj, uint64_t seed, uint64_t* keys, int gbits, uint32_t* table,
+                        const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map, const CircuitInfo* circuits,
+                        long long root_base, uint64_t* keys, int gbits, int mbits, uint32_t* table,
                         cudaStream_t st);   // table != NULL: also counts the keys into the grouping table
 template <typename T>
 void launch_child_scale(const DevProgram<T>& prog, NodeRec* children, uint32_t max_children, const uint32_t* n_children,
                         const double* P, cudaStream_t st);
-// trajectories (keys = owner << 32 | branch word, ~0 = finished) -> child NodeRecs (dst_slot unassigned) ordered by
-// (parent, word), totals[0] = trajectories placed, totals[1] = children; shots permuted so that each child's
-// trajectories are contiguous.  table [M = n_parents << gbits] must be all-zero on entry and is all-zero on exit.
-void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, uint32_t* table,
-                           uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
+// trajectories (keys = parent << 32 | member << gbits | branch word, ~0 = finished) -> child NodeRecs (dst_slot
+// unassigned) ordered by (parent, member, word), totals[0] = trajectories placed, totals[1] = children; trajectory ids
+// permuted so that each child's trajectories are contiguous.  table [M = n_parents << (gbits + mbits)] must be all-zero
+// on entry and is all-zero on exit.
+void launch_group_children(const uint64_t* keys, const uint32_t* shots_in, uint32_t n_traj, int gbits, int mbits,
+                           uint32_t* table, uint32_t M, uint2* bsum, uint32_t* totals, const NodeRec* parents,
                            const CircuitInfo* circuits, uint32_t traj_base, uint32_t* offs, NodeRec* children,
                            uint32_t* shots_out, bool counted, cudaStream_t st);   // counted: traj_branch filled the table
 void launch_root_shots(const NodeRec* nodes, const uint32_t* owner, uint32_t* shots, uint32_t n_traj, cudaStream_t st);
@@ -115,10 +150,9 @@ void launch_scan_chunks(const NodeRec* leaves, uint32_t n_leaves, double* chunk_
 template <typename T>
 void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states, uint64_t slot_stride,
                    const double* chunk_sums, uint64_t chunk_stride, const double* block_sums, uint64_t block_stride,
-                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* shots, uint32_t n_traj,
-                   uint64_t seed, const double* flip /*dev [circuit][n][2] = P(1|0), P(0|1); or null*/,
-                   uint32_t* hist, uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin,
-                   cudaStream_t st);
+                   uint32_t n_chunks, int n_bits, const uint32_t* owner, const uint32_t* tids, uint32_t n_traj,
+                   uint64_t seed, TrajMap map, const double* flip /*dev [circuit][n][2] = P(1|0), P(0|1); or null*/,
+                   uint32_t* hist, uint32_t* outcomes, uint64_t shot_begin, cudaStream_t st);
 
 // ---- density-matrix helpers / probability vectors
 template <typename T>

@@ -728,6 +728,18 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     CircuitInfo ci;
     ci.sweep_begin = (uint32_t)P.sweeps.size();
     ci.n_sites = (uint32_t)lw.sites.size();
+    ci.lead = (uint32_t)P.circuits.size();
+    // array sizes at the start of this circuit and where its final sweep's own passes begin (prefix signature)
+    struct Mark {
+        size_t sweeps, passes, kops, pool, masks, groups, subs, gdata;
+    };
+    auto mark = [&]() {
+        return Mark{P.sweeps.size(), P.passes.size(), P.kops.size(), P.pool.size(), P.masks.size(), P.groups.size(),
+                    P.subs.size(), P.gdata.size()};
+    };
+    const Mark m0 = mark();
+    Mark m1 = m0;
+    int32_t final_group_rel = -1;
     uint32_t prep_off = (uint32_t)P.pool.size();
     P.pool.insert(P.pool.end(), prep.begin(), prep.end());
     // ---- late peephole inside each sweep: a per-branch 1q matrix and a plain 1q matrix on the same bit, with nothing
@@ -871,6 +883,10 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
             P.groups.push_back(G);
             P.max_group_bits = std::max(P.max_group_bits, s.bits);
         }
+        if (si + 1 == sw.size()) {   // everything emitted so far (incl. the final sweep's site group) is shared prefix
+            m1 = mark();
+            final_group_rel = S.group >= 0 ? S.group - (int32_t)m0.groups : -1;
+        }
         // passes
         S.pass_begin = (uint32_t)P.passes.size();
         struct PB {
@@ -998,6 +1014,60 @@ int compile_circuit(Program& P, const qcd_op* in, uint32_t n_ops, const double* 
     ci.sweep_end = (uint32_t)P.sweeps.size();
     P.max_sweeps = std::max(P.max_sweeps, (int)(ci.sweep_end - ci.sweep_begin));
     P.circuits.push_back(ci);
+    // ---- prefix signature: two independent 64-bit hashes over the prefix content with circuit-relative offsets
+    {
+        struct Hasher {
+            uint64_t a = 0xcbf29ce484222325ull, b = 0x9e3779b97f4a7c15ull;
+            void bytes(const void* p, size_t n) {
+                const unsigned char* c = static_cast<const unsigned char*>(p);
+                for (size_t i = 0; i < n; i++) {
+                    a = (a ^ c[i]) * 0x100000001b3ull;
+                    b = (b + c[i] + 0x632be59bd9b4e019ull) * 0xff51afd7ed558ccdull;
+                    b ^= b >> 29;
+                }
+            }
+        } H;
+        auto pod = [&H](const auto& v) { H.bytes(&v, sizeof(v)); };
+        for (size_t i = m0.sweeps; i < m1.sweeps; i++) {
+            Sweep S = P.sweeps[i];
+            S.pass_begin -= (uint32_t)m0.passes;
+            S.pass_end -= (uint32_t)m0.passes;
+            S.prep_off -= (uint32_t)m0.pool;
+            if (S.group >= 0) S.group -= (int32_t)m0.groups;
+            pod(S);
+        }
+        for (size_t i = m0.passes; i < m1.passes; i++) {
+            Pass ps = P.passes[i];
+            ps.op_begin -= (uint32_t)m0.kops;
+            ps.op_end -= (uint32_t)m0.kops;
+            pod(ps);
+        }
+        for (size_t i = m0.kops; i < m1.kops; i++) {
+            KOp k = P.kops[i];
+            k.off -= (uint32_t)(k.kind == K_SIGNS ? m0.masks : m0.pool);
+            pod(k);
+        }
+        if (m1.pool > m0.pool) H.bytes(&P.pool[m0.pool], (m1.pool - m0.pool) * sizeof(cd));
+        if (m1.masks > m0.masks) H.bytes(&P.masks[m0.masks], (m1.masks - m0.masks) * sizeof(uint64_t));
+        for (size_t i = m0.groups; i < m1.groups; i++) {
+            Group g = P.groups[i];
+            g.sub_begin -= (uint32_t)m0.subs;
+            g.sub_end -= (uint32_t)m0.subs;
+            pod(g);
+        }
+        for (size_t i = m0.subs; i < m1.subs; i++) {
+            SubSite ss = P.subs[i];
+            ss.data_off -= (uint32_t)m0.gdata;
+            pod(ss);
+        }
+        if (m1.gdata > m0.gdata) H.bytes(&P.gdata[m0.gdata], (m1.gdata - m0.gdata) * sizeof(double));
+        pod(final_group_rel);
+        PrefixSig sig;
+        sig.h0 = H.a;
+        sig.h1 = H.b;
+        sig.n_sweeps = (uint32_t)(m1.sweeps - m0.sweeps);
+        P.prefix.push_back(sig);
+    }
     return QCD_OK;
 }
 
@@ -1035,11 +1105,14 @@ void merge_program(Program& dst, const Program& src, long long pool_base) {
         dst.subs.push_back(ss);
     }
     dst.gdata.insert(dst.gdata.end(), src.gdata.begin(), src.gdata.end());
+    const uint32_t circ0 = (uint32_t)dst.circuits.size();
     for (CircuitInfo ci : src.circuits) {
         ci.sweep_begin += sweep0;
         ci.sweep_end += sweep0;
+        ci.lead += circ0;
         dst.circuits.push_back(ci);
     }
+    dst.prefix.insert(dst.prefix.end(), src.prefix.begin(), src.prefix.end());
     dst.max_group_bits = std::max(dst.max_group_bits, src.max_group_bits);
     dst.max_sweeps = std::max(dst.max_sweeps, src.max_sweeps);
 }
@@ -1049,7 +1122,11 @@ std::string program_to_json(const Program& P, int c) {
     o.precision(17);
     const CircuitInfo& ci = P.circuits[c];
     o << "{\"n_qubits\":" << P.n_qubits << ",\"n_bits\":" << P.n_bits << ",\"mode\":" << P.mode
-      << ",\"n_sites\":" << ci.n_sites << ",\"sweeps\":[";
+      << ",\"n_sites\":" << ci.n_sites;
+    if ((size_t)c < P.prefix.size())
+        o << ",\"prefix_sig\":[\"" << std::hex << P.prefix[c].h0 << "\",\"" << P.prefix[c].h1 << "\"," << std::dec
+          << P.prefix[c].n_sweeps << "]";
+    o << ",\"sweeps\":[";
     auto cplx = [&](cd v) { o << "[" << v.real() << "," << v.imag() << "]"; };
     for (uint32_t si = ci.sweep_begin; si < ci.sweep_end; si++) {
         const Sweep& S = P.sweeps[si];

@@ -13,6 +13,15 @@ typedef std::complex<double> cd;
 
 enum Mode { MODE_SV = 0, MODE_DM = 1 };
 
+// Content hash of everything a circuit executes before its final sweep (sweeps, passes, ops, matrices, sign masks, site
+// groups -- including the group the final sweep resolves), with offsets taken relative to the circuit's own arrays.
+// Equal signatures <=> the trajectory tree of the two circuits is identical down to the parents of the leaves.
+struct PrefixSig {
+    uint64_t h0 = 0, h1 = 0;
+    uint32_t n_sweeps = 0;
+    bool operator==(const PrefixSig& o) const { return h0 == o.h0 && h1 == o.h1 && n_sweeps == o.n_sweeps; }
+};
+
 struct Program {
     int n_qubits = 0;
     int n_bits = 0;   // n_qubits (MODE_SV) or 2 n_qubits (MODE_DM)
@@ -29,6 +38,7 @@ struct Program {
     std::vector<SubSite> subs;
     std::vector<double> gdata;
     std::vector<CircuitInfo> circuits;
+    std::vector<PrefixSig> prefix;   // one per circuit
 };
 
 // Appends one circuit to P. Returns QCD_OK or an error code with a message in err.

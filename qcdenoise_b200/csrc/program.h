@@ -92,6 +92,10 @@ struct DirectSweep {
 struct CircuitInfo {
     uint32_t sweep_begin, sweep_end;   // range in sweeps[]
     uint32_t n_sites;
+    uint32_t lead;                     // first circuit of the run of consecutive circuits that share this circuit's
+                                       // sweeps up to (not including) the final one -- e.g. a graph circuit and its
+                                       // n + 1 stabilizer settings (stabilizers.py:194-199).  lead == own index: none.
 };
+constexpr int MAX_MEMBER_BITS = 6;     // a run holds at most 2^6 circuits (longer runs are cut)
 
 }  // namespace qcd

@@ -346,8 +346,8 @@ template <typename T>
 __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
     DevProgram<T> prog, const NodeRec* leaves, const void* states, uint64_t slot_stride, const double* chunk_sums,
     uint64_t chunk_stride, const double* block_sums, uint64_t block_stride, uint32_t n_chunks, int n_bits,
-    const uint32_t* owner, const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
-    uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin) {
+    const uint32_t* owner, const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map, const double* flip,
+    uint32_t* hist, uint32_t* outcomes, uint64_t shot_begin) {
     typedef typename Cx<T>::C C;
     __shared__ Staged<T> S_all[SN_WARPS];
     __shared__ double s_w[SN_WARPS][32];
@@ -365,12 +365,13 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
         nd = leaves[owner[i]];
         live = (nd.flags & NODE_LEAF) && (nd.flags & NODE_NOSTORE);
     }
+    const uint32_t pcirc = map.first_circuit + nd.circuit;      // circuit index in the Philox counters
     if (live) {
-        shot = shots[i];
+        shot = traj_shot(map, tids[i], nd.circuit);
         const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
         const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
         const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
-        target = u53(draw(seed, nd.circuit, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
+        target = u53(draw(seed, pcirc, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
         const uint32_t b = upper_search(bs, 0, n_blocks, target);
         if (b > 0) target -= bs[b - 1];
         const uint32_t cbeg = b << SCAN_BLOCK_LOG;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
     if (flip) {
         const double* fc = flip + (uint64_t)nd.circuit * n_bits * 2u;
         for (int blk = 0; blk * 4 < n_bits; blk++) {
-            const uint4 w = draw(seed, nd.circuit, shot, QCD_STREAM_READOUT + blk);
+            const uint4 w = draw(seed, pcirc, shot, QCD_STREAM_READOUT + blk);
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
         }
     }
     if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
-    if (outcomes) outcomes[(uint64_t)nd.circuit * shots_per_circuit + shot - shot_begin] = x;
+    if (outcomes) outcomes[(uint64_t)nd.circuit * map.spc + shot - shot_begin] = x;
 }
 
 }  // namespace
@@ -478,25 +479,25 @@ template <typename T>
 void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, const void* states, uint64_t slot_stride,
                            const double* chunk_sums, uint64_t chunk_stride, const double* block_sums,
                            uint64_t block_stride, uint32_t n_chunks, int n_bits, const uint32_t* owner,
-                           const uint32_t* shots, uint32_t n_traj, uint64_t seed, const double* flip, uint32_t* hist,
-                           uint32_t* outcomes, uint64_t shots_per_circuit, uint64_t shot_begin, cudaStream_t st) {
+                           const uint32_t* tids, uint32_t n_traj, uint64_t seed, TrajMap map, const double* flip,
+                           uint32_t* hist, uint32_t* outcomes, uint64_t shot_begin, cudaStream_t st) {
     if (!n_traj) return;
     const uint32_t bs = 32 * SN_WARPS;
     sample_nostore_kernel<T><<<(n_traj + bs - 1) / bs, bs, 0, st>>>(prog, leaves, states, slot_stride, chunk_sums,
                                                                     chunk_stride, block_sums, block_stride, n_chunks,
-                                                                    n_bits, owner, shots, n_traj, seed, flip, hist,
-                                                                    outcomes, shots_per_circuit, shot_begin);
+                                                                    n_bits, owner, tids, n_traj, seed, map, flip, hist,
+                                                                    outcomes, shot_begin);
 }
 
 template void launch_sweep_direct<float>(const DevProgram<float>&, const SweepArgs&, cudaStream_t);
 template void launch_sweep_direct<double>(const DevProgram<double>&, const SweepArgs&, cudaStream_t);
 template void launch_sample_nostore<float>(const DevProgram<float>&, const NodeRec*, const void*, uint64_t, const double*,
                                            uint64_t, const double*, uint64_t, uint32_t, int, const uint32_t*,
-                                           const uint32_t*, uint32_t, uint64_t, const double*, uint32_t*, uint32_t*,
-                                           uint64_t, uint64_t, cudaStream_t);
+                                           const uint32_t*, uint32_t, uint64_t, TrajMap, const double*, uint32_t*,
+                                           uint32_t*, uint64_t, cudaStream_t);
 template void launch_sample_nostore<double>(const DevProgram<double>&, const NodeRec*, const void*, uint64_t,
                                             const double*, uint64_t, const double*, uint64_t, uint32_t, int,
-                                            const uint32_t*, const uint32_t*, uint32_t, uint64_t, const double*,
-                                            uint32_t*, uint32_t*, uint64_t, uint64_t, cudaStream_t);
+                                            const uint32_t*, const uint32_t*, uint32_t, uint64_t, TrajMap, const double*,
+                                            uint32_t*, uint32_t*, uint64_t, cudaStream_t);
 
 }  // namespace qcd

@@ -107,9 +107,11 @@ class Engine:
 
     # ---------------------------------------------------------------- simulation
     def run_trajectories(self, shots, seed=1234, precision=32, shot_range=None, readout=None, hist=None,
-                         want_outcomes=False, dedup=True):
+                         want_outcomes=False, dedup=True, first_circuit=0):
         """Statevector trajectories.  Returns (hist [B, 2^n] int32 or None, outcomes [range] int32 or None).
-        shot_range = (begin, end) in the flattened [circuit][shot] space (default: everything)."""
+        shot_range = (begin, end) in the flattened [circuit][shot] space (default: everything).
+        first_circuit: index of uploaded circuit 0 in the whole batch (a rank that uploaded only its slice of the
+        circuits draws exactly what a single-GPU run of the whole batch draws)."""
         n, B = self.n_qubits, self.n_circuits
         begin, end = shot_range if shot_range is not None else (0, B * shots)
         with torch.cuda.device(self.device):
@@ -119,7 +121,7 @@ class Engine:
                 if (want_outcomes or hist is None) else None
             r = self._readout_array(readout, B, n)
             self._check(self.lib.qcd_run_sv_trajectories(
-                self._h, precision, shots, seed, begin, end, _ptr(r), _ptr(hist), _ptr(outcomes),
+                self._h, precision, shots, seed, begin, end, first_circuit, _ptr(r), _ptr(hist), _ptr(outcomes),
                 0 if dedup else _lib.QCD_RUN_NO_DEDUP, self._stream()))
         if outcomes is not None:
             outcomes = outcomes[: end - begin]

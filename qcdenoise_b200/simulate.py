@@ -222,7 +222,10 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
             hist = eng.sample_from_probs(probs, sampler.n_shots, seed=seed, first_circuit=lo, readout=readout)
         else:
             sampler.last_probs = None
-            hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed + lo, precision=sampler.precision, readout=readout)
+            # the rank uploaded only its slice [lo, hi) of the circuits: first_circuit keeps the Philox counters on the
+            # GLOBAL circuit index, so the assembled histograms do not depend on the number of ranks
+            hist, _ = eng.run_trajectories(sampler.n_shots, seed=seed, precision=sampler.precision, readout=readout,
+                                           first_circuit=lo)
     lap("lower_and_enqueue")       # channels + lowering on host threads, program upload, kernel launches
     # host-only stages while the GPU works on what was just enqueued
     adj = None

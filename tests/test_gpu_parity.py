@@ -26,7 +26,8 @@ def _circ(n, ops):
 
 
 def _reset_opts(eng):
-    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1)):
+    for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1),
+                 ("share_prefix", 1)):
         eng.set_option(k, v)
 
 
@@ -437,3 +438,91 @@ def test_two_qubit_kraus_channels(eng):
     _, out = eng.run_trajectories(200, seed=8, precision=64, want_outcomes=True)
     want = cpu_build.run_trajectories(encode_programs([_circ(n, ops)]), 200, 8)
     assert np.array_equal(out.cpu().numpy().astype(np.uint64), want)
+
+
+# ------------------------------------------------------------------------------------------- shared trajectory trees
+def _settings_batch(n, rng, graphs):
+    """[graph circuit, its n + 1 Toth settings] per graph, plus one unrelated circuit at the end: runs of circuits that
+    share everything up to their final sweep (stabilizers.py:194-199)."""
+    batch = []
+    for gi, all_sites in graphs:
+        edges = circuits.ref_graph(n if n <= 10 else 14, gi)
+        if n == 13:
+            edges = [e for e in edges if max(e) < 13] + [(11, 12)]
+        ops = circuits.graph_circuit_amp_damp(n, edges, rng, max_prob=0.3, all_sites=all_sites)
+        batch.append(ops)
+        for v in range(n):
+            batch.append(ops + ([("sdg", (v,))] if v % 3 == 2 else []) + [("h", (v,))])
+        batch.append(list(ops))
+    batch.append(circuits.random_circuit(n, 30, rng))
+    return batch
+
+
+@pytest.mark.parametrize("n", [7, 13])
+def test_shared_prefix_tree_is_bit_identical_to_per_circuit_trees(eng, n):
+    """One trajectory tree per run of circuits with a common prefix == one tree per circuit: same histograms, same
+    outcomes (every draw is keyed by the trajectory's own circuit and shot), fewer state sweeps; also when a run is cut
+    by chunk boundaries, by the grouping-table cap, by a partial shot range and under the depth-first schedule."""
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    _reset_opts(eng)
+    rng = np.random.default_rng(70 + n)
+    batch = _settings_batch(n, rng, [(0, True), (1, False)])
+    B = len(batch)
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 200, 31
+    res = {}
+    for prec in (32, 64):
+        for share in (1, 0):
+            eng.set_option("share_prefix", share)
+            h, o = eng.run_trajectories(shots, seed=seed, precision=prec, want_outcomes=True)
+            res[prec, share] = (h.cpu().numpy(), o.cpu().numpy(), eng.stats())
+        assert np.array_equal(res[prec, 1][0], res[prec, 0][0]) and np.array_equal(res[prec, 1][1], res[prec, 0][1])
+        assert res[prec, 1][2]["node_sweeps"] < 0.75 * res[prec, 0][2]["node_sweeps"]
+        assert res[prec, 1][2]["leaves"] == res[prec, 0][2]["leaves"]
+    eng.set_option("share_prefix", 1)
+    out = res[64, 1][1].reshape(B, shots).astype(np.int64)
+    for c in (0, 1, n, n + 1, n + 2, n + 3, B - 2, B - 1):
+        run = cpu_build.run_trajectories if n >= 12 else None
+        if run is not None:
+            want = run(encode_programs([_circ(n, batch[c])]), shots, seed, circuit=c).astype(np.int64)
+        else:
+            want = sim.run_trajectories(batch[c], n, shots, seed, circuit=c).astype(np.int64)
+        assert np.array_equal(out[c], want), f"circuit {c}"
+    # runs cut by chunk boundaries / the table cap / few slots / a partial shot range
+    ref_h, ref_o = res[64, 1][0], res[64, 1][1]
+    for opts in ({"max_chunk": 3 * shots + 17}, {"table_cap_log2": 5}, {"max_slots": 40}, {"max_chunk": shots // 3}):
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        h, o = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
+        assert np.array_equal(h.cpu().numpy(), ref_h) and np.array_equal(o.cpu().numpy(), ref_o), opts
+        _reset_opts(eng)
+    lo, hi = 2 * shots + 50, (B - 3) * shots + 120
+    _, o = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True, shot_range=(lo, hi))
+    assert np.array_equal(o.cpu().numpy(), ref_o[lo:hi])
+    # literal mode (one state per shot) is unaffected by the option
+    _, o = eng.run_trajectories(16, seed=seed, precision=64, want_outcomes=True, dedup=False)
+    assert np.array_equal(o.cpu().numpy().reshape(B, 16), ref_o.reshape(B, shots)[:, :16])
+
+
+def test_first_circuit_makes_a_circuit_split_reproduce_the_whole_batch(eng):
+    """qcd_run_sv_trajectories(first_circuit): a rank that uploads only its slice of the circuits draws what a single
+    GPU draws for the whole batch -- the 2-way split reproduces the unsplit histograms bit for bit."""
+    _reset_opts(eng)
+    n = 7
+    rng = np.random.default_rng(5)
+    batch = _settings_batch(n, rng, [(2, True)]) + [circuits.device_noise_circuit(n, circuits.ref_graph(7, 3), rng)[0]]
+    B = len(batch)
+    conf = np.stack([np.array([[[1 - a, a], [b, 1 - b]] for a, b in rng.uniform(0, 0.1, (n, 2))]) for _ in range(B)])
+    eng.upload([_circ(n, ops) for ops in batch])
+    for prec in (32, 64):
+        whole, _ = eng.run_trajectories(300, seed=9, precision=prec, readout=conf)
+        whole = whole.cpu().numpy()
+        cut = 4                                   # inside the run of settings
+        parts = []
+        for lo, hi in ((0, cut), (cut, B)):
+            eng.upload([_circ(n, ops) for ops in batch[lo:hi]])
+            h, _ = eng.run_trajectories(300, seed=9, precision=prec, readout=conf[lo:hi], first_circuit=lo)
+            parts.append(h.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts), whole)
+        eng.upload([_circ(n, ops) for ops in batch])

@@ -157,3 +157,24 @@ def test_dm_asymmetric_pauli_mixtures():
         ops += [("pauli", (1,), p1), ("t", (1,)), ("pauli", (3, 0), p2), ("ry", (3,), 0.3), ("s", (0,)), ("h", (0,)),
                 ("pauli", (0, 2), rng.dirichlet(np.ones(16))), ("h", (2,)), ("rx", (3,), 0.9)]
         np.testing.assert_allclose(si.run_dm(_sched(n, ops, 1)), sim.density_matrix_probs(ops, n), atol=1e-12)
+
+
+def test_prefix_signature_groups_a_circuit_with_its_stabilizer_settings():
+    """Circuits that differ only after their last state-dependent noise site (a graph circuit and its Toth settings,
+    stabilizers.py:194-199) get the same prefix signature -- the engine runs ONE trajectory tree for such a run down to
+    the parents of the leaves; different channel parameters or an extra gate before the last site give another one."""
+    import qcdenoise_b200 as qb
+    n = 6
+    edges = circuits.ref_graph(5, 1) + [(3, 5)]
+    rng = np.random.default_rng(11)
+    ops = circuits.graph_circuit_amp_damp(n, edges, rng, max_prob=0.3, all_sites=True)
+    sig = lambda o: tuple(qb.debug_schedule(qb.Circuit(n, o))["prefix_sig"])      # noqa: E731
+    base = sig(ops)
+    assert base[2] >= 2                                                             # shared sweeps before the final one
+    for q in range(n):
+        assert sig(ops + [("h", (q,))]) == base
+        assert sig(ops + [("sdg", (q,)), ("h", (q,))]) == base
+    other = circuits.graph_circuit_amp_damp(n, edges, np.random.default_rng(12), max_prob=0.3, all_sites=True)
+    assert sig(other) != base
+    first_kraus = next(i for i, op in enumerate(ops) if op[0] == "kraus")
+    assert sig(ops[:first_kraus] + [("x", (0,))] + ops[first_kraus:]) != base

@@ -49,7 +49,7 @@ def main():
     my_masks = np.array(masks[lo:hi], dtype=np.uint32)
 
     def step():
-        _, out = eng.run_trajectories(SHOTS, seed=1234 + rank, precision=32, want_outcomes=True)
+        _, out = eng.run_trajectories(SHOTS, seed=1234, precision=32, want_outcomes=True, first_circuit=lo)
         st = eng.stats()
         out = out.reshape(hi - lo, SHOTS)
         ss = eng.parity_outcomes(out, my_masks)
