@@ -2,27 +2,30 @@
 """bench.py -- headline benchmark of the B200-native noisy-circuit sampling engine.
 
 Workload (BASELINE.json configs[3], "C4" in SURVEY.md 8d -- the largest single-GPU configuration the metric's
-20-28 qubit range is quoted on): one 20-qubit reference-sampled graph state, CXGateCircuit gate list with
-stochastic labelled sites, two amplitude-damping Kraus channels per site (max_prob 0.1), 1,000,000 noisy
-statevector-trajectory shots of the graph circuit AND of each of its n+1 = 21 Toth stabilizer settings
-(22 circuits x 1M shots per step), dense 2^20 histograms, bitmask-parity <S> for the 21 settings -> genuine witness.
-complex64 amplitudes.
+20-28 qubit range is quoted on): 20-qubit reference-sampled graph states, CXGateCircuit gate lists with stochastic
+labelled sites, two amplitude-damping Kraus channels per site (max_prob 0.1), 1,000,000 noisy statevector-trajectory
+shots of the graph circuit AND of each of its n + 1 = 21 Toth stabilizer settings (22 circuits x 1M shots per graph),
+dense 2^20 histograms, bitmask-parity <S> for the 21 settings -> genuine witness.  complex64 amplitudes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--shots S] [--literal]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--graphs G] [--scaling strong|weak]
+                    [--shots S] [--literal] [--precision 32|64]
 
-One step = one pass of that path.  `value` = noisy shots/s with the lowered programs resident on the GPU (timed with
-CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API (UnitaryNoiseSampler.sample
-+ StabilizerSampler.sample + GenuineWitness.estimate) from host gate lists to host numpy results, every step
-including encode, upload + lowering, the device->host copy of the dataset histogram and of the 21 parity sums (the
-stabilizer histograms stay on the GPU until somebody reads `Counts.hist`).  `roofline` = algorithmic
-bytes moved by the state-sweep kernel / its CUDA-event time, against the measured HBM copy bandwidth.
-`cpu_baseline` / `--impl reference` = the compiled CPU port of the qiskit-Aer statevector-trajectory algorithm
-(oracle/cpu_sim.c, OpenMP over shots) on a bounded number of shots of the same noisy circuit.
+The JOB is G = 8 graphs (176 circuits, 176 M shots) per step.  One step = one pass of the path over the job; `value` =
+noisy shots/s with the lowered programs resident on the GPU (CUDA events, max over ranks); `e2e` = the same through
+the reference-facing Python API (UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate per
+graph) from host gate lists to host numpy results, every step including encode, upload + lowering and the
+device->host copy of the dataset histograms and parity sums.  `roofline` = algorithmic bytes moved by the state-sweep
+kernel / its CUDA-event time, against the measured HBM copy bandwidth.  `cpu_baseline` / `--impl reference` = the
+reference's CPU implementation of the path (real qiskit-aer if importable, else the compiled port oracle/cpu_sim.c) on
+a bounded number of shots of the same circuits (baseline/run_cpu.py; that arm never imports the product).
 
-N > 1 (torchrun): the job is the same 22 circuits with N x 1M shots each; rank r simulates its own 1M-shot slice of
-every circuit (independent Philox streams: seed + r), so per-GPU work is fixed (weak scaling) and there is no
-data-path communication; ONE NCCL all_reduce(SUM) assembles the 22 dataset histograms (92 MB), after which the
-stabilizer parity sums are taken on the assembled counts.
+N > 1 (torchrun), default `--scaling strong`: the SAME 8-graph job is partitioned by circuit index
+(distributed.circuit_slice: whole graphs per rank), ONE seed, Philox counters on the global circuit index
+(qcd_run_sv_trajectories first_circuit) -- the assembled results are bit-identical to the single-GPU run, which rank 0
+asserts in warm-up by re-simulating the last rank's slice.  No data-path collective; ONE NCCL all_gather assembles the
+dataset histogram rows and the parity sums.  `--scaling weak`: N x G graphs instead (fixed work per GPU).
+Outside the timed region the sampled <S_k> and the witness of every graph are checked against their EXACT values
+(oracle/pauli_prop.py).  `other_configs` carries C2 / C3 / C5 and the complex128 / literal variants of C4.
 """
 import argparse
 import json
@@ -150,59 +153,101 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+METRIC = "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)"
+CIRCUITS_PER_GRAPH = N_QUBITS + 2
+
+
+def workload_config(n_graphs, n_sites, shots, precision, scaling):
+    return {"workload": "C4: 20-qubit graph-state stochastic-trajectory sampling, 1M shots, stabilizer witnesses "
+                        "(BASELINE.json configs[3])",
+            "n_qubits": N_QUBITS, "graphs_per_step": n_graphs, "circuits_per_step": n_graphs * CIRCUITS_PER_GRAPH,
+            "noise_sites_per_graph": n_sites, "kraus_channels_per_graph": [2 * s for s in n_sites], "max_prob": 0.1,
+            "shots_per_circuit": shots, "precision": "complex64" if precision == 32 else "complex128",
+            "partition": f"{scaling}: circuits by index, whole graphs per rank, one seed, Philox on the global circuit index",
+            "cache": "working set per tree level (hundreds to thousands of 8 MiB states) >> 126 MB L2; "
+                     "histograms re-zeroed every step"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(work, n_shots, threads=0):
-    """Literal one-trajectory-per-shot CPU port on the noisy graph circuit.  Returns (shots/s, seconds, threads)."""
-    from oracle import cpu_build
-    from qcdenoise_b200.ir import encode_programs
-    enc = encode_programs([work["programs"][0]])
-    cores = threads or host_threads()
-    t0 = time.perf_counter()
-    cpu_build.run_trajectories(enc, n_shots, SEED, circuit=0, n_threads=cores)
-    dt = time.perf_counter() - t0
-    return n_shots / dt, dt, cores
+def cpu_sample(graph_index, shots_per_circuit, threads=0, circuits=None):
+    """Bounded sample of the CPU implementation on graph `graph_index` of the job (baseline/run_cpu.py: real qiskit-aer
+    if importable, else the compiled port).  The gate lists come from oracle/workload.py, not from the product."""
+    from baseline import run_cpu
+    from oracle import workload
+    return run_cpu.run(workload.c4_workload(graph_index), shots_per_circuit, threads, circuits)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    work = build_workload(0, args.shots)
+    from oracle import workload
     cores = host_threads()
-    per_step = max(4 * cores, 8)
+    per_circuit = max(cores // 2, 2)
+    n_graphs = args.graphs * (world if args.scaling == "weak" else 1)
     for _ in range(args.warmup):
-        cpu_arm(work, max(cores // 4, 2))
-    t = 0.0
-    for _ in range(args.steps):
-        _, dt, _ = cpu_arm(work, per_step)
-        t += dt
-    v = per_step * args.steps / t
-    sample = f"{per_step} shots per step of the {N_QUBITS}-qubit noisy graph circuit (circuit 0 of the step), one " \
-             f"trajectory per shot, complex128"
-    line = {"impl": "reference", "metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
-            "value": v, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "c128", "data": "synthetic", "config": workload_config(work, args.shots),
-            "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample},
+        cpu_sample(0, 1, circuits=[0, 1])
+    t, shots, kind = 0.0, 0, "port"
+    for k in range(args.steps):
+        r = cpu_sample(k % n_graphs, per_circuit)
+        t += r["seconds"]
+        shots += r["shots"]
+        kind = r["kind"]
+    v = shots / t
+    one = cpu_sample(0, 2, threads=1, circuits=[0])          # the reference's tests pin OMP_NUM_THREADS=1
+    sample = (f"per step {per_circuit} shots of EACH of the 22 circuits of one graph of the job (graph = step mod "
+              f"{n_graphs}), one trajectory per shot, complex128, gate at a time; no extrapolation inside the sample")
+    sites = [workload.c4_workload(g)["n_sites"] for g in range(n_graphs)]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": workload_config(n_graphs, sites, args.shots, 64, args.scaling),
+            "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": kind, "sample": sample,
+                             "value_1thread": one["shots"] / one["seconds"],
+                             "qiskit_aer_importable": kind == "reference",
+                             "product_imported": "qcdenoise_b200" in sys.modules},
             "e2e": {"value": v, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(work, shots):
-    return {"workload": "C4: 20-qubit graph-state stochastic-trajectory sampling, 1M shots, stabilizer witnesses "
-                        "(BASELINE.json configs[3])",
-            "n_qubits": N_QUBITS, "graph_edges": len(work["edges"]), "noise_sites": work["n_sites"],
-            "kraus_channels": 2 * work["n_sites"], "max_prob": 0.1, "circuits_per_step": len(work["programs"]),
-            "shots_per_circuit": shots, "precision": "complex64",
-            "cache": "working set per tree level (up to thousands of 8 MiB states) >> 126 MB L2; "
-                     "histograms re-zeroed every step"}
+# ------------------------------------------------------------------------------------------------ secondary configs
+def _timed(torch, fn, reps=1):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
+def _kind_rates(st, peak):
+    """Per launch kind (prep / inner / leaf / mixed): algorithmic GB/s and fraction of the measured copy bandwidth."""
+    out = {}
+    for i, nm in enumerate(("prep", "inner", "leaf", "mixed")):
+        if st["kind_launches"][i] and st["kind_ms"][i] > 0:
+            gbs = st["kind_bytes"][i] / (st["kind_ms"][i] * 1e-3) / 1e9
+            out[nm] = {"launches": int(st["kind_launches"][i]), "ms": st["kind_ms"][i], "algorithmic_GBps": gbs,
+                       "frac": gbs / peak}
+    return out
+
+
+def _add_stats(agg, st):
+    for k, v in st.items():
+        if isinstance(v, list):
+            agg[k] = [a + b for a, b in zip(agg.get(k, [0] * len(v)), v)]
+        elif k == "max_live_states":
+            agg[k] = max(agg.get(k, 0), v)
+        else:
+            agg[k] = agg.get(k, 0) + v
+    return agg
+
+
 def c2_end_to_end(qcd, torch, n_circ=10000):
     """BASELINE.json configs[1] (8-qubit random graph states, 10k circuits, device noise model, count histograms)
     end to end through qcd.simulate(): host stages (graph sampling, gate lists, calibration draws, channels, lowering),
-    upload, simulation and the histograms back on the host, all inside the timed call.  Secondary line, N = 1 only."""
+    upload, simulation and the histograms back on the host, all inside the timed call."""
     import random
     random.seed(SEED)
     spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 100.0, "readout_error": 0.25, "prob_meas0_prep1": 0.1,
@@ -213,14 +258,15 @@ def c2_end_to_end(qcd, torch, n_circ=10000):
                                     circuit=qcd.CircuitSpecs(builder=qcd.CXGateCircuit, stochastic=False))
     sampler_specs = qcd.SamplingSpecs(sampler=qcd.DeviceNoiseSampler, noise_specs=spec, n_shots=1024)
     best = None
-    for _ in range(3):       # first call pays allocations; report the best of the next two
+    for it in range(3):       # first call pays allocations; report the best of the next two
+        diag = {}
         t0 = time.perf_counter()
-        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7))
+        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), diagnostics=diag)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert len(res) == n_circ and abs(res[n_circ - 1]["prob_vec"].sum() - 1) < 1e-9
-        if _ > 0 and (best is None or dt < best[0]):
-            best = (dt, dict(qcd.simulate.__globals__["last_timing"]))
+        if it > 0 and (best is None or dt < best[0]):
+            best = (dt, dict(diag["timing"]))
     dt, stages = best
     return {"workload": f"C2: 8-qubit random graph states, {n_circ} circuits, device noise model, 1024-shot count "
                         "histograms (BASELINE.json configs[1]), through qcd.simulate()",
@@ -228,16 +274,158 @@ def c2_end_to_end(qcd, torch, n_circ=10000):
             "host_stages_s": {k: round(v, 4) for k, v in stages.items()}}
 
 
+def _noisy_programs(qcd, n, graph_indices, seed):
+    """Reference-shaped noisy graph circuits at n qubits: CXGateCircuit (stochastic sites) + UnitaryNoiseSampler draws."""
+    import networkx as nx
+    with open(os.path.join(ROOT, "tests", "golden", "graphs.json")) as f:
+        graphs = json.load(f)["graphs"][str(n)]
+    np.random.seed(seed)
+    sampler = qcd.UnitaryNoiseSampler(None, n_shots=1024, method="statevector")
+    progs, masks, sites = [], [], []
+    for gi in graph_indices:
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from([tuple(e) for e in graphs[gi % len(graphs)]])
+        cd = qcd.CXGateCircuit(n_qubits=n, stochastic=True).build(g)
+        sampler.build_noise_model(cd["ops"])
+        progs.append(sampler.noise_model.instantiate(cd["circuit"])[0])
+        # <g_k> of the UNROTATED state's Z-type part is not a stabilizer; the masks only exercise the parity reduction
+        masks.append([qcd.pauli_mask(nm) for nm in qcd.TothStabilizer(g, n).build()])
+        sites.append(len(cd["ops"]))
+    return progs, np.array(masks, dtype=np.uint32), sites
+
+
+def c3_density_matrix(qcd, torch, eng, peak, n_circ=16):
+    """BASELINE.json configs[2]: 14-qubit density matrices (2 GiB complex64 each), custom-unitary Kraus sites, 1024-shot
+    multinomial sampling from the exact distribution, 15 Toth <S> + genuine witness per circuit (settings read off the
+    circuit's density matrix)."""
+    n = 14
+    progs, _, sites = _noisy_programs(qcd, n, range(n_circ), SEED + 14)
+    eng.upload(progs)
+    eng.set_option("time_sweeps", 1)
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2)
+    sq = np.broadcast_to(np.array([k if k < n else 0xFF for k in range(n + 1)], dtype=np.uint8), (n_circ, n + 1)).copy()
+    sop = np.broadcast_to(np.kron(H.conj(), H), (n_circ, n + 1, 4, 4)).copy()
+
+    def probs_only():
+        p = eng.run_density_matrix(32)
+        st = eng.stats()
+        h = eng.sample_from_probs(p, 1024, seed=SEED)
+        return p, h, st
+
+    probs_only()
+    ms, (p, h, st) = _timed(torch, probs_only)
+    assert abs(float(p.sum(dim=1).min()) - 1) < 1e-4 and h.sum(dim=1).tolist() == [1024] * n_circ
+    del p, h
+
+    def with_witness():
+        ps = eng.run_density_matrix_settings(sq, sop, precision=32)             # [B, n + 1, 2^n]
+        hs = eng.sample_from_probs(ps.reshape(-1, 2 ** n), 1024, seed=SEED + 1)
+        return eng.parity_counts(hs, np.array([[1 << k] if k < n else [0] for k in range(n + 1)] * n_circ, dtype=np.uint32))
+
+    with_witness()
+    ms_w, _ = _timed(torch, with_witness)
+    eng.set_option("time_sweeps", 0)
+    kinds = _kind_rates(st, peak)
+    gbs = st["sweep_bytes"] / (st["sweep_ms"] * 1e-3) / 1e9
+    return {"workload": f"C3: {n}-qubit density-matrix simulation (4^14 complex64 = 2 GiB per circuit), {n_circ} circuits, "
+                        "amplitude-damping Kraus sites (max_prob 0.1), 1024 shots from the exact distribution "
+                        "(BASELINE.json configs[2])",
+            "circuits_per_s": n_circ / (ms * 1e-3), "ms_per_batch": ms, "noise_sites": sites,
+            "circuits_per_s_with_15_settings_and_witness": n_circ / (ms_w * 1e-3),
+            "state_passes_per_circuit": st["node_sweeps"] / n_circ,
+            "roofline": {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (density-matrix passes)",
+                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "per_kind": kinds, "sweep_share_of_batch": st["sweep_ms"] / ms,
+                         "algorithmic_bytes": "passes x 2 x 4^14 x 8 B per circuit (the first pass writes only)"}}
+
+
+def c5_trajectories(qcd, torch, dist, eng, peak, rank, world, local):
+    """BASELINE.json configs[4]: 28-qubit noisy statevector trajectories (2 GiB complex64 per state), 64 circuits x 8
+    shots sharded by circuit index over the ranks (N = 1: one GPU's share of 8 circuits), sparse outcome lists + 29
+    parity sums per circuit, one all_gather."""
+    from qcdenoise_b200 import distributed as qd
+    n, shots = 28, 8
+    total = 64 if world > 1 else 8
+    progs, masks, sites = _noisy_programs(qcd, n, range(total), SEED + 28)
+    lo, hi = qd.circuit_slice(total, rank, world)
+    eng.upload(progs[lo:hi])
+    eng.set_option("time_sweeps", 1)
+
+    def step():
+        _, out = eng.run_trajectories(shots, seed=SEED, precision=32, want_outcomes=True, first_circuit=lo)
+        st = eng.stats()
+        out = out.reshape(hi - lo, shots)
+        ss = eng.parity_outcomes(out, masks[lo:hi])
+        rows = torch.cat([out.to(torch.int64), ss], dim=1).contiguous()
+        return st, (qd.gather_rows(rows) if world > 1 else rows)
+
+    step()
+    if world > 1:
+        dist.barrier()
+    ms, (st, rows) = _timed(torch, step)
+    eng.set_option("time_sweeps", 0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert rows.shape == (total, shots + n + 1) and int(rows[:, -1].min()) == shots      # identity setting: +1 always
+    gbs = st["sweep_bytes"] / (st["sweep_ms"] * 1e-3) / 1e9
+    return {"workload": f"C5: {n}-qubit noisy statevector trajectories, {total} circuits x {shots} shots, sharded by circuit "
+                        f"index over {world} GPU(s) (BASELINE.json configs[4])",
+            "shots_per_s": total * shots / (ms * 1e-3), "circuits_per_s": total / (ms * 1e-3), "ms_per_step": ms,
+            "n_gpus": world, "state_sweeps_rank0": int(st["node_sweeps"]), "live_states_rank0": int(st["max_live_states"]),
+            "noise_sites": sites[:8],
+            "roofline_rank0": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                               "per_kind": _kind_rates(st, peak), "sweep_share_of_step": st["sweep_ms"] / ms}}
+
+
+def c4_variant(torch, eng, work, peak, shots, precision, literal):
+    """One graph of the job at complex128, or executed literally (one state per shot, the way Aer runs it)."""
+    B = len(work["programs"])
+    eng.upload(work["programs"])
+    eng.set_option("time_sweeps", 1)
+    hist = torch.zeros((B, 2 ** N_QUBITS), dtype=torch.int32, device=eng.device)
+
+    def step():
+        hist.zero_()
+        eng.run_trajectories(shots, seed=SEED, precision=precision, hist=hist, dedup=not literal)
+        return eng.stats()
+
+    eng.run_trajectories(max(shots // 20, 64), seed=SEED, precision=precision, hist=hist, dedup=not literal)
+    ms, st = _timed(torch, step)
+    eng.set_option("time_sweeps", 0)
+    assert hist.sum(dim=1).tolist() == [shots] * B
+    gbs = st["sweep_bytes"] / (st["sweep_ms"] * 1e-3) / 1e9
+    out = {"shots_per_s": B * shots / (ms * 1e-3), "ms_per_step": ms, "shots_per_circuit": shots,
+           "states_swept": int(st["node_sweeps"]),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "per_kind": _kind_rates(st, peak), "sweep_share_of_step": st["sweep_ms"] / ms}}
+    if literal:
+        # SURVEY.md 8d's own per-shot accounting: A_unit = N b (1 + 2 K + 1), K = state-dependent site groups
+        k_sites = work["n_sites"]
+        a_unit = (2 ** N_QUBITS) * (8 if precision == 32 else 16) * (2 + 2 * k_sites)
+        out["survey_8d"] = {"A_unit_bytes_per_shot": a_unit, "K_sites": k_sites,
+                            "achieved_GBps": out["shots_per_s"] * a_unit / 1e9,
+                            "frac": out["shots_per_s"] * a_unit / 1e9 / peak,
+                            "note": "whole-step wall time, per-shot algorithmic bytes N b (2 + 2K) of SURVEY.md 8d"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs", type=int, default=8, help="graphs of the job (per GPU with --scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--shots", type=int, default=1_000_000, help="shots per circuit (1M = the BASELINE config)")
     ap.add_argument("--literal", action="store_true", help="one state per shot (no trajectory-tree sharing)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary configurations")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64], help="32 = complex64 (default), 64 = complex128")
     ap.add_argument("--max-chunk", type=int, default=0, help="engine option max_chunk (trajectories per tree); 0 = default")
     ap.add_argument("--nostore-max", type=int, default=-1, help="engine option nostore_max (A/B measurements); -1 = default")
@@ -254,6 +442,7 @@ def main():
     import torch.distributed as dist
 
     import qcdenoise_b200 as qcd
+    from qcdenoise_b200 import distributed as qd
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -262,28 +451,53 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    work = build_workload(0, args.shots)
-    B = len(work["programs"])
+    # ---- the job and this rank's slice of it (whole graphs: the circuit slice falls on graph boundaries)
+    G = args.graphs * (world if args.scaling == "weak" else 1)
+    if G % world:
+        raise SystemExit(f"--graphs {G} must be a multiple of the number of ranks ({world})")
+    CPG = CIRCUITS_PER_GRAPH
+    c_lo, c_hi = qd.circuit_slice(G * CPG, rank, world)
+    g_lo, g_hi = c_lo // CPG, c_hi // CPG
+    assert c_lo == g_lo * CPG and c_hi == g_hi * CPG
+    works = {g: build_workload(g, args.shots) for g in range(g_lo, g_hi)}
+    n_sites_all = None
+    mine = [works[g] for g in range(g_lo, g_hi)]
+    programs = [p for w in mine for p in w["programs"]]
+    masks = np.concatenate([w["masks"] for w in mine])
+    B = len(programs)
     N = 2 ** N_QUBITS
     eng = qcd.get_engine(local)
-    eng.upload(work["programs"])
+    eng.upload(programs)
     eng.set_option("time_sweeps", 1)
     if args.max_chunk:
         eng.set_option("max_chunk", args.max_chunk)
     if args.nostore_max >= 0:
         eng.set_option("nostore_max", args.nostore_max)
-    for key in ("nostore_max", "use_direct", "no_slots", "tile_bits"):        # tuning experiments only
+    for key in ("nostore_max", "use_direct", "no_slots", "tile_bits", "share_prefix"):        # tuning experiments only
         if os.environ.get("QCD_" + key.upper()):
             eng.set_option(key, float(os.environ["QCD_" + key.upper()]))
     hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
-    def step():
-        hist.zero_()
-        eng.run_trajectories(args.shots, seed=SEED + rank, precision=args.precision, hist=hist, dedup=not args.literal)
+    n_mine = g_hi - g_lo
+
+    def simulate_slice(first_circuit, out_hist):
+        out_hist.zero_()
+        eng.run_trajectories(args.shots, seed=SEED, precision=args.precision, hist=out_hist, dedup=not args.literal,
+                             first_circuit=first_circuit)
         st = eng.stats()
-        if world > 1:   # assemble the dataset histograms: counts are additive over the ranks' shot slices
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        ss, tot = eng.parity_counts(hist, work["masks"])
-        return st, ss, tot
+        ss, tot = eng.parity_counts(out_hist, masks)
+        return st, ss[:, 0].contiguous(), tot
+
+    def step():
+        st, ss, tot = simulate_slice(c_lo, hist)
+        rows = hist[0::CPG]                                   # dataset rows: the noisy graph circuits' histograms
+        sums = torch.stack([ss, tot], dim=1)                  # [B, 2] int64
+        if world > 1:       # assemble: ONE all_gather (equal counts per rank) of the dataset rows + parity sums
+            payload = torch.cat([rows.reshape(-1).to(torch.int64), sums.reshape(-1)])
+            gathered = torch.empty((world, payload.numel()), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, payload)
+            rows = gathered[:, : n_mine * N].reshape(G, N)
+            sums = gathered[:, n_mine * N:].reshape(G * CPG, 2)
+        return st, rows, sums
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,17 +505,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    rows = sums = None
+    for _ in range(max(args.warmup, 1)):
+        st, rows, sums = step()
+    # ---- warm-up checks (outside the timed region)
+    partition_check = None
+    if world > 1 and rank == 0:
+        # the partitioned job equals the single-GPU job: rank 0 re-simulates the LAST rank's slice with the same seed and
+        # the global circuit offset and compares with what that rank contributed -- bit for bit
+        other = {g: build_workload(g, args.shots) for g in range(G - n_mine, G)}
+        eng.upload([p for g in sorted(other) for p in other[g]["programs"]])
+        h2 = torch.zeros_like(hist)
+        _, ss2, tot2 = simulate_slice((G - n_mine) * CPG, h2)
+        same_rows = bool(torch.equal(h2[0::CPG].to(torch.int64), rows[G - n_mine:]))
+        same_sums = bool(torch.equal(torch.stack([ss2, tot2], dim=1), sums[(G - n_mine) * CPG:]))
+        del h2
+        eng.upload(programs)
+        if not (same_rows and same_sums):
+            raise AssertionError("partitioned run differs from the single-GPU run of the same circuits")
+        partition_check = {"slice": f"rank {world - 1}'s graphs re-simulated on rank 0", "dataset_rows_identical": same_rows,
+                           "parity_sums_identical": same_sums}
+    witness_check = None
+    if not args.literal or args.shots >= 100_000:
+        sm = sums.cpu().numpy().astype(np.float64)
+        res = []
+        graphs_here = range(G) if world > 1 else range(g_lo, g_hi)
+        for g in (graphs_here if rank == 0 else []):
+            w = works[g] if g in works else build_workload(g, args.shots)
+            res.append(check_witness(w, sm[g * CPG:(g + 1) * CPG, 0], sm[g * CPG:(g + 1) * CPG, 1], f"graph {g}"))
+        if res:
+            witness_check = {"graphs": len(res), "worst_setting_sigmas": max(r["worst_setting_sigmas"] for r in res),
+                             "witness_sampled": [r["witness_sampled"] for r in res],
+                             "witness_exact": [r["witness_exact"] for r in res],
+                             "witness_sigma": [r["witness_sigma"] for r in res], "checker": res[0]["checker"]}
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"sweep_launches": 0, "aux_launches": 0, "sweep_bytes": 0, "sweep_ms": 0.0, "node_sweeps": 0, "leaves": 0}
+    agg = {}
     with ClockSampler(local) as clk:
         ev0.record()
         for _ in range(args.steps):
-            st, ss, tot = step()
-            for k in agg:
-                agg[k] += st[k]
+            st, rows, sums = step()
+            _add_stats(agg, st)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -309,25 +553,29 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    assert tot.cpu().tolist() == [args.shots * world] * B, "histograms do not hold every shot"
-    shots_per_step = B * args.shots * world
+    assert sums[:, 1].cpu().tolist() == [args.shots] * (G * CPG), "histograms do not hold every shot"
+    shots_per_step = G * CPG * args.shots
     value = shots_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the reference-facing API (host gate lists in, host numpy out), rank-local
+    # ---- end to end through the reference-facing API (host gate lists in, host numpy out), this rank's graphs
     e2e = None
     if not args.no_e2e:
-        g, cd, stab = work["graph"], work["circuit_dict"], work["stab"]
-        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=args.precision,
-                                          seed=SEED + 100 * rank)
-        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=args.precision,
-                                     seed=SEED + 100 * rank + 1)
+        sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=args.precision, seed=SEED)
+        ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=args.precision, seed=SEED + 1)
 
-        def e2e_step():
-            np.random.set_state(work["rng_state"])      # sample() draws its noise model: the device leg's channels
-            p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
-            counts = ssam.sample(stab, cd["circuit"], noise_model=sampler.noise_model)   # 21 Counts (host histograms)
-            w = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
-            return p, w
+        def e2e_step(counts_to_host=False):
+            out = []
+            for w in mine:
+                g, cd, stab = w["graph"], w["circuit_dict"], w["stab"]
+                np.random.set_state(w["rng_state"])      # sample() draws its noise model: the device leg's channels
+                p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
+                counts = ssam.sample(stab, cd["circuit"], noise_model=sampler.noise_model)   # 21 Counts
+                if counts_to_host:
+                    for c in counts:
+                        c.hist                                                             # host histograms, as Aer returns
+                wit = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
+                out.append((p, wit))
+            return out
 
         eng.set_option("time_sweeps", 0)
         e2e_step()
@@ -335,73 +583,102 @@ def main():
         k_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            p, w = e2e_step()
+            res = e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        e2e_step(counts_to_host=True)
+        torch.cuda.synchronize()
+        dt_full = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, dt_full], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, dt_full = float(t[0].item()), float(t[1].item())
         from qcdenoise_b200.ir import encode_programs
-        enc = encode_programs(work["programs"])
-        h2d = int(enc[0].nbytes + enc[1].nbytes + enc[2].nbytes)
-        d2h = int(N * 4 + (B - 1) * 16)     # the dataset row; the 21 stabilizer histograms stay on the GPU (lazy Counts)
+        h2d = sum(int(a.nbytes) for w in mine for a in encode_programs(w["programs"])[:3])
+        d2h = n_mine * int(N * 4 + (CPG - 1) * 16)
         e2e = {"value": shots_per_step * k_e2e / dt, "unit": "shots/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": k_e2e, "witness_value": float(w.value),
-               "api": "UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate"}
+               "d2h_bytes_per_step": d2h, "steps": k_e2e,
+               "witness_values": [float(w.value) for _, w in res],
+               "api": "per graph: UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate",
+               "stabilizer_histograms": "stay on the GPU behind lazy Counts (the witness reduces them on the device); "
+                                        "`with_counts_on_host` copies all 21 per graph to the host as well, as Aer "
+                                        "returns them",
+               "with_counts_on_host": {"value": shots_per_step / dt_full, "d2h_bytes_per_step": n_mine * CPG * N * 4}}
 
+    # ---- secondary configurations (C5 runs on every rank count; the others at N = 1)
+    peak, peak_src = measured_hbm_peak()
+    other = None
+    if not args.no_other:
+        other = {}
+        try:
+            other["C5"] = c5_trajectories(qcd, torch, dist, eng, peak, rank, world, local)
+        except Exception as exc:     # a secondary measurement must not lose the headline
+            other["C5"] = {"failed": repr(exc)}
+        if world == 1:
+            for name, fn in (("C3", lambda: c3_density_matrix(qcd, torch, eng, peak)),
+                             ("C4_complex128", lambda: c4_variant(torch, eng, mine[0], peak, args.shots, 64, False)),
+                             ("C4_literal", lambda: c4_variant(torch, eng, mine[0], peak, 4000, 32, True)),
+                             ("C2", lambda: c2_end_to_end(qcd, torch))):
+                try:
+                    other[name] = fn()
+                except Exception as exc:
+                    other[name] = {"failed": repr(exc)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_hbm_peak()
     achieved = agg["sweep_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9 if agg["sweep_ms"] > 0 else None
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01t_traffic.json")
-    if os.path.exists(tp):   # DRAM bytes per algorithmic byte of this kernel, from the committed ncu --set full capture
+    kinds = _kind_rates(agg, peak)
+    traffic, traffic_src, dram_frac = None, None, None
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tp):   # DRAM bytes per algorithmic byte PER LAUNCH KIND, from the committed ncu --set full capture
         with open(tp) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_per_algorithmic_byte"] * agg["sweep_bytes"] / max(agg["sweep_launches"], 1)
-        traffic_src = "profiles/r01t_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per algorithmic byte) x bytes_per_launch"
+            tj = json.load(f)["dram_bytes_per_algorithmic_byte"]
+        dram_bytes = sum(tj.get(nm, tj.get("inner", 1.0)) * agg["kind_bytes"][i]
+                         for i, nm in enumerate(("prep", "inner", "leaf", "mixed")))
+        traffic = dram_bytes / max(agg["sweep_launches"], 1)
+        traffic_src = "profiles/r02_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum per algorithmic byte, " \
+                      "per launch kind, x this run's bytes per kind"
+        dram_frac = dram_bytes / (agg["sweep_ms"] * 1e-3) / 1e9 / peak
+        for nm, k in kinds.items():
+            k["dram_frac"] = k["frac"] * tj.get(nm, tj.get("inner", 1.0))
     roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (+ qcd::sweep_kernel<float> for prep sweeps)",
-                "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
-                "traffic_source": traffic_src, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_launch": agg["sweep_bytes"] / max(agg["sweep_launches"], 1),
                 "avg_launch_ms": agg["sweep_ms"] / max(agg["sweep_launches"], 1),
-                "sweep_share_of_step": agg["sweep_ms"] / ms,
+                "sweep_share_of_step": agg["sweep_ms"] / ms, "per_kind": kinds,
                 # the same launches measured in DRAM bytes (ncu capture) instead of algorithmic bytes: sibling states
                 # share their parent through L2, so `frac` can exceed 1 while the DRAM interface stays below its peak
-                "dram_frac": (traffic / (agg["sweep_ms"] * 1e-3 / max(agg["sweep_launches"], 1)) / 1e9 / peak)
-                if (traffic and agg["sweep_ms"] > 0) else None,
-                "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep]; "
-                                     "one sweep per state-dependent noise-site group"}
+                "dram_frac": dram_frac,
+                "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep, read-only for a "
+                                     "leaf that is not stored]; one sweep per state-dependent noise-site group"}
     cpu = None
     if not args.no_cpu and world == 1:      # reported at N = 1 only
         cores = host_threads()
-        n_cpu = max(16 * cores, 16)
         try:
-            v, dt_cpu, cores = cpu_arm(work, n_cpu)
-            cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu} shots of the noisy 20-qubit graph circuit (circuit 0 of the step), one "
-                             f"trajectory per shot, complex128, {dt_cpu:.1f} s"}
+            r = cpu_sample(0, max(cores // 2, 2))
+            one = cpu_sample(0, 2, threads=1, circuits=[0])
+            cpu = {"value": r["shots"] / r["seconds"], "unit": "shots/s", "cores": r["cores"], "kind": r["kind"],
+                   "value_1thread": one["shots"] / one["seconds"],
+                   "sample": f"{r['shots']} shots: {max(cores // 2, 2)} of each of the 22 circuits of graph 0 of the job, one "
+                             f"trajectory per shot, complex128, {r['seconds']:.1f} s (oracle/cpu_sim.c via "
+                             f"baseline/run_cpu.py; gate lists from oracle/workload.py)"}
         except Exception as exc:     # a CPU-baseline problem must not lose the GPU measurement
-            cpu = {"value": None, "unit": "shots/s", "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
-    other = None
-    if not args.no_e2e and world == 1:
-        try:
-            other = {"C2": c2_end_to_end(qcd, torch)}
-        except Exception as exc:     # a secondary measurement must not lose the headline
-            other = {"C2": {"failed": str(exc)}}
-    line = {"metric": "noisy shots/sec at 20 qubits (statevector trajectories + stabilizer witnesses)",
-            "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            cpu = {"value": None, "unit": "shots/s", "cores": cores, "kind": "port", "sample": f"failed: {exc!r}"}
+    sites = [works[g]["n_sites"] if g in works else None for g in range(G)]
+    line = {"metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "c64" if args.precision == 32 else "c128", "data": "synthetic",
-            "config": workload_config(work, args.shots),
-            "circuits_per_s": B * world * args.steps / (ms * 1e-3),
+            "config": workload_config(G, sites, args.shots, args.precision, args.scaling),
+            "circuits_per_s": G * CPG * args.steps / (ms * 1e-3),
             "trajectory_sharing": not args.literal,
-            "states_swept_per_step": agg["node_sweeps"] / args.steps, "leaf_states_per_step": agg["leaves"] / args.steps,
+            "states_swept_per_step_rank0": agg["node_sweeps"] / args.steps,
+            "leaf_states_per_step_rank0": agg["leaves"] / args.steps,
+            "states_swept_per_graph": agg["node_sweeps"] / args.steps / n_mine,
+            "partition_check": partition_check, "witness_check": witness_check,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "other_configs": other,
             "gpu_launches": int(agg["sweep_launches"] + agg["aux_launches"] + args.steps),
             "clocks": clk.summary()}

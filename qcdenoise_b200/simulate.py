@@ -131,7 +131,7 @@ def _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
 
 
 def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
-                     distributed=False, entangle_specs=None):
+                     distributed=False, entangle_specs=None, diagnostics=None):
     """simulate() without per-circuit Python objects: graphs, gate lists, calibration draws and adjacency tensors are
     built for the whole batch (natively / in numpy), the noise channels are written natively at upload, one engine
     call simulates everything.  Draws come from numpy / Philox generators seeded from `random`, so `random.seed()`
@@ -288,29 +288,30 @@ def _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, gr
             a = adj[num]
             results[num]["adj_tensor"] = a if adj_tensor_specs.fixed_size else a[np.any(a != 0, axis=(1, 2))]
     lap("results")
-    global last_timing, last_batch
-    last_timing = timing
-    last_batch = {"edges": edges, "n_edges": n_edges, "programs": enc}
-    if isinstance(sampler, DeviceNoiseSampler):
-        last_batch["device_props"] = props
-    else:
-        last_batch.update(coins=coins, gammas=gammas)
+    if diagnostics is not None:      # per call, owned by the caller: nothing is published through module state
+        batch = {"edges": edges, "n_edges": n_edges, "programs": enc}
+        if isinstance(sampler, DeviceNoiseSampler):
+            batch["device_props"] = props
+        else:
+            batch.update(coins=coins, gammas=gammas)
+        diagnostics["timing"] = timing
+        diagnostics["batch"] = batch
     return results
 
 
 PIPELINE_MIN = 2048    # density-matrix batches of at least this many circuits run as 4 pipelined chunks
-last_timing = {}       # seconds per host stage of the last array-route simulate() call
-last_batch = {}        # the drawn inputs of that call (graphs, encoded programs, calibration numbers / coins + dampings)
 
 
 def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entangle_specs=None, *, route="auto",
-             distributed=False) -> Dict:
+             distributed=False, diagnostics=None) -> Dict:
     """-> {i: {"graph_data": edges, "prob_vec": np.ndarray (2^n,), ["adj_tensor"], ["entanglement": {"value",
     "variance"}]}}.  route: "auto" (whole-batch array route where it applies, see _array_route_ok) or "objects"
     (always build a Circuit + NoiseModel per circuit, like the reference's loop, simulate.py:276-322).
     distributed=True (array route, torch.distributed initialised, one process per GPU): every rank simulates its
     contiguous slice of the circuits and all ranks return the complete result (one all_gather) -- the reference's
-    mp.Pool.map + np.concatenate (older_version/circuit_sampling_utils.py:81-89)."""
+    mp.Pool.map + np.concatenate (older_version/circuit_sampling_utils.py:81-89).
+    diagnostics: an optional dict the array route fills with "timing" (seconds per host stage) and "batch" (the drawn
+    inputs: graphs, encoded programs, calibration numbers / coins + dampings) of THIS call."""
     if not isinstance(sim_specs, SimulationSpecs):
         raise AssertionError("sim_specs must be an instance of SimulationSpecs")
     if not isinstance(sampler_specs, SamplingSpecs):
@@ -335,7 +336,7 @@ def simulate(sim_specs, sampler_specs, graph_specs, adj_tensor_specs=None, entan
         raise ValueError("route must be 'auto' or 'objects'")
     if route == "auto" and _array_route_ok(sim_specs, sampler, builder, graph_specs, entangle_specs):
         return _simulate_arrays(sim_specs, sampler_specs, graph_specs, adj_tensor_specs, graph_state, builder, sampler,
-                                distributed=distributed, entangle_specs=entangle_specs)
+                                distributed=distributed, entangle_specs=entangle_specs, diagnostics=diagnostics)
     if distributed:
         raise NotImplementedError("distributed=True is implemented for the array route (see _array_route_ok)")
 

@@ -441,9 +441,10 @@ def test_simulate_array_route_with_entanglement_matches_oracle(qcd, kind, monkey
     noisy = kind != "device-ideal-settings"
     wit = qcd.BiSeparableWitness if kind == "unitary-biseparable" else qcd.GenuineWitness
     ent = qcd.EntanglementSpecs(witness=wit, stabilizer=qcd.TothStabilizer, n_shots=shots, noisy=noisy)
-    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), entangle_specs=ent)
-    lb = qcd.simulate.__globals__["last_batch"]
-    assert "entanglement" in qcd.simulate.__globals__["last_timing"]          # the array route ran
+    diag = {}
+    res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=4), entangle_specs=ent, diagnostics=diag)
+    lb = diag["batch"]
+    assert "entanglement" in diag["timing"]          # the array route ran
     coin_iter = iter(lb["coins"].ravel().tolist()) if not device else None
     gamma_iter = iter(lb["gammas"]) if not device else None
     for i, ed in enumerate(batch.edge_lists(lb["edges"], lb["n_edges"])):

@@ -21,8 +21,11 @@ def test_reference_arm_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "shots/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value_1thread"] > 0
+    # the CPU arm is independent of the product: it builds its gate lists on the oracle side and never loads the package
+    assert d["cpu_baseline"]["product_imported"] is False
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["config"]["n_qubits"] == 20 and d["config"]["circuits_per_step"] == 22
+    assert d["config"]["n_qubits"] == 20 and d["config"]["circuits_per_step"] == 8 * 22 and d["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

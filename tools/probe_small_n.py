@@ -13,8 +13,8 @@ for n, B in ((9, 4000), (11, 4000), (12, 2000), (13, 1000)):
     sampler_specs = qcd.SamplingSpecs(sampler=qcd.UnitaryNoiseSampler, noise_specs=qcd.unitary_noise_spec, n_shots=1024)
     for it in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7))
+        diag = {}; res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), diagnostics=diag)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     st = qcd.get_engine().stats()
-    print(json.dumps({"n": n, "circuits": B, "s": round(dt, 4), "circuits_per_s": round(B / dt), "stages": {k: round(v, 3) for k, v in qcd.simulate.__globals__["last_timing"].items()},
+    print(json.dumps({"n": n, "circuits": B, "s": round(dt, 4), "circuits_per_s": round(B / dt), "stages": {k: round(v, 3) for k, v in diag["timing"].items()},
                       "sweep_launches": st["sweep_launches"], "node_sweeps": st["node_sweeps"], "leaves": st["leaves"]}), flush=True)

@@ -56,15 +56,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        diag = {}
         res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), distributed=world > 1,
-                           entangle_specs=ent)
+                           entangle_specs=ent, diagnostics=diag)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if it > 0:
             best = float(dt.item()) if best is None else min(best, float(dt.item()))
-    stages = dict(qcd.simulate.__globals__["last_timing"])
+    stages = dict(diag["timing"])
     same = None
     if rank == 0 and world > 1:
         random.seed(1234)

@@ -138,8 +138,9 @@ def c2_simulate(n_circ):
                                    ("auto", n_circ, True), ("auto", n_circ, True), ("objects", min(n_circ, 500), True)):
         sim_specs.n_circuits = count
         t0 = time.perf_counter()
+        diag = {}
         res = qcd.simulate(sim_specs, sampler_specs, qcd.GraphSpecs(max_num_edges=7), adj_tensor_specs=adj, route=route,
-                           entangle_specs=ent if with_ent else None)
+                           entangle_specs=ent if with_ent else None, diagnostics=diag)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert len(res) == count and abs(res[count - 1]["prob_vec"].sum() - 1) < 1e-9
@@ -149,7 +150,7 @@ def c2_simulate(n_circ):
                                     f"tensors{' + 9 Toth settings x 1024 shots + genuine witness' if with_ent else ''}, "
                                     f"route={route}", "s": dt, "value": count / dt, "unit": "circuits/s",
                           "shots_per_s": 1024 * count / dt,
-                          "stages_s": {k: round(v, 4) for k, v in qcd.simulate.__globals__["last_timing"].items()}
+                          "stages_s": {k: round(v, 4) for k, v in diag["timing"].items()}
                           if route == "auto" else None}), flush=True)
 
 
