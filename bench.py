@@ -19,11 +19,14 @@ kernel / its CUDA-event time, against the measured HBM copy bandwidth.  `cpu_bas
 reference's CPU implementation of the path (real qiskit-aer if importable, else the compiled port oracle/cpu_sim.c) on
 a bounded number of shots of the same circuits (baseline/run_cpu.py; that arm never imports the product).
 
-N > 1 (torchrun), default `--scaling strong`: the SAME 8-graph job is partitioned by circuit index
-(distributed.circuit_slice: whole graphs per rank), ONE seed, Philox counters on the global circuit index
-(qcd_run_sv_trajectories first_circuit) -- the assembled results are bit-identical to the single-GPU run, which rank 0
-asserts in warm-up by re-simulating the last rank's slice.  No data-path collective; ONE NCCL all_gather assembles the
-dataset histogram rows and the parity sums.  `--scaling weak`: N x G graphs instead (fixed work per GPU).
+N > 1 (torchrun), default `--scaling weak`: the job is N x G graphs (fixed work per GPU), DISTINCT graphs by global graph
+index, ONE seed, Philox counters on the global circuit index -- a partition of one dataset-generation job, not N
+copies of it.  Every rank holds the programs of the whole job and pulls the next graph from one shared counter
+(distributed.WorkQueue: an atomic add on the process group's store, heaviest graph first) because graphs differ ~10x in
+cost; the assembled results are bit-identical to a single-GPU run, which rank 0 asserts in warm-up by re-simulating
+graphs other ranks ran.  No data-path collective; ONE NCCL all_reduce assembles the dataset rows and the parity sums.
+At N > 1 `other_configs.C4_strong` times the FIXED single-GPU job (G graphs) over the N ranks as well (strong scaling;
+`--scaling strong` makes that the headline).
 Outside the timed region the sampled <S_k> and the witness of every graph are checked against their EXACT values
 (oracle/pauli_prop.py).  `other_configs` carries C2 / C3 / C5 and the complex128 / literal variants of C4.
 """
@@ -161,9 +164,10 @@ def workload_config(n_graphs, n_sites, shots, precision, scaling):
     return {"workload": "C4: 20-qubit graph-state stochastic-trajectory sampling, 1M shots, stabilizer witnesses "
                         "(BASELINE.json configs[3])",
             "n_qubits": N_QUBITS, "graphs_per_step": n_graphs, "circuits_per_step": n_graphs * CIRCUITS_PER_GRAPH,
-            "noise_sites_per_graph": n_sites, "kraus_channels_per_graph": [2 * s for s in n_sites], "max_prob": 0.1,
+            "noise_sites_per_graph": n_sites, "kraus_channels_per_graph": [None if s is None else 2 * s for s in n_sites], "max_prob": 0.1,
             "shots_per_circuit": shots, "precision": "complex64" if precision == 32 else "complex128",
-            "partition": f"{scaling}: circuits by index, whole graphs per rank, one seed, Philox on the global circuit index",
+            "partition": "self-scheduled: every rank pulls the next graph (22 circuits) from one shared counter, heaviest "
+                         "first; one seed, Philox on the global circuit index (results independent of the partition)",
             "cache": "working set per tree level (hundreds to thousands of 8 MiB states) >> 126 MB L2; "
                      "histograms re-zeroed every step"}
 
@@ -420,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graphs", type=int, default=8, help="graphs of the job (per GPU with --scaling weak)")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
     ap.add_argument("--shots", type=int, default=1_000_000, help="shots per circuit (1M = the BASELINE config)")
     ap.add_argument("--literal", action="store_true", help="one state per shot (no trajectory-tree sharing)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -451,23 +455,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # ---- the job and this rank's slice of it (whole graphs: the circuit slice falls on graph boundaries)
+    # ---- the job: G graphs x 22 circuits.  Every rank holds the programs of the WHOLE job (a few KB per circuit) and
+    # pulls one graph at a time from a shared counter (qd.WorkQueue), heaviest first: a static slice per rank balances
+    # counts, not cost (a 17-site graph sweeps ~10x the states of a 7-site one)
     G = args.graphs * (world if args.scaling == "weak" else 1)
-    if G % world:
-        raise SystemExit(f"--graphs {G} must be a multiple of the number of ranks ({world})")
     CPG = CIRCUITS_PER_GRAPH
-    c_lo, c_hi = qd.circuit_slice(G * CPG, rank, world)
-    g_lo, g_hi = c_lo // CPG, c_hi // CPG
-    assert c_lo == g_lo * CPG and c_hi == g_hi * CPG
-    works = {g: build_workload(g, args.shots) for g in range(g_lo, g_hi)}
-    n_sites_all = None
-    mine = [works[g] for g in range(g_lo, g_hi)]
-    programs = [p for w in mine for p in w["programs"]]
-    masks = np.concatenate([w["masks"] for w in mine])
-    B = len(programs)
+    works = [build_workload(g, args.shots) for g in range(G)]
+    masks_all = np.concatenate([w["masks"] for w in works])
     N = 2 ** N_QUBITS
+    WIDTH = N + CPG * 4                                     # int32 words per graph: dataset row + [22][2] int64 sums
     eng = qcd.get_engine(local)
-    eng.upload(programs)
+    eng.upload([p for w in works for p in w["programs"]])
     eng.set_option("time_sweeps", 1)
     if args.max_chunk:
         eng.set_option("max_chunk", args.max_chunk)
@@ -476,28 +474,37 @@ def main():
     for key in ("nostore_max", "use_direct", "no_slots", "tile_bits", "share_prefix"):        # tuning experiments only
         if os.environ.get("QCD_" + key.upper()):
             eng.set_option(key, float(os.environ["QCD_" + key.upper()]))
-    hist = torch.zeros((B, N), dtype=torch.int32, device=dev)
-    n_mine = g_hi - g_lo
+    hist = torch.zeros((CPG, N), dtype=torch.int32, device=dev)          # one graph's 22 histograms at a time
 
-    def simulate_slice(first_circuit, out_hist):
+    def heaviest_first(n_units):
+        return sorted(range(n_units), key=lambda g: -works[g]["n_sites"])
+
+    def run_graph(g, out_hist):
+        """Graph g of the job: its 22 circuits x shots trajectories -> histograms, 21 parity sums."""
         out_hist.zero_()
         eng.run_trajectories(args.shots, seed=SEED, precision=args.precision, hist=out_hist, dedup=not args.literal,
-                             first_circuit=first_circuit)
+                             shot_range=(g * CPG * args.shots, (g + 1) * CPG * args.shots), hist_row0=g * CPG)
         st = eng.stats()
-        ss, tot = eng.parity_counts(out_hist, masks)
-        return st, ss[:, 0].contiguous(), tot
+        ss, tot = eng.parity_counts(out_hist, masks_all[g * CPG:(g + 1) * CPG])
+        return st, torch.stack([ss[:, 0], tot], dim=1)                    # [22, 2] int64
 
-    def step():
-        st, ss, tot = simulate_slice(c_lo, hist)
-        rows = hist[0::CPG]                                   # dataset rows: the noisy graph circuits' histograms
-        sums = torch.stack([ss, tot], dim=1)                  # [B, 2] int64
-        if world > 1:       # assemble: ONE all_gather (equal counts per rank) of the dataset rows + parity sums
-            payload = torch.cat([rows.reshape(-1).to(torch.int64), sums.reshape(-1)])
-            gathered = torch.empty((world, payload.numel()), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered, payload)
-            rows = gathered[:, : n_mine * N].reshape(G, N)
-            sums = gathered[:, n_mine * N:].reshape(G * CPG, 2)
-        return st, rows, sums
+    def step(queue):
+        """One pass over the queue's graphs.  Assembly: ONE all_reduce of the [graphs, dataset row + parity sums] buffer
+        in which every rank filled the rows of the graphs it ran."""
+        full = torch.zeros((queue.n_units, WIDTH), dtype=torch.int32, device=dev)
+        st_sum, ran = {}, []
+        t0 = time.perf_counter()
+        for g in queue.epoch():
+            st, sums_g = run_graph(g, hist)
+            full[g, :N] = hist[0]                                         # dataset row: the noisy graph circuit
+            full[g, N:] = sums_g.reshape(-1).view(torch.int32)
+            _add_stats(st_sum, st)
+            ran.append(g)
+        torch.cuda.synchronize()
+        busy = time.perf_counter() - t0
+        qd.assemble_rows(full)
+        sums = full[:, N:].contiguous().view(torch.int64).reshape(queue.n_units * CPG, 2)
+        return st_sum, full[:, :N], sums, ran, busy
 
     def barrier():
         torch.cuda.synchronize()
@@ -505,67 +512,96 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rows = sums = None
+    def timed_steps(queue, k):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        agg, busy = {}, 0.0
+        ev0.record()
+        for _ in range(k):
+            st, rows, sums, ran, b = step(queue)
+            _add_stats(agg, st)
+            busy += b
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1), 1e3 * busy, float(len(ran))], dtype=torch.float64, device=dev)
+        if world > 1:
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            t = torch.stack(every)
+        else:
+            t = t[None]
+        return float(t[:, 0].max().item()), agg, rows, sums, (t[:, 1] / k).tolist(), [int(x) for x in t[:, 2].tolist()]
+
+    wq = qd.WorkQueue(G, order=heaviest_first(G), name="qcd_c4")
+    rows = sums = ran = None
     for _ in range(max(args.warmup, 1)):
-        st, rows, sums = step()
+        st, rows, sums, ran, _ = step(wq)
     # ---- warm-up checks (outside the timed region)
     partition_check = None
-    if world > 1 and rank == 0:
-        # the partitioned job equals the single-GPU job: rank 0 re-simulates the LAST rank's slice with the same seed and
-        # the global circuit offset and compares with what that rank contributed -- bit for bit
-        other = {g: build_workload(g, args.shots) for g in range(G - n_mine, G)}
-        eng.upload([p for g in sorted(other) for p in other[g]["programs"]])
-        h2 = torch.zeros_like(hist)
-        _, ss2, tot2 = simulate_slice((G - n_mine) * CPG, h2)
-        same_rows = bool(torch.equal(h2[0::CPG].to(torch.int64), rows[G - n_mine:]))
-        same_sums = bool(torch.equal(torch.stack([ss2, tot2], dim=1), sums[(G - n_mine) * CPG:]))
-        del h2
-        eng.upload(programs)
-        if not (same_rows and same_sums):
-            raise AssertionError("partitioned run differs from the single-GPU run of the same circuits")
-        partition_check = {"slice": f"rank {world - 1}'s graphs re-simulated on rank 0", "dataset_rows_identical": same_rows,
-                           "parity_sums_identical": same_sums}
+    if world > 1:
+        # the partitioned job equals the single-GPU job: rank 0 re-simulates graphs that OTHER ranks ran in the last
+        # warm-up step (same seed, same global circuit indices) and compares with what they contributed -- bit for bit
+        theirs = [g for g in range(G) if g not in ran]
+        if rank == 0 and theirs:
+            picks = sorted({theirs[0], theirs[-1], max(theirs, key=lambda g: works[g]["n_sites"])})
+            h2 = torch.zeros_like(hist)
+            same_rows = same_sums = True
+            for g in picks:
+                _, s2 = run_graph(g, h2)
+                same_rows &= bool(torch.equal(h2[0], rows[g]))
+                same_sums &= bool(torch.equal(s2, sums[g * CPG:(g + 1) * CPG]))
+            del h2
+            if not (same_rows and same_sums):
+                raise AssertionError("partitioned run differs from the single-GPU run of the same circuits "
+                                     f"(dataset rows identical: {same_rows}, parity sums identical: {same_sums})")
+            partition_check = {"graphs_rerun_on_rank0": picks, "ran_by_other_ranks": True,
+                               "dataset_rows_identical": same_rows, "parity_sums_identical": same_sums}
     witness_check = None
     if not args.literal or args.shots >= 100_000:
         sm = sums.cpu().numpy().astype(np.float64)
-        res = []
-        graphs_here = range(G) if world > 1 else range(g_lo, g_hi)
-        for g in (graphs_here if rank == 0 else []):
-            w = works[g] if g in works else build_workload(g, args.shots)
-            res.append(check_witness(w, sm[g * CPG:(g + 1) * CPG, 0], sm[g * CPG:(g + 1) * CPG, 1], f"graph {g}"))
-        if res:
-            witness_check = {"graphs": len(res), "worst_setting_sigmas": max(r["worst_setting_sigmas"] for r in res),
-                             "witness_sampled": [r["witness_sampled"] for r in res],
-                             "witness_exact": [r["witness_exact"] for r in res],
-                             "witness_sigma": [r["witness_sigma"] for r in res], "checker": res[0]["checker"]}
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {}
+        res = {g: check_witness(works[g], sm[g * CPG:(g + 1) * CPG, 0], sm[g * CPG:(g + 1) * CPG, 1], f"graph {g}")
+               for g in ran}                                  # every rank checks the graphs it ran
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, res)
+            res = {g: r for p in parts for g, r in p.items()}
+        assert sorted(res) == list(range(G))
+        witness_check = {"graphs": len(res), "worst_setting_sigmas": max(r["worst_setting_sigmas"] for r in res.values()),
+                         "witness_sampled": [res[g]["witness_sampled"] for g in range(G)],
+                         "witness_exact": [res[g]["witness_exact"] for g in range(G)],
+                         "witness_sigma": [res[g]["witness_sigma"] for g in range(G)], "checker": res[0]["checker"]}
     with ClockSampler(local) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            st, rows, sums = step()
-            _add_stats(agg, st)
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, agg, rows, sums, rank_busy_ms, rank_graphs = timed_steps(wq, args.steps)
     assert sums[:, 1].cpu().tolist() == [args.shots] * (G * CPG), "histograms do not hold every shot"
     shots_per_step = G * CPG * args.shots
     value = shots_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the reference-facing API (host gate lists in, host numpy out), this rank's graphs
+    # ---- the FIXED job of --graphs graphs on all ranks (strong scaling), next to the weak-scaling headline
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        sq = qd.WorkQueue(args.graphs, order=heaviest_first(args.graphs), name="qcd_c4_strong")
+        step(sq)
+        ms_s, _, _, sums_s, busy_s, graphs_s = timed_steps(sq, 2)
+        assert torch.equal(sums_s, sums[: args.graphs * CPG]), "strong-scaling pass differs from the weak-scaling pass"
+        strong = {"workload": f"the single-GPU job ({args.graphs} graphs x {CPG} circuits x {args.shots} shots) "
+                              f"self-scheduled over {world} GPUs at graph granularity",
+                  "scaling": "strong", "shots_per_s": args.graphs * CPG * args.shots * 2 / (ms_s * 1e-3),
+                  "ms_per_step": ms_s / 2, "rank_busy_ms": busy_s, "graphs_per_rank": graphs_s,
+                  "noise_sites_per_graph": [w["n_sites"] for w in works[: args.graphs]],
+                  "limiter": "load imbalance at graph granularity: the step lasts as long as the rank that drew the "
+                             "heaviest graph(s) (rank_busy_ms); the all_reduce of the assembled rows is < 1 ms"}
+
+    # ---- end to end through the reference-facing API (host gate lists in, host numpy out), self-scheduled the same way
     e2e = None
     if not args.no_e2e:
         sampler = qcd.UnitaryNoiseSampler(None, n_shots=args.shots, method="statevector", precision=args.precision, seed=SEED)
         ssam = qcd.StabilizerSampler(None, n_shots=args.shots, method="statevector", precision=args.precision, seed=SEED + 1)
+        eq = qd.WorkQueue(G, order=heaviest_first(G), name="qcd_c4_e2e")
 
         def e2e_step(counts_to_host=False):
-            out = []
-            for w in mine:
+            out = {}
+            for gi in eq.epoch():
+                w = works[gi]
                 g, cd, stab = w["graph"], w["circuit_dict"], w["stab"]
                 np.random.set_state(w["rng_state"])      # sample() draws its noise model: the device leg's channels
                 p = sampler.sample(cd["circuit"], cd["ops"])                               # np.ndarray (2^n,) float64
@@ -574,7 +610,7 @@ def main():
                     for c in counts:
                         c.hist                                                             # host histograms, as Aer returns
                 wit = qcd.GenuineWitness(N_QUBITS, stab, counts).estimate(g)
-                out.append((p, wit))
+                out[gi] = (p, wit)
             return out
 
         eng.set_option("time_sweeps", 0)
@@ -586,6 +622,7 @@ def main():
             res = e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        barrier()
         t0 = time.perf_counter()
         e2e_step(counts_to_host=True)
         torch.cuda.synchronize()
@@ -595,16 +632,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt, dt_full = float(t[0].item()), float(t[1].item())
         from qcdenoise_b200.ir import encode_programs
-        h2d = sum(int(a.nbytes) for w in mine for a in encode_programs(w["programs"])[:3])
-        d2h = n_mine * int(N * 4 + (CPG - 1) * 16)
+        h2d = sum(int(a.nbytes) for w in works for a in encode_programs(w["programs"])[:3])
+        d2h = G * int(N * 4 + (CPG - 1) * 16)
         e2e = {"value": shots_per_step * k_e2e / dt, "unit": "shots/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e,
-               "witness_values": [float(w.value) for _, w in res],
+               "witness_values_rank0": {str(g): float(w.value) for g, (_, w) in sorted(res.items())},
                "api": "per graph: UnitaryNoiseSampler.sample + StabilizerSampler.sample + GenuineWitness.estimate",
                "stabilizer_histograms": "stay on the GPU behind lazy Counts (the witness reduces them on the device); "
                                         "`with_counts_on_host` copies all 21 per graph to the host as well, as Aer "
                                         "returns them",
-               "with_counts_on_host": {"value": shots_per_step / dt_full, "d2h_bytes_per_step": n_mine * CPG * N * 4}}
+               "with_counts_on_host": {"value": shots_per_step / dt_full, "d2h_bytes_per_step": G * CPG * N * 4}}
 
     # ---- secondary configurations (C5 runs on every rank count; the others at N = 1)
     peak, peak_src = measured_hbm_peak()
@@ -615,10 +652,12 @@ def main():
             other["C5"] = c5_trajectories(qcd, torch, dist, eng, peak, rank, world, local)
         except Exception as exc:     # a secondary measurement must not lose the headline
             other["C5"] = {"failed": repr(exc)}
+        if strong is not None:
+            other["C4_strong"] = strong
         if world == 1:
             for name, fn in (("C3", lambda: c3_density_matrix(qcd, torch, eng, peak)),
-                             ("C4_complex128", lambda: c4_variant(torch, eng, mine[0], peak, args.shots, 64, False)),
-                             ("C4_literal", lambda: c4_variant(torch, eng, mine[0], peak, 4000, 32, True)),
+                             ("C4_complex128", lambda: c4_variant(torch, eng, works[0], peak, args.shots, 64, False)),
+                             ("C4_literal", lambda: c4_variant(torch, eng, works[0], peak, 4000, 32, True)),
                              ("C2", lambda: c2_end_to_end(qcd, torch))):
                 try:
                     other[name] = fn()
@@ -629,6 +668,10 @@ def main():
             dist.destroy_process_group()
         return
 
+    for k in ("sweep_bytes", "sweep_ms", "sweep_launches", "aux_launches", "node_sweeps", "leaves"):
+        agg.setdefault(k, 0)
+    for k in ("kind_launches", "kind_bytes", "kind_ms"):
+        agg.setdefault(k, [0, 0, 0, 0])
     achieved = agg["sweep_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9 if agg["sweep_ms"] > 0 else None
     kinds = _kind_rates(agg, peak)
     traffic, traffic_src, dram_frac = None, None, None
@@ -668,7 +711,7 @@ def main():
                              f"baseline/run_cpu.py; gate lists from oracle/workload.py)"}
         except Exception as exc:     # a CPU-baseline problem must not lose the GPU measurement
             cpu = {"value": None, "unit": "shots/s", "cores": cores, "kind": "port", "sample": f"failed: {exc!r}"}
-    sites = [works[g]["n_sites"] if g in works else None for g in range(G)]
+    sites = [w["n_sites"] for w in works]
     line = {"metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "c64" if args.precision == 32 else "c128", "data": "synthetic",
@@ -677,10 +720,11 @@ def main():
             "trajectory_sharing": not args.literal,
             "states_swept_per_step_rank0": agg["node_sweeps"] / args.steps,
             "leaf_states_per_step_rank0": agg["leaves"] / args.steps,
-            "states_swept_per_graph": agg["node_sweeps"] / args.steps / n_mine,
+            "states_swept_per_graph_rank0": agg["node_sweeps"] / args.steps / max(rank_graphs[0], 1),
+            "rank_busy_ms_per_step": rank_busy_ms, "graphs_per_rank_last_step": rank_graphs,
             "partition_check": partition_check, "witness_check": witness_check,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "other_configs": other,
-            "gpu_launches": int(agg["sweep_launches"] + agg["aux_launches"] + args.steps),
+            "gpu_launches": int(agg["sweep_launches"] + agg["aux_launches"]),
             "clocks": clk.summary()}
     print(json.dumps(line), flush=True)
     if world > 1:

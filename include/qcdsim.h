@@ -121,7 +121,11 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "share_prefix" 0/1 (1)  consecutive circuits whose sweeps are identical up to the final one (a graph circuit and
  *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the
  *                           parents of the leaves; every draw stays keyed by the trajectory's own (circuit, shot), so
- *                           results are bit-identical with the option off */
+ *                           results are bit-identical with the option off
+ *   "hist_row0" (0)         qcd_run_sv_trajectories: the uploaded circuit that row 0 of `hist` stands for.  A rank that
+ *                           holds the whole batch's programs and runs one slice of circuits at a time (self-scheduled
+ *                           partition, qcdenoise_b200/distributed.py WorkQueue) passes a buffer with rows for that slice
+ *                           only; must not exceed the first circuit of the shot range */
 QCD_API int qcd_set_option(qcd_ctx* ctx, const char* key, double value);
 QCD_API int qcd_get_stats(qcd_ctx* ctx, qcd_stats* out);
 

@@ -151,6 +151,7 @@ struct qcd_ctx {
     bool no_slots = false;
     uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
+    uint32_t hist_row0 = 0;      // uploaded circuit that row 0 of the caller's histogram buffer stands for
     size_t cached_budget = 0;    // last usable_budget() answer and how many runs have reused it
     int budget_age = 0;
     // programs (host copy of the IR; compiled lazily per (mode, precision))
@@ -872,7 +873,9 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     R.seed = seed;
     R.spc = spc;
     R.shot_begin = shot_begin;
-    R.hist = hist;
+    // histogram rows are only ever addressed through a trajectory's circuit index, so a caller that runs a slice of the
+    // uploaded circuits may pass a buffer whose row 0 is circuit hist_row0 (checked against the slice by the caller below)
+    R.hist = hist ? hist - ((size_t)ctx->hist_row0 << n) : nullptr;
     R.outcomes = outcomes;
     const bool no_dedup = (flags & QCD_RUN_NO_DEDUP) != 0;
     const bool share = ctx->share_prefix && !no_dedup && dp->member_bits > 0;
@@ -1287,6 +1290,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
     else if (k == "no_slots") ctx->no_slots = value != 0;
     else if (k == "share_prefix") ctx->share_prefix = value != 0;
+    else if (k == "hist_row0") ctx->hist_row0 = (uint32_t)value;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }
@@ -1575,6 +1579,8 @@ int qcd_run_sv_trajectories(qcd_ctx* ctx, int precision, uint64_t shots_per_circ
     if (shot_begin > shot_end || shot_end > shots_per_circuit * (uint64_t)ctx->n_circuits)
         return fail(ctx, QCD_E_INVALID, "shot range outside [0, n_circuits * shots_per_circuit]");
     if (!hist && !outcomes) return fail(ctx, QCD_E_INVALID, "hist and outcomes are both NULL");
+    if (hist && shot_begin < shot_end && (uint64_t)ctx->hist_row0 > shot_begin / shots_per_circuit)
+        return fail(ctx, QCD_E_INVALID, "option hist_row0 lies beyond the first circuit of the shot range");
     cudaSetDevice(ctx->device);
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->ev_used = 0;

@@ -116,8 +116,8 @@ int qcd_sample_graph_states(const uint8_t* lib_edges, const uint32_t* lib_edge_o
                 // 1. a random combination of sub-graph orders, a random library graph per order
                 const uint32_t c = rng.below((uint32_t)n_combs);
                 const uint32_t nb = comb_offsets[c + 1] - comb_offsets[c];
-                uint32_t pick[64];
-                for (uint32_t j = 0; j < nb && j < 64; j++) {
+                uint32_t pick[128];   // blocks have >= 2 vertices and n_qubits <= 255: at most 127 blocks
+                for (uint32_t j = 0; j < nb; j++) {
                     const int k = comb_sizes[comb_offsets[c] + j];
                     pick[j] = order_graphs[order_offsets[k] + rng.below(order_offsets[k + 1] - order_offsets[k])];
                 }
@@ -125,7 +125,7 @@ int qcd_sample_graph_states(const uint8_t* lib_edges, const uint32_t* lib_edge_o
                 //    order(block) draws from its first order(block) - 1 vertices (duplicates collapse)
                 edges.clear();
                 int order = 0;
-                for (uint32_t j = 0; j < nb && j < 64; j++) {
+                for (uint32_t j = 0; j < nb; j++) {
                     const uint32_t lg = pick[j];
                     const int k = lib_orders[lg];
                     if (order > 1) {

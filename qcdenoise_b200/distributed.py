@@ -9,7 +9,7 @@ tests) instead of fork + pickle.  No state is ever sharded and there is no per-g
 import torch
 import torch.distributed as dist
 
-__all__ = ["shot_slice", "circuit_slice", "sharded_histograms", "gather_rows"]
+__all__ = ["shot_slice", "circuit_slice", "sharded_histograms", "gather_rows", "WorkQueue", "assemble_rows"]
 
 
 def shot_slice(n_circuits, shots_per_circuit, rank=None, world=None):
@@ -58,3 +58,51 @@ def gather_rows(rows, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+class WorkQueue:
+    """Self-scheduled partition of independent work units (graphs, blocks of circuits) over the ranks.
+
+    A static slice per rank balances COUNTS, not COST: the trajectory tree of a graph circuit with 17 noise sites has
+    ~10x the states of one with 7, so equal counts leave most GPUs idle behind the unlucky one.  Here every rank pulls
+    the index of its next unit from one shared counter (an atomic `add` on the process group's key-value store -- host
+    side, no GPU collective, no data on the wire) whenever it becomes free; `order` lists the units heaviest first so
+    that the cheap ones fill the gaps at the end.  Because every draw is keyed by the GLOBAL circuit index, the results
+    do not depend on which rank ran which unit.  Without an initialised process group it is a plain local counter.
+
+        q = WorkQueue(n_graphs, order=np.argsort(-cost))
+        for unit in q.epoch():          # every rank calls epoch() once per pass, the same number of times
+            ...
+    """
+
+    def __init__(self, n_units, order=None, name="qcd_wq"):
+        self.n_units = int(n_units)
+        self.order = list(range(self.n_units)) if order is None else [int(u) for u in order]
+        if sorted(self.order) != list(range(self.n_units)):
+            raise ValueError("order must be a permutation of range(n_units)")
+        self.name = name
+        self._epoch = 0
+        self._store = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from torch.distributed import distributed_c10d
+            self._store = distributed_c10d._get_default_store()
+
+    def epoch(self):
+        """Iterator over the units this rank wins in one pass over the queue."""
+        self._epoch += 1
+        key = f"{self.name}/{self._epoch}"
+        local = iter(range(self.n_units))
+        while True:
+            k = (self._store.add(key, 1) - 1) if self._store is not None else next(local, self.n_units)
+            if k >= self.n_units:
+                return
+            yield self.order[k]
+
+
+def assemble_rows(full, group=None):
+    """Assembly after a self-scheduled pass: `full` is an integer tensor [n_units, width] in which this rank filled the
+    rows of the units it ran and left the others ZERO; one all_reduce(SUM) completes it on every rank (exactly one rank
+    contributes to a row, so the sum is exact for any integer dtype)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full

@@ -107,22 +107,33 @@ class Engine:
 
     # ---------------------------------------------------------------- simulation
     def run_trajectories(self, shots, seed=1234, precision=32, shot_range=None, readout=None, hist=None,
-                         want_outcomes=False, dedup=True, first_circuit=0):
+                         want_outcomes=False, dedup=True, first_circuit=0, hist_row0=0):
         """Statevector trajectories.  Returns (hist [B, 2^n] int32 or None, outcomes [range] int32 or None).
         shot_range = (begin, end) in the flattened [circuit][shot] space (default: everything).
         first_circuit: index of uploaded circuit 0 in the whole batch (a rank that uploaded only its slice of the
-        circuits draws exactly what a single-GPU run of the whole batch draws)."""
+        circuits draws exactly what a single-GPU run of the whole batch draws).
+        hist_row0: uploaded circuit that row 0 of `hist` stands for (a caller running one slice of the uploaded circuits
+        passes a histogram with rows for that slice only)."""
         n, B = self.n_qubits, self.n_circuits
         begin, end = shot_range if shot_range is not None else (0, B * shots)
+        if hist_row0 and hist is None:
+            raise ValueError("hist_row0 needs a caller-owned hist")
+        if hist is not None and begin < end and \
+                not (hist_row0 <= begin // shots and (end - 1) // shots < hist_row0 + hist.shape[0]):
+            raise ValueError("hist has no rows for some circuits of the shot range")
         with torch.cuda.device(self.device):
             if hist is None and n <= 26:
                 hist = torch.zeros((B, 2 ** n), dtype=torch.int32, device=self.device)
             outcomes = torch.empty((max(end - begin, 1),), dtype=torch.int32, device=self.device) \
                 if (want_outcomes or hist is None) else None
             r = self._readout_array(readout, B, n)
-            self._check(self.lib.qcd_run_sv_trajectories(
-                self._h, precision, shots, seed, begin, end, first_circuit, _ptr(r), _ptr(hist), _ptr(outcomes),
-                0 if dedup else _lib.QCD_RUN_NO_DEDUP, self._stream()))
+            self.set_option("hist_row0", hist_row0)
+            try:
+                self._check(self.lib.qcd_run_sv_trajectories(
+                    self._h, precision, shots, seed, begin, end, first_circuit, _ptr(r), _ptr(hist), _ptr(outcomes),
+                    0 if dedup else _lib.QCD_RUN_NO_DEDUP, self._stream()))
+            finally:
+                self.set_option("hist_row0", 0)
         if outcomes is not None:
             outcomes = outcomes[: end - begin]
         return hist, outcomes

@@ -1,9 +1,10 @@
-"""Random graph states for `simulate()`: a library of small connected graphs and a sampler that partitions the
-qubits into library sub-graphs and joins them with random connector edges.  Same role and call surface as the
-reference's GraphDB / GraphState (graph_data.py:274-390, graph_state.py:40-215).  NOT a copy of its data: the
-reference ships the 45 local-unitary-inequivalent graphs of Hein et al.'s table; this library is every connected
-graph on 2..7 vertices from the networkx graph atlas (a superset up to isomorphism), thinned per order.  Parity
-fixtures that need the reference's exact graphs use tests/golden/graphs.json instead."""
+"""Random graph states for `simulate()`: a sampler that partitions the qubits into library sub-graphs and joins them
+with random connector edges -- the reference's GraphState (graph_state.py:40-215) over the reference's graph library
+(graph_data.py, here `qcdenoise_b200.graph_data`).  `sample()` makes the same `random` / `np.random` calls in the same
+order over the same library and the same list of combinations, so under the same seeds it returns the reference's
+graphs edge for edge (tests/golden/graphs.json was written by the reference's own code).  `sample_batch()` draws whole
+batches natively (C ABI qcd_sample_graph_states, Philox streams): the same distribution, checked against statistics
+of the reference's sampler (tests/golden/graph_sampling_stats.json)."""
 import ctypes
 import random
 
@@ -12,57 +13,9 @@ import numpy as np
 from networkx.algorithms.approximation import vertex_cover
 
 from . import _lib
+from .graph_data import GraphData, GraphDB, HeinGraphData, atlas_graph_data, partition_GraphData  # noqa: F401
 
-__all__ = ["GraphData", "GraphDB", "GraphState"]
-
-
-class GraphData:
-    """Edge-list container: {name: {"G": edge tuples}}."""
-
-    def __init__(self, data=None):
-        self.data = data if data is not None else self._atlas()
-
-    _atlas_cache = {}
-
-    @staticmethod
-    def _atlas(max_per_order=12):
-        if max_per_order not in GraphData._atlas_cache:
-            GraphData._atlas_cache[max_per_order] = GraphData._scan_atlas(max_per_order)
-        return {k: {"G": list(v["G"])} for k, v in GraphData._atlas_cache[max_per_order].items()}
-
-    @staticmethod
-    def _scan_atlas(max_per_order):
-        out, per = {}, {}
-        for g in nx.graph_atlas_g():
-            k = g.number_of_nodes()
-            if k < 2 or k > 7 or not nx.is_connected(g) or per.get(k, 0) >= max_per_order:
-                continue
-            # spread the picks over the edge-count range instead of taking the sparsest ones only
-            per[k] = per.get(k, 0) + 1
-            out[f"{k}_{per[k]}"] = {"G": sorted(tuple(sorted(e)) for e in g.edges())}
-        return out
-
-
-class GraphDB(dict):
-    """name -> {"G": nx.Graph | nx.DiGraph, "LUclass": None, "2Color": None}."""
-
-    def __init__(self, graph_data=None, directed=False):
-        super().__init__()
-        gd = graph_data if graph_data is not None else GraphData()
-        self.directed = directed
-        for name, ent in gd.data.items():
-            g = nx.DiGraph() if directed else nx.Graph()
-            g.add_edges_from(ent["G"], weight=1)
-            self[name] = {"G": nx.convert_node_labels_to_integers(g, ordering="sorted"), "LUclass": None,
-                          "2Color": None}
-
-    def get_edge_sorted_graphs(self):
-        """Lists of graphs indexed by node count (index k -> graphs with k nodes), up to the largest order."""
-        top = max(ent["G"].order() for ent in self.values())
-        out = [[] for _ in range(top + 3)]
-        for ent in self.values():
-            out[ent["G"].order()].append(ent["G"])
-        return out
+__all__ = ["GraphData", "GraphDB", "GraphState", "HeinGraphData", "partition_GraphData", "atlas_graph_data"]
 
 
 def _partitions(n, start=2):
@@ -83,16 +36,19 @@ class GraphState:
             raise AssertionError(f"n_qubits={n_qubits} < 2")
         self.graph_db = graph_db
         self.n_qubits = n_qubits
-        self.all_graphs = graph_db.get_edge_sorted_graphs()
-        avail = [k for k, lst in enumerate(self.all_graphs) if lst]
+        self.all_graphs = graph_db.get_edge_sorted_graphs()         # {order: [graphs]}
+        avail = [k for k, lst in self.all_graphs.items() if lst]
         self.largest_subgraph = max(avail) if max_num_edges is None else min(max_num_edges, max(avail))
         if min_num_edges > n_qubits:
             min_num_edges = int((n_qubits // 2) - 1)
         self.smallest_subgraph = max(2, min_num_edges)
         self.directed = directed
-        self.graph_combs = sorted(c for c in set(_partitions(n_qubits, self.smallest_subgraph))
-                                  if all(self.smallest_subgraph <= k <= self.largest_subgraph and self.all_graphs[k]
-                                         for k in c))
+        # the reference's list, in the reference's order: list(set(partitions)) filtered on the part sizes
+        # (graph_state.py:145-172; the set's iteration order decides which combination a draw selects).  Combinations
+        # naming an order the library has no graph of are dropped (the reference would fail on drawing one).
+        self.graph_combs = [c for c in list(set(_partitions(n_qubits, self.smallest_subgraph)))
+                            if all(self.smallest_subgraph <= k <= self.largest_subgraph and self.all_graphs.get(k)
+                                   for k in c)]
         if not self.graph_combs:
             raise ValueError("no combination of library sub-graphs adds up to n_qubits")
         self._tables = None
@@ -137,8 +93,8 @@ class GraphState:
         order because that is how networkx's disjoint_union relabels a block."""
         if self._tables is None:
             lib_edges, lib_off, lib_orders, order_off, order_graphs = [], [0], [], [0], []
-            for k, pool in enumerate(self.all_graphs):
-                for sg in pool:
+            for k in range(max(self.all_graphs) + 1):
+                for sg in self.all_graphs.get(k, []):
                     idx = {v: i for i, v in enumerate(sg.nodes())}
                     lib_edges += [(idx[u], idx[v]) for u, v in sg.edges()]
                     lib_off.append(len(lib_edges))

@@ -25,7 +25,7 @@ def test_reference_arm_json_line():
     # the CPU arm is independent of the product: it builds its gate lists on the oracle side and never loads the package
     assert d["cpu_baseline"]["product_imported"] is False
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["config"]["n_qubits"] == 20 and d["config"]["circuits_per_step"] == 8 * 22 and d["scaling"] == "strong"
+    assert d["config"]["n_qubits"] == 20 and d["config"]["circuits_per_step"] == 8 * 22 and d["scaling"] == "weak"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

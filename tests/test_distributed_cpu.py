@@ -41,8 +41,24 @@ def _worker(rank, world, port, q):
     hist = qd.sharded_histograms(lambda b, e: _oracle_slice(batch, b, e), len(batch), SHOTS)
     cb, ce = qd.circuit_slice(len(batch))
     rows = qd.gather_rows(torch.arange(cb, ce, dtype=torch.float64).reshape(-1, 1) * torch.ones(1, 5, dtype=torch.float64))
+    # self-scheduled partition: units pulled from one shared counter, results assembled by ONE all_reduce
+    import time
+    wq = qd.WorkQueue(7, order=[6, 5, 4, 3, 2, 1, 0])
+    passes = []
+    for _ in range(2):
+        full = torch.zeros((7, 2 ** N), dtype=torch.int64)
+        mine = []
+        for unit in wq.epoch():
+            time.sleep(0.02 * (1 + rank))           # unequal speeds: the faster rank wins more units
+            full[unit] = _oracle_slice(batch[:1], unit * 10, unit * 10 + 10)[0]
+            mine.append(unit)
+        own = torch.zeros(7, dtype=torch.int64)
+        own[mine] = 1
+        passes.append((qd.assemble_rows(full).numpy(), qd.assemble_rows(own).numpy(), mine))
+        dist.barrier()
     if rank == 0:
-        q.put((hist.numpy(), rows.numpy(), qd.shot_slice(len(batch), SHOTS, 0, world), qd.shot_slice(len(batch), SHOTS, 1, world)))
+        q.put((hist.numpy(), rows.numpy(), qd.shot_slice(len(batch), SHOTS, 0, world), qd.shot_slice(len(batch), SHOTS, 1, world),
+               passes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,7 +77,7 @@ def test_two_rank_partition_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    hist, rows, s0, s1 = q.get(timeout=240)
+    hist, rows, s0, s1, passes = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -70,6 +86,22 @@ def test_two_rank_partition_matches_single_process():
     assert np.array_equal(hist, want)                      # the slice boundary (151) falls inside circuit 1
     assert s0 == (0, 151) and s1 == (151, 303)
     assert np.array_equal(rows[:, 0], np.arange(3.0)) and rows.shape == (3, 5)
+    # work queue: every unit ran on exactly one rank, in both passes; the assembled rows equal the single-process ones
+    want_units = np.stack([_oracle_slice(batch[:1], u * 10, u * 10 + 10)[0].numpy() for u in range(7)])
+    for full, owners, mine in passes:
+        assert np.array_equal(owners, np.ones(7, dtype=np.int64)) and np.array_equal(full, want_units)
+        assert 0 < len(mine) < 7 and mine == sorted(mine, reverse=True)         # heaviest-first order respected
+
+
+def test_work_queue_without_a_process_group_is_a_local_counter():
+    from qcdenoise_b200 import distributed as qd
+    wq = qd.WorkQueue(5, order=[4, 0, 3, 1, 2])
+    assert list(wq.epoch()) == [4, 0, 3, 1, 2] and list(wq.epoch()) == [4, 0, 3, 1, 2]
+    assert list(qd.WorkQueue(0).epoch()) == []
+    with pytest.raises(ValueError):
+        qd.WorkQueue(3, order=[0, 0, 1])
+    t = torch.arange(6).reshape(2, 3)
+    assert qd.assemble_rows(t) is t
 
 
 def test_slices_cover_everything():
