@@ -523,14 +523,16 @@ def main():
             busy += b
         ev1.record()
         barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1), 1e3 * busy, float(len(ran))], dtype=torch.float64, device=dev)
+        t = torch.tensor([ev0.elapsed_time(ev1), 1e3 * busy, float(len(ran)), float(agg.get("sweep_bytes", 0)),
+                          float(agg.get("node_sweeps", 0))], dtype=torch.float64, device=dev)
         if world > 1:
             every = [torch.zeros_like(t) for _ in range(world)]
             dist.all_gather(every, t)
             t = torch.stack(every)
         else:
             t = t[None]
-        return float(t[:, 0].max().item()), agg, rows, sums, (t[:, 1] / k).tolist(), [int(x) for x in t[:, 2].tolist()]
+        job = {"sweep_bytes_per_step": float(t[:, 3].sum().item()) / k, "states_swept_per_step": float(t[:, 4].sum().item()) / k}
+        return float(t[:, 0].max().item()), agg, rows, sums, (t[:, 1] / k).tolist(), [int(x) for x in t[:, 2].tolist()], job
 
     wq = qd.WorkQueue(G, order=heaviest_first(G), name="qcd_c4")
     rows = sums = ran = None
@@ -571,7 +573,7 @@ def main():
                          "witness_exact": [res[g]["witness_exact"] for g in range(G)],
                          "witness_sigma": [res[g]["witness_sigma"] for g in range(G)], "checker": res[0]["checker"]}
     with ClockSampler(local) as clk:
-        ms, agg, rows, sums, rank_busy_ms, rank_graphs = timed_steps(wq, args.steps)
+        ms, agg, rows, sums, rank_busy_ms, rank_graphs, job = timed_steps(wq, args.steps)
     assert sums[:, 1].cpu().tolist() == [args.shots] * (G * CPG), "histograms do not hold every shot"
     shots_per_step = G * CPG * args.shots
     value = shots_per_step * args.steps / (ms * 1e-3)
@@ -581,7 +583,7 @@ def main():
     if world > 1 and args.scaling == "weak":
         sq = qd.WorkQueue(args.graphs, order=heaviest_first(args.graphs), name="qcd_c4_strong")
         step(sq)
-        ms_s, _, _, sums_s, busy_s, graphs_s = timed_steps(sq, 2)
+        ms_s, _, _, sums_s, busy_s, graphs_s, _ = timed_steps(sq, 2)
         assert torch.equal(sums_s, sums[: args.graphs * CPG]), "strong-scaling pass differs from the weak-scaling pass"
         strong = {"workload": f"the single-GPU job ({args.graphs} graphs x {CPG} circuits x {args.shots} shots) "
                               f"self-scheduled over {world} GPUs at graph granularity",
@@ -722,6 +724,12 @@ def main():
             "leaf_states_per_step_rank0": agg["leaves"] / args.steps,
             "states_swept_per_graph_rank0": agg["node_sweeps"] / args.steps / max(rank_graphs[0], 1),
             "rank_busy_ms_per_step": rank_busy_ms, "graphs_per_rank_last_step": rank_graphs,
+            # the job's cost depends on which graphs it holds (noise sites per graph), so shots/s of different job sizes
+            # are not directly comparable; the bytes the sweeps of ALL ranks moved per second are
+            "whole_job": {"states_swept_per_step": job["states_swept_per_step"],
+                          "algorithmic_sweep_GB_per_step": job["sweep_bytes_per_step"] / 1e9,
+                          "aggregate_algorithmic_GBps": job["sweep_bytes_per_step"] / (ms / args.steps * 1e-3) / 1e9,
+                          "per_gpu_algorithmic_GBps": job["sweep_bytes_per_step"] / (ms / args.steps * 1e-3) / 1e9 / world},
             "partition_check": partition_check, "witness_check": witness_check,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "other_configs": other,
             "gpu_launches": int(agg["sweep_launches"] + agg["aux_launches"]),
