@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 2
+#define QCD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define QCD_API __attribute__((visibility("default")))
@@ -122,6 +122,10 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the
  *                           parents of the leaves; every draw stays keyed by the trajectory's own (circuit, shot), so
  *                           results are bit-identical with the option off
+ *   "dm_on_chip" 0/1 (1)    density-matrix mode, n <= 9 qubits (complex64) / n <= 8 (complex128): the gate list is interpreted
+ *                           with the whole density matrix in the shared memory of a thread-block cluster (no host
+ *                           lowering); 0 = always lower to state sweeps
+ *   "dm_max_clusters" (0)   cap on concurrently resident clusters of that kernel (0 = what the device holds)
  *   "hist_row0" (0)         qcd_run_sv_trajectories: the uploaded circuit that row 0 of `hist` stands for.  A rank that
  *                           holds the whole batch's programs and runs one slice of circuits at a time (self-scheduled
  *                           partition, qcdenoise_b200/distributed.py WorkQueue) passes a buffer with rows for that slice
@@ -196,6 +200,28 @@ QCD_API int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begi
 QCD_API int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end,
                                             int n_settings, const uint8_t* setting_qubits,
                                             const double* setting_superops, void* probs_out, void* stream);
+
+/* Replaces: one simulation + one sampled measurement setting PER ELEMENT of the full stabilizer group of a graph state
+ * (the "Jung" stabilizers of circuit_constructors.py:554-590; JungStabilizer, stabilizers.py:171-172, fed to
+ * StabilizerSampler.sample, stabilizers.py:183-215).  In density-matrix mode the exact <S> = Tr(rho S) of ALL 2^n
+ * elements is read off the circuit's density matrix in one pass: S = (+-) X^sx Z^sz has one non-zero per column, so
+ * every entry of rho belongs to exactly one element (sx = row ^ column).
+ *   adjacency   [host] [n_qubits] uint32: bit j of row k set <=> edge (k, j); generators g_k = X_k prod_j Z_j;
+ *   expvals_out [dev]  [count][2^n] double, index = the element's x mask sx (element = product of g_k over the bits of
+ *               sx), signed: the ideal graph state gives +1 everywhere; index 0 is the identity (= Tr rho).
+ * Graph-state fidelity <G|rho|G> = mean of a row.  Complete on return (synchronises `stream`). */
+QCD_API int qcd_run_density_matrix_group(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end,
+                                         const uint32_t* adjacency, double* expvals_out, void* stream);
+
+/* Replaces: the enumeration of the full signed stabilizer group through sympy Pauli algebra (sigma_prod,
+ * stabilizers.py:39-79, driven by circuit_constructors.py:554-590) by bit arithmetic on the device: element `sel` in
+ * [begin, end) is the product of the generators j whose bit (n_gens - 1 - j) of sel is set (the reference's
+ * np.binary_repr order), generators and elements as (x, z) masks (bit q: X on qubit q / Z on qubit q / both: Y).
+ *   gen_x, gen_z [host] [n_gens] uint32;  x_out, z_out [dev] [end - begin] uint32;
+ *   sign_out [dev] [end - begin] uint8: 0 = '+', 1 = '-' (sign of the LABEL, Y = i X Z), 2 = the product is not
+ *   Hermitian (the generators do not commute).  Complete on return (synchronises `stream`). */
+QCD_API int qcd_stabilizer_group(qcd_ctx* ctx, const uint32_t* gen_x, const uint32_t* gen_z, int n_gens, uint64_t begin,
+                                 uint64_t end, uint32_t* x_out, uint32_t* z_out, uint8_t* sign_out, void* stream);
 
 /* Classical readout error applied to probability vectors, in place: probs [dev] [n_vectors][2^n] (float/double by
  * precision), readout [host] [n_vectors][n][2][2].  Replaces Aer's ReadoutError on `measure` in distribution. */
@@ -274,6 +300,14 @@ QCD_API int qcd_adjacency_tensors(const qcd_op* ops, const uint32_t* op_offsets,
  * Used by the CPU tests to check the host logic against the oracle. */
 QCD_API int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
                             int mode, int precision, int tile_bits, char* buf, size_t cap, size_t* needed);
+
+/* Host-only introspection (no GPU needed): the pass schedule of ONE circuit for the on-chip density-matrix interpreter
+ * (option "dm_on_chip").  Pass p acts inside the qubit pair pass_qubits[2 p], pass_qubits[2 p + 1] (0xFF = one qubit
+ * only) and executes the next pass_n_ops[p] entries of `order` (indices into ops[], identity gates left out).  Returns
+ * QCD_E_NOMEM when a capacity is too small; the sizes needed are always stored in *n_passes / *n_order. */
+QCD_API int qcd_debug_dm_schedule(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
+                                  uint8_t* pass_qubits, uint32_t* pass_n_ops, size_t pass_cap, uint32_t* order,
+                                  size_t order_cap, size_t* n_passes, size_t* n_order);
 
 #ifdef __cplusplus
 }

@@ -247,3 +247,48 @@ def bisep_witnesses(meas, edges):
         sigma = math.sqrt(meas[gi][1] ** 2 + meas[gj][1] ** 2)
         res[idx] = witness_output(W_ij=(e0, e1), value=val, variance=sigma)
     return res
+
+
+# ------------------------------------------------------------------ full-group ("noise-robust") witnesses
+# The reference leaves these levels unimplemented ("WIP", circuit_constructors.py:677-680; GenuineWitness.estimate
+# asserts noise_robust == 0, witnesses.py:114-116) -- PARITY UNPINNED: there is no reference output to hold them to.
+# They are restated here from the paper the legacy docstrings cite (Toth & Guehne, PRA 72, 022340) with DENSE matrices,
+# independently of the product's bit arithmetic.
+_PAULI = {"I": np.eye(2, dtype=complex), "X": np.array([[0, 1], [1, 0]], dtype=complex),
+          "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1.0 + 0j, -1.0])}
+
+
+def pauli_matrix(label):
+    """Dense matrix of a Pauli string; character j acts on qubit n-1-j (the reference's reversed labels)."""
+    m = np.ones((1, 1), dtype=complex)
+    for ch in label:
+        m = np.kron(m, _PAULI[ch])
+    return m
+
+
+def group_expectations_dense(rho, signed_group):
+    """{label: Tr(rho * sign * P)} for the signed elements ('+XZII', '-ZYXY', ...), rho [2^n, 2^n]."""
+    return OrderedDict((s[1:], float(np.real(np.trace(rho @ pauli_matrix(s[1:]))) * (1 if s[0] == "+" else -1)))
+                       for s in signed_group)
+
+
+def graph_state_projector(signed_group, n):
+    return sum((1 if s[0] == "+" else -1) * pauli_matrix(s[1:]) for s in signed_group) / 2 ** n
+
+
+def projector_witness_dense(rho, signed_group, n):
+    """<W> for W = 1/2 - |G><G|."""
+    return float(np.real(np.trace(rho @ (np.eye(2 ** n) / 2 - graph_state_projector(signed_group, n)))))
+
+
+def two_colour_witness_dense(rho, generators, colours, n):
+    """<W> for W = 3 - 2 [prod_{k in A} (1 + g_k)/2 + prod_{k in B} (1 + g_k)/2]; generators[k] belongs to vertex k,
+    colours[k] in {0, 1}."""
+    w = 3 * np.eye(2 ** n, dtype=complex)
+    for c in (0, 1):
+        p = np.eye(2 ** n, dtype=complex)
+        for k, g in enumerate(generators):
+            if colours[k] == c:
+                p = p @ (np.eye(2 ** n) + pauli_matrix(g)) / 2
+        w = w - 2 * p
+    return float(np.real(np.trace(rho @ w)))

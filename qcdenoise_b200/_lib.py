@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libqcdsim.so")
 
-QCD_ABI_VERSION = 2
+QCD_ABI_VERSION = 3
 QCD_OK, QCD_E_INVALID, QCD_E_CUDA, QCD_E_NOMEM, QCD_E_UNSUPPORTED, QCD_E_STATE = range(6)
 QCD_RUN_NO_DEDUP = 1
 _ERR_NAMES = {1: "QCD_E_INVALID", 2: "QCD_E_CUDA", 3: "QCD_E_NOMEM", 4: "QCD_E_UNSUPPORTED", 5: "QCD_E_STATE"}
@@ -66,12 +66,16 @@ _PROTOS = {
     "qcd_parity_outcomes": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_uint64, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "qcd_parity_probs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int,
                                         ctypes.c_int, _P, _P]),
+    "qcd_run_density_matrix_group": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P]),
+    "qcd_stabilizer_group": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P]),
     "qcd_device_gate_superops_1q": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P, _P, _P]),
     "qcd_sample_graph_states": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int, _P, _P, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                                ctypes.c_uint64, _P, ctypes.c_uint32, _P]),
     "qcd_adjacency_tensors": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, _P]),
+    "qcd_debug_dm_schedule": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, _P, _P, ctypes.c_size_t,
+                                             _P, ctypes.c_size_t, _P, _P]),
     "qcd_debug_schedule_json": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t,
                                                ctypes.POINTER(ctypes.c_size_t)]),

@@ -10,10 +10,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqcdsim.so")
-SOURCES = ["engine.cu", "sweep.cu", "sweep_direct.cu", "kernels.cu", "lower.cpp", "device_noise.cpp", "host_batch.cpp"]
-HEADERS = ["kernels.cuh", "direct_ops.cuh", "program.h", "lower.h", "device_noise.h", os.path.join("..", "..", "include", "qcdsim.h")]
+SOURCES = ["engine.cu", "sweep.cu", "sweep_direct.cu", "kernels.cu", "stab_group.cu", "dm_cluster.cu", "lower.cpp", "device_noise.cpp", "host_batch.cpp"]
+HEADERS = ["kernels.cuh", "dm_cluster.h", "direct_ops.cuh", "program.h", "lower.h", "device_noise.h", os.path.join("..", "..", "include", "qcdsim.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall"]     # IEEE arithmetic: no --use_fast_math
 
 
 def _nvcc():
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src + ".o")
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         cmd += os.environ.get("QCD_NVCC_EXTRA", "").split()       # tuning experiments only (e.g. -DDIRECT_MINB=3)
         if src.endswith(".cpp"):
             cmd.insert(1, "-x")

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/qcdsim.h"
+#include "dm_cluster.h"
 #include "kernels.cuh"
 #include "device_noise.h"
 #include "lower.h"
@@ -152,6 +153,9 @@ struct qcd_ctx {
     uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
     uint32_t hist_row0 = 0;      // uploaded circuit that row 0 of the caller's histogram buffer stands for
+    bool dm_on_chip = true;      // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
+                                 // there (dm_cluster.cu) instead of lowering it to sweeps
+    int dm_max_clusters = 0;     // 0 = as many clusters as are resident at once
     size_t cached_budget = 0;    // last usable_budget() answer and how many runs have reused it
     int budget_age = 0;
     // programs (host copy of the IR; compiled lazily per (mode, precision))
@@ -163,6 +167,12 @@ struct qcd_ctx {
     // circuit's channels into a small private buffer right before compiling it (no expanded copy of the batch)
     bool device_noise = false;
     std::vector<double> qubit_t1_t2, op_gate_props;
+    // on-chip interpreter: explicit ops + pass schedule of the batch on the device (built at the first run)
+    struct InterpProg {
+        bool ready = false;
+        DevBuf ops, params, sched, passes, pass_off;
+        size_t n_passes = 0;
+    } interp;
     DevProg prog[2][2];  // [mode][precision == 64]
     int prog_tile_bits[2][2] = {{0, 0}, {0, 0}};
     // arenas / scratch
@@ -1028,13 +1038,164 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
 }
 
 // ============================================================================================ density matrix
+
+// ---------------------------------------------------------------------------------------------- on-chip density matrices
+bool interp_eligible(const qcd_ctx* ctx, int precision) {
+    return ctx->dm_on_chip && dm_interp_cluster_size(ctx->n_qubits, precision) > 0;
+}
+
+// Explicit ops (device-noise batches: the channels written natively, circuit block by circuit block) + the pass schedule
+// of every circuit, built on host threads and copied to the device.  O(ops) per circuit, no matrix arithmetic.
+int prepare_interp(qcd_ctx* ctx) {
+    if (ctx->interp.ready) return QCD_OK;
+    const double t_begin = Trace::now();
+    const int nc = ctx->n_circuits, n = ctx->n_qubits;
+    int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    n_thr = std::max(1, std::min(n_thr, nc / 64));
+    struct Part {
+        std::vector<qcd_op> ops;
+        std::vector<double> par;
+        std::vector<DmPass> passes;
+        std::vector<uint32_t> sched, pass_cnt;
+        int rc = QCD_OK;
+        std::string err;
+    };
+    std::vector<Part> parts(n_thr);
+    const bool expand = ctx->device_noise;
+    auto build = [&](int t) {
+        Part& Q = parts[t];
+        const int c_lo = (int)((long long)nc * t / n_thr), c_hi = (int)((long long)nc * (t + 1) / n_thr);
+        std::string err;
+        if (expand) {
+            std::vector<uint32_t> cnt;
+            Q.rc = expand_device_noise(ctx->ops.data(), ctx->offsets.data(), ctx->params.data(), ctx->params.size(), c_lo, c_hi,
+                                       n, ctx->qubit_t1_t2.data(), ctx->op_gate_props.data(), Q.ops, cnt, Q.par, err);
+            if (Q.rc != QCD_OK) { Q.err = err; return; }
+            uint32_t base = 0;
+            for (int c = c_lo; c < c_hi; c++) {
+                const size_t p0 = Q.passes.size();
+                Q.rc = dm_interp_schedule(Q.ops.data() + base, cnt[c - c_lo], base, Q.par.data(), Q.par.size(), n, Q.passes,
+                                          Q.sched, err);
+                if (Q.rc != QCD_OK) { Q.err = "circuit " + std::to_string(c) + ": " + err; return; }
+                Q.pass_cnt.push_back((uint32_t)(Q.passes.size() - p0));
+                base += cnt[c - c_lo];
+            }
+        } else {
+            for (int c = c_lo; c < c_hi; c++) {
+                const uint32_t b = ctx->offsets[c], e = ctx->offsets[c + 1];
+                const size_t p0 = Q.passes.size();
+                Q.rc = dm_interp_schedule(ctx->ops.data() + b, e - b, b, ctx->params.data(), ctx->params.size(), n, Q.passes,
+                                          Q.sched, err);
+                if (Q.rc != QCD_OK) { Q.err = "circuit " + std::to_string(c) + ": " + err; return; }
+                Q.pass_cnt.push_back((uint32_t)(Q.passes.size() - p0));
+            }
+        }
+    };
+    auto run_all = [&](auto&& fn) {
+        if (n_thr == 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; t++) pool.emplace_back(fn, t);
+        for (std::thread& th : pool) th.join();
+    };
+    run_all(build);
+    for (int t = 0; t < n_thr; t++)
+        if (parts[t].rc != QCD_OK) return fail(ctx, parts[t].rc, parts[t].err);
+    std::vector<size_t> ops_base(n_thr + 1, 0), par_base(n_thr + 1, 0), sched_base(n_thr + 1, 0), pass_base(n_thr + 1, 0);
+    for (int t = 0; t < n_thr; t++) {
+        ops_base[t + 1] = ops_base[t] + parts[t].ops.size();
+        par_base[t + 1] = par_base[t] + parts[t].par.size();
+        sched_base[t + 1] = sched_base[t] + parts[t].sched.size();
+        pass_base[t + 1] = pass_base[t] + parts[t].passes.size();
+    }
+    if (ops_base[n_thr] > 0xffffffffull || par_base[n_thr] > 0xffffffffull || sched_base[n_thr] > 0xffffffffull)
+        return fail(ctx, QCD_E_UNSUPPORTED, "batch exceeds 2^32 ops / parameters: split the upload");
+    std::vector<uint32_t> pass_off;
+    pass_off.reserve((size_t)nc + 1);
+    pass_off.push_back(0);
+    for (int t = 0; t < n_thr; t++)
+        for (uint32_t k : parts[t].pass_cnt) pass_off.push_back(pass_off.back() + k);
+    qcd_ctx::InterpProg& I = ctx->interp;
+    CU(cudaDeviceSynchronize());      // kernels of an earlier run may still read the previous batch's buffers
+    if (expand) {
+        CU(I.ops.ensure(std::max<size_t>(ops_base[n_thr], 1) * sizeof(qcd_op)));
+        CU(I.params.ensure(std::max<size_t>(par_base[n_thr], 1) * sizeof(double)));
+    } else {
+        int rc;
+        if ((rc = upload_vec(ctx, I.ops, ctx->ops))) return rc;
+        if ((rc = upload_vec(ctx, I.params, ctx->params))) return rc;
+    }
+    CU(I.sched.ensure(std::max<size_t>(sched_base[n_thr], 1) * sizeof(uint32_t)));
+    CU(I.passes.ensure(std::max<size_t>(pass_base[n_thr], 1) * sizeof(DmPass)));
+    std::vector<cudaError_t> cp_rc(n_thr, cudaSuccess);
+    auto fix_and_copy = [&](int t) {     // re-base the block's offsets, then copy it from its own host thread
+        Part& Q = parts[t];
+        cudaSetDevice(ctx->device);
+        auto cp = [&](void* dst, const void* src, size_t bytes) {
+            if (bytes && cp_rc[t] == cudaSuccess) cp_rc[t] = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        if (expand) {
+            for (qcd_op& o : Q.ops) o.param_off += (uint32_t)par_base[t];
+            for (uint32_t& s : Q.sched) s += (uint32_t)ops_base[t];
+            cp(I.ops.as<qcd_op>() + ops_base[t], Q.ops.data(), Q.ops.size() * sizeof(qcd_op));
+            cp(I.params.as<double>() + par_base[t], Q.par.data(), Q.par.size() * sizeof(double));
+        }
+        for (DmPass& p : Q.passes) p.first += (uint32_t)sched_base[t];
+        cp(I.sched.as<uint32_t>() + sched_base[t], Q.sched.data(), Q.sched.size() * sizeof(uint32_t));
+        cp(I.passes.as<DmPass>() + pass_base[t], Q.passes.data(), Q.passes.size() * sizeof(DmPass));
+    };
+    run_all(fix_and_copy);
+    for (cudaError_t ce : cp_rc)
+        if (ce != cudaSuccess) return fail(ctx, QCD_E_CUDA, std::string("interpreter program upload: ") + cudaGetErrorString(ce));
+    int rc;
+    if ((rc = upload_vec(ctx, I.pass_off, pass_off))) return rc;
+    I.n_passes = pass_base[n_thr];
+    I.ready = true;
+    if (g_trace.on)
+        fprintf(stderr, "[qcd] on-chip DM program: %d circuits, %zu passes, %zu ops, %.2f ms on %d host threads\n", nc,
+                I.n_passes, expand ? ops_base[n_thr] : ctx->ops.size(), 1e3 * (Trace::now() - t_begin), n_thr);
+    return QCD_OK;
+}
+
+template <typename T>
+int launch_interp(qcd_ctx* ctx, int precision, int c0, int c1, void* probs, void* rho, uint64_t slot_stride, cudaStream_t st) {
+    const qcd_ctx::InterpProg& I = ctx->interp;
+    DmInterpArgs a;
+    a.ops = I.ops.as<qcd_op>();
+    a.params = I.params.as<double>();
+    a.sched = I.sched.as<uint32_t>();
+    a.passes = I.passes.as<DmPass>();
+    a.pass_off = I.pass_off.as<uint32_t>();
+    a.n_qubits = ctx->n_qubits;
+    a.n_circuits = c1 - c0;
+    a.circuit0 = c0;
+    a.local_bits = std::min(2 * ctx->n_qubits, precision == 64 ? 13 : 14);
+    a.probs = probs;
+    a.rho_out = rho;
+    a.slot_stride = slot_stride;
+    CU(launch_dm_interp<T>(a, dm_interp_cluster_size(ctx->n_qubits, precision), ctx->dm_max_clusters, st));
+    ctx->stats.aux_launches++;
+    return QCD_OK;
+}
+
 template <typename T>
 int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStream_t st, int n_settings = 0,
-           const uint8_t* setting_qubits = nullptr, const double* setting_superops = nullptr) {
+           const uint8_t* setting_qubits = nullptr, const double* setting_superops = nullptr,
+           const uint32_t* group_adj = nullptr /*host [n]: read <S> of the whole stabilizer group into probs_out (double)*/) {
     typedef typename Cplx<T>::type C;
-    const Program& P = dp->P;
-    const int nb = P.n_bits, n = P.n_qubits;
-    const int k = std::min(P.k_max, nb);
+    // dp == nullptr: the circuits are interpreted on chip (dm_cluster.cu); the state arena is only needed when a
+    // read-out kernel wants the whole density matrix (settings, stabilizer group)
+    const bool on_chip = dp == nullptr;
+    const int prec = sizeof(T) == 8 ? 64 : 32;
+    if (on_chip && n_settings == 0 && !group_adj) {
+        int rc = launch_interp<T>(ctx, prec, cb, ce, probs_out, nullptr, 0, st);
+        if (rc) return rc;
+        ctx->stats.leaves += ce - cb;
+        return QCD_OK;
+    }
+    static const Program no_program;
+    const Program& P = on_chip ? no_program : dp->P;
+    const int nb = on_chip ? 2 * ctx->n_qubits : P.n_bits, n = on_chip ? ctx->n_qubits : P.n_qubits;
+    const int k = std::min(on_chip ? 13 : P.k_max, nb);
     const uint32_t tiles_log2 = (uint32_t)(nb - k);
     const uint32_t tiles = 1u << tiles_log2;
     const uint64_t slot_stride = (uint64_t)1 << nb;
@@ -1045,10 +1206,15 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
     if (n_slots < 1) return fail(ctx, QCD_E_NOMEM, "memory budget too small for one density matrix");
     if (n_slots * tiles > 0x7fffffffull) n_slots = 0x7fffffffull / tiles;
     CU(ctx->states.ensure(n_slots * slot_bytes));
-    DevProgram<T> prog = dev_view<T>(*dp);
+    DevProgram<T> prog;
+    if (!on_chip) prog = dev_view<T>(*dp);
     T* out = reinterpret_cast<T*>(probs_out);
     for (int c0 = cb; c0 < ce; c0 += (int)n_slots) {
         const int c1 = (int)std::min<uint64_t>((uint64_t)ce, (uint64_t)c0 + n_slots);
+        if (on_chip) {
+            int rc = launch_interp<T>(ctx, prec, c0, c1, nullptr, ctx->states.p, slot_stride, st);
+            if (rc) return rc;
+        } else {
         // Register-only path: every pass of every circuit of the chunk becomes a launch level of its own on the direct
         // kernel (more state passes than the tiled kernel's one-per-sweep, each at streaming speed).
         bool all_direct = ctx->use_direct && nb >= 13;
@@ -1166,11 +1332,22 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
             ctx->stats.node_sweeps += cnt;
         }
         }
+        }   // lowered route
         std::vector<uint32_t> slots(c1 - c0);
         for (int i = 0; i < c1 - c0; i++) slots[i] = (uint32_t)i;
         CU(ctx->slots.ensure(slots.size() * 4));
         CU(cudaMemcpyAsync(ctx->slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
-        if (n_settings > 0) {
+        if (group_adj) {
+            // <S> of all 2^n elements of the graph state's stabilizer group, one pass over each density matrix
+            const uint32_t chunks = group_expvals_chunks(n);
+            const size_t part_bytes = (size_t)(c1 - c0) * chunks * ((size_t)1 << n) * sizeof(double);
+            CU(ctx->scratch.ensure(part_bytes + 32 * sizeof(uint32_t)));
+            uint32_t* adj_dev = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scratch.p) + part_bytes);
+            CU(cudaMemcpyAsync(adj_dev, group_adj, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            launch_group_expvals<T>(ctx->states.p, slot_stride, (uint32_t)(c1 - c0), n, adj_dev, ctx->scratch.as<double>(),
+                                    reinterpret_cast<double*>(probs_out) + ((size_t)(c0 - cb) << n), st);
+            ctx->stats.aux_launches++;
+        } else if (n_settings > 0) {
             // measurement settings of this batch's density matrices (slot i holds circuit c0 + i)
             const size_t cnt = (size_t)(c1 - c0) * n_settings;
             CU(ctx->scratch.ensure(cnt * (16 * sizeof(double2) + 1)));
@@ -1263,6 +1440,8 @@ void qcd_destroy(qcd_ctx* ctx) {
                       &ctx->probs4, &ctx->table, &ctx->offs, &ctx->children, &ctx->counter, &ctx->bsum, &ctx->flip,
                       &ctx->masks, &ctx->scratch, &ctx->slots};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf* b : {&ctx->interp.ops, &ctx->interp.params, &ctx->interp.sched, &ctx->interp.passes, &ctx->interp.pass_off})
+        b->release();
     for (DevBuf& b : ctx->level_nodes) b.release();
     for (DevBuf& b : ctx->level_shots) b.release();
     for (PinBuf& b : ctx->host_nodes) b.release();
@@ -1291,6 +1470,8 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     else if (k == "no_slots") ctx->no_slots = value != 0;
     else if (k == "share_prefix") ctx->share_prefix = value != 0;
     else if (k == "hist_row0") ctx->hist_row0 = (uint32_t)value;
+    else if (k == "dm_on_chip") ctx->dm_on_chip = value != 0;
+    else if (k == "dm_max_clusters") ctx->dm_max_clusters = (int)value;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }
@@ -1447,6 +1628,7 @@ int qcd_upload_programs(qcd_ctx* ctx, const qcd_op* ops, const uint32_t* op_offs
     ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
     ctx->params.assign(params, params + n_params);
     ctx->device_noise = false;
+    ctx->interp.ready = false;
     ctx->qubit_t1_t2.clear();
     ctx->op_gate_props.clear();
     adopt_programs(ctx, n_circuits, n_qubits);
@@ -1476,6 +1658,7 @@ int qcd_upload_device_noise_programs(qcd_ctx* ctx, const qcd_op* ops, const uint
     ctx->offsets.assign(op_offsets, op_offsets + n_circuits + 1);
     ctx->params.assign(params, params + n_params);
     ctx->device_noise = true;
+    ctx->interp.ready = false;
     ctx->qubit_t1_t2.assign(qubit_t1_t2, qubit_t1_t2 + (size_t)n_circuits * n_qubits * 2);
     ctx->op_gate_props.assign(op_gate_props, op_gate_props + (size_t)n_ops * 2);
     adopt_programs(ctx, n_circuits, n_qubits);
@@ -1610,7 +1793,7 @@ int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int c
     ctx->ev_used = 0;
     if (circuit_begin == circuit_end) return QCD_OK;
     DevProg* dp = nullptr;
-    int rc = get_program(ctx, MODE_DM, precision, &dp);
+    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == 64) return run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
@@ -1637,7 +1820,7 @@ int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_beg
     ctx->ev_used = 0;
     if (circuit_begin == circuit_end) return QCD_OK;
     DevProg* dp = nullptr;
-    int rc = get_program(ctx, MODE_DM, precision, &dp);
+    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // the per-batch host -> device copies of the setting tables read caller memory asynchronously: drain before returning
@@ -1647,6 +1830,58 @@ int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_beg
         rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));
+    return QCD_OK;
+}
+
+int qcd_run_density_matrix_group(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end,
+                                 const uint32_t* adjacency, double* expvals_out, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, QCD_E_INVALID, "precision must be 32 or 64");
+    if (ctx->n_circuits <= 0) return fail(ctx, QCD_E_STATE, "no programs uploaded (call qcd_upload_programs first)");
+    if (circuit_begin < 0 || circuit_begin > circuit_end || circuit_end > ctx->n_circuits)
+        return fail(ctx, QCD_E_INVALID, "circuit range outside [0, n_circuits]");
+    if (!adjacency || !expvals_out) return fail(ctx, QCD_E_INVALID, "NULL argument");
+    if (ctx->n_qubits > 15) return fail(ctx, QCD_E_UNSUPPORTED, "density-matrix mode supports at most 15 qubits");
+    for (int k = 0; k < ctx->n_qubits; k++) {
+        if (adjacency[k] >> ctx->n_qubits || (adjacency[k] >> k) & 1u)
+            return fail(ctx, QCD_E_INVALID, "adjacency row " + std::to_string(k) + " names a vertex >= n_qubits or itself");
+        for (int j = 0; j < ctx->n_qubits; j++)
+            if (((adjacency[k] >> j) & 1u) != ((adjacency[j] >> k) & 1u))
+                return fail(ctx, QCD_E_INVALID, "adjacency is not symmetric (the generators would not commute)");
+    }
+    cudaSetDevice(ctx->device);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->ev_used = 0;
+    if (circuit_begin == circuit_end) return QCD_OK;
+    DevProg* dp = nullptr;
+    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 64)
+        rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
+    else
+        rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));       // the adjacency rows were read from caller memory asynchronously
+    return QCD_OK;
+}
+
+int qcd_stabilizer_group(qcd_ctx* ctx, const uint32_t* gen_x, const uint32_t* gen_z, int n_gens, uint64_t begin,
+                         uint64_t end, uint32_t* x_out, uint32_t* z_out, uint8_t* sign_out, void* stream) {
+    if (!ctx) return QCD_E_INVALID;
+    if (!gen_x || !gen_z || !x_out || !z_out || !sign_out) return fail(ctx, QCD_E_INVALID, "NULL argument");
+    if (n_gens < 1 || n_gens > 32) return fail(ctx, QCD_E_INVALID, "n_gens must be in [1, 32]");
+    if (begin > end || end > ((uint64_t)1 << n_gens)) return fail(ctx, QCD_E_INVALID, "element range outside [0, 2^n_gens]");
+    if (begin == end) return QCD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(ctx->masks.ensure(64 * sizeof(uint32_t)));
+    uint32_t* g = ctx->masks.as<uint32_t>();
+    CU(cudaMemcpyAsync(g, gen_x, (size_t)n_gens * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g + 32, gen_z, (size_t)n_gens * 4, cudaMemcpyHostToDevice, st));
+    launch_stabilizer_group(g, g + 32, n_gens, begin, end - begin, x_out, z_out, sign_out, st);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));       // generator masks were read from caller memory asynchronously
     return QCD_OK;
 }
 
@@ -1766,6 +2001,32 @@ int qcd_parity_probs(qcd_ctx* ctx, int precision, const void* probs, int n_vecto
         launch_parity_probs<float>((const float*)probs, n_vectors, n_qubits, ctx->masks.as<uint32_t>(), n_masks,
                                    per_vector_masks, ctx->scratch.as<double>(), n_part, expvals, st);
     CU(cudaGetLastError());
+    return QCD_OK;
+}
+
+int qcd_debug_dm_schedule(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
+                          uint8_t* pass_qubits, uint32_t* pass_n_ops, size_t pass_cap, uint32_t* order, size_t order_cap,
+                          size_t* n_passes, size_t* n_order) {
+    if ((!ops && n_ops) || !n_passes || !n_order || n_qubits < 1 || n_qubits > 15) return QCD_E_INVALID;
+    std::vector<DmPass> passes;
+    std::vector<uint32_t> sched;
+    std::string err;
+    int rc = dm_interp_schedule(ops, n_ops, 0, params, n_params, n_qubits, passes, sched, err);
+    if (rc != QCD_OK) {
+        g_create_error = "qcd_debug_dm_schedule: " + err;
+        return rc;
+    }
+    *n_passes = passes.size();
+    *n_order = sched.size();
+    if (passes.size() > pass_cap || sched.size() > order_cap || (passes.size() && (!pass_qubits || !pass_n_ops)) ||
+        (sched.size() && !order))
+        return QCD_E_NOMEM;
+    for (size_t p = 0; p < passes.size(); p++) {
+        pass_qubits[2 * p] = passes[p].q0;
+        pass_qubits[2 * p + 1] = passes[p].q1;
+        pass_n_ops[p] = passes[p].n_ops;
+    }
+    std::copy(sched.begin(), sched.end(), order);
     return QCD_OK;
 }
 

@@ -183,4 +183,12 @@ template <typename T>
 void launch_parity_probs(const T* probs, uint32_t n_vec, int n, const uint32_t* masks, int n_masks, int per_vec,
                          double* partial, uint32_t n_part, double* expvals, cudaStream_t st);
 
+// ---- full stabilizer group (stab_group.cu)
+void launch_stabilizer_group(const uint32_t* gen_x, const uint32_t* gen_z, int n_gens, uint64_t begin, uint64_t count,
+                             uint32_t* x_out, uint32_t* z_out, uint8_t* sign_out, cudaStream_t st);
+uint32_t group_expvals_chunks(int n);    // column chunks per density matrix: partial holds [vec][chunks][2^n] doubles
+template <typename T>
+void launch_group_expvals(const void* states, uint64_t slot_stride, uint32_t n_vec, int n, const uint32_t* adj_dev,
+                          double* partial, double* out /*[vec][2^n], indexed by the element's x mask*/, cudaStream_t st);
+
 }  // namespace qcd

@@ -168,6 +168,40 @@ class Engine:
                                                                  _ptr(sop.view(np.float64)), _ptr(out), self._stream()))
         return out
 
+    def run_density_matrix_group(self, adjacency, precision=32, circuit_range=None):
+        """Exact <S> of ALL 2^n elements of a graph state's stabilizer group, read off each circuit's density matrix in
+        one pass (qcd_run_density_matrix_group).  adjacency: uint32 [n], bit j of row k = edge (k, j).
+        -> tensor [count, 2^n] float64 indexed by the element's x mask (element = product of the generators g_k over the
+        set bits); column 0 is the identity, the row mean is the fidelity with the ideal graph state."""
+        n, B = self.n_qubits, self.n_circuits
+        cb, ce = circuit_range if circuit_range is not None else (0, B)
+        adj = np.ascontiguousarray(adjacency, dtype=np.uint32)
+        if adj.shape != (n,):
+            raise ValueError(f"adjacency must hold {n} rows")
+        with torch.cuda.device(self.device):
+            out = torch.empty((ce - cb, 2 ** n), dtype=torch.float64, device=self.device)
+            self._check(self.lib.qcd_run_density_matrix_group(self._h, precision, cb, ce, _ptr(adj), _ptr(out),
+                                                              self._stream()))
+        return out
+
+    def stabilizer_group(self, gen_x, gen_z, begin=0, end=None):
+        """Elements [begin, end) of the signed stabilizer group generated by (gen_x[j], gen_z[j]), enumerated on the
+        device (qcd_stabilizer_group) -> (x uint32, z uint32, sign uint8) tensors; sign 0 = '+', 1 = '-'."""
+        gx = np.ascontiguousarray(gen_x, dtype=np.uint32)
+        gz = np.ascontiguousarray(gen_z, dtype=np.uint32)
+        if gx.ndim != 1 or gx.shape != gz.shape:
+            raise ValueError("gen_x and gen_z must be 1-d arrays of the same length")
+        end = 2 ** len(gx) if end is None else end
+        with torch.cuda.device(self.device):
+            x = torch.empty((max(end - begin, 0),), dtype=torch.int32, device=self.device)
+            z = torch.empty_like(x)
+            s = torch.empty((max(end - begin, 0),), dtype=torch.uint8, device=self.device)
+            self._check(self.lib.qcd_stabilizer_group(self._h, _ptr(gx), _ptr(gz), len(gx), begin, end, _ptr(x), _ptr(z),
+                                                      _ptr(s), self._stream()))
+        if bool((s == 2).any()):
+            raise ArithmeticError("non-Hermitian product in a stabilizer group (the generators do not commute)")
+        return x, z, s
+
     def apply_readout(self, probs, readout):
         n_vec, N = probs.shape
         n = N.bit_length() - 1
@@ -253,6 +287,30 @@ def debug_schedule(circuit, mode=0, precision=32, tile_bits=0):
         if rc:
             raise _lib.QcdError(rc, d.get("error", "schedule failed"))
         return d
+
+
+def debug_dm_schedule(circuit):
+    """Host-only: the pass schedule of the on-chip density-matrix interpreter for one circuit ->
+    [((q0, q1 or None), [op indices in execution order]), ...] (no GPU needed)."""
+    lib = _lib.load()
+    ops, offsets, params, n = encode_programs([circuit])
+    cap = max(len(ops), 1)
+    pq = np.zeros((cap, 2), dtype=np.uint8)
+    pn = np.zeros(cap, dtype=np.uint32)
+    order = np.zeros(cap, dtype=np.uint32)
+    n_p, n_o = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = lib.qcd_debug_dm_schedule(_ptr(ops) if len(ops) else None, len(ops), _ptr(params) if len(params) else None,
+                                   len(params), n, _ptr(pq), _ptr(pn), cap, _ptr(order), cap, ctypes.byref(n_p),
+                                   ctypes.byref(n_o))
+    if rc:
+        raise _lib.QcdError(rc, lib.qcd_last_error(None).decode())
+    out, pos = [], 0
+    for p in range(n_p.value):
+        k = int(pn[p])
+        out.append(((int(pq[p, 0]), None if pq[p, 1] == 0xFF else int(pq[p, 1])), [int(i) for i in order[pos:pos + k]]))
+        pos += k
+    assert pos == n_o.value
+    return out
 
 
 def expand_device_noise(enc, qubit_t1_t2, op_gate_props):

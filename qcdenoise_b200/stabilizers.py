@@ -12,7 +12,7 @@ from .ir import Circuit
 from .samplers import CircuitSampler, NoiseModel
 
 __all__ = ["TothStabilizer", "JungStabilizer", "StabilizerSampler", "StabilizerCircuit", "get_unique_operators",
-           "sigma_prod", "pauli_mask", "single_qubit_settings", "run_settings_batch"]
+           "sigma_prod", "pauli_mask", "single_qubit_settings", "run_settings_batch", "graph_adjacency_masks"]
 
 # single-qubit Pauli products: (a, b) -> (power of i, result) with a.b = i^power * result
 _IDX = {"I": 0, "X": 1, "Y": 2, "Z": 3}
@@ -116,17 +116,31 @@ class JungStabilizer(StabilizerCircuit):
     (circuit_constructors.py:554-590) as bit arithmetic on (x, z) masks: products of generators by symplectic
     composition with the phase tracked mod 4."""
 
-    def find_stabilizers(self, max_elements=None):
+    def generator_masks(self):
+        """(x, z) bit masks of the generators: bit q of x / z set <=> X / Z on qubit q (Y: both)."""
+        return [(sum(1 << q for q, ch in enumerate(g[::-1]) if ch in "XY"),
+                 sum(1 << q for q, ch in enumerate(g[::-1]) if ch in "ZY")) for g in self.generators]
+
+    def find_stabilizers(self, max_elements=None, engine=None):
+        """All 2^n signed elements, in the reference's order (element `sel` multiplies the generators picked by the
+        characters of np.binary_repr(sel, n)).  With `engine` the enumeration runs on the GPU (qcd_stabilizer_group) and
+        only the label strings are formed here."""
         n = self.n_qubits
-        gens = []
-        for g in self.generators:
-            x = sum(1 << q for q, ch in enumerate(g[::-1]) if ch in "XY")
-            z = sum(1 << q for q, ch in enumerate(g[::-1]) if ch in "ZY")
-            gens.append((x, z))
-        out = []
+        gens = self.generator_masks()
         total = 2 ** len(gens)
-        for sel in range(total if max_elements is None else min(total, max_elements)):
-            # the reference selects generator j by character j of np.binary_repr(sel, n) (MSB first)
+        count = total if max_elements is None else min(total, max_elements)
+        if engine is not None:
+            xs, zs, sg = engine.stabilizer_group([g[0] for g in gens], [g[1] for g in gens], 0, count)
+            xs = xs.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            zs = zs.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            q = np.arange(n - 1, -1, -1)
+            code = ((xs[:, None] >> q) & 1) | (((zs[:, None] >> q) & 1) << 1)          # [count, n], qubit n-1 first
+            letters = np.array(list("IXZY"))[code]
+            out = [("-" if s else "+") + "".join(row) for s, row in zip(sg.cpu().numpy(), letters)]
+            self.stabilizers = out
+            return deepcopy(out)
+        out = []
+        for sel in range(count):
             x = z = 0
             power = 0          # element = i^power * X^x Z^z
             for j, (gx, gz) in enumerate(gens):
@@ -144,6 +158,17 @@ class JungStabilizer(StabilizerCircuit):
             out.append(("+" if power == 0 else "-") + label)
         self.stabilizers = out
         return deepcopy(out)
+
+
+def graph_adjacency_masks(graph, n_qubits):
+    """uint32 [n]: bit j of row k set <=> edge (k, j) (either direction for a DiGraph) -- the form
+    qcd_run_density_matrix_group takes."""
+    adj = np.zeros(n_qubits, dtype=np.uint32)
+    for u, v in graph.edges():
+        if u != v:
+            adj[u] |= np.uint32(1 << v)
+            adj[v] |= np.uint32(1 << u)
+    return adj
 
 
 _SQ2 = 2 ** -0.5
