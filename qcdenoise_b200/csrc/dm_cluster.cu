@@ -35,10 +35,13 @@ namespace qcd {
 
 namespace {
 
+#ifndef DMI_F32_THREADS
+#define DMI_F32_THREADS 512
+#endif
 constexpr int IR_THREADS = 256;
 constexpr int IR_MAX_OPS = DMI_MAX_PASS_OPS;
 
-enum RecType : int { R_SKIP = 0, R_SUPER1, R_SUPER1_X, R_SUPER1_R, R_SUPER1_XR, R_CX, R_CZ, R_SWAP, R_U2, R_PAULI2, R_KRAUS2 };
+enum RecType : int { R_SKIP = 0, R_SUPER1, R_SUPER1_X, R_SUPER1_R, R_SUPER1_XR, R_CX, R_CZ, R_SWAP, R_U2, R_PAULI2, R_DEPOL2, R_KRAUS2 };
 
 template <typename T>
 struct OpRec {
@@ -46,6 +49,8 @@ struct OpRec {
     int slot;          // 1q: slot of the qubit; CX: slot of the control
     uint32_t param;    // KRAUS2Q: offset of its parameters
     int perm;          // 2q ops given as (q1, q0) of the pass: 1 = swap the two slot bits of every index
+    T aux[2];          // uniform two-qubit depolarizing: B' = aux[0] B + aux[1] tr(B) 1
+    T mr[16];          // real-valued superoperators, packed (4 x 128-bit shared loads instead of 16 x 64-bit)
     typename Cplx<T>::type m[16];   // superoperator / 4x4 unitary; PAULI2: W in .x
 };
 
@@ -117,11 +122,21 @@ struct Block {
     typename Cplx<T>::type b[D * D];   // b[r * D + c]
 };
 
-// 1q superoperator on slot S of the register block; REAL: all 16 entries are real (Hadamard, Pauli mixtures, damping)
+// 1q superoperator on slot S of the register block; REAL: all 16 entries are real (Hadamard, Pauli mixtures, damping) and
+// come packed in mr[]
 template <typename T, int NS, int S, bool XSHAPE, bool REAL>
-__device__ __forceinline__ void apply_super1(Block<T, NS>& B, const typename Cplx<T>::type* m) {
+__device__ __forceinline__ void apply_super1(Block<T, NS>& B, const typename Cplx<T>::type* m, const T* mr) {
     typedef typename Cplx<T>::type C;
     constexpr int D = 1 << NS, M = 1 << S;
+    C k[16];
+    if (REAL) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) k[i] = C{mr[i], (T)0};
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (!XSHAPE || i == 0 || i == 3 || i == 5 || i == 6 || i == 9 || i == 10 || i == 12 || i == 15) k[i] = m[i];
+    }
     auto mul = [](C a, C v) { return REAL ? C{a.x * v.x, a.x * v.y} : cmul(a, v); };
     auto fma = [](C& acc, C a, C v) {
         if (REAL) { acc.x += a.x * v.x; acc.y += a.x * v.y; }
@@ -136,15 +151,15 @@ __device__ __forceinline__ void apply_super1(Block<T, NS>& B, const typename Cpl
             const C v0 = B.b[ro * D + co], v1 = B.b[ro * D + (co | M)], v2 = B.b[(ro | M) * D + co], v3 = B.b[(ro | M) * D + (co | M)];
             C w0, w1, w2, w3;
             if (XSHAPE) {
-                w0 = mul(m[0], v0); fma(w0, m[3], v3);
-                w1 = mul(m[5], v1); fma(w1, m[6], v2);
-                w2 = mul(m[9], v1); fma(w2, m[10], v2);
-                w3 = mul(m[12], v0); fma(w3, m[15], v3);
+                w0 = mul(k[0], v0); fma(w0, k[3], v3);
+                w1 = mul(k[5], v1); fma(w1, k[6], v2);
+                w2 = mul(k[9], v1); fma(w2, k[10], v2);
+                w3 = mul(k[12], v0); fma(w3, k[15], v3);
             } else {
-                w0 = mul(m[0], v0); fma(w0, m[1], v1); fma(w0, m[2], v2); fma(w0, m[3], v3);
-                w1 = mul(m[4], v0); fma(w1, m[5], v1); fma(w1, m[6], v2); fma(w1, m[7], v3);
-                w2 = mul(m[8], v0); fma(w2, m[9], v1); fma(w2, m[10], v2); fma(w2, m[11], v3);
-                w3 = mul(m[12], v0); fma(w3, m[13], v1); fma(w3, m[14], v2); fma(w3, m[15], v3);
+                w0 = mul(k[0], v0); fma(w0, k[1], v1); fma(w0, k[2], v2); fma(w0, k[3], v3);
+                w1 = mul(k[4], v0); fma(w1, k[5], v1); fma(w1, k[6], v2); fma(w1, k[7], v3);
+                w2 = mul(k[8], v0); fma(w2, k[9], v1); fma(w2, k[10], v2); fma(w2, k[11], v3);
+                w3 = mul(k[12], v0); fma(w3, k[13], v1); fma(w3, k[14], v2); fma(w3, k[15], v3);
             }
             B.b[ro * D + co] = w0; B.b[ro * D + (co | M)] = w1; B.b[(ro | M) * D + co] = w2; B.b[(ro | M) * D + (co | M)] = w3;
         }
@@ -241,8 +256,25 @@ __device__ __forceinline__ void apply_pauli2(Block<T, 2>& B, const typename Cplx
 #pragma unroll
     for (int i = 0; i < 16; i++) B.b[i] = t[i];
 }
+// uniform two-qubit depolarizing (all 15 non-identity Paulis equally likely): sum_P P B P = 4 tr(B) 1
 template <typename T>
-__device__ __noinline__ void apply_kraus2(Block<T, 2>& B, const double* params, uint32_t off, int perm) {
+__device__ __forceinline__ void apply_depol2(Block<T, 2>& B, T c0, T c1) {
+    const T tx = c1 * (B.b[0].x + B.b[5].x + B.b[10].x + B.b[15].x), ty = c1 * (B.b[0].y + B.b[5].y + B.b[10].y + B.b[15].y);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        B.b[i].x *= c0;
+        B.b[i].y *= c0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        B.b[r * 5].x += tx;
+        B.b[r * 5].y += ty;
+    }
+}
+// by value: a reference handed to a non-inlined function would make the caller's register block addressable and send
+// EVERY access to it through local memory (measured: 10 % of all instructions were local loads / stores)
+template <typename T>
+__device__ __noinline__ Block<T, 2> apply_kraus2(Block<T, 2> B, const double* params, uint32_t off, int perm) {
     typedef typename Cplx<T>::type C;
     const int m = (int)params[off];
     C acc[16];
@@ -265,6 +297,7 @@ __device__ __noinline__ void apply_kraus2(Block<T, 2>& B, const double* params, 
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) B.b[i] = acc[i];
+    return B;
 }
 
 template <typename T, int NS>
@@ -272,16 +305,16 @@ __device__ __forceinline__ void apply_rec(Block<T, NS>& B, const OpRec<T>& rc, c
     const bool hi = NS == 2 && rc.slot == 1;
     switch (rc.type) {
         case R_SUPER1:
-            if (!hi) apply_super1<T, NS, 0, false, false>(B, rc.m); else apply_super1<T, NS, NS - 1, false, false>(B, rc.m);
+            if (!hi) apply_super1<T, NS, 0, false, false>(B, rc.m, rc.mr); else apply_super1<T, NS, NS - 1, false, false>(B, rc.m, rc.mr);
             break;
         case R_SUPER1_X:
-            if (!hi) apply_super1<T, NS, 0, true, false>(B, rc.m); else apply_super1<T, NS, NS - 1, true, false>(B, rc.m);
+            if (!hi) apply_super1<T, NS, 0, true, false>(B, rc.m, rc.mr); else apply_super1<T, NS, NS - 1, true, false>(B, rc.m, rc.mr);
             break;
         case R_SUPER1_R:
-            if (!hi) apply_super1<T, NS, 0, false, true>(B, rc.m); else apply_super1<T, NS, NS - 1, false, true>(B, rc.m);
+            if (!hi) apply_super1<T, NS, 0, false, true>(B, rc.m, rc.mr); else apply_super1<T, NS, NS - 1, false, true>(B, rc.m, rc.mr);
             break;
         case R_SUPER1_XR:
-            if (!hi) apply_super1<T, NS, 0, true, true>(B, rc.m); else apply_super1<T, NS, NS - 1, true, true>(B, rc.m);
+            if (!hi) apply_super1<T, NS, 0, true, true>(B, rc.m, rc.mr); else apply_super1<T, NS, NS - 1, true, true>(B, rc.m, rc.mr);
             break;
         default: break;
     }
@@ -292,50 +325,48 @@ __device__ __forceinline__ void apply_rec(Block<T, NS>& B, const OpRec<T>& rc, c
             case R_SWAP: apply_swap<T>(B); break;
             case R_U2: apply_u2<T>(B, rc.m); break;
             case R_PAULI2: apply_pauli2<T>(B, rc.m); break;
-            case R_KRAUS2: apply_kraus2<T>(B, params, rc.param, rc.perm); break;
+            case R_DEPOL2: apply_depol2<T>(B, rc.aux[0], rc.aux[1]); break;
+            case R_KRAUS2: B = apply_kraus2<T>(B, params, rc.param, rc.perm); break;
             default: break;
         }
     }
 }
 
-// deposit the bits of f into the positions that are NOT in sorted[0..NB)
-template <int NB>
-__device__ __forceinline__ uint32_t spread(uint32_t f, const int* sorted) {
-#pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const uint32_t lo = f & ((1u << sorted[i]) - 1u);
-        f = ((f >> sorted[i]) << (sorted[i] + 1)) | lo;
-    }
-    return f;
+// insert a zero bit at position p
+__device__ __forceinline__ uint32_t gap(uint32_t f, int p) { return ((f >> p) << (p + 1)) | (f & ((1u << p) - 1u)); }
+
+// Shared-memory index swizzle: a gate bit below the bank-index width pins an address bit for the whole warp and would
+// serialise the access 2-4x; XOR-ing the bank bits with the next higher index bits makes them vary with the lane again.
+template <typename C>
+__device__ __forceinline__ uint32_t swz(uint32_t e, uint32_t on) {
+    constexpr int W = sizeof(C) == 8 ? 4 : 3;     // 16 (8) elements of 8 (16) bytes span the 32 banks
+    return e ^ (((e >> W) & ((1u << W) - 1u)) & on);
 }
 
 template <typename T, int NS>
 __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps, const OpRec<T>* recs,
                                          typename Cplx<T>::type* const* part, typename Cplx<T>::type* loc, unsigned rank,
-                                         unsigned csize) {
+                                         unsigned csize, uint32_t swz_on) {
     typedef typename Cplx<T>::type C;
     constexpr int D = 1 << NS, NB = 2 * NS;
     const int n = a.n_qubits, LB = a.local_bits;
-    int pos[NB], sorted[NB];
-    pos[0] = ps.q0;
-    if (NS == 2) pos[1] = ps.q1;
-    for (int s = 0; s < NS; s++) pos[NS + s] = pos[s] + n;
-    for (int i = 0; i < NB; i++) sorted[i] = pos[i];
-    for (int i = 1; i < NB; i++)
-        for (int j = i; j > 0 && sorted[j - 1] > sorted[j]; j--) { const int t = sorted[j]; sorted[j] = sorted[j - 1]; sorted[j - 1] = t; }
-    uint32_t off[D * D];    // element offsets of the block: (r, c) -> bits
+    // gate bit positions: rows q0 (, q1), columns q0 + n (, q1 + n); s0 < s1 (< s2 < s3) the same, sorted -- scalars only,
+    // nothing here may end up in local memory
+    const int p0 = ps.q0, p1 = NS == 2 ? ps.q1 : 0;
+    const int lo = NS == 2 ? min(p0, p1) : p0, hi = NS == 2 ? max(p0, p1) : p0;
+    const int s0 = lo, s1 = NS == 2 ? hi : lo + n, s2 = lo + n, s3 = hi + n;      // rows < n <= columns: already sorted
+    uint32_t off[D * D];    // element offsets of the block: (r, c) -> bits (compile-time indexed after unrolling)
 #pragma unroll
     for (int r = 0; r < D; r++)
 #pragma unroll
         for (int c = 0; c < D; c++) {
-            uint32_t o = 0;
-#pragma unroll
-            for (int s = 0; s < NS; s++) o |= (((uint32_t)r >> s) & 1u) << pos[s] | (((uint32_t)c >> s) & 1u) << pos[NS + s];
+            uint32_t o = (((uint32_t)r & 1u) << p0) | (((uint32_t)c & 1u) << (p0 + n));
+            if (NS == 2) o |= (((uint32_t)r >> 1) << p1) | (((uint32_t)c >> 1) << (p1 + n));
             off[r * D + c] = o;
         }
     const int free_bits = 2 * n - NB;
     const uint32_t lmask = (1u << LB) - 1u;
-    const bool remote = csize > 1 && sorted[NB - 1] >= LB;      // a gate bit names the CTA: blocks span CTAs
+    const bool remote = csize > 1 && (NS == 2 ? s3 : s1) >= LB;      // a gate bit names the CTA: blocks span CTAs
     uint32_t f, f_end, f_step, f_or;
     if (!remote) {
         const int local_free = free_bits - (2 * n - LB);        // the CTA bits are the top free bits
@@ -344,28 +375,29 @@ __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps,
         f = rank * blockDim.x + threadIdx.x; f_end = 1u << free_bits; f_step = csize * blockDim.x; f_or = 0;
     }
     for (; f < f_end; f += f_step) {
-        const uint32_t base = spread<NB>(f | f_or, sorted);
+        uint32_t base = gap(gap(f | f_or, s0), s1);
+        if (NS == 2) base = gap(gap(base, s2), s3);
         Block<T, NS> B;
         if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) B.b[i] = loc[(base | off[i]) & lmask];
+            for (int i = 0; i < D * D; i++) B.b[i] = loc[swz<C>((base | off[i]) & lmask, swz_on)];
         } else {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; B.b[i] = part[e >> LB][e & lmask]; }
+            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; B.b[i] = part[e >> LB][swz<C>(e & lmask, swz_on)]; }
         }
         for (int k = 0; k < ps.n_ops; k++) apply_rec<T, NS>(B, recs[k], a.params);
         if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) loc[(base | off[i]) & lmask] = B.b[i];
+            for (int i = 0; i < D * D; i++) loc[swz<C>((base | off[i]) & lmask, swz_on)] = B.b[i];
         } else {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; part[e >> LB][e & lmask] = B.b[i]; }
+            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; part[e >> LB][swz<C>(e & lmask, swz_on)] = B.b[i]; }
         }
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(IR_THREADS) dm_interp_kernel(const DmInterpArgs a) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS, 1) dm_interp_kernel(const DmInterpArgs a) {
     typedef typename Cplx<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* loc = reinterpret_cast<C*>(smem_raw);
@@ -376,13 +408,14 @@ __global__ void __launch_bounds__(IR_THREADS) dm_interp_kernel(const DmInterpArg
     const unsigned cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
     const int n = a.n_qubits, LB = a.local_bits;
     const uint32_t loc_elems = 1u << LB, N = 1u << n;
+    const uint32_t swz_on = LB >= 8 ? ~0u : 0u;      // the swizzle reads index bits up to 7
     if (threadIdx.x < csize) part[threadIdx.x] = cluster.map_shared_rank(loc, threadIdx.x);
     auto barrier = [&]() {
         if (csize > 1) cluster.sync();
         else __syncthreads();
     };
     for (unsigned c = cluster_id; c < (unsigned)a.n_circuits; c += n_clusters) {
-        for (uint32_t i = threadIdx.x; i < loc_elems; i += blockDim.x) loc[i] = C{(T)((rank == 0 && i == 0) ? 1 : 0), (T)0};
+        for (uint32_t i = threadIdx.x; i < loc_elems; i += blockDim.x) loc[i] = C{(T)((rank == 0 && i == 0) ? 1 : 0), (T)0};   // swz(0) = 0
         barrier();
         const uint32_t p_begin = a.pass_off[a.circuit0 + c], p_end = a.pass_off[a.circuit0 + c + 1];
         for (uint32_t p = p_begin; p < p_end; p++) {
@@ -430,7 +463,14 @@ __global__ void __launch_bounds__(IR_THREADS) dm_interp_kernel(const DmInterpArg
                             if (ff == f) w += (__popc(zz & d) & 1) ? -p : p;
                         }
                     rc.m[e] = C{(T)w, (T)0};
-                    if (e == 0) rc.type = R_PAULI2;
+                    if (e == 0) {
+                        const double* pp = a.params + op.param_off;
+                        bool uniform = true;
+                        for (int q = 2; q < 16; q++) uniform = uniform && pp[q] == pp[1];
+                        rc.type = uniform ? R_DEPOL2 : R_PAULI2;
+                        rc.aux[0] = (T)(pp[0] - pp[1]);
+                        rc.aux[1] = (T)(4.0 * pp[1]);
+                    }
                 } else if (e == 0) {
                     rc.type = op.opcode == QCD_OP_CX ? R_CX : (op.opcode == QCD_OP_CZ ? R_CZ : (op.opcode == QCD_OP_SWAP ? R_SWAP : R_KRAUS2));
                     rc.slot = slot0;           // CX: slot of the control
@@ -475,12 +515,17 @@ __global__ void __launch_bounds__(IR_THREADS) dm_interp_kernel(const DmInterpArg
                     const bool one = ty == R_SUPER1 || ty == R_SUPER1_X;
                     const unsigned nz = __ballot_sync(0xffffu, one && rc.m[e].y != (T)0);
                     __syncwarp(0xffffu);
-                    if (one && nz == 0 && e == 0) rc.type = ty == R_SUPER1 ? R_SUPER1_R : R_SUPER1_XR;
+                    if (one && nz == 0) {
+                        rc.mr[e] = rc.m[e].x;
+                        if (e == 0) rc.type = ty == R_SUPER1 ? R_SUPER1_R : R_SUPER1_XR;
+                    }
                 }
             }
             __syncthreads();
-            if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs, part, loc, rank, csize);
-            else run_pass<T, 2>(a, ps, recs, part, loc, rank, csize);
+            // (a stage-specialised variant -- straight-line code per [supers][gate][Pauli] group, one shared-memory round
+            // trip per stage -- measured slower: unchanged at n = 7, 0.6x at n = 8, 0.45x at n = 9)
+            if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs, part, loc, rank, csize, swz_on);
+            else run_pass<T, 2>(a, ps, recs, part, loc, rank, csize, swz_on);
             barrier();
         }
         // ---- results: the diagonal (outcome probabilities) and / or the whole matrix
@@ -488,12 +533,12 @@ __global__ void __launch_bounds__(IR_THREADS) dm_interp_kernel(const DmInterpArg
             T* out = reinterpret_cast<T*>(a.probs) + (uint64_t)c * N;
             for (uint32_t x = threadIdx.x; x < N; x += blockDim.x) {
                 const uint32_t e = x + (x << n);
-                if ((e >> LB) == rank) out[x] = loc[e & (loc_elems - 1u)].x;
+                if ((e >> LB) == rank) out[x] = loc[swz<C>(e & (loc_elems - 1u), swz_on)].x;
             }
         }
         if (a.rho_out) {
             C* out = reinterpret_cast<C*>(a.rho_out) + (uint64_t)c * a.slot_stride + (uint64_t)rank * loc_elems;
-            for (uint32_t i = threadIdx.x; i < loc_elems; i += blockDim.x) out[i] = loc[i];
+            for (uint32_t i = threadIdx.x; i < loc_elems; i += blockDim.x) out[i] = loc[swz<C>(i, swz_on)];
         }
         __syncthreads();    // the next circuit's first barrier orders everything else
     }
@@ -635,7 +680,7 @@ cudaError_t launch_dm_interp(const DmInterpArgs& a, int cluster_size, int max_cl
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(IR_THREADS);
+    cfg.blockDim = dim3(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

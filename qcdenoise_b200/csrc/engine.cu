@@ -15,6 +15,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -172,6 +173,8 @@ struct qcd_ctx {
         bool ready = false;
         DevBuf ops, params, sched, passes, pass_off;
         size_t n_passes = 0;
+        cudaEvent_t done = nullptr;       // recorded after the last launch that reads these buffers
+        cudaStream_t copy = nullptr;      // non-blocking: uploads do not queue behind kernels on the legacy stream
     } interp;
     DevProg prog[2][2];  // [mode][precision == 64]
     int prog_tile_bits[2][2] = {{0, 0}, {0, 0}};
@@ -1115,14 +1118,21 @@ int prepare_interp(qcd_ctx* ctx) {
     for (int t = 0; t < n_thr; t++)
         for (uint32_t k : parts[t].pass_cnt) pass_off.push_back(pass_off.back() + k);
     qcd_ctx::InterpProg& I = ctx->interp;
-    CU(cudaDeviceSynchronize());      // kernels of an earlier run may still read the previous batch's buffers
+    // the previous batch's buffers may still be read by THIS context's last interpreter launch (and by nothing else):
+    // wait for that launch only -- another context's kernels keep running while this one prepares its next chunk
+    if (I.done) CU(cudaEventSynchronize(I.done));
+    if (!I.copy) CU(cudaStreamCreateWithFlags(&I.copy, cudaStreamNonBlocking));
+    auto upload_on_copy = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t ce = b.ensure(std::max<size_t>(bytes, 1));
+        if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, I.copy);
+        return ce;
+    };
     if (expand) {
         CU(I.ops.ensure(std::max<size_t>(ops_base[n_thr], 1) * sizeof(qcd_op)));
         CU(I.params.ensure(std::max<size_t>(par_base[n_thr], 1) * sizeof(double)));
     } else {
-        int rc;
-        if ((rc = upload_vec(ctx, I.ops, ctx->ops))) return rc;
-        if ((rc = upload_vec(ctx, I.params, ctx->params))) return rc;
+        CU(upload_on_copy(I.ops, ctx->ops.data(), ctx->ops.size() * sizeof(qcd_op)));
+        CU(upload_on_copy(I.params, ctx->params.data(), ctx->params.size() * sizeof(double)));
     }
     CU(I.sched.ensure(std::max<size_t>(sched_base[n_thr], 1) * sizeof(uint32_t)));
     CU(I.passes.ensure(std::max<size_t>(pass_base[n_thr], 1) * sizeof(DmPass)));
@@ -1131,7 +1141,7 @@ int prepare_interp(qcd_ctx* ctx) {
         Part& Q = parts[t];
         cudaSetDevice(ctx->device);
         auto cp = [&](void* dst, const void* src, size_t bytes) {
-            if (bytes && cp_rc[t] == cudaSuccess) cp_rc[t] = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+            if (bytes && cp_rc[t] == cudaSuccess) cp_rc[t] = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, I.copy);
         };
         if (expand) {
             for (qcd_op& o : Q.ops) o.param_off += (uint32_t)par_base[t];
@@ -1146,8 +1156,8 @@ int prepare_interp(qcd_ctx* ctx) {
     run_all(fix_and_copy);
     for (cudaError_t ce : cp_rc)
         if (ce != cudaSuccess) return fail(ctx, QCD_E_CUDA, std::string("interpreter program upload: ") + cudaGetErrorString(ce));
-    int rc;
-    if ((rc = upload_vec(ctx, I.pass_off, pass_off))) return rc;
+    CU(upload_on_copy(I.pass_off, pass_off.data(), pass_off.size() * sizeof(uint32_t)));
+    CU(cudaStreamSynchronize(I.copy));      // the host vectors go out of scope; the launch stream sees complete buffers
     I.n_passes = pass_base[n_thr];
     I.ready = true;
     if (g_trace.on)
@@ -1173,6 +1183,8 @@ int launch_interp(qcd_ctx* ctx, int precision, int c0, int c1, void* probs, void
     a.rho_out = rho;
     a.slot_stride = slot_stride;
     CU(launch_dm_interp<T>(a, dm_interp_cluster_size(ctx->n_qubits, precision), ctx->dm_max_clusters, st));
+    if (!ctx->interp.done) CU(cudaEventCreateWithFlags(&ctx->interp.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->interp.done, st));
     ctx->stats.aux_launches++;
     return QCD_OK;
 }
@@ -1426,6 +1438,7 @@ int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out) {
     qcd_ctx* c = new qcd_ctx();
     c->device = cuda_device;
     c->budget = mem_budget_bytes;
+    if (const char* v = getenv("QCD_DM_ON_CHIP")) c->dm_on_chip = atoi(v) != 0;     // A/B measurements of whole programs
     memset(&c->stats, 0, sizeof(c->stats));
     *out = c;
     return QCD_OK;
@@ -1442,6 +1455,8 @@ void qcd_destroy(qcd_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (DevBuf* b : {&ctx->interp.ops, &ctx->interp.params, &ctx->interp.sched, &ctx->interp.passes, &ctx->interp.pass_off})
         b->release();
+    if (ctx->interp.done) cudaEventDestroy(ctx->interp.done);
+    if (ctx->interp.copy) cudaStreamDestroy(ctx->interp.copy);
     for (DevBuf& b : ctx->level_nodes) b.release();
     for (DevBuf& b : ctx->level_shots) b.release();
     for (PinBuf& b : ctx->host_nodes) b.release();
