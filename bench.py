@@ -658,6 +658,8 @@ def main():
             other["C4_strong"] = strong
         if world == 1:
             for name, fn in (("C3", lambda: c3_density_matrix(qcd, torch, eng, peak)),
+                             # round 1's headline job (graph 0 alone, complex64), for continuity with BENCH_r01
+                             ("C4_graph0", lambda: c4_variant(torch, eng, works[0], peak, args.shots, 32, False)),
                              ("C4_complex128", lambda: c4_variant(torch, eng, works[0], peak, args.shots, 64, False)),
                              ("C4_literal", lambda: c4_variant(torch, eng, works[0], peak, 4000, 32, True)),
                              ("C2", lambda: c2_end_to_end(qcd, torch))):

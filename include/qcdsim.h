@@ -116,7 +116,7 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "max_slots" (0 = memory budget)   cap on resident states (exercises the depth-first schedule)
  *   "table_cap_log2" (22)   size of the trajectory-grouping table
  *   "use_direct" 0/1 (1)    register-only kernel for single-pass sweeps / density-matrix passes
- *   "nostore_max" (8)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
+ *   "nostore_max" (256)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
  *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements)
  *   "share_prefix" 0/1 (1)  consecutive circuits whose sweeps are identical up to the final one (a graph circuit and
  *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the
@@ -293,6 +293,14 @@ QCD_API int qcd_sample_graph_states(const uint8_t* lib_edges, const uint32_t* li
  * codes [QCD_OP_COUNT]; out [host] [n_circuits][planes][rows][cols] doubles, overwritten. */
 QCD_API int qcd_adjacency_tensors(const qcd_op* ops, const uint32_t* op_offsets, int n_circuits, const int32_t* codes,
                                   int planes, int rows, int cols, int directed, double* out);
+
+/* Host-only: the distinct (gate, qubits) calibration entries of every circuit of a batch -- what
+ * DeviceNoiseSampler.build_noise_model collects per circuit before drawing one (gate_error, gate_length) per entry
+ * (samplers.py:613-727).  Entries are sorted by (circuit, opcode << 16 | q0 << 8 | q1), i.e. the order of
+ * numpy.unique over those keys; op_entry_out[i] = entry of op i.
+ *   entry_key_out, entry_circuit_out [host] capacity op_offsets[n_circuits]; *n_entries = entries written. */
+QCD_API int qcd_gate_entries(const qcd_op* ops, const uint32_t* op_offsets, int n_circuits, uint32_t* entry_key_out,
+                             uint32_t* entry_circuit_out, uint32_t* op_entry_out, size_t* n_entries);
 
 /* Host-only introspection (no GPU needed): lower + schedule ONE circuit and write a JSON description of the sweep
  * program (tile bits, passes, fused matrices, sign terms, site groups) into buf.  mode: 0 = statevector

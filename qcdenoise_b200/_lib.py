@@ -74,6 +74,7 @@ _PROTOS = {
                                                ctypes.c_uint64, _P, ctypes.c_uint32, _P]),
     "qcd_adjacency_tensors": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, _P]),
+    "qcd_gate_entries": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, _P, _P, _P]),
     "qcd_debug_dm_schedule": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, _P, _P, ctypes.c_size_t,
                                              _P, ctypes.c_size_t, _P, _P]),
     "qcd_debug_schedule_json": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,

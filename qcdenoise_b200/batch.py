@@ -168,9 +168,23 @@ def draw_device_props(noise_specs, enc, rng):
     specs = noise_specs.specs
     B = len(offsets) - 1
     qubit = {nm: rng.uniform(0.0, float(top), size=(B, n)) for nm, top in specs["qubit"].items()}
-    circ = np.repeat(np.arange(B, dtype=np.int64), np.diff(offsets.astype(np.int64)))
-    key = (ops["opcode"].astype(np.int64) << 16) | (ops["q0"].astype(np.int64) << 8) | ops["q1"].astype(np.int64)
-    full, op_entry = np.unique((circ << 24) | key, return_inverse=True)
+    # distinct (circuit, gate, qubits), sorted as numpy.unique((circuit << 24) | opcode << 16 | q0 << 8 | q1) would list them,
+    # natively and per circuit (qcd_gate_entries): the sort over all ops of the batch was 14 of this stage's 20 ms
+    lib = _lib.load()
+    n_ops = len(ops)
+    ekey = np.empty(max(n_ops, 1), dtype=np.uint32)
+    ecirc = np.empty(max(n_ops, 1), dtype=np.uint32)
+    op_entry = np.empty(max(n_ops, 1), dtype=np.uint32)
+    n_ent = ctypes.c_size_t()
+    off32 = np.ascontiguousarray(offsets, dtype=np.uint32)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)       # noqa: E731
+    rc = lib.qcd_gate_entries(ptr(ops) if n_ops else None, ptr(off32), B, ptr(ekey), ptr(ecirc), ptr(op_entry),
+                              ctypes.byref(n_ent))
+    if rc:
+        raise _lib.QcdError(rc, "qcd_gate_entries: malformed gate lists")
+    U = n_ent.value
+    full = (ecirc[:U].astype(np.int64) << 24) | ekey[:U].astype(np.int64)
+    op_entry = op_entry[:n_ops]
     opcode = (full >> 16) & 0xFF
     gate = {}
     for nm in specs["cx"].keys():

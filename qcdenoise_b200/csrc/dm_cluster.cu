@@ -49,6 +49,7 @@ struct OpRec {
     int slot;          // 1q: slot of the qubit; CX: slot of the control
     uint32_t param;    // KRAUS2Q: offset of its parameters
     int perm;          // 2q ops given as (q1, q0) of the pass: 1 = swap the two slot bits of every index
+    int pass_q;        // pass of the current group the record belongs to
     T aux[2];          // uniform two-qubit depolarizing: B' = aux[0] B + aux[1] tr(B) 1
     T mr[16];          // real-valued superoperators, packed (4 x 128-bit shared loads instead of 16 x 64-bit)
     typename Cplx<T>::type m[16];   // superoperator / 4x4 unitary; PAULI2: W in .x
@@ -355,17 +356,20 @@ __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps,
     const int p0 = ps.q0, p1 = NS == 2 ? ps.q1 : 0;
     const int lo = NS == 2 ? min(p0, p1) : p0, hi = NS == 2 ? max(p0, p1) : p0;
     const int s0 = lo, s1 = NS == 2 ? hi : lo + n, s2 = lo + n, s3 = hi + n;      // rows < n <= columns: already sorted
-    uint32_t off[D * D];    // element offsets of the block: (r, c) -> bits (compile-time indexed after unrolling)
+    // element (r, c) of a block: swizzled local offset and CTA-rank bits, relative to the block base.  The swizzle is
+    // XOR-linear and base / offset bits are disjoint, so swz(base | off) = swz(base) ^ swz(off): one XOR per element
+    const uint32_t lmask = (1u << LB) - 1u;
+    uint32_t soff[D * D], roff[D * D];
 #pragma unroll
     for (int r = 0; r < D; r++)
 #pragma unroll
         for (int c = 0; c < D; c++) {
             uint32_t o = (((uint32_t)r & 1u) << p0) | (((uint32_t)c & 1u) << (p0 + n));
             if (NS == 2) o |= (((uint32_t)r >> 1) << p1) | (((uint32_t)c >> 1) << (p1 + n));
-            off[r * D + c] = o;
+            soff[r * D + c] = swz<C>(o & lmask, swz_on);
+            roff[r * D + c] = o >> LB;
         }
     const int free_bits = 2 * n - NB;
-    const uint32_t lmask = (1u << LB) - 1u;
     const bool remote = csize > 1 && (NS == 2 ? s3 : s1) >= LB;      // a gate bit names the CTA: blocks span CTAs
     uint32_t f, f_end, f_step, f_or;
     if (!remote) {
@@ -377,21 +381,22 @@ __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps,
     for (; f < f_end; f += f_step) {
         uint32_t base = gap(gap(f | f_or, s0), s1);
         if (NS == 2) base = gap(gap(base, s2), s3);
+        const uint32_t sb = swz<C>(base & lmask, swz_on), rb = base >> LB;
         Block<T, NS> B;
         if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) B.b[i] = loc[swz<C>((base | off[i]) & lmask, swz_on)];
+            for (int i = 0; i < D * D; i++) B.b[i] = loc[sb ^ soff[i]];
         } else {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; B.b[i] = part[e >> LB][swz<C>(e & lmask, swz_on)]; }
+            for (int i = 0; i < D * D; i++) B.b[i] = part[rb ^ roff[i]][sb ^ soff[i]];
         }
         for (int k = 0; k < ps.n_ops; k++) apply_rec<T, NS>(B, recs[k], a.params);
         if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) loc[swz<C>((base | off[i]) & lmask, swz_on)] = B.b[i];
+            for (int i = 0; i < D * D; i++) loc[sb ^ soff[i]] = B.b[i];
         } else {
 #pragma unroll
-            for (int i = 0; i < D * D; i++) { const uint32_t e = base | off[i]; part[e >> LB][swz<C>(e & lmask, swz_on)] = B.b[i]; }
+            for (int i = 0; i < D * D; i++) part[rb ^ roff[i]][sb ^ soff[i]] = B.b[i];
         }
     }
 }
@@ -402,7 +407,14 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* loc = reinterpret_cast<C*>(smem_raw);
     __shared__ C* part[16];
-    __shared__ OpRec<T> recs[IR_MAX_OPS];
+    // op records of a GROUP of consecutive passes (as many as fit): built once, then the group's passes run back to back.
+    // Building per pass left 15 of 16 warps waiting at a barrier for the sequential composition step (ncu: "barrier" was
+    // the top stall, 3.1 warps per issue slot).
+    constexpr int GP = 64;                    // passes per group
+    __shared__ DmPass spass[GP];
+    __shared__ uint32_t srec[GP + 1];         // first record of pass q of the group
+    __shared__ int s_gcount;
+    OpRec<T>* recs = reinterpret_cast<OpRec<T>*>(smem_raw + ((size_t)1 << a.local_bits) * sizeof(C));
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
     const unsigned cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
@@ -418,15 +430,36 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
         for (uint32_t i = threadIdx.x; i < loc_elems; i += blockDim.x) loc[i] = C{(T)((rank == 0 && i == 0) ? 1 : 0), (T)0};   // swz(0) = 0
         barrier();
         const uint32_t p_begin = a.pass_off[a.circuit0 + c], p_end = a.pass_off[a.circuit0 + c + 1];
-        for (uint32_t p = p_begin; p < p_end; p++) {
-            const DmPass ps = a.passes[p];
-            // ---- the pass's op records, once per CTA
-            for (int k0 = (threadIdx.x >> 5) * 2; k0 < ps.n_ops; k0 += (blockDim.x >> 5) * 2) {   // two ops per warp
+        for (uint32_t p = p_begin; p < p_end;) {
+            // ---- the group: passes p .. p + g_count whose records fit the buffer
+            if (threadIdx.x < GP && p + threadIdx.x < p_end) spass[threadIdx.x] = a.passes[p + threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tot = 0;
+                int g = 0;
+                const int lim = (int)min((uint32_t)GP, p_end - p);
+                while (g < lim && (g == 0 || tot + spass[g].n_ops <= (uint32_t)a.rec_cap)) {
+                    srec[g] = tot;
+                    tot += spass[g].n_ops;
+                    g++;
+                }
+                srec[g] = tot;
+                s_gcount = g;
+            }
+            __syncthreads();
+            const int g_count = s_gcount;
+            const int g_ops = (int)srec[g_count];
+            if (threadIdx.x < g_count)
+                for (uint32_t j = srec[threadIdx.x]; j < srec[threadIdx.x + 1]; j++) recs[j].pass_q = threadIdx.x;
+            __syncthreads();
+            // ---- phase A: one record per op, two ops per warp, all ops of the group
+            for (int k0 = (threadIdx.x >> 5) * 2; k0 < g_ops; k0 += (blockDim.x >> 5) * 2) {
                 const int k = k0 + ((threadIdx.x >> 4) & 1), e = threadIdx.x & 15;
-                const bool valid = k < ps.n_ops;
+                const bool valid = k < g_ops;
+                const DmPass ps = spass[valid ? recs[k].pass_q : 0];
                 qcd_op op;
                 op.opcode = QCD_OP_ID; op.q0 = ps.q0; op.q1 = 0xFF; op.param_off = 0;
-                if (valid) op = a.ops[a.sched[ps.first + k]];
+                if (valid) op = a.ops[a.sched[spass[0].first + k]];      // the group's ops are contiguous in the schedule
                 const bool two = op.opcode == QCD_OP_CX || op.opcode == QCD_OP_CZ || op.opcode == QCD_OP_SWAP ||
                                  op.opcode == QCD_OP_U2Q || op.opcode == QCD_OP_KRAUS2Q || op.opcode == QCD_OP_PAULI2Q;
                 const int slot0 = op.q0 == ps.q0 ? 0 : 1;       // slot of the op's first qubit
@@ -459,8 +492,8 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
                             const int fb = (k1p == 1 || k1p == 2), zb = (k1p == 2 || k1p == 3);    // op.q1
                             const int ff = slot0 ? (fb | (fa << 1)) : (fa | (fb << 1));
                             const int zz = slot0 ? (zb | (za << 1)) : (za | (zb << 1));
-                            const double p = a.params[op.param_off + k0p + 4 * k1p];
-                            if (ff == f) w += (__popc(zz & d) & 1) ? -p : p;
+                            const double pr = a.params[op.param_off + k0p + 4 * k1p];
+                            if (ff == f) w += (__popc(zz & d) & 1) ? -pr : pr;
                         }
                     rc.m[e] = C{(T)w, (T)0};
                     if (e == 0) {
@@ -479,54 +512,66 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
                 }
             }
             __syncthreads();
-            // ---- consecutive single-qubit records on one slot collapse into ONE superoperator (later op on the left);
-            // records on the other slot commute with them, a two-qubit record ends the run.  One half-warp, sequential.
-            if (threadIdx.x < 16) {
-                const int e = threadIdx.x, i = e >> 2, j = e & 3;
-                int head[2] = {-1, -1};
-                for (int k = 0; k < ps.n_ops; k++) {
-                    OpRec<T>& rc = recs[k];
-                    const int ty = rc.type;
-                    if (ty != R_SUPER1 && ty != R_SUPER1_X) {
-                        head[0] = head[1] = -1;
-                        continue;
+            // ---- phase B: consecutive single-qubit records on one slot collapse into ONE superoperator (later op on the
+            // left); records on the other slot commute with them, a two-qubit record ends the run.  One half-warp per PASS
+            // (the passes of the group in parallel), sequential inside a pass.
+            {
+                const int e = threadIdx.x & 15, i = e >> 2, j = e & 3;
+                const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+                for (int q = threadIdx.x >> 4; q < g_count; q += blockDim.x >> 4) {
+                    OpRec<T>* pr = recs + srec[q];
+                    const int n_ops = (int)(srec[q + 1] - srec[q]);
+                    int head0 = -1, head1 = -1;
+                    for (int k = 0; k < n_ops; k++) {
+                        OpRec<T>& rc = pr[k];
+                        const int ty = rc.type;
+                        if (ty != R_SUPER1 && ty != R_SUPER1_X) {
+                            head0 = head1 = -1;
+                            continue;
+                        }
+                        const int sl = rc.slot;
+                        const int hd = sl == 0 ? head0 : head1;
+                        if (hd < 0) {
+                            if (sl == 0) head0 = k; else head1 = k;
+                            continue;
+                        }
+                        OpRec<T>& h = pr[hd];
+                        C acc = cmul(rc.m[i * 4], h.m[j]);
+                        cfma(acc, rc.m[i * 4 + 1], h.m[4 + j]);
+                        cfma(acc, rc.m[i * 4 + 2], h.m[8 + j]);
+                        cfma(acc, rc.m[i * 4 + 3], h.m[12 + j]);
+                        __syncwarp(hmask);
+                        h.m[e] = acc;
+                        if (e == 0) {
+                            if (ty == R_SUPER1) h.type = R_SUPER1;
+                            rc.type = R_SKIP;
+                        }
+                        __syncwarp(hmask);
                     }
-                    const int sl = rc.slot;
-                    if (head[sl] < 0) {
-                        head[sl] = k;
-                        continue;
-                    }
-                    OpRec<T>& h = recs[head[sl]];
-                    C acc = cmul(rc.m[i * 4], h.m[j]);
-                    cfma(acc, rc.m[i * 4 + 1], h.m[4 + j]);
-                    cfma(acc, rc.m[i * 4 + 2], h.m[8 + j]);
-                    cfma(acc, rc.m[i * 4 + 3], h.m[12 + j]);
-                    __syncwarp(0xffffu);
-                    h.m[e] = acc;
-                    if (e == 0) {
-                        if (ty == R_SUPER1) h.type = R_SUPER1;
-                        rc.type = R_SKIP;
-                    }
-                    __syncwarp(0xffffu);
-                }
-                for (int k = 0; k < ps.n_ops; k++) {       // real-arithmetic variants
-                    OpRec<T>& rc = recs[k];
-                    const int ty = rc.type;
-                    const bool one = ty == R_SUPER1 || ty == R_SUPER1_X;
-                    const unsigned nz = __ballot_sync(0xffffu, one && rc.m[e].y != (T)0);
-                    __syncwarp(0xffffu);
-                    if (one && nz == 0) {
-                        rc.mr[e] = rc.m[e].x;
-                        if (e == 0) rc.type = ty == R_SUPER1 ? R_SUPER1_R : R_SUPER1_XR;
+                    for (int k = 0; k < n_ops; k++) {       // real-arithmetic variants
+                        OpRec<T>& rc = pr[k];
+                        const int ty = rc.type;
+                        const bool one = ty == R_SUPER1 || ty == R_SUPER1_X;
+                        const unsigned nz = __ballot_sync(hmask, one && rc.m[e].y != (T)0);
+                        __syncwarp(hmask);
+                        if (one && nz == 0) {
+                            rc.mr[e] = rc.m[e].x;
+                            if (e == 0) rc.type = ty == R_SUPER1 ? R_SUPER1_R : R_SUPER1_XR;
+                        }
                     }
                 }
             }
             __syncthreads();
+            // ---- the group's passes, back to back
             // (a stage-specialised variant -- straight-line code per [supers][gate][Pauli] group, one shared-memory round
             // trip per stage -- measured slower: unchanged at n = 7, 0.6x at n = 8, 0.45x at n = 9)
-            if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs, part, loc, rank, csize, swz_on);
-            else run_pass<T, 2>(a, ps, recs, part, loc, rank, csize, swz_on);
-            barrier();
+            for (int q = 0; q < g_count; q++) {
+                const DmPass ps = spass[q];
+                if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
+                else run_pass<T, 2>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
+                barrier();
+            }
+            p += g_count;
         }
         // ---- results: the diagonal (outcome probabilities) and / or the whole matrix
         if (a.probs) {
@@ -562,6 +607,16 @@ size_t op_param_len(const qcd_op& op, const double* params, size_t n_params) {
 }
 
 }  // namespace
+
+size_t dm_interp_record_bytes(int precision) { return precision == 64 ? sizeof(OpRec<double>) : sizeof(OpRec<float>); }
+
+int dm_interp_rec_cap(int n_qubits, int precision, uint32_t max_circuit_ops) {
+    const int lb = std::min(2 * n_qubits, precision == 64 ? 13 : 14);
+    const size_t amp = ((size_t)1 << lb) * (precision == 64 ? 16 : 8);
+    const size_t room = (size_t)227 * 1024 - 3072 - amp;            // static shared memory + slack
+    const size_t fit = room / dm_interp_record_bytes(precision);
+    return (int)std::min<size_t>(fit, std::max<uint32_t>(max_circuit_ops, (uint32_t)IR_MAX_OPS));
+}
 
 int dm_interp_cluster_size(int n_qubits, int precision) {
     const int lb = precision == 64 ? 13 : 14;               // 128 KB of amplitudes per CTA
@@ -672,7 +727,7 @@ int dm_interp_schedule(const qcd_op* ops, uint32_t n_ops, uint32_t op_base, cons
 template <typename T>
 cudaError_t launch_dm_interp(const DmInterpArgs& a, int cluster_size, int max_clusters, cudaStream_t st) {
     typedef typename Cplx<T>::type C;
-    const size_t smem = ((size_t)1 << a.local_bits) * sizeof(C);
+    const size_t smem = ((size_t)1 << a.local_bits) * sizeof(C) + (size_t)a.rec_cap * dm_interp_record_bytes(sizeof(T) == 8 ? 64 : 32);
     cudaError_t e = cudaFuncSetAttribute(dm_interp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (cluster_size > 8) {

@@ -30,6 +30,7 @@ struct DmInterpArgs {
     int n_circuits;             // circuits of this launch: circuit0 .. circuit0 + n_circuits of the batch
     int circuit0;
     int local_bits;             // index bits held by one CTA
+    int rec_cap;                // op records that fit the dynamic shared memory behind the amplitudes (>= DMI_MAX_PASS_OPS)
     void* probs;                // [dev] T [n_circuits][2^n] or NULL
     void* rho_out;              // [dev] complex<T> [n_circuits][slot_stride] or NULL
     uint64_t slot_stride;
@@ -37,6 +38,11 @@ struct DmInterpArgs {
 
 // CTAs per cluster that hold one density matrix of n_qubits (1, 2, 4, 8, 16), or 0 if it does not fit on chip.
 int dm_interp_cluster_size(int n_qubits, int precision);
+
+// Records the kernel can hold per CTA next to the amplitudes: enough for a whole circuit when that fits (max_circuit_ops =
+// most scheduled ops of any circuit of the batch), so that one build phase serves all its passes.
+int dm_interp_rec_cap(int n_qubits, int precision, uint32_t max_circuit_ops);
+size_t dm_interp_record_bytes(int precision);
 
 // Host scheduler, O(ops), no matrix arithmetic: validates the ops of one circuit (op_base = index of ops[0] in the batch
 // array) and appends its passes / execution order.  Every two-qubit gate opens (or extends) a pass on its pair; single-

@@ -151,7 +151,8 @@ struct qcd_ctx {
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
     bool use_direct = true;      // register-only kernel for single-pass sweeps
     bool no_slots = false;
-    uint32_t nostore_max = 8;    // leaves with at most this many trajectories are sampled without writing their state
+    uint32_t nostore_max = 256;  // leaves with at most this many trajectories are sampled without writing their state
+                                 // (measured on C4: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3 ms per step)
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
     uint32_t hist_row0 = 0;      // uploaded circuit that row 0 of the caller's histogram buffer stands for
     bool dm_on_chip = true;      // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
@@ -173,6 +174,7 @@ struct qcd_ctx {
         bool ready = false;
         DevBuf ops, params, sched, passes, pass_off;
         size_t n_passes = 0;
+        uint32_t max_circuit_ops = 0;     // most scheduled ops of one circuit
         cudaEvent_t done = nullptr;       // recorded after the last launch that reads these buffers
         cudaStream_t copy = nullptr;      // non-blocking: uploads do not queue behind kernels on the legacy stream
     } interp;
@@ -182,6 +184,8 @@ struct qcd_ctx {
     DevBuf states, partials, chunk_sums, block_sums;
     DevBuf owner, keys, probs4, table, offs, children, counter, bsum, flip, masks, scratch, slots;
     std::vector<DevBuf> level_nodes, level_shots;
+    PinBuf flip_host;                 // staging of the readout flip table (asynchronous upload)
+    cudaEvent_t flip_staged = nullptr;
     std::vector<PinBuf> host_nodes;   // children read back at depth d (= the nodes of depth d + 1), page-locked
     std::vector<cudaEvent_t> ev_pool;
     std::vector<uint8_t> ev_kind;     // kind of the launch bracketed by events (2 i, 2 i + 1)
@@ -1115,8 +1119,17 @@ int prepare_interp(qcd_ctx* ctx) {
     std::vector<uint32_t> pass_off;
     pass_off.reserve((size_t)nc + 1);
     pass_off.push_back(0);
-    for (int t = 0; t < n_thr; t++)
-        for (uint32_t k : parts[t].pass_cnt) pass_off.push_back(pass_off.back() + k);
+    uint32_t max_circuit_ops = 0;
+    for (int t = 0; t < n_thr; t++) {
+        size_t pi = 0;
+        for (uint32_t k : parts[t].pass_cnt) {
+            pass_off.push_back(pass_off.back() + k);
+            uint32_t ops_c = 0;
+            for (uint32_t j = 0; j < k; j++) ops_c += parts[t].passes[pi + j].n_ops;
+            pi += k;
+            max_circuit_ops = std::max(max_circuit_ops, ops_c);
+        }
+    }
     qcd_ctx::InterpProg& I = ctx->interp;
     // the previous batch's buffers may still be read by THIS context's last interpreter launch (and by nothing else):
     // wait for that launch only -- another context's kernels keep running while this one prepares its next chunk
@@ -1159,6 +1172,7 @@ int prepare_interp(qcd_ctx* ctx) {
     CU(upload_on_copy(I.pass_off, pass_off.data(), pass_off.size() * sizeof(uint32_t)));
     CU(cudaStreamSynchronize(I.copy));      // the host vectors go out of scope; the launch stream sees complete buffers
     I.n_passes = pass_base[n_thr];
+    I.max_circuit_ops = max_circuit_ops;
     I.ready = true;
     if (g_trace.on)
         fprintf(stderr, "[qcd] on-chip DM program: %d circuits, %zu passes, %zu ops, %.2f ms on %d host threads\n", nc,
@@ -1179,6 +1193,7 @@ int launch_interp(qcd_ctx* ctx, int precision, int c0, int c1, void* probs, void
     a.n_circuits = c1 - c0;
     a.circuit0 = c0;
     a.local_bits = std::min(2 * ctx->n_qubits, precision == 64 ? 13 : 14);
+    a.rec_cap = dm_interp_rec_cap(ctx->n_qubits, precision, I.max_circuit_ops);
     a.probs = probs;
     a.rho_out = rho;
     a.slot_stride = slot_stride;
@@ -1385,16 +1400,27 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
     return QCD_OK;
 }
 
-int upload_flip(qcd_ctx* ctx, const double* readout, int n_vec, int n, const double** out) {
+// Readout flip table [vector][n][2] = P(1|0), P(0|1) -> ctx->flip, ASYNCHRONOUSLY on the caller's stream from a page-locked
+// staging buffer: a blocking cudaMemcpy here would make the host wait for every kernel enqueued before it (in the chunked
+// array route: for the whole simulation of the chunk, so that no chunk ever overlapped the next one's preparation).
+int upload_flip(qcd_ctx* ctx, const double* readout, int n_vec, int n, const double** out, cudaStream_t st) {
     *out = nullptr;
     if (!readout) return QCD_OK;
-    std::vector<double> flip((size_t)n_vec * n * 2);
+    const size_t cnt = (size_t)n_vec * n * 2;
+    if (ctx->flip_staged) CU(cudaEventSynchronize(ctx->flip_staged));      // the previous copy has read the staging buffer
+    CU(ctx->flip_host.ensure(cnt * sizeof(double)));
+    double* flip = ctx->flip_host.as<double>();
     for (size_t cq = 0; cq < (size_t)n_vec * n; cq++) {
         flip[cq * 2] = readout[cq * 4 + 1];
         flip[cq * 2 + 1] = readout[cq * 4 + 2];
     }
-    int rc = upload_vec(ctx, ctx->flip, flip);
-    if (rc) return rc;
+    if (ctx->flip.cap < cnt * sizeof(double)) {
+        CU(cudaStreamSynchronize(st));                 // growing frees the old buffer: kernels in flight may still read it
+        CU(ctx->flip.ensure(cnt * sizeof(double)));
+    }
+    CU(cudaMemcpyAsync(ctx->flip.p, flip, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!ctx->flip_staged) CU(cudaEventCreateWithFlags(&ctx->flip_staged, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->flip_staged, st));
     *out = ctx->flip.as<double>();
     return QCD_OK;
 }
@@ -1460,6 +1486,8 @@ void qcd_destroy(qcd_ctx* ctx) {
     for (DevBuf& b : ctx->level_nodes) b.release();
     for (DevBuf& b : ctx->level_shots) b.release();
     for (PinBuf& b : ctx->host_nodes) b.release();
+    ctx->flip_host.release();
+    if (ctx->flip_staged) cudaEventDestroy(ctx->flip_staged);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
@@ -1934,9 +1962,9 @@ int qcd_sample_from_probs(qcd_ctx* ctx, int precision, const void* probs, int n_
     CU(ctx->chunk_sums.ensure((size_t)n_vectors * n_chunks * 8));
     CU(ctx->block_sums.ensure((size_t)n_vectors * n_blocks * 8));
     const double* flip = nullptr;
-    int rc = upload_flip(ctx, readout, n_vectors, n, &flip);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_flip(ctx, readout, n_vectors, n, &flip, st);
+    if (rc) return rc;
     double* cs = ctx->chunk_sums.as<double>();
     double* bs = ctx->block_sums.as<double>();
     if (precision == 64) {

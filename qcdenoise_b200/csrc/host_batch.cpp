@@ -214,4 +214,56 @@ int qcd_adjacency_tensors(const qcd_op* ops, const uint32_t* op_offsets, int n_c
     return QCD_OK;
 }
 
+int qcd_gate_entries(const qcd_op* ops, const uint32_t* op_offsets, int n_circuits, uint32_t* entry_key_out,
+                     uint32_t* entry_circuit_out, uint32_t* op_entry_out, size_t* n_entries) {
+    if (!op_offsets || !entry_key_out || !entry_circuit_out || !op_entry_out || !n_entries || n_circuits < 0) return QCD_E_INVALID;
+    const size_t n_ops = op_offsets[n_circuits];
+    if (n_ops && !ops) return QCD_E_INVALID;
+    // pass 1 (threads): per circuit, the sorted distinct keys go to the circuit's own op range of entry_key_out (a circuit
+    // has at most as many entries as ops) and every op learns its entry's rank inside the circuit
+    std::vector<uint32_t> count((size_t)n_circuits + 1, 0);
+    auto pass1 = [&](int c_lo, int c_hi) {
+        std::vector<uint32_t> keys;
+        for (int c = c_lo; c < c_hi; c++) {
+            const uint32_t b = op_offsets[c], e = op_offsets[c + 1];
+            keys.clear();
+            for (uint32_t i = b; i < e; i++) keys.push_back(((uint32_t)ops[i].opcode << 16) | ((uint32_t)ops[i].q0 << 8) | ops[i].q1);
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            for (uint32_t i = b; i < e; i++) {
+                const uint32_t k = ((uint32_t)ops[i].opcode << 16) | ((uint32_t)ops[i].q0 << 8) | ops[i].q1;
+                op_entry_out[i] = (uint32_t)(std::lower_bound(keys.begin(), keys.end(), k) - keys.begin());
+            }
+            std::copy(keys.begin(), keys.end(), entry_key_out + b);
+            count[c + 1] = (uint32_t)keys.size();
+        }
+    };
+    int n_thr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    n_thr = std::max(1, std::min(n_thr, n_circuits / 256));
+    auto run = [&](auto&& fn) {
+        if (n_thr == 1) { fn(0, n_circuits); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; t++)
+            pool.emplace_back(fn, (int)((long long)n_circuits * t / n_thr), (int)((long long)n_circuits * (t + 1) / n_thr));
+        for (std::thread& th : pool) th.join();
+    };
+    run(pass1);
+    for (int c = 0; c < n_circuits; c++) count[c + 1] += count[c];          // first entry of every circuit
+    // pass 2 (in order, in place: the packed position never overtakes the source): compact the keys, globalise the ranks
+    for (int c = 0; c < n_circuits; c++) {
+        const uint32_t b = op_offsets[c], first = count[c], k = count[c + 1] - count[c];
+        for (uint32_t j = 0; j < k; j++) {
+            entry_key_out[first + j] = entry_key_out[b + j];
+            entry_circuit_out[first + j] = (uint32_t)c;
+        }
+    }
+    auto pass3 = [&](int c_lo, int c_hi) {
+        for (int c = c_lo; c < c_hi; c++)
+            for (uint32_t i = op_offsets[c]; i < op_offsets[c + 1]; i++) op_entry_out[i] += count[c];
+    };
+    run(pass3);
+    *n_entries = count[n_circuits];
+    return QCD_OK;
+}
+
 }  // extern "C"

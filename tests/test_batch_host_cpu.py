@@ -310,3 +310,22 @@ def test_stochastic_builder_with_no_coin_set_equals_plain_builder():
         one = np.ones((int(n_edges.sum()), 1), dtype=np.int64)
         batch.build_gate_lists(qcd.CXGateCircuit(n_qubits=n, stochastic=True), edges, n_edges, coins=one,
                                gammas=np.full((int(one.sum()), 2), 1.5))                             # gamma > 1
+
+
+def test_native_gate_entries_equal_numpy_unique():
+    """qcd_gate_entries (the distinct (gate, qubits) calibration entries per circuit) lists exactly what
+    numpy.unique((circuit << 24) | opcode << 16 | q0 << 8 | q1) lists, in the same order, for every builder -- the
+    calibration draws therefore did not change when the sort over the whole batch was replaced."""
+    for cls, n, B in ((qcd.CXGateCircuit, 8, 700), (qcd.CZGateCircuit, 5, 300), (qcd.CPhaseGateCircuit, 6, 257)):
+        gs = qcd.GraphState(qcd.GraphDB(), n_qubits=n)
+        edges, n_edges = gs.sample_batch(B, seed=11)
+        enc = batch.build_gate_lists(cls(n_qubits=n, stochastic=False), edges, n_edges)
+        ops, offsets, _, _ = enc
+        spec = qcd.NoiseSpec(specs={"qubit": {"T1": 100.0, "T2": 100.0}, "cx": {"gate_error": 0.25, "gate_length": 500.0},
+                                    "h": {"gate_error": 0.05, "gate_length": 50.0}})
+        props = batch.draw_device_props(spec, enc, np.random.default_rng(1))
+        circ = np.repeat(np.arange(B, dtype=np.int64), np.diff(offsets.astype(np.int64)))
+        key = (ops["opcode"].astype(np.int64) << 16) | (ops["q0"].astype(np.int64) << 8) | ops["q1"].astype(np.int64)
+        full, inv = np.unique((circ << 24) | key, return_inverse=True)
+        assert np.array_equal(props["gate_key"], (full & 0xFFFFFF).astype(np.uint32))
+        assert np.array_equal(props["gate_circuit"], full >> 24) and np.array_equal(props["op_entry"], inv)

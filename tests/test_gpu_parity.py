@@ -27,7 +27,7 @@ def _circ(n, ops):
 
 def _reset_opts(eng):
     for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1),
-                 ("share_prefix", 1)):
+                 ("share_prefix", 1), ("nostore_max", 256)):
         eng.set_option(k, v)
 
 
@@ -526,3 +526,39 @@ def test_first_circuit_makes_a_circuit_split_reproduce_the_whole_batch(eng):
             parts.append(h.cpu().numpy())
         assert np.array_equal(np.concatenate(parts), whole)
         eng.upload([_circ(n, ops) for ops in batch])
+
+
+@pytest.mark.parametrize("n", [13, 16])
+def test_stored_and_unstored_leaves_sample_the_same_outcomes(eng, n):
+    """A leaf sampled by few trajectories is never written: its chunk is recomputed from the parent per shot
+    (sample_nostore_kernel); a leaf above the `nostore_max` threshold is stored and sampled from memory (sample_kernel).
+    Both must give the oracle's outcomes shot for shot, whatever the threshold (0 = every leaf stored)."""
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    _reset_opts(eng)
+    rng = np.random.default_rng(900 + n)
+    batch = [circuits.graph_circuit_amp_damp(n, circuits.ref_graph(14 if n == 13 else n, i)[: n - 1] if n == 13 else
+                                             circuits.ref_graph(14, i) + [(13, 14), (14, 15)], rng, max_prob=0.15)
+             for i in range(2)]
+    batch = [[op for op in ops if max(op[1]) < n] for ops in batch]
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 3000, 77
+    ref = None
+    for thr in (0, 8, 256, 1 << 20):
+        eng.set_option("nostore_max", thr)
+        res = {}
+        for prec in (64, 32):
+            h, o = eng.run_trajectories(shots, seed=seed, precision=prec, want_outcomes=True)
+            res[prec] = (h.cpu().numpy(), o.cpu().numpy())
+            assert res[prec][0].sum(axis=1).tolist() == [shots] * len(batch)
+        if ref is None:
+            ref = res
+            out = res[64][1].reshape(len(batch), shots).astype(np.int64)
+            for c, ops in enumerate(batch):
+                want = cpu_build.run_trajectories(encode_programs([_circ(n, ops)]), shots, seed, circuit=c).astype(np.int64)
+                assert np.array_equal(out[c], want), f"circuit {c}"
+            assert (res[32][1] != res[64][1]).sum() <= 6          # complex64: a few draws on a CDF boundary
+        else:
+            for prec in (64, 32):
+                assert np.array_equal(res[prec][0], ref[prec][0]) and np.array_equal(res[prec][1], ref[prec][1]), (thr, prec)
+    _reset_opts(eng)
