@@ -122,6 +122,8 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the
  *                           parents of the leaves; every draw stays keyed by the trajectory's own (circuit, shot), so
  *                           results are bit-identical with the option off
+ *   "release_memory" (any value)   free the state arena and per-level scratch now (a context keeps the arena it sized from
+ *                           the device's free memory at its first large run); the next run allocates what it needs
  *   "dm_on_chip" 0/1 (1)    density-matrix mode, n <= 9 qubits (complex64) / n <= 8 (complex128): the gate list is interpreted
  *                           with the whole density matrix in the shared memory of a thread-block cluster (no host
  *                           lowering); 0 = always lower to state sweeps

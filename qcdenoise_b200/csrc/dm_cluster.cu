@@ -401,6 +401,92 @@ __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps,
     }
 }
 
+// The dominant pass shape of noisy graph circuits after composition: [S0] [S1] CX DEPOL [S0'] [S1'] with real
+// superoperators (Hadamards, Pauli mixtures, relaxation).  Such a pass runs as ONE straight-line function per block --
+// same single shared-memory round trip as the generic loop, without the per-record dispatch and the register shuffling
+// it causes (22 % MOV in the generic loop, ncu).
+struct FusedPass {
+    int ok;              // 0 = generic loop
+    int ctrl;            // slot of the CX control
+    int pre0, pre1, post0, post1, depol;   // record indices inside the pass, -1 = absent
+};
+
+template <typename T, int S>
+__device__ __forceinline__ void fused_super(Block<T, 2>& B, const OpRec<T>* r) {
+    if (r == nullptr) return;
+    if (r->type == R_SUPER1_XR) apply_super1<T, 2, S, true, true>(B, r->m, r->mr);
+    else apply_super1<T, 2, S, false, true>(B, r->m, r->mr);
+}
+
+template <typename T, int CTRL>
+__device__ __forceinline__ void run_pass_fused(const DmInterpArgs& a, const DmPass ps, const OpRec<T>* recs, const FusedPass fp,
+                                               typename Cplx<T>::type* const* part, typename Cplx<T>::type* loc,
+                                               unsigned rank, unsigned csize, uint32_t swz_on) {
+    typedef typename Cplx<T>::type C;
+    const int n = a.n_qubits, LB = a.local_bits;
+    const int p0 = ps.q0, p1 = ps.q1;
+    const int s0 = min(p0, p1), s1 = max(p0, p1), s2 = s0 + n, s3 = s1 + n;
+    const uint32_t lmask = (1u << LB) - 1u;
+    uint32_t soff[16], roff[16];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t o = (((uint32_t)r & 1u) << p0) | (((uint32_t)c & 1u) << (p0 + n)) | (((uint32_t)r >> 1) << p1) |
+                               (((uint32_t)c >> 1) << (p1 + n));
+            soff[r * 4 + c] = swz<C>(o & lmask, swz_on);
+            roff[r * 4 + c] = o >> LB;
+        }
+    const int free_bits = 2 * n - 4;
+    const bool remote = csize > 1 && s3 >= LB;
+    uint32_t f, f_end, f_step, f_or;
+    if (!remote) {
+        const int local_free = free_bits - (2 * n - LB);
+        f = threadIdx.x; f_end = 1u << local_free; f_step = blockDim.x; f_or = rank << local_free;
+    } else {
+        f = rank * blockDim.x + threadIdx.x; f_end = 1u << free_bits; f_step = csize * blockDim.x; f_or = 0;
+    }
+    const OpRec<T>* pre0 = fp.pre0 >= 0 ? recs + fp.pre0 : nullptr;
+    const OpRec<T>* pre1 = fp.pre1 >= 0 ? recs + fp.pre1 : nullptr;
+    const OpRec<T>* post0 = fp.post0 >= 0 ? recs + fp.post0 : nullptr;
+    const OpRec<T>* post1 = fp.post1 >= 0 ? recs + fp.post1 : nullptr;
+    const bool depol = fp.depol >= 0;
+    const T c0 = depol ? recs[fp.depol].aux[0] : (T)1, c1 = depol ? recs[fp.depol].aux[1] : (T)0;
+    for (; f < f_end; f += f_step) {
+        const uint32_t base = gap(gap(gap(gap(f | f_or, s0), s1), s2), s3);
+        const uint32_t sb = swz<C>(base & lmask, swz_on), rb = base >> LB;
+        Block<T, 2> B;
+        if (!remote) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) B.b[i] = loc[sb ^ soff[i]];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) B.b[i] = part[rb ^ roff[i]][sb ^ soff[i]];
+        }
+        fused_super<T, 0>(B, pre0);
+        fused_super<T, 1>(B, pre1);
+        // CX as a renaming of the stores: element (r, c) of the result is element (pi r, pi c) of the block
+        if (depol) apply_depol2<T>(B, c0, c1);         // depolarizing commutes with the permutation (trace and scaling)
+        Block<T, 2> P;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int pr = r ^ (((r >> CTRL) & 1) << (1 - CTRL)), pc = c ^ (((c >> CTRL) & 1) << (1 - CTRL));
+                P.b[r * 4 + c] = B.b[pr * 4 + pc];
+            }
+        fused_super<T, 0>(P, post0);
+        fused_super<T, 1>(P, post1);
+        if (!remote) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) loc[sb ^ soff[i]] = P.b[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) part[rb ^ roff[i]][sb ^ soff[i]] = P.b[i];
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS, 1) dm_interp_kernel(const DmInterpArgs a) {
     typedef typename Cplx<T>::type C;
@@ -414,6 +500,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
     __shared__ DmPass spass[GP];
     __shared__ uint32_t srec[GP + 1];         // first record of pass q of the group
     __shared__ int s_gcount;
+    __shared__ FusedPass sfused[GP];
     OpRec<T>* recs = reinterpret_cast<OpRec<T>*>(smem_raw + ((size_t)1 << a.local_bits) * sizeof(C));
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
@@ -559,6 +646,32 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
                             if (e == 0) rc.type = ty == R_SUPER1 ? R_SUPER1_R : R_SUPER1_XR;
                         }
                     }
+                    __syncwarp(hmask);
+                    if (e == 0) {      // does the pass have the fused shape [S0] [S1] CX [DEPOL] [S0'] [S1'] with real S?
+                        FusedPass fp{0, 0, -1, -1, -1, -1, -1};
+                        int stage = 0;             // 0 before the CX, 1 after the CX, 2 after the Pauli mixture
+                        bool ok = spass[q].q1 != 0xFF;
+                        for (int k = 0; k < n_ops && ok; k++) {
+                            const int ty = pr[k].type;
+                            if (ty == R_SKIP) continue;
+                            if (ty == R_SUPER1_R || ty == R_SUPER1_XR) {
+                                int& dst = stage == 0 ? (pr[k].slot == 0 ? fp.pre0 : fp.pre1) : (pr[k].slot == 0 ? fp.post0 : fp.post1);
+                                ok = dst < 0;
+                                dst = k;
+                                if (stage == 1) stage = 2;      // a superoperator after the CX: a Pauli mixture may no longer follow
+                            } else if (ty == R_CX && stage == 0) {
+                                fp.ctrl = pr[k].slot;
+                                stage = 1;
+                            } else if (ty == R_DEPOL2 && stage == 1) {
+                                fp.depol = k;
+                                stage = 2;
+                            } else {
+                                ok = false;
+                            }
+                        }
+                        fp.ok = ok && stage >= 1;
+                        sfused[q] = fp;
+                    }
                 }
             }
             __syncthreads();
@@ -567,7 +680,10 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
             // trip per stage -- measured slower: unchanged at n = 7, 0.6x at n = 8, 0.45x at n = 9)
             for (int q = 0; q < g_count; q++) {
                 const DmPass ps = spass[q];
+                const FusedPass fp = sfused[q];
                 if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
+                else if (fp.ok && fp.ctrl == 0) run_pass_fused<T, 0>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
+                else if (fp.ok) run_pass_fused<T, 1>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
                 else run_pass<T, 2>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
                 barrier();
             }

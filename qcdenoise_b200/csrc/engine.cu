@@ -1227,8 +1227,10 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
     const uint32_t tiles = 1u << tiles_log2;
     const uint64_t slot_stride = (uint64_t)1 << nb;
     const size_t slot_bytes = slot_stride * sizeof(C);
-    uint64_t n_slots = usable_budget(ctx) / slot_bytes;
-    n_slots = std::min<uint64_t>(n_slots, (uint64_t)(ce - cb));
+    // The free-memory query behind usable_budget() costs 0.1 - 86 ms depending on the box (it walks the allocations): only
+    // ask when the arena we already hold cannot take the whole batch.
+    uint64_t n_slots = (uint64_t)(ce - cb);
+    if (ctx->states.cap / slot_bytes < n_slots) n_slots = std::min<uint64_t>(n_slots, usable_budget(ctx) / slot_bytes);
     if (ctx->max_slots) n_slots = std::min<uint64_t>(n_slots, ctx->max_slots);
     if (n_slots < 1) return fail(ctx, QCD_E_NOMEM, "memory budget too small for one density matrix");
     if (n_slots * tiles > 0x7fffffffull) n_slots = 0x7fffffffull / tiles;
@@ -1513,7 +1515,19 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     else if (k == "no_slots") ctx->no_slots = value != 0;
     else if (k == "share_prefix") ctx->share_prefix = value != 0;
     else if (k == "hist_row0") ctx->hist_row0 = (uint32_t)value;
-    else if (k == "dm_on_chip") ctx->dm_on_chip = value != 0;
+    else if (k == "release_memory") {
+        // hand the state arena and the per-level scratch back to the device (they are sized from the free memory of the
+        // first large run and otherwise kept for the life of the context); the next run allocates what it needs
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        for (DevBuf* b : {&ctx->states, &ctx->partials, &ctx->chunk_sums, &ctx->block_sums, &ctx->owner, &ctx->keys,
+                          &ctx->scratch})
+            b->release();
+        for (DevBuf& b : ctx->level_nodes) b.release();
+        for (DevBuf& b : ctx->level_shots) b.release();
+        ctx->cached_budget = 0;
+        ctx->budget_age = 0;
+    } else if (k == "dm_on_chip") ctx->dm_on_chip = value != 0;
     else if (k == "dm_max_clusters") ctx->dm_max_clusters = (int)value;
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;

@@ -562,3 +562,20 @@ def test_stored_and_unstored_leaves_sample_the_same_outcomes(eng, n):
             for prec in (64, 32):
                 assert np.array_equal(res[prec][0], ref[prec][0]) and np.array_equal(res[prec][1], ref[prec][1]), (thr, prec)
     _reset_opts(eng)
+
+
+def test_release_memory_returns_the_arena_and_keeps_results(eng):
+    import torch
+    _reset_opts(eng)
+    n = 14
+    rng = np.random.default_rng(5)
+    ops = circuits.graph_circuit_amp_damp(n, circuits.ref_graph(n, 0), rng, max_prob=0.2)
+    eng.upload([_circ(n, ops)])
+    h1, o1 = eng.run_trajectories(500, seed=3, precision=32, want_outcomes=True)
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info()
+    eng.set_option("release_memory", 1)
+    free_after, _ = torch.cuda.mem_get_info()
+    assert free_after > free_before + (1 << 20)                 # the arena went back to the device
+    h2, o2 = eng.run_trajectories(500, seed=3, precision=32, want_outcomes=True)
+    assert torch.equal(h1, h2) and torch.equal(o1, o2)
