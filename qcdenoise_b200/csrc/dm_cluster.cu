@@ -401,13 +401,13 @@ __device__ __forceinline__ void run_pass(const DmInterpArgs& a, const DmPass ps,
     }
 }
 
-// The dominant pass shape of noisy graph circuits after composition: [S0] [S1] CX DEPOL [S0'] [S1'] with real
+// The dominant pass shape of noisy graph circuits after composition: [S0] [S1] CX|CZ DEPOL [S0'] [S1'] with real
 // superoperators (Hadamards, Pauli mixtures, relaxation).  Such a pass runs as ONE straight-line function per block --
 // same single shared-memory round trip as the generic loop, without the per-record dispatch and the register shuffling
 // it causes (22 % MOV in the generic loop, ncu).
 struct FusedPass {
     int ok;              // 0 = generic loop
-    int ctrl;            // slot of the CX control
+    int ctrl;            // slot of the CX control; 2 = the gate is a CZ
     int pre0, pre1, post0, post1, depol;   // record indices inside the pass, -1 = absent
 };
 
@@ -472,8 +472,14 @@ __device__ __forceinline__ void run_pass_fused(const DmInterpArgs& a, const DmPa
         for (int r = 0; r < 4; r++)
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const int pr = r ^ (((r >> CTRL) & 1) << (1 - CTRL)), pc = c ^ (((c >> CTRL) & 1) << (1 - CTRL));
-                P.b[r * 4 + c] = B.b[pr * 4 + pc];
+                if (CTRL == 2) {           // CZ: element (r, c) changes sign when exactly one of r, c is |11>
+                    const bool neg = (r == 3) != (c == 3);
+                    P.b[r * 4 + c] = C{neg ? -B.b[r * 4 + c].x : B.b[r * 4 + c].x, neg ? -B.b[r * 4 + c].y : B.b[r * 4 + c].y};
+                } else {
+                    constexpr int CT = CTRL == 2 ? 0 : CTRL;
+                    const int pr = r ^ (((r >> CT) & 1) << (1 - CT)), pc = c ^ (((c >> CT) & 1) << (1 - CT));
+                    P.b[r * 4 + c] = B.b[pr * 4 + pc];
+                }
             }
         fused_super<T, 0>(P, post0);
         fused_super<T, 1>(P, post1);
@@ -659,8 +665,8 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
                                 ok = dst < 0;
                                 dst = k;
                                 if (stage == 1) stage = 2;      // a superoperator after the CX: a Pauli mixture may no longer follow
-                            } else if (ty == R_CX && stage == 0) {
-                                fp.ctrl = pr[k].slot;
+                            } else if ((ty == R_CX || ty == R_CZ) && stage == 0) {
+                                fp.ctrl = ty == R_CZ ? 2 : pr[k].slot;
                                 stage = 1;
                             } else if (ty == R_DEPOL2 && stage == 1) {
                                 fp.depol = k;
@@ -683,7 +689,8 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? DMI_F32_THREADS : IR_THREADS,
                 const FusedPass fp = sfused[q];
                 if (ps.q1 == 0xFF) run_pass<T, 1>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
                 else if (fp.ok && fp.ctrl == 0) run_pass_fused<T, 0>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
-                else if (fp.ok) run_pass_fused<T, 1>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
+                else if (fp.ok && fp.ctrl == 1) run_pass_fused<T, 1>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
+                else if (fp.ok) run_pass_fused<T, 2>(a, ps, recs + srec[q], fp, part, loc, rank, csize, swz_on);
                 else run_pass<T, 2>(a, ps, recs + srec[q], part, loc, rank, csize, swz_on);
                 barrier();
             }

@@ -49,10 +49,12 @@ def depolarizing_circuit(n, edges, p1=0.001, p2=0.01):
     return out
 
 
-def device_noise_circuit(n, edges, rng, gate_error=0.05, t1_us=(50, 150), gate_len_ns=(50, 500), excited=False):
+def device_noise_circuit(n, edges, rng, gate_error=0.05, t1_us=(50, 150), gate_len_ns=(50, 500), excited=False,
+                         builder="cx"):
     """Device-model semantics (samplers.py:577-727, backend=None branch): per (gate, qubits) a depolarizing Pauli
     mixture then thermal relaxation on each gate qubit; parameters drawn uniformly."""
-    ops, _ = ref_glue.cx_gate_circuit(n, edges)
+    ops, _ = {"cx": ref_glue.cx_gate_circuit, "cz": ref_glue.cz_gate_circuit,
+              "cphase": ref_glue.cphase_gate_circuit}[builder](n, edges)
     t1 = rng.uniform(*t1_us, n)
     t2 = rng.uniform(0.3, 1.9, n) * t1
     table = {}

@@ -61,6 +61,23 @@ def test_every_opcode_against_the_oracle(eng, n, precision):
     eng.set_option("dm_on_chip", 1)
 
 
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("builder", ["cx", "cz", "cphase"])
+def test_device_noise_circuits_of_every_builder(eng, builder, precision):
+    """The pass shapes of the reference's three builders under device noise (CX and CZ entangling gates run the fused
+    straight-line pass, CPhase the generic loop), local and cluster-spanning passes, against the oracle."""
+    for n in (6, 8):
+        rng = np.random.default_rng(40 + n)
+        batch = [circuits.device_noise_circuit(n, circuits.ref_graph(8 if n == 8 else 5, i) + ([(4, 5)] if n == 6 else []),
+                                               rng, builder=builder)[0] for i in range(3)]
+        eng.upload([_circ(n, ops) for ops in batch])
+        eng.set_option("dm_on_chip", 1)
+        got = eng.run_density_matrix(precision).cpu().numpy()
+        for i, ops in enumerate(batch):
+            np.testing.assert_allclose(got[i], sim.density_matrix_probs(ops, n), atol=TOL[precision], rtol=0,
+                                       err_msg=f"{builder} n={n} circuit {i}")
+
+
 def test_nine_qubits_sixteen_cta_cluster(eng):
     n = 9
     rng = np.random.default_rng(9)
