@@ -864,6 +864,8 @@ struct SvRunner {
     }
 };
 
+int upload_flip(qcd_ctx* ctx, const double* readout, int n_vec, int n, const double** out, cudaStream_t st);
+
 template <typename T>
 int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot_begin, uint64_t shot_end,
            uint32_t first_circuit, const double* readout, uint32_t* hist, uint32_t* outcomes, uint32_t flags,
@@ -962,15 +964,11 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     const double t_setup = g_trace.on ? Trace::now() - g_trace.t_run0 : 0;
 
     // ---- readout flip table [circuit][n][2] = P(1|0), P(0|1)
-    if (readout) {
-        std::vector<double> flip((size_t)ctx->n_circuits * n * 2);
-        for (size_t cq = 0; cq < (size_t)ctx->n_circuits * n; cq++) {
-            flip[cq * 2] = readout[cq * 4 + 1];
-            flip[cq * 2 + 1] = readout[cq * 4 + 2];
-        }
-        int rc = upload_vec(ctx, ctx->flip, flip);
+    if (readout) {      // stream-ordered upload: never overwrites the table under a kernel still reading it
+        const double* fd = nullptr;
+        int rc = upload_flip(ctx, readout, ctx->n_circuits, n, &fd, st);
         if (rc) return rc;
-        R.flip_dev = ctx->flip.as<double>();
+        R.flip_dev = fd;
     }
 
     // ---- outer loop over trajectory chunks of the flattened [circuit][shot] space
