@@ -292,3 +292,33 @@ def two_colour_witness_dense(rho, generators, colours, n):
                 p = p @ (np.eye(2 ** n) + pauli_matrix(g)) / 2
         w = w - 2 * p
     return float(np.real(np.trace(rho @ w)))
+
+
+# ------------------------------------------------------------------ adjacency tensor
+def adjacency_tensor(ops, encoding, tensor_shape=(32, 32, 32), fixed_size=True, directed=False):
+    """generate_adjacency_tensor (samplers.py:119-192) over a gate list instead of a qiskit DAG: `dag.gate_nodes()` yields
+    the gates in a topological order, and the plane a gate lands in depends only on the earlier gates that hit the SAME
+    [q, q] / [q1, q2] slot, whose relative order every topological order keeps.  Literal restatement, quirks included: a
+    slot counts as free while it holds 0, so a gate whose code is 0 never occupies one; an undirected two-qubit gate tests
+    [q1, q2] only and writes both [q1, q2] and [q2, q1]; gates beyond the last plane are dropped."""
+    adj = np.zeros(tensor_shape)
+    for op in ops:
+        name, qubits = op[0], op[1]
+        if name in ("barrier", "measure_all", "kraus", "pauli", "reset"):      # not gate nodes / not in the circuit
+            continue
+        if len(qubits) == 1:
+            row = col = qubits[0]
+        else:
+            row, col = qubits
+        plane = 0
+        while plane < adj.shape[0]:
+            if adj[plane, row, col] == 0:
+                adj[plane, row, col] = encoding[name]
+                if len(qubits) == 2 and not directed:
+                    adj[plane, col, row] = encoding[name]
+                break
+            plane += 1
+    if not fixed_size:
+        zero = np.zeros_like(adj[0])
+        adj = np.array([pl for pl in adj if np.any(pl != zero)])
+    return adj

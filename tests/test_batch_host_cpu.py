@@ -329,3 +329,38 @@ def test_native_gate_entries_equal_numpy_unique():
         full, inv = np.unique((circ << 24) | key, return_inverse=True)
         assert np.array_equal(props["gate_key"], (full & 0xFFFFFF).astype(np.uint32))
         assert np.array_equal(props["gate_circuit"], full >> 24) and np.array_equal(props["op_entry"], inv)
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_adjacency_tensors_equal_the_oracle_restatement(directed):
+    """Python walk (dataset.generate_adjacency_tensor) and native batch (qcd_adjacency_tensors) against the oracle's
+    restatement of samplers.py:119-192 on random circuits: repeated gates on one slot (several planes), both orders of a
+    qubit pair, more gates than planes (truncation), a gate encoded as 0 (never occupies a slot), trimmed output."""
+    from oracle import ref_glue
+    from tests import circuits
+    rng = np.random.default_rng(12)
+    names = ["h", "x", "s", "cx", "cz", "swap", "id"]
+    enc = {nm: i for i, nm in enumerate(names)}            # "h" -> 0: the reference's enumerate-from-0 quirk
+    n = 5
+    circs = []
+    for _ in range(12):
+        ops = []
+        for _ in range(int(rng.integers(5, 60))):
+            nm = names[rng.integers(0, len(names))]
+            q = int(rng.integers(0, n))
+            if nm in ("cx", "cz", "swap"):
+                ops.append((nm, (q, int((q + 1 + rng.integers(0, n - 1)) % n))))
+            else:
+                ops.append((nm, (q,)))
+        circs.append(ops)
+    for shape in ((4, n, n), (32, n, n)):
+        for ops in circs:
+            want = ref_glue.adjacency_tensor(ops, enc, shape, True, directed)
+            got = generate_adjacency_tensor(qcd.Circuit(n, ops), enc, shape, True, directed)
+            assert np.array_equal(got, want)
+            trimmed = generate_adjacency_tensor(qcd.Circuit(n, ops), enc, shape, False, directed)
+            assert np.array_equal(trimmed, ref_glue.adjacency_tensor(ops, enc, shape, False, directed))
+        encp = encode_programs([qcd.Circuit(n, ops) for ops in circs])
+        native = batch.adjacency_tensors_batch(encp, enc, shape, directed)
+        for i, ops in enumerate(circs):
+            assert np.array_equal(native[i], ref_glue.adjacency_tensor(ops, enc, shape, True, directed)), i
