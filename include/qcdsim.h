@@ -126,7 +126,10 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *                           the device's free memory at its first large run); the next run allocates what it needs
  *   "dm_on_chip" 0/1 (1)    density-matrix mode, n <= 9 qubits (complex64) / n <= 8 (complex128): the gate list is interpreted
  *                           with the whole density matrix in the shared memory of a thread-block cluster (no host
- *                           lowering); 0 = always lower to state sweeps
+ *                           lowering); 0 = always lower to state sweeps.  If the device refuses the cluster launch (16 CTAs
+ *                           per cluster is a non-portable size) the context falls back to lowered sweeps for good
+ *   "dm_test_refuse" 0/1 (0)  test hook: 1 = treat the next cluster launch as refused by the device (exercises the fall
+ *                           back to lowered sweeps), 0 = forget an earlier refusal
  *   "dm_max_clusters" (0)   cap on concurrently resident clusters of that kernel (0 = what the device holds)
  *   "hist_row0" (0)         qcd_run_sv_trajectories: the uploaded circuit that row 0 of `hist` stands for.  A rank that
  *                           holds the whole batch's programs and runs one slice of circuits at a time (self-scheduled

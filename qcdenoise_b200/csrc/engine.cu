@@ -158,6 +158,8 @@ struct qcd_ctx {
     bool dm_on_chip = true;      // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
                                  // there (dm_cluster.cu) instead of lowering it to sweeps
     int dm_max_clusters = 0;     // 0 = as many clusters as are resident at once
+    bool dm_cluster_refused = false;   // the device refused the cluster launch once: use the lowered route from then on
+    bool dm_test_refuse = false;       // test hook: behave as if the next cluster launch were refused
     size_t cached_budget = 0;    // last usable_budget() answer and how many runs have reused it
     int budget_age = 0;
     // programs (host copy of the IR; compiled lazily per (mode, precision))
@@ -1046,7 +1048,7 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
 
 // ---------------------------------------------------------------------------------------------- on-chip density matrices
 bool interp_eligible(const qcd_ctx* ctx, int precision) {
-    return ctx->dm_on_chip && dm_interp_cluster_size(ctx->n_qubits, precision) > 0;
+    return ctx->dm_on_chip && !ctx->dm_cluster_refused && dm_interp_cluster_size(ctx->n_qubits, precision) > 0;
 }
 
 // Explicit ops (device-noise batches: the channels written natively, circuit block by circuit block) + the pass schedule
@@ -1195,7 +1197,20 @@ int launch_interp(qcd_ctx* ctx, int precision, int c0, int c1, void* probs, void
     a.probs = probs;
     a.rho_out = rho;
     a.slot_stride = slot_stride;
-    CU(launch_dm_interp<T>(a, dm_interp_cluster_size(ctx->n_qubits, precision), ctx->dm_max_clusters, st));
+    {
+        // a device (or a partition of one) may not be able to co-schedule the cluster -- 16 CTAs is a non-portable size:
+        // that is not an error of the request, the caller falls back to the lowered sweep route
+        const cudaError_t le = ctx->dm_test_refuse ? cudaErrorLaunchOutOfResources
+                                                   : launch_dm_interp<T>(a, dm_interp_cluster_size(ctx->n_qubits, precision),
+                                                                         ctx->dm_max_clusters, st);
+        if (le == cudaErrorLaunchOutOfResources || le == cudaErrorInvalidConfiguration || le == cudaErrorInvalidValue ||
+            le == cudaErrorNotSupported || le == cudaErrorInvalidClusterSize) {
+            cudaGetLastError();
+            ctx->dm_cluster_refused = true;
+            return fail(ctx, QCD_E_UNSUPPORTED, std::string("cluster launch refused: ") + cudaGetErrorString(le));
+        }
+        CU(le);
+    }
     if (!ctx->interp.done) CU(cudaEventCreateWithFlags(&ctx->interp.done, cudaEventDisableTiming));
     CU(cudaEventRecord(ctx->interp.done, st));
     ctx->stats.aux_launches++;
@@ -1527,6 +1542,10 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
         ctx->budget_age = 0;
     } else if (k == "dm_on_chip") ctx->dm_on_chip = value != 0;
     else if (k == "dm_max_clusters") ctx->dm_max_clusters = (int)value;
+    else if (k == "dm_test_refuse") {          // 1: refuse the next cluster launch; 0: forget an earlier refusal
+        ctx->dm_test_refuse = value != 0;
+        if (value == 0) ctx->dm_cluster_refused = false;
+    }
     else return fail(ctx, QCD_E_INVALID, "unknown option " + k);
     return QCD_OK;
 }
@@ -1847,12 +1866,16 @@ int qcd_run_density_matrix(qcd_ctx* ctx, int precision, int circuit_begin, int c
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->ev_used = 0;
     if (circuit_begin == circuit_end) return QCD_OK;
-    DevProg* dp = nullptr;
-    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == 64) return run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
-    return run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        DevProg* dp = nullptr;
+        int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
+        if (rc) return rc;
+        rc = precision == 64 ? run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st)
+                             : run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st);
+        if (!(rc == QCD_E_UNSUPPORTED && ctx->dm_cluster_refused && dp == nullptr)) return rc;
+    }
+    return QCD_E_UNSUPPORTED;
 }
 
 int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_begin, int circuit_end, int n_settings,
@@ -1874,15 +1897,19 @@ int qcd_run_density_matrix_settings(qcd_ctx* ctx, int precision, int circuit_beg
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->ev_used = 0;
     if (circuit_begin == circuit_end) return QCD_OK;
-    DevProg* dp = nullptr;
-    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    // the per-batch host -> device copies of the setting tables read caller memory asynchronously: drain before returning
-    if (precision == 64)
-        rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
-    else
-        rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
+    int rc = QCD_E_UNSUPPORTED;
+    for (int attempt = 0; attempt < 2; attempt++) {      // second attempt: the lowered route, if the cluster launch was refused
+        DevProg* dp = nullptr;
+        rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
+        if (rc) return rc;
+        // the per-batch host -> device copies of the setting tables read caller memory asynchronously: drain before returning
+        if (precision == 64)
+            rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
+        else
+            rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, probs_out, st, n_settings, setting_qubits, setting_superops);
+        if (!(rc == QCD_E_UNSUPPORTED && ctx->dm_cluster_refused && dp == nullptr)) break;
+    }
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));
     return QCD_OK;
@@ -1908,14 +1935,18 @@ int qcd_run_density_matrix_group(qcd_ctx* ctx, int precision, int circuit_begin,
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->ev_used = 0;
     if (circuit_begin == circuit_end) return QCD_OK;
-    DevProg* dp = nullptr;
-    int rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == 64)
-        rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
-    else
-        rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
+    int rc = QCD_E_UNSUPPORTED;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        DevProg* dp = nullptr;
+        rc = interp_eligible(ctx, precision) ? prepare_interp(ctx) : get_program(ctx, MODE_DM, precision, &dp);
+        if (rc) return rc;
+        if (precision == 64)
+            rc = run_dm<double>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
+        else
+            rc = run_dm<float>(ctx, dp, circuit_begin, circuit_end, expvals_out, st, 0, nullptr, nullptr, adjacency);
+        if (!(rc == QCD_E_UNSUPPORTED && ctx->dm_cluster_refused && dp == nullptr)) break;
+    }
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));       // the adjacency rows were read from caller memory asynchronously
     return QCD_OK;

@@ -167,3 +167,26 @@ def test_read_outs_that_need_the_whole_matrix(eng, n):
     np.testing.assert_allclose(res[1][1], res[0][1], atol=1e-12, rtol=0)
     for i, ops in enumerate(batch):                         # the unrotated setting is the circuit's own distribution
         np.testing.assert_allclose(res[1][0][i, n], sim.density_matrix_probs(ops, n), atol=1e-10, rtol=0)
+
+
+def test_refused_cluster_launch_falls_back_to_lowered_sweeps(eng):
+    """A device that cannot co-schedule the cluster (16 CTAs is a non-portable size) must not fail the call: the context
+    switches to the lowered sweep route for good and gives the same distribution."""
+    n = 8
+    rng = np.random.default_rng(21)
+    batch = [circuits.device_noise_circuit(n, circuits.ref_graph(n, i), rng)[0] for i in range(3)]
+    eng.upload([_circ(n, ops) for ops in batch])
+    eng.set_option("dm_on_chip", 1)
+    want = eng.run_density_matrix(64).cpu().numpy()
+    assert eng.stats()["sweep_launches"] == 0
+    eng.set_option("dm_test_refuse", 1)
+    try:
+        got = eng.run_density_matrix(64).cpu().numpy()
+        assert eng.stats()["sweep_launches"] > 0
+        np.testing.assert_allclose(got, want, atol=1e-12, rtol=0)
+        again = eng.run_density_matrix(64).cpu().numpy()             # no second attempt at the cluster kernel
+        np.testing.assert_allclose(again, want, atol=1e-12, rtol=0)
+    finally:
+        eng.set_option("dm_test_refuse", 0)
+    eng.run_density_matrix(64)
+    assert eng.stats()["sweep_launches"] == 0                        # back on chip
