@@ -53,15 +53,18 @@ def main(src, tag):
         line = json.loads([l for l in f if l.startswith("{")][-1])
     steps = line["steps"] + max(line["warmup"], 1)
     kinds = line["roofline"]["per_kind"]
-    with open(os.path.join(HERE, f"{tag}_launch_summary.md"), "w") as f:
-        rows = load(os.path.join(src, f"{tag}_launches_g1.csv"))
-        f.write(f"# {tag}: `python bench.py --graphs 1 --steps 1 --warmup 1 --no-cpu --no-e2e --no-other` under "
-                "`ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
-        f.write(summarize(rows) + "\n\n")
-        sweep = sum(float(r["Metric Value"]) for r in rows if "sweep_" in r["Kernel Name"])
-        tot = sum(float(r["Metric Value"]) for r in rows if "at::" not in r["Kernel Name"])
-        f.write(f"sweep kernels: {100 * sweep / tot:.1f} % of the engine's kernel time under ncu; bench.py (CUDA events, no "
-                f"profiler) reports sweep_share_of_step = {100 * line['roofline']['sweep_share_of_step']:.1f} %\n")
+    graphs = line["config"]["graphs_per_step"]
+    cmd = f"python bench.py --graphs {graphs} --steps 1 --warmup 1 --no-cpu --no-e2e --no-other"
+    lpath = os.path.join(src, f"{tag}_launches_g1.csv")
+    if os.path.exists(lpath):
+        with open(os.path.join(HERE, f"{tag}_launch_summary.md"), "w") as f:
+            rows = load(lpath)
+            f.write(f"# {tag}: `{cmd}` under `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
+            f.write(summarize(rows) + "\n\n")
+            sweep = sum(float(r["Metric Value"]) for r in rows if "sweep_" in r["Kernel Name"])
+            tot = sum(float(r["Metric Value"]) for r in rows if "at::" not in r["Kernel Name"])
+            f.write(f"sweep kernels: {100 * sweep / tot:.1f} % of the engine's kernel time under ncu; bench.py (CUDA events, no "
+                    f"profiler) reports sweep_share_of_step = {100 * line['roofline']['sweep_share_of_step']:.1f} %\n")
     launches = []
     for d in long_to_launches(os.path.join(src, f"{tag}_traffic_g1.csv")):
         m = re.search(r"sweep_direct_kernel<(\w+),\s*\(?\w*\)?(\d+),\s*(\d+)>", d["kernel"])
@@ -93,8 +96,9 @@ def main(src, tag):
                       "issue_active_pct_time_weighted": sum(x["issue_active_pct"] * x["ms"] for x in sel) / ms,
                       "l2_hit_pct_time_weighted": sum(x["l2_hit_pct"] * x["ms"] for x in sel) / ms}
     with open(os.path.join(HERE, "r02_traffic.json"), "w") as f:
-        json.dump({"source": f"profiles/{tag}_sweep_launches.json: every sweep launch of `bench.py --graphs 1 --steps 1 "
-                             "--warmup 1` (warm-up + timed step) under ncu, dram__bytes_read.sum + dram__bytes_write.sum",
+        json.dump({"source": f"profiles/{tag}_sweep_launches.json: every sweep launch of `{cmd}` (warm-up + timed step; noise "
+                             f"sites per graph {line['config']['noise_sites_per_graph']}) under ncu (application replay), "
+                             "dram__bytes_read.sum + dram__bytes_write.sum",
                    "dram_bytes_per_algorithmic_byte": ratio, "per_kind": detail}, f, indent=1)
     print(json.dumps({"ratio": ratio, "detail": detail}, indent=1))
 
