@@ -870,10 +870,22 @@ cudaError_t launch_dm_interp(const DmInterpArgs& a, int cluster_size, int max_cl
     cfg.numAttrs = 1;
     int n_clusters = max_clusters;
     if (n_clusters <= 0) {
-        cfg.gridDim = dim3((unsigned)cluster_size);
-        e = cudaOccupancyMaxActiveClusters(&n_clusters, dm_interp_kernel<T>, &cfg);
-        if (e != cudaSuccess) return e;
-        if (n_clusters < 1) return cudaErrorLaunchOutOfResources;
+        // resident clusters for this (device, precision, cluster size, shared memory): asked once, not per launch (the object
+        // route of simulate() launches one circuit at a time)
+        struct Key { int dev, cs; size_t smem; int n; };
+        static Key cache[16];
+        static int n_cached = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        for (int i = 0; i < n_cached; i++)
+            if (cache[i].dev == dev && cache[i].cs == cluster_size * (sizeof(T) == 8 ? -1 : 1) && cache[i].smem == smem) n_clusters = cache[i].n;
+        if (n_clusters <= 0) {
+            cfg.gridDim = dim3((unsigned)cluster_size);
+            e = cudaOccupancyMaxActiveClusters(&n_clusters, dm_interp_kernel<T>, &cfg);
+            if (e != cudaSuccess) return e;
+            if (n_clusters < 1) return cudaErrorLaunchOutOfResources;
+            if (n_cached < 16) cache[n_cached++] = Key{dev, cluster_size * (sizeof(T) == 8 ? -1 : 1), smem, n_clusters};
+        }
     }
     n_clusters = std::min(n_clusters, a.n_circuits);
     cfg.gridDim = dim3((unsigned)(n_clusters * cluster_size));

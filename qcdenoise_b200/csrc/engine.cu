@@ -1135,20 +1135,23 @@ int prepare_interp(qcd_ctx* ctx) {
     // wait for that launch only -- another context's kernels keep running while this one prepares its next chunk
     if (I.done) CU(cudaEventSynchronize(I.done));
     if (!I.copy) CU(cudaStreamCreateWithFlags(&I.copy, cudaStreamNonBlocking));
+    // Chunks of one batch differ by a few percent in size: grow with headroom, a re-allocation (cudaFree waits for every
+    // kernel in flight, the other context's included) cost 13 - 74 ms when a chunk was slightly larger than the previous one.
+    auto roomy = [](DevBuf& b, size_t bytes) -> cudaError_t { return bytes <= b.cap ? cudaSuccess : b.ensure(bytes + bytes / 4 + 4096); };
     auto upload_on_copy = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
-        cudaError_t ce = b.ensure(std::max<size_t>(bytes, 1));
+        cudaError_t ce = roomy(b, std::max<size_t>(bytes, 1));
         if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, I.copy);
         return ce;
     };
     if (expand) {
-        CU(I.ops.ensure(std::max<size_t>(ops_base[n_thr], 1) * sizeof(qcd_op)));
-        CU(I.params.ensure(std::max<size_t>(par_base[n_thr], 1) * sizeof(double)));
+        CU(roomy(I.ops, std::max<size_t>(ops_base[n_thr], 1) * sizeof(qcd_op)));
+        CU(roomy(I.params, std::max<size_t>(par_base[n_thr], 1) * sizeof(double)));
     } else {
         CU(upload_on_copy(I.ops, ctx->ops.data(), ctx->ops.size() * sizeof(qcd_op)));
         CU(upload_on_copy(I.params, ctx->params.data(), ctx->params.size() * sizeof(double)));
     }
-    CU(I.sched.ensure(std::max<size_t>(sched_base[n_thr], 1) * sizeof(uint32_t)));
-    CU(I.passes.ensure(std::max<size_t>(pass_base[n_thr], 1) * sizeof(DmPass)));
+    CU(roomy(I.sched, std::max<size_t>(sched_base[n_thr], 1) * sizeof(uint32_t)));
+    CU(roomy(I.passes, std::max<size_t>(pass_base[n_thr], 1) * sizeof(DmPass)));
     std::vector<cudaError_t> cp_rc(n_thr, cudaSuccess);
     auto fix_and_copy = [&](int t) {     // re-base the block's offsets, then copy it from its own host thread
         Part& Q = parts[t];
