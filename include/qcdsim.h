@@ -124,10 +124,12 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *                           results are bit-identical with the option off
  *   "release_memory" (any value)   free the state arena and per-level scratch now (a context keeps the arena it sized from
  *                           the device's free memory at its first large run); the next run allocates what it needs
- *   "dm_on_chip" 0/1 (1)    density-matrix mode, n <= 9 qubits (complex64) / n <= 8 (complex128): the gate list is interpreted
- *                           with the whole density matrix in the shared memory of a thread-block cluster (no host
- *                           lowering); 0 = always lower to state sweeps.  If the device refuses the cluster launch (16 CTAs
- *                           per cluster is a non-portable size) the context falls back to lowered sweeps for good
+ *   "dm_on_chip" 0/1/2 (1)  density-matrix mode: the gate list is interpreted with the whole density matrix in the shared memory
+ *                           of a thread-block cluster (no host lowering).  1 = when the matrix fits a cluster of at most 4
+ *                           CTAs (n <= 8 qubits in complex64, n <= 7 in complex128: where it measured faster end to end),
+ *                           2 = whenever it fits on chip (n <= 9 / n <= 8: clusters of up to 16 CTAs), 0 = always lower to
+ *                           state sweeps.  If the device refuses the cluster launch (16 CTAs per cluster is a non-portable
+ *                           size) the context falls back to lowered sweeps for good
  *   "dm_test_refuse" 0/1 (0)  test hook: 1 = treat the next cluster launch as refused by the device (exercises the fall
  *                           back to lowered sweeps), 0 = forget an earlier refusal
  *   "dm_max_clusters" (0)   cap on concurrently resident clusters of that kernel (0 = what the device holds)

@@ -155,8 +155,11 @@ struct qcd_ctx {
                                  // (measured on C4: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3 ms per step)
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
     uint32_t hist_row0 = 0;      // uploaded circuit that row 0 of the caller's histogram buffer stands for
-    bool dm_on_chip = true;      // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
-                                 // there (dm_cluster.cu) instead of lowering it to sweeps
+    int dm_on_chip = 1;          // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
+                                 // there (dm_cluster.cu) instead of lowering it to sweeps.  0 never, 1 when the cluster
+                                 // has at most 4 CTAs (measured end to end, circuits/s on chip vs lowered: n = 7 226 k vs
+                                 // 136 k / 167 k vs 44 k, n = 8 156 k vs 112 k / 151 k vs 40 k for unitary / device noise;
+                                 // the 16-CTA clusters of n = 9 lose: 33 k vs 101 k / 35 k vs 33 k), 2 whenever it fits
     int dm_max_clusters = 0;     // 0 = as many clusters as are resident at once
     bool dm_cluster_refused = false;   // the device refused the cluster launch once: use the lowered route from then on
     bool dm_test_refuse = false;       // test hook: behave as if the next cluster launch were refused
@@ -1048,7 +1051,8 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
 
 // ---------------------------------------------------------------------------------------------- on-chip density matrices
 bool interp_eligible(const qcd_ctx* ctx, int precision) {
-    return ctx->dm_on_chip && !ctx->dm_cluster_refused && dm_interp_cluster_size(ctx->n_qubits, precision) > 0;
+    const int cs = dm_interp_cluster_size(ctx->n_qubits, precision);
+    return ctx->dm_on_chip && !ctx->dm_cluster_refused && cs > 0 && (ctx->dm_on_chip >= 2 || cs <= 4);
 }
 
 // Explicit ops (device-noise batches: the channels written natively, circuit block by circuit block) + the pass schedule
@@ -1210,6 +1214,9 @@ int launch_interp(qcd_ctx* ctx, int precision, int c0, int c1, void* probs, void
             le == cudaErrorNotSupported || le == cudaErrorInvalidClusterSize) {
             cudaGetLastError();
             ctx->dm_cluster_refused = true;
+            if (g_trace.on)
+                fprintf(stderr, "[qcd] cluster launch refused (%s): n = %d, precision %d, %d CTAs per cluster, %d records -> lowered sweeps\n",
+                        cudaGetErrorString(le), ctx->n_qubits, precision, dm_interp_cluster_size(ctx->n_qubits, precision), a.rec_cap);
             return fail(ctx, QCD_E_UNSUPPORTED, std::string("cluster launch refused: ") + cudaGetErrorString(le));
         }
         CU(le);
@@ -1482,7 +1489,7 @@ int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out) {
     qcd_ctx* c = new qcd_ctx();
     c->device = cuda_device;
     c->budget = mem_budget_bytes;
-    if (const char* v = getenv("QCD_DM_ON_CHIP")) c->dm_on_chip = atoi(v) != 0;     // A/B measurements of whole programs
+    if (const char* v = getenv("QCD_DM_ON_CHIP")) c->dm_on_chip = atoi(v);          // A/B measurements of whole programs
     memset(&c->stats, 0, sizeof(c->stats));
     *out = c;
     return QCD_OK;
@@ -1543,7 +1550,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
         for (DevBuf& b : ctx->level_shots) b.release();
         ctx->cached_budget = 0;
         ctx->budget_age = 0;
-    } else if (k == "dm_on_chip") ctx->dm_on_chip = value != 0;
+    } else if (k == "dm_on_chip") ctx->dm_on_chip = (int)value;
     else if (k == "dm_max_clusters") ctx->dm_max_clusters = (int)value;
     else if (k == "dm_test_refuse") {          // 1: refuse the next cluster launch; 0: forget an earlier refusal
         ctx->dm_test_refuse = value != 0;

@@ -1,4 +1,5 @@
-"""GPU parity of the on-chip density-matrix interpreter (csrc/dm_cluster.cu, option "dm_on_chip"): the whole density matrix
+"""GPU parity of the on-chip density-matrix interpreter (csrc/dm_cluster.cu, option "dm_on_chip"; forced with the value 2 here:
+the default policy only takes clusters of up to 4 CTAs): the whole density matrix
 in the shared memory of a thread-block cluster (1 / 4 / 16 CTAs for n <= 7 / 8 / 9 qubits in complex64; 1 / 2 / 8 for
 n <= 6 / 7 / 8 in complex128), the gate list interpreted there.  Against the numpy oracle's density matrix (1e-5 complex64,
 1e-10 complex128, the north_star bars) and against the lowered sweep route on the same inputs.
@@ -53,12 +54,13 @@ def test_every_opcode_against_the_oracle(eng, n, precision):
         batch.append(ops)
     eng.upload([_circ(n, ops) for ops in batch])
     want = [sim.density_matrix_probs(ops, n) for ops in batch]
-    for on_chip in (1, 0):
+    for on_chip in (2, 0):                                  # 2: on chip whatever the cluster size (complex128 n = 8: 8 CTAs)
         eng.set_option("dm_on_chip", on_chip)
         got = eng.run_density_matrix(precision).cpu().numpy()
+        assert (eng.stats()["sweep_launches"] == 0) == (on_chip == 2)
         for i in range(len(batch)):
             np.testing.assert_allclose(got[i], want[i], atol=TOL[precision], rtol=0, err_msg=f"on_chip={on_chip} circuit {i}")
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)
 
 
 @pytest.mark.parametrize("precision", [32, 64])
@@ -71,8 +73,9 @@ def test_device_noise_circuits_of_every_builder(eng, builder, precision):
         batch = [circuits.device_noise_circuit(n, circuits.ref_graph(8 if n == 8 else 5, i) + ([(4, 5)] if n == 6 else []),
                                                rng, builder=builder)[0] for i in range(3)]
         eng.upload([_circ(n, ops) for ops in batch])
-        eng.set_option("dm_on_chip", 1)
+        eng.set_option("dm_on_chip", 2)
         got = eng.run_density_matrix(precision).cpu().numpy()
+        eng.set_option("dm_on_chip", 2)
         for i, ops in enumerate(batch):
             np.testing.assert_allclose(got[i], sim.density_matrix_probs(ops, n), atol=TOL[precision], rtol=0,
                                        err_msg=f"{builder} n={n} circuit {i}")
@@ -84,11 +87,15 @@ def test_nine_qubits_sixteen_cta_cluster(eng):
     batch = [circuits.device_noise_circuit(n, circuits.ref_graph(n, i), rng)[0] for i in range(2)]
     batch.append(circuits.random_circuit(n, 40, rng))
     eng.upload([_circ(n, ops) for ops in batch])
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)                               # 16-CTA clusters are not the default route (slower end to end)
     got = eng.run_density_matrix(32).cpu().numpy()
     for i, ops in enumerate(batch):
         np.testing.assert_allclose(got[i], sim.density_matrix_probs(ops, n), atol=1e-5, rtol=0)
     assert eng.stats()["sweep_launches"] == 0                     # nothing was lowered to sweeps
+    eng.set_option("dm_on_chip", 1)
+    auto = eng.run_density_matrix(32).cpu().numpy()               # default policy: n = 9 goes to the lowered sweeps
+    assert eng.stats()["sweep_launches"] > 0
+    np.testing.assert_allclose(auto, got, atol=2e-6, rtol=0)
 
 
 @pytest.mark.parametrize("precision", [32, 64])
@@ -99,7 +106,7 @@ def test_many_circuits_walk_over_few_clusters(eng, precision):
     rng = np.random.default_rng(5)
     batch = [circuits.device_noise_circuit(n, circuits.ref_graph(n, i), rng)[0] for i in range(11)]
     eng.upload([_circ(n, ops) for ops in batch])
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)
     eng.set_option("dm_max_clusters", 3)
     got = eng.run_density_matrix(precision).cpu().numpy()
     part = eng.run_density_matrix(precision, circuit_range=(4, 9)).cpu().numpy()
@@ -124,13 +131,13 @@ def test_native_device_noise_upload_runs_on_chip(eng):
     props = batch.draw_device_props(spec, enc, np.random.default_rng(1))
     t1t2, gp, _ = batch.device_noise_inputs(props)
     eng.upload_device_noise(enc, t1t2, gp)
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)
     a = eng.run_density_matrix(64).cpu().numpy()
     assert eng.stats()["sweep_launches"] == 0
     eng.set_option("dm_on_chip", 0)
     b = eng.run_density_matrix(64).cpu().numpy()
     assert eng.stats()["sweep_launches"] > 0
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)
     np.testing.assert_allclose(a, b, atol=1e-12, rtol=0)
     np.testing.assert_allclose(a.sum(axis=1), 1.0, atol=1e-12)
     from qcdenoise_b200.engine import expand_device_noise
@@ -156,17 +163,17 @@ def test_read_outs_that_need_the_whole_matrix(eng, n):
     sq = np.broadcast_to(np.array([k if k < n else 0xFF for k in range(n + 1)], dtype=np.uint8), (5, n + 1)).copy()
     sop = np.broadcast_to(np.kron(H.conj(), H), (5, n + 1, 4, 4)).copy()
     res = {}
-    for on_chip in (1, 0):
+    for on_chip in (2, 0):
         eng.set_option("dm_on_chip", on_chip)
         eng.set_option("max_slots", 2)                     # several arena chunks
         res[on_chip] = (eng.run_density_matrix_settings(sq, sop, precision=64).cpu().numpy(),
                         qb.group_expectations(eng, g, precision=64).cpu().numpy())
     eng.set_option("max_slots", 0)
-    eng.set_option("dm_on_chip", 1)
-    np.testing.assert_allclose(res[1][0], res[0][0], atol=1e-12, rtol=0)
-    np.testing.assert_allclose(res[1][1], res[0][1], atol=1e-12, rtol=0)
+    eng.set_option("dm_on_chip", 2)
+    np.testing.assert_allclose(res[2][0], res[0][0], atol=1e-12, rtol=0)
+    np.testing.assert_allclose(res[2][1], res[0][1], atol=1e-12, rtol=0)
     for i, ops in enumerate(batch):                         # the unrotated setting is the circuit's own distribution
-        np.testing.assert_allclose(res[1][0][i, n], sim.density_matrix_probs(ops, n), atol=1e-10, rtol=0)
+        np.testing.assert_allclose(res[2][0][i, n], sim.density_matrix_probs(ops, n), atol=1e-10, rtol=0)
 
 
 def test_refused_cluster_launch_falls_back_to_lowered_sweeps(eng):
@@ -176,7 +183,7 @@ def test_refused_cluster_launch_falls_back_to_lowered_sweeps(eng):
     rng = np.random.default_rng(21)
     batch = [circuits.device_noise_circuit(n, circuits.ref_graph(n, i), rng)[0] for i in range(3)]
     eng.upload([_circ(n, ops) for ops in batch])
-    eng.set_option("dm_on_chip", 1)
+    eng.set_option("dm_on_chip", 2)
     want = eng.run_density_matrix(64).cpu().numpy()
     assert eng.stats()["sweep_launches"] == 0
     eng.set_option("dm_test_refuse", 1)

@@ -29,7 +29,7 @@ def main():
         props = batch.draw_device_props(spec, enc, np.random.default_rng(1))
         t1t2, gp, _ = batch.device_noise_inputs(props)
         out = {"n_qubits": n, "circuits": B, "cx_per_circuit": float(n_edges.mean())}
-        for on_chip in (1, 0):
+        for on_chip in (2, 0):
             if n == 9 and not on_chip:
                 continue
             eng.set_option("dm_on_chip", on_chip)
