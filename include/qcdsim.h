@@ -116,6 +116,8 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "max_slots" (0 = memory budget)   cap on resident states (exercises the depth-first schedule)
  *   "table_cap_log2" (22)   size of the trajectory-grouping table
  *   "use_direct" 0/1 (1)    register-only kernel for single-pass sweeps / density-matrix passes
+ *   "direct_min_bits" (10)  smallest state (index bits) the register-only kernel takes; smaller states and sweeps of more
+ *                           than 3 passes run on the shared-memory tile kernel
  *   "nostore_max" (256)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
  *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements)
  *   "share_prefix" 0/1 (1)  consecutive circuits whose sweeps are identical up to the final one (a graph circuit and

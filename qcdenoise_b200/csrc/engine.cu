@@ -150,6 +150,10 @@ struct qcd_ctx {
     int table_cap_log2 = 22;
     uint64_t max_slots = 0;      // 0 = as many as the budget allows
     bool use_direct = true;      // register-only kernel for single-pass sweeps
+    int direct_min_bits = 10;    // ... of states with at least this many index bits (smaller states: tile kernel).  Was 13;
+                                 // on resident programs the register-only kernel is 27 / 25 / 45 % faster than the tile
+                                 // kernel at n = 10 / 11 / 12 (2 000 reference-shaped circuits x 1024 shots: 12.4 -> 9.8,
+                                 // 15.3 -> 12.2, 22.0 -> 15.2 ms), same complex128 outcomes
     bool no_slots = false;
     uint32_t nostore_max = 256;  // leaves with at most this many trajectories are sampled without writing their state
                                  // (measured on C4: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3 ms per step)
@@ -752,7 +756,7 @@ struct SvRunner {
                 f_and &= f;
                 f_or |= f;
             }
-            const bool direct = ctx->use_direct && n >= 13 && (f_and & DF_OK);
+            const bool direct = ctx->use_direct && n >= ctx->direct_min_bits && (f_and & DF_OK);
             const bool vec = (f_and & DF_VEC) != 0, need_red = (f_or & DF_RED) != 0, need_chunks = (f_or & DF_FINAL) != 0,
                        need_prep = (f_or & DF_PREP) != 0;
             size_t n_leaf_nodes = 0;
@@ -785,7 +789,7 @@ struct SvRunner {
             // Sweeps of up to 3 passes run pass by pass on the register-only kernel (each pass a streaming read + write:
             // cheaper than one trip through the shared-memory tile kernel); longer ones stay on the tile kernel.
             size_t max_passes = 0;
-            bool by_pass = !direct && ctx->use_direct && n >= 13;
+            bool by_pass = !direct && ctx->use_direct && n >= ctx->direct_min_bits;
             if (by_pass) {
                 const size_t n_sw = dp->P.sweeps.size();
                 for (const NodeRec* rp = chunk; rp != chunk_end; ++rp) {
@@ -1269,7 +1273,7 @@ int run_dm(qcd_ctx* ctx, DevProg* dp, int cb, int ce, void* probs_out, cudaStrea
         } else {
         // Register-only path: every pass of every circuit of the chunk becomes a launch level of its own on the direct
         // kernel (more state passes than the tiled kernel's one-per-sweep, each at streaming speed).
-        bool all_direct = ctx->use_direct && nb >= 13;
+        bool all_direct = ctx->use_direct && nb >= ctx->direct_min_bits;
         for (int c = c0; c < c1 && all_direct; c++) {
             const CircuitInfo& ci = P.circuits[c];
             for (uint32_t si = ci.sweep_begin; si < ci.sweep_end && all_direct; si++) {
@@ -1489,6 +1493,7 @@ int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out) {
     qcd_ctx* c = new qcd_ctx();
     c->device = cuda_device;
     c->budget = mem_budget_bytes;
+    if (const char* v = getenv("QCD_DIRECT_MIN_BITS")) c->direct_min_bits = std::max(9, atoi(v));
     if (const char* v = getenv("QCD_DM_ON_CHIP")) c->dm_on_chip = atoi(v);          // A/B measurements of whole programs
     memset(&c->stats, 0, sizeof(c->stats));
     *out = c;
@@ -1534,6 +1539,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
         ctx->table_cap_log2 = (int)value;
     } else if (k == "max_slots") ctx->max_slots = (uint64_t)value;
     else if (k == "use_direct") ctx->use_direct = value != 0;
+    else if (k == "direct_min_bits") ctx->direct_min_bits = std::max(9, (int)value);
     else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
     else if (k == "no_slots") ctx->no_slots = value != 0;
     else if (k == "share_prefix") ctx->share_prefix = value != 0;

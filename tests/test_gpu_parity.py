@@ -27,7 +27,7 @@ def _circ(n, ops):
 
 def _reset_opts(eng):
     for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1),
-                 ("share_prefix", 1), ("nostore_max", 256)):
+                 ("share_prefix", 1), ("nostore_max", 256), ("direct_min_bits", 10)):
         eng.set_option(k, v)
 
 
@@ -579,3 +579,28 @@ def test_release_memory_returns_the_arena_and_keeps_results(eng):
     assert free_after > free_before + (1 << 20)                 # the arena went back to the device
     h2, o2 = eng.run_trajectories(500, seed=3, precision=32, want_outcomes=True)
     assert torch.equal(h1, h2) and torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("n", [10, 11, 12])
+def test_small_states_on_both_sweep_kernels(eng, n):
+    """States below 13 index bits: the register-only kernel (default from 10 bits) and the shared-memory tile kernel
+    (`direct_min_bits` 13) both reproduce the compiled oracle shot for shot in complex128; complex64 agrees with it up to a
+    few draws on a CDF boundary."""
+    from oracle import cpu_build
+    from qcdenoise_b200.ir import encode_programs
+    _reset_opts(eng)
+    rng = np.random.default_rng(n)
+    edges = circuits.ref_graph(10, 1) + [(9, 10), (10, 11)][: n - 10]
+    batch = [circuits.graph_circuit_amp_damp(n, edges, rng, max_prob=0.25, all_sites=(i == 0)) for i in range(3)]
+    eng.upload([_circ(n, ops) for ops in batch])
+    shots, seed = 700, 5
+    want = np.stack([cpu_build.run_trajectories(encode_programs([_circ(n, ops)]), shots, seed, circuit=c).astype(np.int64)
+                     for c, ops in enumerate(batch)])
+    for min_bits in (13, 10):
+        eng.set_option("direct_min_bits", min_bits)
+        _, o64 = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
+        _, o32 = eng.run_trajectories(shots, seed=seed, precision=32, want_outcomes=True)
+        got = o64.cpu().numpy().reshape(len(batch), shots).astype(np.int64)
+        assert np.array_equal(got, want), min_bits
+        assert (o32.cpu().numpy().reshape(len(batch), shots) != got).sum() <= 4, min_bits
+    _reset_opts(eng)
