@@ -197,3 +197,48 @@ def test_refused_cluster_launch_falls_back_to_lowered_sweeps(eng):
         eng.set_option("dm_test_refuse", 0)
     eng.run_density_matrix(64)
     assert eng.stats()["sweep_launches"] == 0                        # back on chip
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_fused_pass_shapes_and_near_misses(eng, precision):
+    """Every variant of the fused pass [S0] [S1] CX|CZ [DEPOL] [S0'] [S1'] (pieces present or absent, control on either slot,
+    X-shaped and dense real superoperators) and the near-misses that must take the generic per-record loop instead (a complex
+    superoperator, a non-uniform Pauli mixture, a Pauli mixture after a superoperator, two entangling gates in one pass),
+    local (n = 6) and cluster-spanning (n = 8, qubits 6 and 7), against the oracle."""
+    dep = noise.depolarizing_pauli_probs(0.07, 2)
+    skew = np.array(dep, dtype=float)
+    skew[5] += 0.01
+    skew[0] -= 0.01
+    damp = lambda g: ("kraus", None, noise.amplitude_damping_kraus(g))        # noqa: E731
+    relax = ("kraus", None, noise.thermal_relaxation_kraus(60.0, 80.0, 0.4))
+
+    def on(op, *qs):
+        return (op[0], tuple(qs)) + tuple(op[2:])
+
+    def variants(a, b):
+        h = ("h", None)
+        yield [on(("cx", None), a, b)]                                                          # bare CX
+        yield [on(("cx", None), a, b), ("pauli", (a, b), dep)]                                  # CX DEPOL
+        yield [on(h, a), on(("cx", None), b, a), ("pauli", (b, a), dep), on(damp(0.2), a)]      # control on slot 1
+        yield [on(h, a), on(h, b), on(("cz", None), a, b), ("pauli", (a, b), dep), on(relax, a), on(h, b), on(damp(0.1), b)]
+        yield [on(h, b), on(damp(0.3), b), on(("cx", None), a, b), on(relax, b)]                # no DEPOL, one slot only
+        yield [on(("t", None), a), on(("cx", None), a, b), ("pauli", (a, b), dep)]              # complex S0 -> generic
+        yield [on(h, a), on(("cx", None), a, b), ("pauli", (a, b), tuple(skew))]                # non-uniform mixture -> generic
+        yield [on(("cx", None), a, b), on(damp(0.2), a), ("pauli", (a, b), dep)]                # mixture after S0' -> generic
+        yield [on(("cx", None), a, b), ("pauli", (a, b), dep), on(("cx", None), b, a), on(h, a)]  # two gates -> generic
+
+    for n, pairs in ((6, [(0, 1), (4, 2)]), (8, [(7, 0), (3, 6), (6, 7)])):
+        batch = []
+        for a, b in pairs:
+            for body in variants(a, b):
+                # a prologue that makes the state generic (entangled, mixed, complex) before the pass under test
+                pro = [("h", (q,)) for q in range(n)] + [("cz", (q, (q + 1) % n)) for q in range(0, n - 1, 2)] + \
+                      [("s", (a,)), ("kraus", (b,), noise.amplitude_damping_kraus(0.15)), ("ry", ((a + 2) % n,), 0.4)]
+                batch.append(pro + body + [("h", ((b + 1) % n,))])
+        eng.upload([_circ(n, ops) for ops in batch])
+        eng.set_option("dm_on_chip", 2)
+        got = eng.run_density_matrix(precision).cpu().numpy()
+        assert eng.stats()["sweep_launches"] == 0
+        for i, ops in enumerate(batch):
+            np.testing.assert_allclose(got[i], sim.density_matrix_probs(ops, n), atol=TOL[precision], rtol=0,
+                                       err_msg=f"n={n} circuit {i}")
