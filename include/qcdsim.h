@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 3
+#define QCD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define QCD_API __attribute__((visibility("default")))
@@ -101,6 +101,10 @@ typedef struct qcd_stats {
     uint64_t kind_launches[4];
     uint64_t kind_bytes[4];
     double kind_ms[4];
+    /* sibling groups (option "leaf_cross"): shared passes launched, and leaves whose chunk sums came from them instead of
+     * a sweep of their own (both are included in node_sweeps / kind_*[2] as the passes they cost) */
+    uint64_t cross_passes;
+    uint64_t cross_leaves;
 } qcd_stats;
 
 QCD_API int qcd_abi_version(void);
@@ -119,6 +123,11 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "direct_min_bits" (10)  smallest state (index bits) the register-only kernel takes; smaller states and sweeps of more
  *                           than 3 passes run on the shared-memory tile kernel
  *   "nostore_max" (256)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
+ *   "leaf_cross" 0/1 (1)    unstored leaves of one parent and branch word whose circuits differ only in a trailing real 2x2
+ *                           on one qubit k (a graph circuit and its Toth settings, stabilizers.py:136-156) share passes over
+ *                           the parent that reduce |amp|^2 and Re(conj(amp[x]) amp[x ^ 2^k]) per 32-amplitude chunk; every
+ *                           member's chunk sums follow from those (exact in exact arithmetic; rounding differs from a sweep
+ *                           per leaf in the last bits)
  *   "no_slots" 0/1 (0)      disable the slotted op path of the register-only kernel (A/B measurements)
  *   "share_prefix" 0/1 (1)  consecutive circuits whose sweeps are identical up to the final one (a graph circuit and
  *                           its stabilizer settings, stabilizers.py:194-199) share one trajectory tree down to the

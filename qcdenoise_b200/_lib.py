@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libqcdsim.so")
 
-QCD_ABI_VERSION = 3
+QCD_ABI_VERSION = 4
 QCD_OK, QCD_E_INVALID, QCD_E_CUDA, QCD_E_NOMEM, QCD_E_UNSUPPORTED, QCD_E_STATE = range(6)
 QCD_RUN_NO_DEDUP = 1
 _ERR_NAMES = {1: "QCD_E_INVALID", 2: "QCD_E_CUDA", 3: "QCD_E_NOMEM", 4: "QCD_E_UNSUPPORTED", 5: "QCD_E_STATE"}
@@ -33,7 +33,8 @@ class Stats(ctypes.Structure):
                 ("node_sweeps", ctypes.c_uint64), ("sweep_bytes", ctypes.c_uint64), ("leaves", ctypes.c_uint64),
                 ("trajectories", ctypes.c_uint64), ("max_live_states", ctypes.c_uint64),
                 ("sweep_ms", ctypes.c_double), ("kind_launches", ctypes.c_uint64 * 4),
-                ("kind_bytes", ctypes.c_uint64 * 4), ("kind_ms", ctypes.c_double * 4)]
+                ("kind_bytes", ctypes.c_uint64 * 4), ("kind_ms", ctypes.c_double * 4),
+                ("cross_passes", ctypes.c_uint64), ("cross_leaves", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.startswith("kind_") else getattr(self, k)) for k, _ in self._fields_}

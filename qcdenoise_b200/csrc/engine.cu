@@ -114,9 +114,25 @@ struct DevProg {
     std::vector<DirectSweep> direct_host;
     std::vector<uint8_t> direct_flags;   // per descriptor: DF_* (what a launch holding this sweep must provide)
     int member_bits = 0;                 // ceil(log2(longest run of circuits sharing a prefix)), statevector mode
+    // Sibling groups (statevector mode).  The final sweeps of a run of circuits that share a prefix usually differ only in a
+    // trailing real 2x2 on ONE qubit k (stabilizers.py:136-156: the basis change of a Toth generator is one Hadamard).  The
+    // leaves (parent, branch word, member) of such a run then share everything but that last op: see SW_CROSS.
+    struct CrossRun {
+        uint32_t lead = 0, n_members = 0;
+        std::vector<int16_t> kbit;       // per member: >= CHUNK_LOG: the trailing op's qubit; -1: chunk sums = C0; -2: not eligible
+        std::vector<double> u;           // per member: the trailing real 2x2 (row-major), 4 doubles
+        uint32_t desc = 0;               // SW_CROSS descriptor: the shared ops; register bits = their qubits + the lowest others
+        uint32_t reg_mask = 0;           // its register bits
+        int n_high = 0;                  // ... of which this many are >= CHUNK_LOG (the top register indices)
+        uint8_t high_bit[2] = {0, 0};    // ... namely these
+    };
+    std::vector<CrossRun> cross_runs;
+    std::vector<int32_t> cross_of_circuit;   // per circuit: index into cross_runs, -1: none
     // A new upload invalidates the compiled program but keeps the device buffers: the next program of similar size
     // reuses them (cudaFree synchronises the whole device and cudaMalloc of hundreds of MB is not free either).
     void invalidate() {
+        cross_runs.clear();
+        cross_of_circuit.clear();
         direct_host.clear();
         direct_flags.clear();
         valid = false;
@@ -125,6 +141,8 @@ struct DevProg {
     }
     void release() {
         direct.release();
+        cross_runs.clear();
+        cross_of_circuit.clear();
         direct_host.clear();
         direct_flags.clear();
         sweeps.release(); passes.release(); kops.release(); pool.release(); masks.release();
@@ -136,6 +154,259 @@ struct DevProg {
 };
 
 enum { DF_OK = 1, DF_VEC = 2, DF_RED = 4, DF_FINAL = 8, DF_PREP = 16 };
+
+// Sibling-group descriptors of every run of circuits that share a prefix (see DevProg::CrossRun): appended to
+// dp.direct_host behind the per-sweep and per-pass descriptors.
+template <typename PoolAt>
+void build_cross(DevProg& dp, PoolAt pool_at /* pool offset -> std::complex<double>, in device precision */) {
+    const Program& P = dp.P;
+    dp.cross_runs.clear();
+    dp.cross_of_circuit.assign(P.circuits.size(), -1);
+    if (P.mode != MODE_SV || dp.member_bits == 0 || P.n_bits < 10) return;
+    const int chunk_log = CHUNK_LOG;
+    auto final_desc = [&](size_t c) -> const DirectSweep* {
+        const CircuitInfo& ci = P.circuits[c];
+        if (ci.sweep_end <= ci.sweep_begin) return nullptr;
+        const DirectSweep& D = dp.direct_host[ci.sweep_end - 1];
+        if (!D.ok || !(D.flags & SW_FINAL) || (D.flags & SW_PREP)) return nullptr;
+        return &D;
+    };
+    auto n_elems = [](int kind) { return kind == K_M1 ? 4u : (kind == K_M2 ? 16u : (kind == K_D1 ? 2u : 0u)); };
+    // the same op (kind, global qubits, variant selection, matrix / mask contents) in two descriptors
+    auto same_op = [&](const DirectSweep& A, const KOp& a, const DirectSweep& B, const KOp& b) {
+        if (a.kind != b.kind || a.sel_shift != b.sel_shift || a.sel_mask != b.sel_mask) return false;
+        if (a.kind == K_SIGNS) {
+            if (a.count != b.count) return false;
+            for (uint32_t e = 0; e < a.count; e++)
+                if (P.masks[a.off + e] != P.masks[b.off + e]) return false;
+            return true;
+        }
+        if (a.kind == K_M4) return false;
+        if (a.kind == K_D1) {
+            if (a.gbit != b.gbit) return false;
+        } else {
+            if (A.rbit[a.t0] != B.rbit[b.t0]) return false;
+            if (a.kind == K_M2 && A.rbit[a.t1] != B.rbit[b.t1]) return false;
+        }
+        const uint32_t ne = n_elems(a.kind);
+        for (uint32_t v = 0; v <= a.sel_mask; v++)
+            for (uint32_t e = 0; e < ne; e++)
+                if (pool_at(a.off + v * a.stride + e) != pool_at(b.off + v * b.stride + e)) return false;
+        return true;
+    };
+    for (size_t c0 = 0; c0 < P.circuits.size();) {
+        size_t c1 = c0 + 1;
+        while (c1 < P.circuits.size() && P.circuits[c1].lead == (uint32_t)c0) c1++;
+        const size_t m = c1 - c0;
+        const size_t run_begin = c0;
+        c0 = c1;
+        if (m < 2) continue;
+        // base = a member with the fewest ops (the dataset circuit / the identity setting: no basis change).  A setting
+        // whose Hadamard was fused into the site's own matrices has as few ops but other contents: of the candidates,
+        // take the one most members extend.
+        const DirectSweep* base = nullptr;
+        {
+            int min_ops = 1 << 30;
+            for (size_t c = run_begin; c < c1; c++)
+                if (const DirectSweep* D = final_desc(c)) min_ops = std::min<int>(min_ops, D->nops);
+            size_t best = 0;
+            for (size_t c = run_begin; c < c1; c++) {
+                const DirectSweep* B = final_desc(c);
+                if (!B || B->nops != min_ops) continue;
+                size_t cnt = 0;
+                for (size_t c2 = run_begin; c2 < c1; c2++) {
+                    const DirectSweep* D = final_desc(c2);
+                    if (!D || D->nops < B->nops || D->nops > B->nops + 1) continue;
+                    bool same = true;
+                    for (int o = 0; o < B->nops && same; o++) same = same_op(*D, D->ops[o], *B, B->ops[o]);
+                    cnt += same ? 1 : 0;
+                }
+                if (cnt > best) {
+                    best = cnt;
+                    base = B;
+                }
+                if (best * 2 > m) break;      // a majority: no other candidate can beat it
+            }
+        }
+        if (g_trace.on) fprintf(stderr, "[qcd trace] sibling run candidate: circuits %zu..%zu, base %s\n", run_begin, c1 - 1, base ? "found" : "none");
+        if (!base) continue;
+        bool ok = true;
+        uint32_t r0_mask = 0;
+        for (int o = 0; o < base->nops && ok; o++) {
+            const KOp& op = base->ops[o];
+            if (op.kind == K_M4) ok = false;
+            if (op.kind == K_M1 || op.kind == K_M2) r0_mask |= 1u << base->rbit[op.t0];
+            if (op.kind == K_M2) r0_mask |= 1u << base->rbit[op.t1];
+        }
+        if (!ok || __builtin_popcount(r0_mask) > 2) {
+            if (g_trace.on) fprintf(stderr, "[qcd trace] sibling run rejected: shared-op qubits 0x%x\n", r0_mask);
+            continue;
+        }
+        {
+            // the shared passes only implement the slotted shape of stage_sweep (direct_ops.cuh): real 2x2 ops on distinct
+            // qubits, at most one sign layer, real 2x2 ops on distinct qubits -- what a noise site of real Kraus operators
+            // followed by CZ gates lowers to
+            uint32_t seen[2] = {0, 0};
+            int phase = 0;
+            for (int o = 0; o < base->nops && ok; o++) {
+                const KOp& op = base->ops[o];
+                if (op.kind == K_SIGNS) {
+                    if (phase == 1) ok = false;
+                    phase = 1;
+                } else if (op.kind == K_M1) {
+                    const uint32_t b = 1u << base->rbit[op.t0];
+                    if (seen[phase] & b) ok = false;
+                    seen[phase] |= b;
+                    for (uint32_t v = 0; v <= op.sel_mask && ok; v++)
+                        for (uint32_t e = 0; e < 4; e++)
+                            if (pool_at(op.off + v * op.stride + e).imag() != 0.0) ok = false;
+                } else {
+                    ok = false;
+                }
+            }
+            if (!ok) {
+                if (g_trace.on) fprintf(stderr, "[qcd trace] sibling run rejected: shared ops are not of the slotted shape\n");
+                continue;
+            }
+        }
+        DevProg::CrossRun R;
+        R.lead = (uint32_t)run_begin;
+        R.n_members = (uint32_t)m;
+        R.kbit.assign(m, -2);
+        R.u.assign(4 * m, 0.0);
+        uint32_t k_mask = 0;
+        size_t n_ok = 0;
+        // member j ends in the real 2x2 `u` on qubit k after the shared ops
+        auto accept = [&](size_t j, int k, const double* u) {
+            if (k < chunk_log) {
+                // acts inside the 32-amplitude chunks: their sums are unchanged iff the 2x2 is norm preserving
+                const double e0 = u[0] * u[0] + u[2] * u[2] - 1.0, e1 = u[1] * u[1] + u[3] * u[3] - 1.0,
+                             e2 = u[0] * u[1] + u[2] * u[3];
+                if (std::fabs(e0) > 1e-6 || std::fabs(e1) > 1e-6 || std::fabs(e2) > 1e-6) return false;   // device precision
+                R.kbit[j] = -1;
+            } else {
+                if ((k_mask >> k) & 1u) return false;      // a second member on the same qubit: it keeps its own sweep
+                k_mask |= 1u << k;
+                R.kbit[j] = (int16_t)k;
+                for (int e = 0; e < 4; e++) R.u[4 * j + e] = u[e];
+            }
+            return true;
+        };
+        for (size_t c = run_begin; c < c1; c++) {
+            const DirectSweep* D = final_desc(c);
+            if (!D || D->nops < base->nops || D->nops > base->nops + 1) continue;
+            const size_t j = c - run_begin;
+            int n_diff = 0, od = -1;
+            for (int o = 0; o < base->nops; o++)
+                if (!same_op(*D, D->ops[o], *base, base->ops[o])) {
+                    n_diff++;
+                    od = o;
+                }
+            if (n_diff == 0 && D->nops == base->nops) {
+                R.kbit[j] = -1;
+                n_ok++;
+                continue;
+            }
+            if (n_diff == 0) {      // one trailing op
+                const KOp& t = D->ops[base->nops];
+                if (t.kind != K_M1 || t.sel_mask != 0) continue;
+                double u[4];
+                bool real = true;
+                for (int e = 0; e < 4; e++) {
+                    u[e] = pool_at(t.off + e).real();
+                    real = real && pool_at(t.off + e).imag() == 0.0;
+                }
+                if (real && accept(j, D->rbit[t.t0], u)) n_ok++;
+                continue;
+            }
+            // The trailing 2x2 may have been fused into the shared op on its own qubit (no sign mask touches that qubit,
+            // so it commuted there): the one differing op is then U x (the shared op), variant by variant.
+            if (n_diff != 1 || D->nops != base->nops) continue;
+            const KOp &a = D->ops[od], &b = base->ops[od];
+            if (a.kind != K_M1 || b.kind != K_M1 || a.sel_shift != b.sel_shift || a.sel_mask != b.sel_mask ||
+                D->rbit[a.t0] != base->rbit[b.t0])
+                continue;
+            const int k = D->rbit[a.t0];
+            bool commutes = true;
+            for (int o = 0; o < base->nops && commutes; o++) {
+                const KOp& op = base->ops[o];
+                if (op.kind == K_SIGNS)
+                    for (uint32_t e = 0; e < op.count; e++)
+                        if ((P.masks[op.off + e] >> k) & 1u) commutes = false;
+                if (op.kind == K_D1 && op.gbit == k) commutes = false;
+                if (o > od && op.kind == K_M1 && base->rbit[op.t0] == k) commutes = false;
+            }
+            if (!commutes) continue;
+            double u[4] = {0, 0, 0, 0};
+            bool have_u = false, fits = true;
+            for (uint32_t v = 0; v <= a.sel_mask && fits; v++) {
+                double M[4], N[4];
+                for (int e = 0; e < 4; e++) {
+                    M[e] = pool_at(b.off + v * b.stride + e).real();
+                    N[e] = pool_at(a.off + v * a.stride + e).real();
+                    if (pool_at(a.off + v * a.stride + e).imag() != 0.0) fits = false;
+                }
+                const double det = M[0] * M[3] - M[1] * M[2];
+                if (!have_u && std::fabs(det) > 1e-3) {       // U = N M^-1 from an invertible variant (the no-jump operator)
+                    u[0] = (N[0] * M[3] - N[1] * M[2]) / det;
+                    u[1] = (N[1] * M[0] - N[0] * M[1]) / det;
+                    u[2] = (N[2] * M[3] - N[3] * M[2]) / det;
+                    u[3] = (N[3] * M[0] - N[2] * M[1]) / det;
+                    have_u = true;
+                }
+            }
+            if (!have_u || !fits) continue;
+            for (uint32_t v = 0; v <= a.sel_mask && fits; v++) {
+                double M[4], N[4];
+                for (int e = 0; e < 4; e++) {
+                    M[e] = pool_at(b.off + v * b.stride + e).real();
+                    N[e] = pool_at(a.off + v * a.stride + e).real();
+                }
+                const double r[4] = {u[0] * M[0] + u[1] * M[2], u[0] * M[1] + u[1] * M[3], u[2] * M[0] + u[3] * M[2],
+                                     u[2] * M[1] + u[3] * M[3]};
+                for (int e = 0; e < 4; e++) fits = fits && std::fabs(r[e] - N[e]) < 1e-5;
+            }
+            if (fits && accept(j, k, u)) n_ok++;
+        }
+        if (n_ok < 2) {
+            if (g_trace.on) fprintf(stderr, "[qcd trace] sibling run rejected: %zu eligible member(s)\n", n_ok);
+            continue;
+        }
+        // the descriptor: register bits = base's matrix qubits + the lowest other bits (so that index bit 0 is always a
+        // register bit: 128-bit loads)
+        {
+            DirectSweep D = *base;               // (copy first: direct_host grows below)
+            uint32_t bits = r0_mask;
+            for (int b = 0; __builtin_popcount(bits) < REG_BITS; b++) bits |= 1u << b;
+            int idx_of[32];
+            int ri = 0;
+            for (int b = 0; b < 32; b++)
+                if ((bits >> b) & 1u) {
+                    idx_of[b] = ri;
+                    D.rbit[ri++] = (uint8_t)b;
+                    if (b >= chunk_log) R.high_bit[R.n_high++] = (uint8_t)b;
+                }
+            for (int o = 0; o < D.nops; o++) {
+                KOp& op = D.ops[o];
+                if (op.kind == K_M1 || op.kind == K_M2) {
+                    const int g0 = base->rbit[op.t0], g1 = base->rbit[op.t1 & 3];
+                    op.t0 = (uint8_t)idx_of[g0];
+                    if (op.kind == K_M2) op.t1 = (uint8_t)idx_of[g1];
+                }
+            }
+            D.red_q[0] = D.red_q[1] = -1;
+            D.flags = SW_FINAL | SW_CROSS;
+            R.reg_mask = bits;
+            dp.direct_host.push_back(D);
+            R.desc = (uint32_t)(dp.direct_host.size() - 1);
+        }
+        if (g_trace.on)
+            fprintf(stderr, "[qcd trace] sibling run: circuits %zu..%zu, %zu eligible, shared-op qubits 0x%x, %d high\n",
+                    run_begin, c1 - 1, n_ok, r0_mask, R.n_high);
+        for (size_t c = run_begin; c < c1; c++) dp.cross_of_circuit[c] = (int32_t)dp.cross_runs.size();
+        dp.cross_runs.push_back(std::move(R));
+    }
+}
 
 }  // namespace
 
@@ -158,6 +429,8 @@ struct qcd_ctx {
     uint32_t nostore_max = 256;  // leaves with at most this many trajectories are sampled without writing their state
                                  // (measured on C4: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3 ms per step)
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
+    bool leaf_cross = true;      // unstored sibling leaves (same parent, same branch word, members of one run) take their
+                                 // chunk sums from shared passes over the parent (SW_CROSS) instead of one sweep each
     uint32_t hist_row0 = 0;      // uploaded circuit that row 0 of the caller's histogram buffer stands for
     int dm_on_chip = 1;          // density matrices that fit a thread-block cluster's shared memory: interpret the gate list
                                  // there (dm_cluster.cu) instead of lowering it to sweeps.  0 never, 1 when the cluster
@@ -191,7 +464,7 @@ struct qcd_ctx {
     int prog_tile_bits[2][2] = {{0, 0}, {0, 0}};
     // arenas / scratch
     DevBuf states, partials, chunk_sums, block_sums;
-    DevBuf owner, keys, probs4, table, offs, children, counter, bsum, flip, masks, scratch, slots;
+    DevBuf owner, keys, probs4, table, offs, children, counter, bsum, flip, masks, scratch, slots, compose, cross_recs;
     std::vector<DevBuf> level_nodes, level_shots;
     PinBuf flip_host;                 // staging of the readout flip table (asynchronous upload)
     cudaEvent_t flip_staged = nullptr;
@@ -470,6 +743,22 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             for (std::thread& th : pool) th.join();
         }
     }
+    if (mode == MODE_SV) {
+        const size_t n0 = dp.direct_host.size();
+        // the matrix pool only exists per lowering thread, already in device precision
+        build_cross(dp, [&](size_t off) -> std::complex<double> {
+            size_t t = 0;
+            while (t + 1 < pool_elems.size() && off >= pool_elems[t]) off -= pool_elems[t++];
+            if (precision == 64) {
+                const double2 v = reinterpret_cast<const double2*>(dev_pools[t].data())[off];
+                return std::complex<double>(v.x, v.y);
+            }
+            const float2 v = reinterpret_cast<const float2*>(dev_pools[t].data())[off];
+            return std::complex<double>(v.x, v.y);
+        });
+        dp.direct_flags.resize(dp.direct_host.size(), 0);
+        for (size_t i = n0; i < dp.direct_host.size(); i++) flags_of(i);
+    }
     if ((rc = upload_vec(ctx, dp.direct, dp.direct_host))) return rc;
     int k = std::min(P.k_max, P.n_bits);
     if (precision == 64) CU(configure_sweep<double>(k));
@@ -569,6 +858,14 @@ struct SvRunner {
     std::vector<uint32_t> free_slots;
     uint64_t table_cap = 0;
     uint64_t live = 0;
+    uint64_t n_slots = 0;
+    bool cross = false;      // sibling groups enabled for this run (chunk_sums then holds a second region: C0 per slot)
+    std::vector<NodeRec> cross_own;           // per leaf launch: the nodes that keep their own sweep
+    std::vector<CrossRec> cross_passes;       // ... and the shared passes of the sibling groups
+    std::vector<ComposeRec> cross_comp;
+    std::vector<uint32_t> cross_idx;
+    uint64_t grp_members[66] = {0}, grp_passes[66] = {0}, own_leaves = 0;   // QCD_TRACE: sibling groups by size
+    double* c0_sums() const { return cross ? ctx->chunk_sums.as<double>() + n_slots * (uint64_t)n_chunks : nullptr; }
 
     uint32_t alloc_slot() {
         uint32_t s = free_slots.back();
@@ -600,6 +897,112 @@ struct SvRunner {
         return a;
     }
 
+
+    // Sibling groups of a leaf launch: unstored leaves with the same parent and branch word whose circuits belong to one
+    // CrossRun.  Members are flagged NODE_CROSSED (pad = 1 + index of their ComposeRec) and take no sweep of their own;
+    // cross_passes receives the groups' shared passes (4 lane-exchanged cross bits each), cross_own the nodes that keep
+    // their own sweep.  Returns the number of shared passes (0: nothing grouped, the launch is unchanged).
+    size_t plan_cross(NodeRec* chunk, size_t c, size_t* n_crossed, int* n_high) {
+        cross_own.clear();
+        cross_passes.clear();
+        cross_comp.clear();
+        *n_crossed = 0;
+        *n_high = -1;
+        const int chunk_log = std::min(n, CHUNK_LOG);
+        for (size_t i = 0; i < c;) {
+            size_t j = i;
+            while (j < c && chunk[j].parent == chunk[i].parent) j++;
+            cross_idx.clear();
+            for (size_t t = i; t < j; t++) {
+                const NodeRec& r = chunk[t];
+                if ((r.flags & (NODE_LEAF | NODE_NOSTORE)) != (NODE_LEAF | NODE_NOSTORE)) continue;
+                const int32_t cr = dp->cross_of_circuit[r.circuit];
+                if (cr < 0) continue;
+                const DevProg::CrossRun& CR = dp->cross_runs[cr];
+                if (*n_high >= 0 && CR.n_high != *n_high) continue;      // one kernel variant per launch
+                if (CR.kbit[r.circuit - CR.lead] != -2) cross_idx.push_back((uint32_t)t);
+            }
+            i = j;
+            if (cross_idx.size() < 2) continue;
+            std::stable_sort(cross_idx.begin(), cross_idx.end(),
+                             [&](uint32_t a, uint32_t b) { return chunk[a].branch < chunk[b].branch; });
+            for (size_t a = 0; a < cross_idx.size();) {
+                size_t b = a;
+                while (b < cross_idx.size() && chunk[cross_idx[b]].branch == chunk[cross_idx[a]].branch) b++;
+                const size_t members = b - a;
+                const NodeRec first = chunk[cross_idx[a]];
+                const DevProg::CrossRun& CR = dp->cross_runs[dp->cross_of_circuit[first.circuit]];
+                // cross bits of the members: the shared ops' own high qubits come for free with the first pass, the
+                // others ride on lane bits, four per pass
+                uint32_t x_reg[2] = {NO_SLOT, NO_SLOT};
+                std::pair<uint8_t, uint32_t> kl[64];      // (bit, slot of the member that owns it)
+                size_t nk = 0;
+                for (size_t t = a; t < b; t++) {
+                    const NodeRec& r = chunk[cross_idx[t]];
+                    const int k = CR.kbit[r.circuit - CR.lead];
+                    if (k < 0) continue;
+                    if ((CR.reg_mask >> k) & 1u) x_reg[CR.high_bit[0] == k ? 0 : 1] = r.dst_slot;
+                    else kl[nk++] = std::make_pair((uint8_t)k, r.dst_slot);
+                }
+                const size_t n_pass = std::max<size_t>(1, (nk + 3) / 4);
+                // a shared pass costs about 2.5 sweeps of one unstored leaf (measured: 3.1 us against 1.2 us at n = 20)
+                if (5 * n_pass >= 2 * members) {      // nothing saved
+                    a = b;
+                    continue;
+                }
+                *n_high = CR.n_high;
+                for (size_t pi = 0; pi < n_pass; pi++) {
+                    CrossRec pr;
+                    memset(&pr, 0, sizeof(pr));
+                    pr.src_slot = first.src_slot;
+                    pr.c0_slot = pi == 0 ? first.dst_slot : NO_SLOT;
+                    pr.sweep = CR.desc;
+                    pr.branch = first.branch;
+                    pr.scale = first.scale;
+                    uint32_t used = CR.reg_mask;
+                    int nl = 0;
+                    for (size_t q = 4 * pi; q < std::min(nk, 4 * pi + 4); q++) {
+                        pr.lane_bit[nl] = kl[q].first;
+                        pr.x_lane[nl] = kl[q].second;
+                        used |= 1u << kl[q].first;
+                        nl++;
+                    }
+                    pr.n_klanes = (uint8_t)nl;
+                    for (int bb = 0; nl < 5; bb++)      // the lowest free bits fill the warp
+                        if (!((used >> bb) & 1u)) pr.lane_bit[nl++] = (uint8_t)bb;
+                    for (int q = pr.n_klanes; q < 4; q++) pr.x_lane[q] = NO_SLOT;
+                    pr.x_reg[0] = pi == 0 ? x_reg[0] : NO_SLOT;
+                    pr.x_reg[1] = pi == 0 ? x_reg[1] : NO_SLOT;
+                    cross_passes.push_back(pr);
+                }
+                for (size_t t = a; t < b; t++) {
+                    NodeRec& r = chunk[cross_idx[t]];
+                    const size_t m = r.circuit - CR.lead;
+                    const int k = CR.kbit[m];
+                    ComposeRec cr;
+                    cr.c0_slot = first.dst_slot;
+                    cr.kb = k >= 0 ? 1u << (k - chunk_log) : 0u;
+                    const double* u = &CR.u[4 * m];
+                    cr.q[0] = u[0] * u[0]; cr.q[1] = u[1] * u[1]; cr.q[2] = 2.0 * u[0] * u[1];
+                    cr.q[3] = u[2] * u[2]; cr.q[4] = u[3] * u[3]; cr.q[5] = 2.0 * u[2] * u[3];
+                    cross_comp.push_back(cr);
+                    r.flags |= NODE_CROSSED;
+                    r.pad = (uint32_t)cross_comp.size();
+                }
+                *n_crossed += members;
+                if (g_trace.on) {
+                    grp_members[std::min<size_t>(members, 65)]++;
+                    grp_passes[std::min<size_t>(members, 65)] += n_pass;
+                }
+                a = b;
+            }
+        }
+        if (cross_passes.empty()) return 0;
+        for (size_t t = 0; t < c; t++)
+            if (!(chunk[t].flags & NODE_CROSSED)) cross_own.push_back(chunk[t]);
+        return cross_passes.size();
+    }
+
     // Measurement sampling of every leaf of nodes[begin, end) (the WHOLE batch, before anything below it is swept:
     // NODE_NOSTORE leaves read their parent's slot, which the host may already have returned to the free list).
     int sample_leaves(int d, const NodeRec* nodes, size_t begin, size_t end, bool* owner_filled = nullptr) {
@@ -620,7 +1023,8 @@ struct SvRunner {
         launch_fill_owner(ndev, (uint32_t)n_nodes, owner, tc, st);
         if (owner_filled) *owner_filled = true;   // same nodes, same trajectory range: the decide step reuses it
         launch_scan_chunks(ndev, (uint32_t)n_nodes, ctx->chunk_sums.as<double>(), n_chunks,
-                           ctx->block_sums.as<double>(), n_blocks, n_chunks, st);
+                           ctx->block_sums.as<double>(), n_blocks, n_chunks, st,
+                           cross ? ctx->compose.as<ComposeRec>() : nullptr, c0_sums());
         ctx->stats.aux_launches += 3;
         if (any_stored) {
             launch_sample<T>(ndev, (uint32_t)n_nodes, ctx->states.p, slot_stride, ctx->chunk_sums.as<double>(), n_chunks,
@@ -771,16 +1175,56 @@ struct SvRunner {
                         n_nostore++;
                     }
             }
+            // sibling groups: their members take no sweep of their own
+            size_t n_crossed = 0, n_cross_passes = 0;
+            int cross_nh = 0;
+            if (cross && direct && !is_root && n_leaf_nodes == c && n_nostore >= 2)
+                n_cross_passes = plan_cross(chunk, c, &n_crossed, &cross_nh);
+            const size_t n_own = n_cross_passes ? c - n_crossed : c;     // nodes swept by the ordinary launch
             CU(cudaMemcpyAsync(cdev, chunk, c * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
-            SweepArgs sa = sweep_args(cdev, (uint32_t)c);
-            uint32_t parts_used = tiles;
-            if (direct) {
+            const NodeRec* own_dev = cdev;
+            auto ctas_log2 = [&](uint64_t cnt) {
                 // CTAs per state: 8 register groups per thread when there are plenty of states, fewer otherwise
                 int pl = std::max(0, n - 4 - 8 - 3);
-                while (pl < n - 4 - 8 && ((uint64_t)c << pl) < 1184) pl++;
-                while (((uint64_t)c << pl) > 0x7fffffffull) pl--;
+                while (pl < n - 4 - 8 && (cnt << pl) < 1184) pl++;
+                while ((cnt << pl) > 0x7fffffffull) pl--;
+                return pl;
+            };
+            if (n_cross_passes) {
+                CU(ctx->children.ensure(std::max<size_t>(1, cross_own.size()) * sizeof(NodeRec)));
+                CU(cudaMemcpyAsync(ctx->children.p, cross_own.data(), cross_own.size() * sizeof(NodeRec),
+                                   cudaMemcpyHostToDevice, st));
+                CU(ctx->compose.ensure(cross_comp.size() * sizeof(ComposeRec)));
+                CU(cudaMemcpyAsync(ctx->compose.p, cross_comp.data(), cross_comp.size() * sizeof(ComposeRec),
+                                   cudaMemcpyHostToDevice, st));
+                CU(ctx->cross_recs.ensure(cross_passes.size() * sizeof(CrossRec)));
+                CU(cudaMemcpyAsync(ctx->cross_recs.p, cross_passes.data(), cross_passes.size() * sizeof(CrossRec),
+                                   cudaMemcpyHostToDevice, st));
+                own_dev = ctx->children.as<NodeRec>();
+                n_nostore -= n_crossed;
+                ctx->stats.cross_passes += n_cross_passes;
+                ctx->stats.cross_leaves += n_crossed;
+                // a pass has >= 2^(n - 11) warp units (16 amplitudes x 32 lanes x the iteration bits): about 4 per warp,
+                // i.e. as many CTAs per state as the sweep kernel uses -- the CTAs resident at one time then cover a few
+                // parents only, and the later passes of a group find theirs in L2 (one CTA per pass streamed a whole
+                // state each: every pass came from DRAM, 3.9 us per pass measured)
+                int pl = std::max(0, n - 11 - 2 - 2);
+                if (const char* v = getenv("QCD_CROSS_PL")) pl = std::max(0, pl + atoi(v));      // tuning only
+                while (pl < n - 11 - 2 && ((uint64_t)n_cross_passes << pl) < 1184) pl++;
+                sweep_begin(ctx, SK_LEAF, (uint64_t)n_cross_passes * slot_stride * sizeof(C), st);
+                launch_leaf_cross<T>(prog, ctx->cross_recs.as<CrossRec>(), (uint32_t)n_cross_passes, ctx->states.p,
+                                     slot_stride, c0_sums(), ctx->chunk_sums.as<double>(), n_chunks, n, cross_nh,
+                                     (uint32_t)std::max(pl, 0), st);
+                sweep_end(ctx, st);
+                CU(cudaGetLastError());
+                ctx->stats.node_sweeps += n_cross_passes;
+            }
+            SweepArgs sa = sweep_args(own_dev, (uint32_t)n_own);
+            uint32_t parts_used = tiles;
+            if (direct) {
+                const int pl = ctas_log2(std::max<size_t>(n_own, 1));
                 sa.tiles_log2 = (uint32_t)pl;
-                sa.n_items = (uint32_t)(c << pl);
+                sa.n_items = (uint32_t)(n_own << pl);
                 sa.direct_vec = vec ? 1 : 0;
                 sa.direct_kind = (!need_red && !need_chunks) ? 0u : ((need_prep || (need_red && need_chunks)) ? 3u
                                                                      : (need_red ? 1u : 2u));
@@ -848,14 +1292,14 @@ struct SvRunner {
                     CU(cudaGetLastError());
                 }
                 ctx->stats.node_sweeps += c;
-            } else {
+            } else if (n_own) {
                 sweep_begin(ctx, is_root ? SK_PREP : launch_kind_of,
-                            ((uint64_t)c * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C), st);
+                            ((uint64_t)n_own * (is_root ? 1 : 2) - n_nostore) * slot_stride * sizeof(C), st);
                 if (direct) launch_sweep_direct<T>(prog, sa, st);
                 else launch_sweep<T>(prog, sa, k, st);
                 sweep_end(ctx, st);
                 CU(cudaGetLastError());
-                ctx->stats.node_sweeps += c;
+                ctx->stats.node_sweeps += n_own;
             }
             pos += c;
             if (!is_root) {
@@ -920,13 +1364,19 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
     // ---- state slots
     const size_t slot_bytes = R.slot_stride * sizeof(C);
     R.part_stride = std::max<uint32_t>(R.tiles, n >= 12 ? 1u << (n - 12) : 1u);
-    const size_t per_slot = slot_bytes + (size_t)R.part_stride * 32 + (size_t)R.n_chunks * 8 + (size_t)R.n_blocks * 8;
+    // sibling groups: a second chunk-sum region (C0 of the group whose first member owns the slot)
+    // (the region is sized from the options alone: the arena must not change shape between a program with sibling
+    // groups and one without -- the reference-facing API alternates between the dataset circuit and its settings)
+    const bool cross_region = ctx->leaf_cross && ctx->use_direct && n >= ctx->direct_min_bits && ctx->nostore_max > 0;
+    R.cross = cross_region && share && !dp->cross_runs.empty();
+    const size_t cs_per_slot = (size_t)R.n_chunks * 8 * (cross_region ? 2 : 1);
+    const size_t per_slot = slot_bytes + (size_t)R.part_stride * 32 + cs_per_slot + (size_t)R.n_blocks * 8;
     // Keep the arena we already hold when it is adequate: the budget follows the device's free memory, which moves
     // with the caller's own allocations, and re-allocating a ~100 GB arena costs tens of milliseconds per call.  The
     // free-memory query itself is not free either: while the arena is adequate it is repeated every 16th run only.
     const uint64_t have = std::min(std::min<uint64_t>(ctx->states.cap / slot_bytes,
                                                       ctx->partials.cap / ((size_t)R.part_stride * 32)),
-                                   std::min<uint64_t>(ctx->chunk_sums.cap / ((size_t)R.n_chunks * 8),
+                                   std::min<uint64_t>(ctx->chunk_sums.cap / cs_per_slot,
                                                       ctx->block_sums.cap / ((size_t)R.n_blocks * 8)));
     const bool adequate = have >= (uint64_t)R.max_sweeps + 1 && !ctx->max_slots;
     size_t budget;
@@ -957,8 +1407,9 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
                         std::to_string(R.max_sweeps + 1));
     CU(ctx->states.ensure(n_slots * slot_bytes));
     CU(ctx->partials.ensure(n_slots * (size_t)R.part_stride * 32));
-    CU(ctx->chunk_sums.ensure(n_slots * (size_t)R.n_chunks * 8));
+    CU(ctx->chunk_sums.ensure(n_slots * cs_per_slot));
     CU(ctx->block_sums.ensure(n_slots * (size_t)R.n_blocks * 8));
+    R.n_slots = n_slots;
     R.free_slots.resize(n_slots);
     for (uint64_t i = 0; i < n_slots; i++) R.free_slots[i] = (uint32_t)(n_slots - 1 - i);
 
@@ -1047,6 +1498,14 @@ int run_sv(qcd_ctx* ctx, DevProg* dp, uint64_t spc, uint64_t seed, uint64_t shot
                 g_trace.t_leaves * 1e3, g_trace.t_launch * 1e3, g_trace.t_prep * 1e3, (Trace::now() - g_trace.t_run0) * 1e3);
         g_trace.t_sync = g_trace.t_h2d = g_trace.t_prep = g_trace.t_launch = g_trace.t_leaves = 0;
         g_trace.n_sync = 0;
+        if (R.cross) {
+            fprintf(stderr, "[qcd trace] sibling groups (members: groups / passes):");
+            for (int m = 2; m < 66; m++)
+                if (R.grp_members[m]) fprintf(stderr, " %d: %llu / %llu;", m, (unsigned long long)R.grp_members[m],
+                                              (unsigned long long)R.grp_passes[m]);
+            fprintf(stderr, "  leaves %llu, crossed %llu, passes %llu\n", (unsigned long long)ctx->stats.leaves,
+                    (unsigned long long)ctx->stats.cross_leaves, (unsigned long long)ctx->stats.cross_passes);
+        }
     }
     return finish_timing(ctx);
 }
@@ -1495,6 +1954,7 @@ int qcd_create(int cuda_device, size_t mem_budget_bytes, qcd_ctx** out) {
     c->budget = mem_budget_bytes;
     if (const char* v = getenv("QCD_DIRECT_MIN_BITS")) c->direct_min_bits = std::max(9, atoi(v));
     if (const char* v = getenv("QCD_DM_ON_CHIP")) c->dm_on_chip = atoi(v);          // A/B measurements of whole programs
+    if (const char* v = getenv("QCD_LEAF_CROSS")) c->leaf_cross = atoi(v) != 0;
     memset(&c->stats, 0, sizeof(c->stats));
     *out = c;
     return QCD_OK;
@@ -1507,7 +1967,7 @@ void qcd_destroy(qcd_ctx* ctx) {
         for (int p = 0; p < 2; p++) ctx->prog[m][p].release();
     DevBuf* bufs[] = {&ctx->states, &ctx->partials, &ctx->chunk_sums, &ctx->block_sums, &ctx->owner, &ctx->keys,
                       &ctx->probs4, &ctx->table, &ctx->offs, &ctx->children, &ctx->counter, &ctx->bsum, &ctx->flip,
-                      &ctx->masks, &ctx->scratch, &ctx->slots};
+                      &ctx->masks, &ctx->scratch, &ctx->slots, &ctx->compose, &ctx->cross_recs};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf* b : {&ctx->interp.ops, &ctx->interp.params, &ctx->interp.sched, &ctx->interp.passes, &ctx->interp.pass_off})
         b->release();
@@ -1541,6 +2001,7 @@ int qcd_set_option(qcd_ctx* ctx, const char* key, double value) {
     else if (k == "use_direct") ctx->use_direct = value != 0;
     else if (k == "direct_min_bits") ctx->direct_min_bits = std::max(9, (int)value);
     else if (k == "nostore_max") ctx->nostore_max = (uint32_t)value;
+    else if (k == "leaf_cross") ctx->leaf_cross = value != 0;
     else if (k == "no_slots") ctx->no_slots = value != 0;
     else if (k == "share_prefix") ctx->share_prefix = value != 0;
     else if (k == "hist_row0") ctx->hist_row0 = (uint32_t)value;

@@ -378,15 +378,20 @@ __device__ __forceinline__ void block_scan_1024(double (&v)[4], double* warp_tot
     __syncthreads();
 }
 
-// level 1: each CTA scans one block of 1024 chunk sums in place, writes the block total
+// level 1: each CTA scans one block of 1024 chunk sums in place, writes the block total.  Members of a sibling group
+// (NODE_CROSSED) first form their chunk sums from the group's shared sums: see ComposeRec.
 __global__ void scan_l1_kernel(const NodeRec* leaves, const uint32_t* slots, double* chunk_sums, uint64_t chunk_stride,
-                               double* block_sums, uint64_t block_stride, uint32_t n_chunks) {
+                               double* block_sums, uint64_t block_stride, uint32_t n_chunks, const ComposeRec* comp,
+                               const double* c0_sums) {
     __shared__ double warp_tot[8];
     const uint32_t item = blockIdx.y;
     uint32_t slot;
+    const ComposeRec* cr = nullptr;
     if (leaves) {
-        if (!(leaves[item].flags & NODE_LEAF)) return;
+        const uint32_t fl = leaves[item].flags;
+        if (!(fl & NODE_LEAF)) return;
         slot = leaves[item].dst_slot;
+        if (comp && (fl & NODE_CROSSED)) cr = comp + (leaves[item].pad - 1u);
     } else {
         slot = slots ? slots[item] : item;
     }
@@ -394,8 +399,29 @@ __global__ void scan_l1_kernel(const NodeRec* leaves, const uint32_t* slots, dou
     const uint32_t b = blockIdx.x;
     const uint32_t base = (b << SCAN_BLOCK_LOG) + threadIdx.x * 4u;
     double v[4];
+    if (cr) {
+        const double* c0 = c0_sums + (uint64_t)cr->c0_slot * chunk_stride;
+        const uint32_t kb = cr->kb;
 #pragma unroll
-    for (int e = 0; e < 4; e++) v[e] = (base + e < n_chunks) ? cs[base + e] : 0.0;
+        for (int e = 0; e < 4; e++) {
+            const uint32_t c = base + e;
+            double r = 0.0;
+            if (c < n_chunks) {
+                if (kb == 0) {
+                    r = c0[c];
+                } else {
+                    const double A = c0[c & ~kb], B = c0[c | kb], X = cs[c];
+                    const double* q = cr->q + ((c & kb) ? 3 : 0);
+                    r = q[0] * A + q[1] * B + q[2] * X;
+                    r = r > 0.0 ? r : 0.0;      // destructive interference: the exact value is >= 0, rounding may not be
+                }
+            }
+            v[e] = r;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (base + e < n_chunks) ? cs[base + e] : 0.0;
+    }
     block_scan_1024(v, warp_tot, 0.0);
 #pragma unroll
     for (int e = 0; e < 4; e++)
@@ -809,13 +835,14 @@ void launch_iota(uint32_t* p, uint32_t n, uint32_t start, cudaStream_t st) {
     if (n) iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n, start);
 }
 void launch_scan_chunks(const NodeRec* leaves, uint32_t n_leaves, double* chunk_sums, uint64_t chunk_stride,
-                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st) {
+                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st,
+                        const ComposeRec* comp, const double* c0_sums) {
     if (!n_leaves) return;
     const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
     for (uint32_t y0 = 0; y0 < n_leaves; y0 += 32768) {
         uint32_t ny = n_leaves - y0 < 32768 ? n_leaves - y0 : 32768;
         scan_l1_kernel<<<dim3(n_blocks, ny), 256, 0, st>>>(leaves + y0, nullptr, chunk_sums, chunk_stride, block_sums,
-                                                           block_stride, n_chunks);
+                                                           block_stride, n_chunks, comp, c0_sums);
     }
     scan_l2_kernel<<<n_leaves, 256, 0, st>>>(leaves, nullptr, block_sums, block_stride, n_blocks);
 }
@@ -827,7 +854,7 @@ void launch_scan_vectors(uint32_t n_vec, double* chunk_sums, uint64_t chunk_stri
         uint32_t ny = n_vec - y0 < 32768 ? n_vec - y0 : 32768;
         scan_l1_kernel<<<dim3(n_blocks, ny), 256, 0, st>>>(nullptr, nullptr, chunk_sums + (uint64_t)y0 * chunk_stride,
                                                            chunk_stride, block_sums + (uint64_t)y0 * block_stride,
-                                                           block_stride, n_chunks);
+                                                           block_stride, n_chunks, nullptr, nullptr);
     }
     scan_l2_kernel<<<n_vec, 256, 0, st>>>(nullptr, nullptr, block_sums, block_stride, n_blocks);
 }

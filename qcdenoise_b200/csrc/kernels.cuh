@@ -62,6 +62,34 @@ __device__ __forceinline__ uint64_t traj_shot(const TrajMap& m, uint32_t tid, ui
 #endif
 constexpr uint32_t NODE_LEAF = 1;
 constexpr uint32_t NODE_NOSTORE = 2;   // leaf whose state is not written: sampled by recomputing chunks from the parent
+constexpr uint32_t NODE_CROSSED = 4;   // NOSTORE leaf whose chunk sums come from its sibling group's shared passes (pad =
+                                       // 1 + index of its ComposeRec); it takes no sweep of its own
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+
+// Chunk sums of one member of a sibling group from the group's shared sums (see SW_CROSS): with A = C0[c & ~kb],
+// B = C0[c | kb], X = X_k[c]:  sum(c) = q[0] A + q[1] B + q[2] X  (chunk bit kb clear),  q[3] A + q[4] B + q[5] X (set);
+// kb == 0: sum(c) = C0[c] (no trailing op, or one that acts inside the 32-amplitude chunks).
+// One shared pass over the parent state of a sibling group (leaf_cross_kernel).  A thread holds the 16 amplitudes of the
+// SW_CROSS descriptor's register bits (the shared ops' qubits + the lowest other bits); the 5 lane bits of a warp are up to
+// 4 cross bits k (their X_k come from lane exchanges) + the lowest free bits.
+struct CrossRec {
+    uint32_t src_slot;       // parent state
+    uint32_t c0_slot;        // slot of c0_sums that receives C0 (NO_SLOT: not emitted by this pass)
+    uint32_t sweep;          // SW_CROSS descriptor
+    uint32_t branch;
+    double scale;
+    uint8_t lane_bit[5];     // global index bit carried by lane bit j
+    uint8_t n_klanes;        // lane bits [0, n_klanes) are cross bits
+    uint8_t pad[2];
+    uint32_t x_lane[4];      // chunk_sums slot that receives X of lane_bit[j]
+    uint32_t x_reg[2];       // ... of the descriptor's j-th register bit >= CHUNK_LOG (NO_SLOT: not wanted)
+};
+
+struct ComposeRec {
+    uint32_t c0_slot;
+    uint32_t kb;
+    double q[6];
+};
 
 template <typename T> struct Cplx;
 template <> struct Cplx<float> { typedef float2 type; };
@@ -110,6 +138,12 @@ cudaError_t configure_sweep(int k);
 template <typename T>
 void launch_sweep_direct(const DevProgram<T>& prog, const SweepArgs& a, cudaStream_t st);
 
+// c0_sums / chunk_sums: [slot][chunk_stride]; ctas_log2: CTAs per pass
+template <typename T>
+void launch_leaf_cross(const DevProgram<T>& prog, const CrossRec* recs, uint32_t n_recs, const void* states,
+                       uint64_t slot_stride, double* c0_sums, double* chunk_sums, uint64_t chunk_stride, int n_bits,
+                       int n_high_reg, uint32_t ctas_log2, cudaStream_t st);
+
 template <typename T>
 void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, const void* states, uint64_t slot_stride,
                            const double* chunk_sums, uint64_t chunk_stride, const double* block_sums,
@@ -145,8 +179,10 @@ void launch_fill_owner(const NodeRec* nodes, uint32_t n_nodes, uint32_t* owner, 
 void launch_iota(uint32_t* p, uint32_t n, uint32_t start, cudaStream_t st);
 
 // ---- sampling
+// comp != NULL: leaves flagged NODE_CROSSED first form their chunk sums from their group's shared sums (ComposeRec)
 void launch_scan_chunks(const NodeRec* leaves, uint32_t n_leaves, double* chunk_sums, uint64_t chunk_stride,
-                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st);
+                        double* block_sums, uint64_t block_stride, uint32_t n_chunks, cudaStream_t st,
+                        const ComposeRec* comp = nullptr, const double* c0_sums = nullptr);
 template <typename T>
 void launch_sample(const NodeRec* leaves, uint32_t n_leaves, const void* states, uint64_t slot_stride,
                    const double* chunk_sums, uint64_t chunk_stride, const double* block_sums, uint64_t block_stride,

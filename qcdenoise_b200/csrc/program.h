@@ -38,7 +38,11 @@ struct Pass {
 
 enum SweepFlags : uint8_t {
     SW_PREP = 1,   // source is the product state prep[] (no read)
-    SW_FINAL = 2   // last sweep of the circuit: also emit 32-amplitude chunk sums of |amp|^2
+    SW_FINAL = 2,  // last sweep of the circuit: also emit 32-amplitude chunk sums of |amp|^2
+    SW_CROSS = 4   // DirectSweep only: the ops SHARED by the final sweeps of a run of sibling circuits (everything but a
+                   // member's trailing real 2x2 on one qubit k); the launch emits the chunk sums C0 of |amp|^2 and, for the
+                   // register bits named in red_q[], the chunk sums X_k of Re(conj(amp[x]) amp[x ^ 2^k]), from which the
+                   // chunk sums of every member follow without sweeping the state once per member
 };
 
 struct Sweep {
@@ -82,7 +86,7 @@ struct DirectSweep {
     uint8_t nreg;
     uint8_t nops;
     uint8_t rbit[REG_BITS];     // GLOBAL bit of register bit i, ascending
-    int8_t red_q[2];
+    int8_t red_q[2];            // SW_CROSS: REGISTER indices of the (up to two) bits k whose cross sums are emitted
     uint8_t flags;              // SW_PREP: the source is the product state at prep_off (no read)
     uint8_t pad;
     uint32_t prep_off;

@@ -32,6 +32,9 @@ constexpr int DT = DIRECT_DT;  // threads per CTA
 #ifndef DIRECT_MINB
 #define DIRECT_MINB 8
 #endif
+#ifndef CROSS_MINB
+#define CROSS_MINB 4      // leaf_cross_kernel, complex64: 128 registers per thread (5: 96 registers and 88 bytes of spills)
+#endif
 using namespace dops;
 
 // The 16 amplitudes of register group gb BEFORE the sweep's ops: product state (prep sweeps) or the parent state.
@@ -151,6 +154,18 @@ __device__ __forceinline__ void rel_accumulate_dyn(T (&r)[4], const T (&w)[16], 
         RC(3, 0) RC(3, 1) RC(3, 2) RC(3, 4) RC(4, 0) RC(4, 1) RC(4, 2) RC(4, 3)
 #undef RC
         default: rel_accumulate<4, 4>(r, w); break;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void chunk_sums_dyn(int r_low, T (&w)[16], double* csum, uint32_t gb, const uint32_t (&go)[4],
+                                               uint32_t lane) {
+    switch (r_low) {
+        case 0: chunk_sums<0, T>(w, csum, gb, go, lane); break;
+        case 1: chunk_sums<1, T>(w, csum, gb, go, lane); break;
+        case 2: chunk_sums<2, T>(w, csum, gb, go, lane); break;
+        case 3: chunk_sums<3, T>(w, csum, gb, go, lane); break;
+        default: chunk_sums<4, T>(w, csum, gb, go, lane); break;
     }
 }
 
@@ -291,13 +306,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
                 }
             }
             if (do_chunks) {
-                switch (r_low) {
-                    case 0: chunk_sums<0, T>(w, csum, gb, go, tid & 31u); break;
-                    case 1: chunk_sums<1, T>(w, csum, gb, go, tid & 31u); break;
-                    case 2: chunk_sums<2, T>(w, csum, gb, go, tid & 31u); break;
-                    case 3: chunk_sums<3, T>(w, csum, gb, go, tid & 31u); break;
-                    default: chunk_sums<4, T>(w, csum, gb, go, tid & 31u); break;
-                }
+                chunk_sums_dyn<T>(r_low, w, csum, gb, go, tid & 31u);
             }
         }
     }
@@ -457,7 +466,10 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
             if (lane >= (uint32_t)o) acc += nb;
         }
         const uint32_t hit = __ballot_sync(0xffffffffu, acc > t_j);
-        const uint32_t pick = hit ? (uint32_t)(__ffs(hit) - 1) : 31u;
+        // no hit: the target lies within rounding of the chunk's total (chunk sums formed from a sibling group's shared
+        // sums are not the bit-identical total of these 32 values) -> the last element that has any weight
+        const uint32_t has_w = __ballot_sync(0xffffffffu, s_w[wid][lane] > 0.0);
+        const uint32_t pick = hit ? (uint32_t)(__ffs(hit) - 1) : (has_w ? 31u - (uint32_t)__clz(has_w) : 31u);
         if ((int)lane == srcl) e_sel = pick;
     }
     if (!live) return;
@@ -479,6 +491,174 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
     }
     if (hist) atomicAdd(hist + ((uint64_t)nd.circuit << n_bits) + x, 1u);
     if (outcomes) outcomes[(uint64_t)nd.circuit * map.spc + shot - shot_begin] = x;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared passes of sibling groups (see SW_CROSS, CrossRec).  The leaves (parent, branch word, member) of a run of circuits
+// whose final sweeps differ only in a trailing real 2x2 on one qubit k share everything up to that op; with phi = the
+// state after the shared ops, member k's probability chunk sums are
+//     u00^2 C0[c] + u01^2 C0[c ^ k] + 2 u00 u01 X_k[c]   (bit k of c clear; u10, u11 when set),
+//     C0[c] = sum_{x in c} |phi(x)|^2,   X_k[c] = sum_{x in c} Re(conj(phi(x)) phi(x ^ 2^k)),
+// so ONE pass over the parent serves C0, four lane-exchanged X_k and the X of the shared ops' own high qubits, instead of
+// one sweep per member.  Nothing is written but those sums (the members are NODE_NOSTORE leaves: the sampler recomputes
+// the one chunk a trajectory lands in from the parent with the member's own descriptor).
+//
+// Index bits of a pass:  register bits (4; 16 amplitudes per thread; NH of them >= CHUNK_LOG), lane bits (5: the cross bits
+// + the lowest free bits), iteration bits (chunk bits that are neither: a thread loops over them and accumulates), outer
+// bits (everything else: one "unit" per value; a warp owns a strided set of units).  Chunk sums are complete after the
+// iteration loop and one xor-shuffle per lane bit that lies inside the chunk.
+template <typename T, int NH>
+__global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
+    leaf_cross_kernel(DevProgram<T> prog, const CrossRec* recs, const void* states, uint64_t slot_stride, double* c0_sums,
+                      double* chunk_sums, uint64_t chunk_stride, int n_bits, uint32_t ctas_log2) {
+    typedef typename Cx<T>::C C;
+    constexpr int NC = 1 << NH;          // chunks a thread's 16 values fall into
+    constexpr int LOWR = 4 - NH;         // register bits below the chunk size
+    __shared__ Staged<T> S;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const CrossRec R = recs[blockIdx.x >> ctas_log2];
+    const uint32_t part = blockIdx.x & ((1u << ctas_log2) - 1u);
+    stage_sweep<T, DT, false>(S, prog, R.sweep, R.branch, R.scale, tid);
+    const DirectSweep& D = S.D;
+    uint32_t go[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) go[i] = 1u << D.rbit[i];
+    const uint32_t regmask = go[0] | go[1] | go[2] | go[3];
+    uint32_t lanemask = 0, lane_part = 0, red_lanes = 0;      // red_lanes: lane bits that lie inside the chunk
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint32_t b = 1u << R.lane_bit[j];
+        lanemask |= b;
+        lane_part |= ((lane >> j) & 1u) ? b : 0u;
+        if (R.lane_bit[j] < CHUNK_LOG) red_lanes |= 1u << j;
+    }
+    const uint32_t chunkmask = (1u << CHUNK_LOG) - 1u;
+    const uint32_t itermask = chunkmask & ~regmask & ~lanemask;
+    const uint32_t allmask = n_bits >= 32 ? 0xffffffffu : (1u << n_bits) - 1u;
+    const uint32_t outermask = allmask & ~(chunkmask | regmask | lanemask);
+    const uint32_t n_it = 1u << __popc(itermask), n_units = 1u << __popc(outermask);
+    auto deposit = [](uint32_t v, uint32_t mask) {       // bits of v onto the set bits of mask, ascending
+        uint32_t r = 0;
+        for (uint32_t m = mask; m; m &= m - 1u, v >>= 1) r |= (v & 1u) ? (m & (0u - m)) : 0u;
+        return r;
+    };
+    const C* src = reinterpret_cast<const C*>(states) + (uint64_t)R.src_slot * slot_stride;
+    const T sc = (T)R.scale;
+    const bool need_scale = S.scale_op < 0;
+    const int nk = R.n_klanes;
+    const uint32_t slots = S.slots, sign_code = S.sign_code;
+    if (slots == 0) __trap();      // not the slotted shape: build_cross (engine.cu) must not have offered this run
+    C one;
+    one.x = 1;
+    one.y = 0;
+    // units of this warp: u = first, first + stride, ...; the deposited index advances by a masked add (the carry runs
+    // through the gaps of the mask when they are filled with ones)
+    const uint32_t warps_total = (DT / 32) << ctas_log2;
+    const uint32_t ustep = deposit(warps_total, outermask);
+    const bool want_c0 = R.c0_slot != NO_SLOT;
+    const bool want_r0 = NH > 0 && R.x_reg[0] != NO_SLOT, want_r1 = NH > 1 && R.x_reg[1] != NO_SLOT;
+    uint32_t udep = deposit(part * (DT / 32) + warp, outermask);
+    for (uint32_t u = part * (DT / 32) + warp; u < n_units;
+         u += warps_total, udep = ((udep | ~outermask) + ustep) & outermask) {
+        const uint32_t ubase = udep | lane_part;
+        T c0[NC], xl[4][NC], xr[NH > 0 ? NH : 1][NC];
+#pragma unroll
+        for (int h = 0; h < NC; h++) {
+            c0[h] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) xl[j][h] = 0;
+#pragma unroll
+            for (int r = 0; r < (NH > 0 ? NH : 1); r++) xr[r][h] = 0;
+        }
+        uint32_t idep = 0;
+        for (uint32_t it = 0; it < n_it; it++, idep = ((idep | ~itermask) + 1u) & itermask) {
+            const uint32_t gb = ubase | idep;
+            C a[16];
+            load_group<T, true>(a, S, src, gb, go, regmask, sc, false, need_scale, one, 0u);
+            apply_slotted<T>(a, S, slots, sign_code, gb);      // (the host only groups runs whose shared ops have this shape)
+            if (want_c0) {
+#pragma unroll
+                for (int s = 0; s < 16; s++) c0[s >> LOWR] += a[s].x * a[s].x + a[s].y * a[s].y;
+            }
+            // Re(conj(a) a') with a' held by the lane across bit j: the two lanes split the product by component -- the
+            // lower one forms a.x a'.x, the upper one a.y a'.y -- so that ONE exchange per amplitude serves both (the
+            // SM moves 32 lanes of shuffle per clock: two exchanges per amplitude made this kernel shuffle bound);
+            // the halves meet after the iteration loop
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < nk) {      // uniform
+                    const bool up = (lane >> j) & 1u;
+#pragma unroll
+                    for (int s = 0; s < 16; s++) {
+                        const T own = up ? a[s].y : a[s].x, send = up ? a[s].x : a[s].y;
+                        xl[j][s >> LOWR] += own * __shfl_xor_sync(0xffffffffu, send, 1 << j);
+                    }
+                }
+            }
+            // the shared ops' own high qubits: the partner is in this thread; both partner chunks carry the sum
+            if (want_r0) {
+                constexpr int bit = 1 << (NH > 0 ? LOWR : 0);
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    if (s & bit) continue;
+                    const T x = a[s].x * a[s | bit].x + a[s].y * a[s | bit].y;
+                    xr[0][s >> LOWR] += x;
+                    xr[0][(s | bit) >> LOWR] += x;
+                }
+            }
+            if (want_r1) {
+                constexpr int bit = 1 << (NH > 1 ? LOWR + 1 : 0);
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    if (s & bit) continue;
+                    const T x = a[s].x * a[s | bit].x + a[s].y * a[s | bit].y;
+                    xr[NH > 1 ? 1 : 0][s >> LOWR] += x;
+                    xr[NH > 1 ? 1 : 0][(s | bit) >> LOWR] += x;
+                }
+            }
+        }
+        // the two component halves of every lane-exchanged sum
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < nk) {
+#pragma unroll
+                for (int h = 0; h < NC; h++) xl[j][h] += __shfl_xor_sync(0xffffffffu, xl[j][h], 1 << j);
+            }
+        }
+        // complete the chunk sums over the lane bits inside the chunk
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            if ((red_lanes >> j) & 1u) {     // uniform
+#pragma unroll
+                for (int h = 0; h < NC; h++) {
+                    c0[h] += __shfl_xor_sync(0xffffffffu, c0[h], 1 << j);
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++)
+                        if (jj < nk) xl[jj][h] += __shfl_xor_sync(0xffffffffu, xl[jj][h], 1 << j);
+#pragma unroll
+                    for (int r = 0; r < NH; r++) xr[r][h] += __shfl_xor_sync(0xffffffffu, xr[r][h], 1 << j);
+                }
+            }
+        }
+        if ((lane & red_lanes) == 0) {
+#pragma unroll
+            for (int h = 0; h < NC; h++) {
+                uint32_t g = ubase;
+#pragma unroll
+                for (int r = 0; r < NH; r++) g |= ((h >> r) & 1) ? go[LOWR + r] : 0u;
+                const uint64_t c = g >> CHUNK_LOG;
+                if (R.c0_slot != NO_SLOT) c0_sums[(uint64_t)R.c0_slot * chunk_stride + c] = (double)c0[h];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (j < nk && R.x_lane[j] != NO_SLOT)
+                        chunk_sums[(uint64_t)R.x_lane[j] * chunk_stride + c] = (double)xl[j][h];
+#pragma unroll
+                for (int r = 0; r < NH; r++)
+                    if (R.x_reg[r] != NO_SLOT) chunk_sums[(uint64_t)R.x_reg[r] * chunk_stride + c] = (double)xr[r][h];
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -515,6 +695,24 @@ void launch_sample_nostore(const DevProgram<T>& prog, const NodeRec* leaves, con
                                                                     outcomes, shot_begin);
 }
 
+
+template <typename T>
+void launch_leaf_cross(const DevProgram<T>& prog, const CrossRec* recs, uint32_t n_recs, const void* states,
+                       uint64_t slot_stride, double* c0_sums, double* chunk_sums, uint64_t chunk_stride, int n_bits,
+                       int n_high_reg, uint32_t ctas_log2, cudaStream_t st) {
+    if (!n_recs) return;
+    const uint32_t grid = n_recs << ctas_log2;
+    switch (n_high_reg) {
+        case 0: leaf_cross_kernel<T, 0><<<grid, DT, 0, st>>>(prog, recs, states, slot_stride, c0_sums, chunk_sums, chunk_stride, n_bits, ctas_log2); break;
+        case 1: leaf_cross_kernel<T, 1><<<grid, DT, 0, st>>>(prog, recs, states, slot_stride, c0_sums, chunk_sums, chunk_stride, n_bits, ctas_log2); break;
+        default: leaf_cross_kernel<T, 2><<<grid, DT, 0, st>>>(prog, recs, states, slot_stride, c0_sums, chunk_sums, chunk_stride, n_bits, ctas_log2); break;
+    }
+}
+
+template void launch_leaf_cross<float>(const DevProgram<float>&, const CrossRec*, uint32_t, const void*, uint64_t, double*,
+                                       double*, uint64_t, int, int, uint32_t, cudaStream_t);
+template void launch_leaf_cross<double>(const DevProgram<double>&, const CrossRec*, uint32_t, const void*, uint64_t, double*,
+                                        double*, uint64_t, int, int, uint32_t, cudaStream_t);
 template void launch_sweep_direct<float>(const DevProgram<float>&, const SweepArgs&, cudaStream_t);
 template void launch_sweep_direct<double>(const DevProgram<double>&, const SweepArgs&, cudaStream_t);
 template void launch_sample_nostore<float>(const DevProgram<float>&, const NodeRec*, const void*, uint64_t, const double*,

@@ -27,7 +27,7 @@ def _circ(n, ops):
 
 def _reset_opts(eng):
     for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1),
-                 ("share_prefix", 1), ("nostore_max", 256), ("direct_min_bits", 10)):
+                 ("share_prefix", 1), ("nostore_max", 256), ("direct_min_bits", 10), ("leaf_cross", 1)):
         eng.set_option(k, v)
 
 
@@ -466,6 +466,7 @@ def test_shared_prefix_tree_is_bit_identical_to_per_circuit_trees(eng, n):
     from oracle import cpu_build
     from qcdenoise_b200.ir import encode_programs
     _reset_opts(eng)
+    eng.set_option("leaf_cross", 0)        # sibling groups (tests/test_leaf_cross_gpu.py) round complex64 sums differently
     rng = np.random.default_rng(70 + n)
     batch = _settings_batch(n, rng, [(0, True), (1, False)])
     B = len(batch)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.qcd_abi_version() == _lib.QCD_ABI_VERSION == 3
+    assert lib.qcd_abi_version() == _lib.QCD_ABI_VERSION == 4
 
 
 def test_create_fails_loudly_without_gpu():
