@@ -691,7 +691,8 @@ def main():
         dram_frac = dram_bytes / (agg["sweep_ms"] * 1e-3) / 1e9 / peak
         for nm, k in kinds.items():
             k["dram_frac"] = k["frac"] * tj.get(nm, tj.get("inner", 1.0))
-    roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (+ qcd::sweep_kernel<float> for prep sweeps)",
+    roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (inner levels, leaves with their own sweep) + "
+                                          "qcd::leaf_cross_kernel<float> (shared passes of sibling leaves)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_launch": agg["sweep_bytes"] / max(agg["sweep_launches"], 1),
@@ -701,7 +702,8 @@ def main():
                 # share their parent through L2, so `frac` can exceed 1 while the DRAM interface stays below its peak
                 "dram_frac": dram_frac,
                 "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep, read-only for a "
-                                     "leaf that is not stored]; one sweep per state-dependent noise-site group"}
+                                     "leaf that is not stored, one read of the parent per shared pass of a sibling group]; "
+                                     "one sweep per state-dependent noise-site group"}
     cpu = None
     if not args.no_cpu and world == 1:      # reported at N = 1 only
         cores = host_threads()
@@ -725,6 +727,11 @@ def main():
             "states_swept_per_step_rank0": agg["node_sweeps"] / args.steps,
             "leaf_states_per_step_rank0": agg["leaves"] / args.steps,
             "states_swept_per_graph_rank0": agg["node_sweeps"] / args.steps / max(rank_graphs[0], 1),
+            # leaf level: unstored leaves of one parent and branch word whose circuits differ in one trailing Hadamard take
+            # their chunk sums from shared passes over the parent (states_swept counts those passes, not the leaves)
+            "sibling_groups_rank0": {"leaves_per_step": agg.get("cross_leaves", 0) / args.steps,
+                                     "shared_passes_per_step": agg.get("cross_passes", 0) / args.steps,
+                                     "leaves_with_own_sweep_per_step": (agg["leaves"] - agg.get("cross_leaves", 0)) / args.steps},
             "rank_busy_ms_per_step": rank_busy_ms, "graphs_per_rank_last_step": rank_graphs,
             # the job's cost depends on which graphs it holds (noise sites per graph), so shots/s of different job sizes
             # are not directly comparable; the bytes the sweeps of ALL ranks moved per second are

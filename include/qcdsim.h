@@ -122,7 +122,7 @@ QCD_API const char* qcd_last_error(qcd_ctx* ctx); /* ctx may be NULL: message of
  *   "use_direct" 0/1 (1)    register-only kernel for single-pass sweeps / density-matrix passes
  *   "direct_min_bits" (10)  smallest state (index bits) the register-only kernel takes; smaller states and sweeps of more
  *                           than 3 passes run on the shared-memory tile kernel
- *   "nostore_max" (256)       leaves sampled by at most this many trajectories are not written to memory (0 = off)
+ *   "nostore_max" (1024)      leaves sampled by at most this many trajectories are not written to memory (0 = off)
  *   "leaf_cross" 0/1 (1)    unstored leaves of one parent and branch word whose circuits differ only in a trailing real 2x2
  *                           on one qubit k (a graph circuit and its Toth settings, stabilizers.py:136-156) share passes over
  *                           the parent that reduce |amp|^2 and Re(conj(amp[x]) amp[x ^ 2^k]) per 32-amplitude chunk; every

@@ -296,12 +296,34 @@ void build_cross(DevProg& dp, PoolAt pool_at /* pool offset -> std::complex<doub
             const DirectSweep* D = final_desc(c);
             if (!D || D->nops < base->nops || D->nops > base->nops + 1) continue;
             const size_t j = c - run_begin;
-            int n_diff = 0, od = -1;
+            int n_diff = 0, od = -1, om = -1;      // od / om: the differing op in the base / in the member
             for (int o = 0; o < base->nops; o++)
                 if (!same_op(*D, D->ops[o], *base, base->ops[o])) {
                     n_diff++;
-                    od = o;
+                    od = om = o;
                 }
+            if (n_diff > 1 && D->nops == base->nops) {
+                // the same ops in another order (a fused op is emitted where its last factor stood): match them one to one
+                uint32_t used = 0;
+                int un_b = -1, un_m = -1, n_un = 0;
+                for (int o = 0; o < base->nops; o++) {
+                    int hit = -1;
+                    for (int q = 0; q < D->nops && hit < 0; q++)
+                        if (!((used >> q) & 1u) && same_op(*D, D->ops[q], *base, base->ops[o])) hit = q;
+                    if (hit >= 0) used |= 1u << hit;
+                    else {
+                        un_b = o;
+                        n_un++;
+                    }
+                }
+                for (int q = 0; q < D->nops; q++)
+                    if (!((used >> q) & 1u)) un_m = q;
+                if (n_un == 1 && un_m >= 0) {      // (whether the odd op commutes past the others is checked below)
+                    n_diff = 1;
+                    od = un_b;
+                    om = un_m;
+                }
+            }
             if (n_diff == 0 && D->nops == base->nops) {
                 R.kbit[j] = -1;
                 n_ok++;
@@ -322,7 +344,7 @@ void build_cross(DevProg& dp, PoolAt pool_at /* pool offset -> std::complex<doub
             // The trailing 2x2 may have been fused into the shared op on its own qubit (no sign mask touches that qubit,
             // so it commuted there): the one differing op is then U x (the shared op), variant by variant.
             if (n_diff != 1 || D->nops != base->nops) continue;
-            const KOp &a = D->ops[od], &b = base->ops[od];
+            const KOp &a = D->ops[om], &b = base->ops[od];
             if (a.kind != K_M1 || b.kind != K_M1 || a.sel_shift != b.sel_shift || a.sel_mask != b.sel_mask ||
                 D->rbit[a.t0] != base->rbit[b.t0])
                 continue;
@@ -334,7 +356,7 @@ void build_cross(DevProg& dp, PoolAt pool_at /* pool offset -> std::complex<doub
                     for (uint32_t e = 0; e < op.count; e++)
                         if ((P.masks[op.off + e] >> k) & 1u) commutes = false;
                 if (op.kind == K_D1 && op.gbit == k) commutes = false;
-                if (o > od && op.kind == K_M1 && base->rbit[op.t0] == k) commutes = false;
+                if (o != od && op.kind == K_M1 && base->rbit[op.t0] == k) commutes = false;
             }
             if (!commutes) continue;
             double u[4] = {0, 0, 0, 0};
@@ -426,8 +448,9 @@ struct qcd_ctx {
                                  // kernel at n = 10 / 11 / 12 (2 000 reference-shaped circuits x 1024 shots: 12.4 -> 9.8,
                                  // 15.3 -> 12.2, 22.0 -> 15.2 ms), same complex128 outcomes
     bool no_slots = false;
-    uint32_t nostore_max = 256;  // leaves with at most this many trajectories are sampled without writing their state
-                                 // (measured on C4: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3 ms per step)
+    uint32_t nostore_max = 1024; // leaves with at most this many trajectories are sampled without writing their state
+                                 // (graph 0 before sibling groups: 8 -> 56.6, 64 -> 54.2, 512 -> 54.0, 4096 -> 55.3, 32768 -> 65.3
+                                 // ms per step; with sibling groups, the 8-graph job: 256 -> 2640, 1024 -> 2603, 4096 -> 2600 ms)
     bool share_prefix = true;    // consecutive circuits with identical sweeps up to the final one share their tree
     bool leaf_cross = true;      // unstored sibling leaves (same parent, same branch word, members of one run) take their
                                  // chunk sums from shared passes over the parent (SW_CROSS) instead of one sweep each
@@ -975,10 +998,19 @@ struct SvRunner {
                     pr.x_reg[1] = pi == 0 ? x_reg[1] : NO_SLOT;
                     cross_passes.push_back(pr);
                 }
+                uint32_t c0_owner = NO_SLOT;      // first member whose chunk sums are C0 itself: the others share its scan
                 for (size_t t = a; t < b; t++) {
                     NodeRec& r = chunk[cross_idx[t]];
                     const size_t m = r.circuit - CR.lead;
                     const int k = CR.kbit[m];
+                    if (k < 0) {
+                        if (c0_owner != NO_SLOT) {
+                            r.flags |= NODE_CROSSED | NODE_SHARED;
+                            r.pad = c0_owner;
+                            continue;
+                        }
+                        c0_owner = r.dst_slot;
+                    }
                     ComposeRec cr;
                     cr.c0_slot = first.dst_slot;
                     cr.kb = k >= 0 ? 1u << (k - chunk_log) : 0u;

@@ -389,7 +389,7 @@ __global__ void scan_l1_kernel(const NodeRec* leaves, const uint32_t* slots, dou
     const ComposeRec* cr = nullptr;
     if (leaves) {
         const uint32_t fl = leaves[item].flags;
-        if (!(fl & NODE_LEAF)) return;
+        if (!(fl & NODE_LEAF) || (fl & NODE_SHARED)) return;
         slot = leaves[item].dst_slot;
         if (comp && (fl & NODE_CROSSED)) cr = comp + (leaves[item].pad - 1u);
     } else {
@@ -437,7 +437,7 @@ __global__ void scan_l2_kernel(const NodeRec* leaves, const uint32_t* slots, dou
     const uint32_t item = blockIdx.x;
     uint32_t slot;
     if (leaves) {
-        if (!(leaves[item].flags & NODE_LEAF)) return;
+        if (!(leaves[item].flags & NODE_LEAF) || (leaves[item].flags & NODE_SHARED)) return;
         slot = leaves[item].dst_slot;
     } else {
         slot = slots ? slots[item] : item;

@@ -64,6 +64,9 @@ constexpr uint32_t NODE_LEAF = 1;
 constexpr uint32_t NODE_NOSTORE = 2;   // leaf whose state is not written: sampled by recomputing chunks from the parent
 constexpr uint32_t NODE_CROSSED = 4;   // NOSTORE leaf whose chunk sums come from its sibling group's shared passes (pad =
                                        // 1 + index of its ComposeRec); it takes no sweep of its own
+constexpr uint32_t NODE_SHARED = 8;    // NODE_CROSSED leaf whose chunk sums ARE its group's C0 (no trailing op, or one inside the
+                                       // chunks) and whose group has an earlier such member: it reads the scanned sums of that
+                                       // member's slot (pad = that slot) instead of scanning a copy
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 // Chunk sums of one member of a sibling group from the group's shared sums (see SW_CROSS): with A = C0[c & ~kb],

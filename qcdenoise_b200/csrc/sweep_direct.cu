@@ -399,8 +399,9 @@ __global__ void __launch_bounds__(32 * SN_WARPS) sample_nostore_kernel(
     const uint32_t pcirc = map.first_circuit + nd.circuit;      // circuit index in the Philox counters
     if (live) {
         shot = traj_shot(map, tids[i], nd.circuit);
-        const double* cs = chunk_sums + (uint64_t)nd.dst_slot * chunk_stride;
-        const double* bs = block_sums + (uint64_t)nd.dst_slot * block_stride;
+        const uint32_t sum_slot = (nd.flags & NODE_SHARED) ? nd.pad : nd.dst_slot;
+        const double* cs = chunk_sums + (uint64_t)sum_slot * chunk_stride;
+        const double* bs = block_sums + (uint64_t)sum_slot * block_stride;
         const uint32_t n_blocks = (n_chunks + (1u << SCAN_BLOCK_LOG) - 1u) >> SCAN_BLOCK_LOG;
         target = u53(draw(seed, pcirc, shot, QCD_STREAM_MEASURE)) * bs[n_blocks - 1];
         const uint32_t b = upper_search(bs, 0, n_blocks, target);

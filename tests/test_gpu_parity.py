@@ -27,7 +27,7 @@ def _circ(n, ops):
 
 def _reset_opts(eng):
     for k, v in (("tile_bits", 0), ("max_slots", 0), ("table_cap_log2", 22), ("max_chunk", 1 << 25), ("use_direct", 1),
-                 ("share_prefix", 1), ("nostore_max", 256), ("direct_min_bits", 10), ("leaf_cross", 1)):
+                 ("share_prefix", 1), ("nostore_max", 1024), ("direct_min_bits", 10), ("leaf_cross", 1)):
         eng.set_option(k, v)
 
 

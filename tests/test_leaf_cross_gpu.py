@@ -19,7 +19,7 @@ def eng():
     import qcdenoise_b200 as qb
     e = qb.Engine(0)
     yield e
-    for k, v in (("leaf_cross", 1), ("nostore_max", 256), ("max_slots", 0), ("max_chunk", 1 << 25), ("table_cap_log2", 22)):
+    for k, v in (("leaf_cross", 1), ("nostore_max", 1024), ("max_slots", 0), ("max_chunk", 1 << 25), ("table_cap_log2", 22)):
         e.set_option(k, v)
     e.close()
 
@@ -94,7 +94,7 @@ def test_sibling_groups_with_stored_leaves_and_cut_launches(eng):
     B = len(batch)
     eng.upload([_circ(n, ops) for ops in batch])
     shots, seed = 3000, 11
-    eng.set_option("nostore_max", 256)
+    eng.set_option("nostore_max", 1024)
     eng.set_option("leaf_cross", 0)
     h0, o0 = eng.run_trajectories(shots, seed=seed, precision=64, want_outcomes=True)
     h0, o0 = h0.cpu().numpy(), o0.cpu().numpy()
@@ -121,7 +121,7 @@ def test_sibling_group_expectation_values(eng):
     batch = _graph_and_settings(n, edges, rng)
     eng.upload([_circ(n, ops) for ops in batch])
     eng.set_option("leaf_cross", 1)
-    eng.set_option("nostore_max", 256)
+    eng.set_option("nostore_max", 1024)
     shots = 100_000
     hist, _ = eng.run_trajectories(shots, seed=3, precision=32)
     assert eng.stats()["cross_leaves"] > 0
