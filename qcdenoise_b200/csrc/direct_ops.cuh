@@ -386,23 +386,40 @@ __device__ __forceinline__ void apply_sweep(typename Cx<T>::C (&a)[16], const St
     }
 }
 
-// Slotted fast path (see stage_sweep): `slots` != 0.
+// Slotted fast path (see stage_sweep): `slots` != 0.  `diag_bits`: bit i set <=> the op of slot i is real diagonal
+// (slot_diag_bits, formed once per CTA: the streaming loop then branches on registers only -- with the classification read
+// from shared memory in the loop, every slot cost a dependent LDS -> compare -> branch, the top stall of the leaf kernels).
+template <typename T>
+__device__ __forceinline__ uint32_t slot_diag_bits(const Staged<T>& S, uint32_t slots) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t o = (slots >> (4 * i)) & 0xFu;
+        if (o != 0xFu && S.kind_flags[o] == 2u) bits |= 1u << i;
+    }
+    return bits;
+}
 template <typename T>
 __device__ __forceinline__ void apply_slotted(typename Cx<T>::C (&a)[16], const Staged<T>& S, uint32_t slots,
-                                              uint32_t sign_code, uint32_t gb) {
+                                              uint32_t sign_code, uint32_t gb, uint32_t diag_bits) {
     // the pre-sign slots hold the Kraus variants: the no-jump operators are diagonal (two multipliers per pair)
-#define QCD_SLOT(shift, r)                                                   \
+#define QCD_SLOT(i, r)                                                       \
     {                                                                        \
-        const uint32_t o = (slots >> (shift)) & 0xFu;                        \
+        const uint32_t o = (slots >> (4 * (i))) & 0xFu;                      \
         if (o != 0xFu) {                                                     \
-            if (S.kind_flags[o] == 2u) m1d<r>(a, S.mats[o]);                 \
+            if ((diag_bits >> (i)) & 1u) m1d<r>(a, S.mats[o]);               \
             else m1r<r>(a, S.mats[o]);                                       \
         }                                                                    \
     }
-    QCD_SLOT(0, 0) QCD_SLOT(4, 1) QCD_SLOT(8, 2) QCD_SLOT(12, 3)
+    QCD_SLOT(0, 0) QCD_SLOT(1, 1) QCD_SLOT(2, 2) QCD_SLOT(3, 3)
     if (sign_code) apply_signs<T>(a, S, sign_code, gb);
-    QCD_SLOT(16, 0) QCD_SLOT(20, 1) QCD_SLOT(24, 2) QCD_SLOT(28, 3)
+    QCD_SLOT(4, 0) QCD_SLOT(5, 1) QCD_SLOT(6, 2) QCD_SLOT(7, 3)
 #undef QCD_SLOT
+}
+template <typename T>
+__device__ __forceinline__ void apply_slotted(typename Cx<T>::C (&a)[16], const Staged<T>& S, uint32_t slots,
+                                              uint32_t sign_code, uint32_t gb) {
+    apply_slotted<T>(a, S, slots, sign_code, gb, slot_diag_bits<T>(S, slots));
 }
 
 

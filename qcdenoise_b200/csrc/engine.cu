@@ -956,7 +956,7 @@ struct SvRunner {
                 const NodeRec first = chunk[cross_idx[a]];
                 const DevProg::CrossRun& CR = dp->cross_runs[dp->cross_of_circuit[first.circuit]];
                 // cross bits of the members: the shared ops' own high qubits come for free with the first pass, the
-                // others ride on lane bits, four per pass
+                // others ride on lane bits, five per pass
                 uint32_t x_reg[2] = {NO_SLOT, NO_SLOT};
                 std::pair<uint8_t, uint32_t> kl[64];      // (bit, slot of the member that owns it)
                 size_t nk = 0;
@@ -967,7 +967,10 @@ struct SvRunner {
                     if ((CR.reg_mask >> k) & 1u) x_reg[CR.high_bit[0] == k ? 0 : 1] = r.dst_slot;
                     else kl[nk++] = std::make_pair((uint8_t)k, r.dst_slot);
                 }
-                const size_t n_pass = std::max<size_t>(1, (nk + 3) / 4);
+                static const size_t KL = getenv("QCD_CROSS_KLANES")       // tuning only (measured: 5 > 4 > 3 > 2)
+                                             ? std::min(CROSS_KLANES, std::max(1, atoi(getenv("QCD_CROSS_KLANES"))))
+                                             : CROSS_KLANES;
+                const size_t n_pass = std::max<size_t>(1, (nk + KL - 1) / KL);
                 // a shared pass costs about 2.5 sweeps of one unstored leaf (measured: 3.1 us against 1.2 us at n = 20)
                 if (5 * n_pass >= 2 * members) {      // nothing saved
                     a = b;
@@ -984,7 +987,7 @@ struct SvRunner {
                     pr.scale = first.scale;
                     uint32_t used = CR.reg_mask;
                     int nl = 0;
-                    for (size_t q = 4 * pi; q < std::min(nk, 4 * pi + 4); q++) {
+                    for (size_t q = KL * pi; q < std::min(nk, KL * pi + KL); q++) {
                         pr.lane_bit[nl] = kl[q].first;
                         pr.x_lane[nl] = kl[q].second;
                         used |= 1u << kl[q].first;
@@ -993,7 +996,7 @@ struct SvRunner {
                     pr.n_klanes = (uint8_t)nl;
                     for (int bb = 0; nl < 5; bb++)      // the lowest free bits fill the warp
                         if (!((used >> bb) & 1u)) pr.lane_bit[nl++] = (uint8_t)bb;
-                    for (int q = pr.n_klanes; q < 4; q++) pr.x_lane[q] = NO_SLOT;
+                    for (int q = pr.n_klanes; q < CROSS_KLANES; q++) pr.x_lane[q] = NO_SLOT;
                     pr.x_reg[0] = pi == 0 ? x_reg[0] : NO_SLOT;
                     pr.x_reg[1] = pi == 0 ? x_reg[1] : NO_SLOT;
                     cross_passes.push_back(pr);

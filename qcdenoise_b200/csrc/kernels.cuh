@@ -74,7 +74,7 @@ constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 // kb == 0: sum(c) = C0[c] (no trailing op, or one that acts inside the 32-amplitude chunks).
 // One shared pass over the parent state of a sibling group (leaf_cross_kernel).  A thread holds the 16 amplitudes of the
 // SW_CROSS descriptor's register bits (the shared ops' qubits + the lowest other bits); the 5 lane bits of a warp are up to
-// 4 cross bits k (their X_k come from lane exchanges) + the lowest free bits.
+// 5 cross bits k (their X_k come from lane exchanges) + the lowest free bits.
 struct CrossRec {
     uint32_t src_slot;       // parent state
     uint32_t c0_slot;        // slot of c0_sums that receives C0 (NO_SLOT: not emitted by this pass)
@@ -84,9 +84,11 @@ struct CrossRec {
     uint8_t lane_bit[5];     // global index bit carried by lane bit j
     uint8_t n_klanes;        // lane bits [0, n_klanes) are cross bits
     uint8_t pad[2];
-    uint32_t x_lane[4];      // chunk_sums slot that receives X of lane_bit[j]
+    uint32_t x_lane[5];      // chunk_sums slot that receives X of lane_bit[j]
     uint32_t x_reg[2];       // ... of the descriptor's j-th register bit >= CHUNK_LOG (NO_SLOT: not wanted)
+    uint32_t pad2;
 };
+constexpr int CROSS_KLANES = 5;
 
 struct ComposeRec {
     uint32_t c0_slot;

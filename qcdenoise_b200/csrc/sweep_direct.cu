@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
     const bool is_prep = HAS_PREP && (D.flags & SW_PREP) != 0, need_scale = S.scale_op < 0;
     const int nops = D.nops;
     const uint32_t slots = args.no_slots ? 0u : S.slots, sign_code = S.sign_code;
+    const uint32_t diag_bits = slots ? slot_diag_bits<T>(S, slots) : 0u;
     const uint32_t groups_per_cta = 1u << (n_bits - 4 - (int)args.tiles_log2);
     const uint32_t grp0 = part * groups_per_cta;
     const int rq0 = D.red_q[0], rq1 = D.red_q[1];
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? DIRECT_MINB : DIRECT_MINB
         gb = ((gb & ~(go[3] - 1u)) << 1) | (gb & (go[3] - 1u));
         C a[16];
         load_group<T, VEC>(a, S, src, gb, go, regmask, sc, is_prep, need_scale, prep_rest, prep_vmask);
-        if (slots) apply_slotted<T>(a, S, slots, sign_code, gb);
+        if (slots) apply_slotted<T>(a, S, slots, sign_code, gb, diag_bits);
         else apply_sweep<T>(a, S, nops, gb, go, HAS_M4 ? &s_ybuf[0][0] : nullptr, DT, tid);
         if (store) {
             if (VEC) {
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
     const int nk = R.n_klanes;
     const uint32_t slots = S.slots, sign_code = S.sign_code;
     if (slots == 0) __trap();      // not the slotted shape: build_cross (engine.cu) must not have offered this run
+    const uint32_t diag_bits = slot_diag_bits<T>(S, slots);
     C one;
     one.x = 1;
     one.y = 0;
@@ -563,12 +565,12 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
     for (uint32_t u = part * (DT / 32) + warp; u < n_units;
          u += warps_total, udep = ((udep | ~outermask) + ustep) & outermask) {
         const uint32_t ubase = udep | lane_part;
-        T c0[NC], xl[4][NC], xr[NH > 0 ? NH : 1][NC];
+        T c0[NC], xl[CROSS_KLANES][NC], xr[NH > 0 ? NH : 1][NC];
 #pragma unroll
         for (int h = 0; h < NC; h++) {
             c0[h] = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) xl[j][h] = 0;
+            for (int j = 0; j < CROSS_KLANES; j++) xl[j][h] = 0;
 #pragma unroll
             for (int r = 0; r < (NH > 0 ? NH : 1); r++) xr[r][h] = 0;
         }
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
             const uint32_t gb = ubase | idep;
             C a[16];
             load_group<T, true>(a, S, src, gb, go, regmask, sc, false, need_scale, one, 0u);
-            apply_slotted<T>(a, S, slots, sign_code, gb);      // (the host only groups runs whose shared ops have this shape)
+            apply_slotted<T>(a, S, slots, sign_code, gb, diag_bits);      // (the host only groups runs of this shape)
             if (want_c0) {
 #pragma unroll
                 for (int s = 0; s < 16; s++) c0[s >> LOWR] += a[s].x * a[s].x + a[s].y * a[s].y;
@@ -586,14 +588,22 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
             // lower one forms a.x a'.x, the upper one a.y a'.y -- so that ONE exchange per amplitude serves both (the
             // SM moves 32 lanes of shuffle per clock: two exchanges per amplitude made this kernel shuffle bound);
             // the halves meet after the iteration loop
+#pragma unroll 1
+            for (int j = 0; j < nk; j++) {      // one copy of the exchange code (the kernel is instruction-fetch sensitive)
+                const bool up = (lane >> j) & 1u;
+                T part[NC];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j < nk) {      // uniform
-                    const bool up = (lane >> j) & 1u;
+                for (int h = 0; h < NC; h++) part[h] = 0;
 #pragma unroll
-                    for (int s = 0; s < 16; s++) {
-                        const T own = up ? a[s].y : a[s].x, send = up ? a[s].x : a[s].y;
-                        xl[j][s >> LOWR] += own * __shfl_xor_sync(0xffffffffu, send, 1 << j);
+                for (int s = 0; s < 16; s++) {
+                    const T own = up ? a[s].y : a[s].x, send = up ? a[s].x : a[s].y;
+                    part[s >> LOWR] += own * __shfl_xor_sync(0xffffffffu, send, 1 << j);
+                }
+#pragma unroll
+                for (int jj = 0; jj < CROSS_KLANES; jj++) {
+                    if (jj == j) {
+#pragma unroll
+                        for (int h = 0; h < NC; h++) xl[jj][h] += part[h];
                     }
                 }
             }
@@ -621,7 +631,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
         }
         // the two component halves of every lane-exchanged sum
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < CROSS_KLANES; j++) {
             if (j < nk) {
 #pragma unroll
                 for (int h = 0; h < NC; h++) xl[j][h] += __shfl_xor_sync(0xffffffffu, xl[j][h], 1 << j);
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
                 for (int h = 0; h < NC; h++) {
                     c0[h] += __shfl_xor_sync(0xffffffffu, c0[h], 1 << j);
 #pragma unroll
-                    for (int jj = 0; jj < 4; jj++)
+                    for (int jj = 0; jj < CROSS_KLANES; jj++)
                         if (jj < nk) xl[jj][h] += __shfl_xor_sync(0xffffffffu, xl[jj][h], 1 << j);
 #pragma unroll
                     for (int r = 0; r < NH; r++) xr[r][h] += __shfl_xor_sync(0xffffffffu, xr[r][h], 1 << j);
@@ -651,7 +661,7 @@ __global__ void __launch_bounds__(DT, sizeof(T) == 4 ? CROSS_MINB : 2)
                 const uint64_t c = g >> CHUNK_LOG;
                 if (R.c0_slot != NO_SLOT) c0_sums[(uint64_t)R.c0_slot * chunk_stride + c] = (double)c0[h];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < CROSS_KLANES; j++)
                     if (j < nk && R.x_lane[j] != NO_SLOT)
                         chunk_sums[(uint64_t)R.x_lane[j] * chunk_stride + c] = (double)xl[j][h];
 #pragma unroll
