@@ -678,11 +678,12 @@ def main():
         agg.setdefault(k, [0, 0, 0, 0])
     achieved = agg["sweep_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9 if agg["sweep_ms"] > 0 else None
     kinds = _kind_rates(agg, peak)
-    traffic, traffic_src, dram_frac = None, None, None
+    traffic, traffic_src, dram_frac, tj_inner = None, None, None, None
     tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp):   # DRAM bytes per algorithmic byte PER LAUNCH KIND, from the committed ncu --set full capture
         with open(tp) as f:
             tj = json.load(f)["dram_bytes_per_algorithmic_byte"]
+        tj_inner = tj.get("inner")
         dram_bytes = sum(tj.get(nm, tj.get("inner", 1.0)) * agg["kind_bytes"][i]
                          for i, nm in enumerate(("prep", "inner", "leaf", "mixed")))
         traffic = dram_bytes / max(agg["sweep_launches"], 1)
@@ -691,16 +692,31 @@ def main():
         dram_frac = dram_bytes / (agg["sweep_ms"] * 1e-3) / 1e9 / peak
         for nm, k in kinds.items():
             k["dram_frac"] = k["frac"] * tj.get(nm, tj.get("inner", 1.0))
-    roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float> (inner levels, leaves with their own sweep) + "
-                                          "qcd::leaf_cross_kernel<float> (shared passes of sibling leaves)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "bytes_per_launch": agg["sweep_bytes"] / max(agg["sweep_launches"], 1),
-                "avg_launch_ms": agg["sweep_ms"] / max(agg["sweep_launches"], 1),
+    # The dominant kernel is the register-only sweep of the INNER tree levels (about half of the step, HBM-bound): the
+    # top-level figures are its own.  The leaf level (sweep_direct_kernel<.,.,2> for leaves that keep their own sweep +
+    # leaf_cross_kernel for the shared passes of sibling leaves) is bounded by instruction issue / latency, not by HBM:
+    # its entry under per_kind says how far below the HBM roofline that leaves it; `all_sweeps` aggregates every launch.
+    inner = kinds.get("inner") or {}
+    n_inner = max(agg["kind_launches"][1], 1)
+    if "leaf" in kinds and agg["kind_ms"][2] > 0:
+        state_bytes = (1 << N_QUBITS) * (8 if args.precision == 32 else 16)
+        kinds["leaf"]["leaves_per_ms"] = agg["leaves"] / agg["kind_ms"][2]
+        # what the same leaves would have requested at one read of the parent per leaf (the accounting before sibling groups)
+        kinds["leaf"]["one_read_per_leaf_equivalent_GBps"] = agg["leaves"] * state_bytes / (agg["kind_ms"][2] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "qcd::sweep_direct_kernel<float, true, 1> (register-only sweep, inner tree levels)",
+                "achieved": inner.get("algorithmic_GBps"), "peak": peak, "unit": "GB/s", "frac": inner.get("frac"),
+                "traffic": (tj_inner * agg["kind_bytes"][1] / n_inner) if tj_inner is not None else None,
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "bytes_per_launch": agg["kind_bytes"][1] / n_inner, "avg_launch_ms": agg["kind_ms"][1] / n_inner,
+                # the same launches in DRAM bytes (ncu capture): sibling states re-read their parent from L2, so `frac` can
+                # exceed 1 while the DRAM interface stays below its peak
+                "dram_frac": inner.get("dram_frac"),
+                "share_of_step": agg["kind_ms"][1] / ms,
                 "sweep_share_of_step": agg["sweep_ms"] / ms, "per_kind": kinds,
-                # the same launches measured in DRAM bytes (ncu capture) instead of algorithmic bytes: sibling states
-                # share their parent through L2, so `frac` can exceed 1 while the DRAM interface stays below its peak
-                "dram_frac": dram_frac,
+                "all_sweeps": {"achieved": achieved, "frac": achieved / peak if achieved else None, "dram_frac": dram_frac,
+                               "dram_bytes_per_launch": traffic,
+                               "bytes_per_launch": agg["sweep_bytes"] / max(agg["sweep_launches"], 1),
+                               "avg_launch_ms": agg["sweep_ms"] / max(agg["sweep_launches"], 1)},
                 "algorithmic_bytes": "2 x 2^20 x 8 B per (state, sweep) [write-only for the prep sweep, read-only for a "
                                      "leaf that is not stored, one read of the parent per shared pass of a sibling group]; "
                                      "one sweep per state-dependent noise-site group"}
