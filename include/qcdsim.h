@@ -327,6 +327,13 @@ QCD_API int qcd_gate_entries(const qcd_op* ops, const uint32_t* op_offsets, int 
 QCD_API int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* params, size_t n_params, int n_qubits,
                             int mode, int precision, int tile_bits, char* buf, size_t cap, size_t* needed);
 
+/* Host-only introspection (no GPU needed): the sibling runs the engine would form for this batch in statevector mode
+ * (option "leaf_cross"): consecutive circuits that share everything but a trailing real 2x2 on one qubit.  JSON:
+ * {"runs": [{"lead", "members", "n_high", "reg_bits": [4], "nops", "kbit": [per member: qubit of the trailing op (>= 5),
+ * -1 = chunk sums are the shared C0, -2 = keeps its own sweep], "u": [4 per member, row-major]}]}. */
+QCD_API int qcd_debug_sibling_runs_json(const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                                int n_circuits, int n_qubits, int precision, char* buf, size_t cap, size_t* needed);
+
 /* Host-only introspection (no GPU needed): the pass schedule of ONE circuit for the on-chip density-matrix interpreter
  * (option "dm_on_chip").  Pass p acts inside the qubit pair pass_qubits[2 p], pass_qubits[2 p + 1] (0xFF = one qubit
  * only) and executes the next pass_n_ops[p] entries of `order` (indices into ops[], identity gates left out).  Returns

@@ -81,6 +81,8 @@ _PROTOS = {
     "qcd_debug_schedule_json": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t,
                                                ctypes.POINTER(ctypes.c_size_t)]),
+    "qcd_debug_sibling_runs_json": (ctypes.c_int, [_P, _P, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
 }
 EXPORTS = tuple(_PROTOS)
 _lib = None

@@ -155,6 +155,54 @@ struct DevProg {
 
 enum { DF_OK = 1, DF_VEC = 2, DF_RED = 4, DF_FINAL = 8, DF_PREP = 16 };
 
+// Descriptor of pass `pi` of sweep S for the register-only kernel (D.ok stays 0 when the pass does not qualify).
+void describe_pass(const Program& P, DirectSweep& D, const Sweep& S, uint32_t pi, uint8_t flags, bool reduce) {
+    // (states below 13 index bits still get descriptors: the tile kernel stages its passes from them)
+    const Pass& ps = P.passes[pi];
+    const uint32_t nops = ps.op_end - ps.op_begin;
+    if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) return;
+    uint32_t n_signs = 0, n_m4 = 0;
+    for (uint32_t o = 0; o < nops; o++) {
+        KOp op = P.kops[ps.op_begin + o];
+        if (op.kind == K_SIGNS) {
+            if (n_signs + op.count > 48) return;
+            op.t1 = (uint8_t)n_signs;
+            n_signs += op.count;
+        }
+        if (op.kind == K_M4 && (++n_m4 > 1 || op.sel_mask != 0)) return;  // one plain 16x16 superoperator per pass
+        D.ops[o] = op;
+    }
+    D.ok = 1;
+    D.n_bits = S.n_bits;
+    D.nreg = ps.nreg;
+    D.nops = (uint8_t)nops;
+    for (int i = 0; i < REG_BITS; i++) {
+        const int b = ps.rbits[i];
+        D.rbit[i] = (uint8_t)(b < S.L ? b : S.high[b - S.L]);
+    }
+    D.red_q[0] = reduce ? S.red_q[0] : -1;
+    D.red_q[1] = reduce ? S.red_q[1] : -1;
+    D.flags = flags;
+    D.prep_off = S.prep_off;
+}
+
+// Runs of consecutive circuits whose sweeps are identical up to the final one (a graph circuit followed by its stabilizer
+// settings): one trajectory tree serves the whole run down to the parents of the leaves.  -> member bits.
+int assign_runs(Program& P, int mode) {
+    size_t longest = 1;
+    for (size_t c = 0; c < P.circuits.size(); c++) {
+        uint32_t lead = (uint32_t)c;
+        if (mode == MODE_SV && c > 0 && P.prefix[c] == P.prefix[c - 1] &&
+            c - P.circuits[c - 1].lead < ((size_t)1 << MAX_MEMBER_BITS))
+            lead = P.circuits[c - 1].lead;
+        P.circuits[c].lead = lead;
+        longest = std::max(longest, c - lead + 1);
+    }
+    int bits = 0;
+    while (((size_t)1 << bits) < longest) bits++;
+    return bits;
+}
+
 // Sibling-group descriptors of every run of circuits that share a prefix (see DevProg::CrossRun): appended to
 // dp.direct_host behind the per-sweep and per-pass descriptors.
 template <typename PoolAt>
@@ -633,19 +681,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
             parts[t] = Program();
         }
         if (pool_total > 0xffffffffull) return fail(ctx, QCD_E_UNSUPPORTED, "matrix pool exceeds 2^32 entries: split the upload");
-        // runs of consecutive circuits whose sweeps are identical up to the final one (a graph circuit followed by its
-        // stabilizer settings): one trajectory tree serves the whole run down to the parents of the leaves
-        size_t longest = 1;
-        for (size_t c = 0; c < P.circuits.size(); c++) {
-            uint32_t lead = (uint32_t)c;
-            if (mode == MODE_SV && c > 0 && P.prefix[c] == P.prefix[c - 1] &&
-                c - P.circuits[c - 1].lead < ((size_t)1 << MAX_MEMBER_BITS))
-                lead = P.circuits[c - 1].lead;
-            P.circuits[c].lead = lead;
-            longest = std::max(longest, c - lead + 1);
-        }
-        dp.member_bits = 0;
-        while (((size_t)1 << dp.member_bits) < longest) dp.member_bits++;
+        dp.member_bits = assign_runs(P, mode);
     }
     const double t_lowered = Trace::now();
     dp.host_ready = false;
@@ -698,33 +734,7 @@ int get_program(qcd_ctx* ctx, int mode, int precision, DevProg** out) {
         dp.direct_host.assign(P.sweeps.size() + P.passes.size(), zero);
     }
     auto describe = [&](DirectSweep& D, const Sweep& S, uint32_t pi, uint8_t flags, bool reduce) {
-        // (states below 13 index bits still get descriptors: the tile kernel stages its passes from them)
-        const Pass& ps = P.passes[pi];
-        const uint32_t nops = ps.op_end - ps.op_begin;
-        if (ps.nreg != REG_BITS || nops > (uint32_t)MAX_DIRECT_OPS) return;
-        uint32_t n_signs = 0, n_m4 = 0;
-        for (uint32_t o = 0; o < nops; o++) {
-            KOp op = P.kops[ps.op_begin + o];
-            if (op.kind == K_SIGNS) {
-                if (n_signs + op.count > 48) return;
-                op.t1 = (uint8_t)n_signs;
-                n_signs += op.count;
-            }
-            if (op.kind == K_M4 && (++n_m4 > 1 || op.sel_mask != 0)) return;  // one plain 16x16 superoperator per pass
-            D.ops[o] = op;
-        }
-        D.ok = 1;
-        D.n_bits = S.n_bits;
-        D.nreg = ps.nreg;
-        D.nops = (uint8_t)nops;
-        for (int i = 0; i < REG_BITS; i++) {
-            const int b = ps.rbits[i];
-            D.rbit[i] = (uint8_t)(b < S.L ? b : S.high[b - S.L]);
-        }
-        D.red_q[0] = reduce ? S.red_q[0] : -1;
-        D.red_q[1] = reduce ? S.red_q[1] : -1;
-        D.flags = flags;
-        D.prep_off = S.prep_off;
+        describe_pass(P, D, S, pi, flags, reduce);
     };
     dp.direct_flags.assign(dp.direct_host.size(), 0);
     auto flags_of = [&](size_t i) {
@@ -2645,4 +2655,58 @@ int qcd_debug_schedule_json(const qcd_op* ops, uint32_t n_ops, const double* par
     return rc;
 }
 
+int qcd_debug_sibling_runs_json(const qcd_op* ops, const uint32_t* op_offsets, const double* params, size_t n_params,
+                                int n_circuits, int n_qubits, int precision, char* buf, size_t cap, size_t* needed) {
+    if (n_qubits < 1 || n_qubits > 30 || n_circuits < 1 || !ops || !op_offsets) return QCD_E_INVALID;
+    DevProg dp;
+    Program& P = dp.P;
+    P.n_qubits = n_qubits;
+    P.mode = MODE_SV;
+    P.n_bits = n_qubits;
+    P.k_max = default_tile_bits(precision);
+    std::string err;
+    int rc = QCD_OK;
+    for (int c = 0; c < n_circuits && rc == QCD_OK; c++)
+        rc = compile_circuit(P, ops + op_offsets[c], op_offsets[c + 1] - op_offsets[c], params, n_params, err);
+    std::string js;
+    if (rc != QCD_OK) {
+        js = "{\"error\":\"" + err + "\"}";
+    } else {
+        dp.member_bits = assign_runs(P, MODE_SV);
+        DirectSweep zero;
+        memset(&zero, 0, sizeof(zero));
+        dp.direct_host.assign(P.sweeps.size() + P.passes.size(), zero);
+        for (size_t si = 0; si < P.sweeps.size(); si++) {
+            const Sweep& S = P.sweeps[si];
+            if (S.pass_end - S.pass_begin == 1) describe_pass(P, dp.direct_host[si], S, S.pass_begin, S.flags, true);
+        }
+        build_cross(dp, [&](size_t off) -> std::complex<double> {       // the pool in device precision, as the engine sees it
+            const cd v = P.pool[off];
+            return precision == 64 ? v : cd((double)(float)v.real(), (double)(float)v.imag());
+        });
+        js = "{\"runs\":[";
+        char tmp[128];
+        for (size_t r = 0; r < dp.cross_runs.size(); r++) {
+            const DevProg::CrossRun& R = dp.cross_runs[r];
+            const DirectSweep& D = dp.direct_host[R.desc];
+            snprintf(tmp, sizeof(tmp), "%s{\"lead\":%u,\"members\":%u,\"n_high\":%d,\"reg_bits\":[%d,%d,%d,%d],\"nops\":%d,\"kbit\":[",
+                     r ? "," : "", R.lead, R.n_members, R.n_high, D.rbit[0], D.rbit[1], D.rbit[2], D.rbit[3], D.nops);
+            js += tmp;
+            for (size_t j = 0; j < R.kbit.size(); j++) js += (j ? "," : "") + std::to_string((int)R.kbit[j]);
+            js += "],\"u\":[";
+            for (size_t j = 0; j < R.u.size(); j++) {
+                snprintf(tmp, sizeof(tmp), "%s%.17g", j ? "," : "", R.u[j]);
+                js += tmp;
+            }
+            js += "]}";
+        }
+        js += "]}";
+    }
+    if (needed) *needed = js.size() + 1;
+    if (!buf || cap < js.size() + 1) return QCD_E_NOMEM;
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return rc;
+}
+
 }  // extern "C"
+

@@ -289,6 +289,26 @@ def debug_schedule(circuit, mode=0, precision=32, tile_bits=0):
         return d
 
 
+def debug_sibling_runs(circuits, precision=32):
+    """Host-only: the sibling runs the engine forms for this batch in statevector mode (option "leaf_cross") -> list of
+    dicts {lead, members, n_high, reg_bits, nops, kbit, u} (see include/qcdsim.h; no GPU needed)."""
+    lib = _lib.load()
+    ops, offsets, params, n = encode_programs(circuits)
+    cap = 1 << 16
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        need = ctypes.c_size_t()
+        rc = lib.qcd_debug_sibling_runs_json(_ptr(ops), _ptr(offsets), _ptr(params) if len(params) else None, len(params),
+                                             len(circuits), n, precision, buf, cap, ctypes.byref(need))
+        if rc == _lib.QCD_E_NOMEM and need.value > cap:
+            cap = need.value + 16
+            continue
+        d = json.loads(buf.value.decode())
+        if rc:
+            raise _lib.QcdError(rc, d.get("error", "lowering failed"))
+        return d["runs"]
+
+
 def debug_dm_schedule(circuit):
     """Host-only: the pass schedule of the on-chip density-matrix interpreter for one circuit ->
     [((q0, q1 or None), [op indices in execution order]), ...] (no GPU needed)."""
