@@ -1254,7 +1254,8 @@ struct SvRunner {
                 // parents only, and the later passes of a group find theirs in L2 (one CTA per pass streamed a whole
                 // state each: every pass came from DRAM, 3.9 us per pass measured)
                 int pl = std::max(0, n - 11 - 2 - 2);
-                if (const char* v = getenv("QCD_CROSS_PL")) pl = std::max(0, pl + atoi(v));      // tuning only
+                static const int pl_bias = getenv("QCD_CROSS_PL") ? atoi(getenv("QCD_CROSS_PL")) : 0;      // tuning only
+                pl = std::max(0, pl + pl_bias);
                 while (pl < n - 11 - 2 && ((uint64_t)n_cross_passes << pl) < 1184) pl++;
                 sweep_begin(ctx, SK_LEAF, (uint64_t)n_cross_passes * slot_stride * sizeof(C), st);
                 launch_leaf_cross<T>(prog, ctx->cross_recs.as<CrossRec>(), (uint32_t)n_cross_passes, ctx->states.p,
