@@ -183,21 +183,26 @@ def draw_device_props(noise_specs, enc, rng):
     if rc:
         raise _lib.QcdError(rc, "qcd_gate_entries: malformed gate lists")
     U = n_ent.value
-    full = (ecirc[:U].astype(np.int64) << 24) | ekey[:U].astype(np.int64)
+    ekey, ecirc = ekey[:U], ecirc[:U]
     op_entry = op_entry[:n_ops]
-    opcode = (full >> 16) & 0xFF
+    opcode = ((ekey >> np.uint32(16)) & np.uint32(0xFF)).astype(np.intp)
+    present = np.flatnonzero(np.bincount(opcode, minlength=256))
     gate = {}
     for nm in specs["cx"].keys():
-        top = np.full(len(full), np.nan)
-        for code in np.unique(opcode):
-            gname = _GATE_NAMES.get(int(code))
+        table = np.full(256, np.nan)          # spec value by opcode (NaN: the gate's spec has no such entry, quirk Q4)
+        for code in present:
             try:
-                top[opcode == code] = float(specs[gname][nm])
+                table[code] = float(specs[_GATE_NAMES.get(int(code))][nm])
             except KeyError:
                 pass
-        draw = rng.uniform(0.0, 1.0, size=len(full)) * np.where(np.isnan(top), 0.0, top)
-        gate[nm] = np.where(np.isnan(top), 1e-6, draw)
-    return {"qubit": qubit, "gate_key": (full & 0xFFFFFF).astype(np.uint32), "gate_circuit": (full >> 24).astype(np.int64),
+        top = table[opcode]
+        draw = rng.uniform(0.0, 1.0, size=U)
+        if np.isnan(table[present]).any():
+            missing = np.isnan(top)
+            gate[nm] = np.where(missing, 1e-6, draw * np.where(missing, 0.0, top))
+        else:
+            gate[nm] = draw * top
+    return {"qubit": qubit, "gate_key": ekey.copy(), "gate_circuit": ecirc.astype(np.int64),
             "gate": gate, "op_entry": op_entry.astype(np.int64), "n_circuits": B, "n_qubits": n}
 
 
